@@ -1,0 +1,256 @@
+/*
+ * libb200dm — C ABI of the B200 (sm_100a) diffusion hot path.
+ *
+ * The reference (seungjunlee96/lightning-generative-models) has no native/FFI layer: the path sits
+ * behind the Python classes Unet / GaussianDiffusion in models/generative/diffusion/ddpm.py.  Each
+ * entry point below therefore cites the reference Python lines whose arithmetic it replaces; the
+ * Python host mirror (lightning-generative-models_b200/b200dm) binds them with ctypes and re-creates
+ * the reference's class surface on top.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - the library never allocates, frees or synchronises; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*);
+ *   - return 0 on success; <0 on error: -1 bad shape/alignment, -2 unsupported configuration,
+ *     -3 workspace too small, -4 CUDA error (text via b200dm_last_error(), thread-local);
+ *   - dtype: 0 = fp32 activations ("fp32 mode"), 1 = bf16 activations with fp32 accumulation;
+ *   - activations are NHWC with an explicit pixel stride `ld` (elements) so that channel slices of a
+ *     concat buffer are addressable without copies (replaces torch.cat, ddpm.py:459,462,468).
+ */
+#ifndef B200DM_H
+#define B200DM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DM_OK 0
+#define B200DM_ERR_SHAPE (-1)
+#define B200DM_ERR_UNSUPPORTED (-2)
+#define B200DM_ERR_WORKSPACE (-3)
+#define B200DM_ERR_CUDA (-4)
+
+#define B200DM_F32 0
+#define B200DM_BF16 1
+
+/* objective enum — GaussianDiffusion(objective=...), ddpm.py:540,562-566 */
+#define B200DM_PRED_NOISE 0
+#define B200DM_PRED_X0 1
+#define B200DM_PRED_V 2
+
+int b200dm_version(void);
+const char* b200dm_last_error(void);
+/* number of kernels launched by this library on the calling thread since the last reset */
+int64_t b200dm_launch_count(void);
+void b200dm_reset_launch_count(void);
+/* 1 if the tcgen05/TMA path can be used on the current device (sm_100), else 0 */
+int b200dm_tc_available(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused scheduler / loss kernels (HBM-bound, vectorised).  Images are NCHW fp32 [B, C*H*W].
+ * `coef` tables are the fp32 schedule buffers registered at ddpm.py:601-662 (length T).
+ * Noise: if `noise` != NULL it is read (exact-parity mode); otherwise it is generated in registers
+ * with Philox4x32-10 keyed by (seed, stream_id) and counter = global element index / 4 + elem_offset/4,
+ * so results do not depend on how a batch is sharded over GPUs.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* normalize + q_sample: x_t = sqrt_ac[t]*(2*img-1 if normalize) + sqrt_1mac[t]*eps.
+ * Replaces ddpm.py:945 (normalize), :881 (randn_like), :869-876 (q_sample).
+ * Optionally writes eps (noise_out) and the normalised x0 (x0_out) for the loss. */
+int b200dm_q_sample(const float* img, const int64_t* t, const float* noise, float* x_t,
+                    float* noise_out, float* x0_out, const float* sqrt_ac, const float* sqrt_1mac,
+                    int32_t B, int64_t chw, int32_t normalize, uint64_t seed, uint64_t stream_id,
+                    uint64_t elem_offset, void* stream);
+
+/* target + MSE + loss weight + mean, and dL/d(model_out).  Replaces ddpm.py:911-925, :684-688.
+ * loss_acc: fp32[1] accumulator (must be zeroed by the caller); per-element grad
+ * d_out = 2*w[t]*(out-target)/(B*chw) written if d_out != NULL. */
+int b200dm_loss_fwd_bwd(const float* model_out, const float* x0, const float* noise,
+                        const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
+                        const float* loss_weight, float* loss_acc, float* d_out, int32_t B,
+                        int64_t chw, int32_t objective, void* stream);
+
+/* DDIM update for one (time, time_next) pair given the UNet output.
+ * Replaces model_predictions(clip_x_start=True, rederive_pred_noise=True) ddpm.py:707-734 and the
+ * update at :812-827.  coefficient scalars are computed on the host from the fp32 buffers exactly as
+ * the reference does (`alpha_next.sqrt()`, `c`, `sigma`).  last != 0: x_next = x0 (time_next < 0).
+ * x0_out optional. */
+int b200dm_ddim_step(const float* x_t, const float* model_out, const float* noise, float* x_next,
+                     float* x0_out, float c_sqrt_ac, float c_sqrt_1mac, float c_sqrt_recip,
+                     float c_sqrt_recipm1, float sqrt_alpha_next, float c, float sigma, int32_t last,
+                     int32_t objective, int64_t n, uint64_t seed, uint64_t stream_id,
+                     uint64_t elem_offset, void* stream);
+
+/* DDPM ancestral step.  Replaces p_mean_variance + p_sample, ddpm.py:736-757 (x0 clamped to [-1,1],
+ * posterior mean, + noise_std*z with noise_std = exp(0.5*logvar) computed by the host in fp32,
+ * z = 0 when add_noise == 0 i.e. t == 0). */
+int b200dm_ddpm_step(const float* x_t, const float* model_out, const float* noise, float* x_prev,
+                     float* x0_out, float c_sqrt_ac, float c_sqrt_1mac, float c_sqrt_recip,
+                     float c_sqrt_recipm1, float coef1, float coef2, float noise_std,
+                     int32_t add_noise, int32_t objective, int64_t n, uint64_t seed,
+                     uint64_t stream_id, uint64_t elem_offset, void* stream);
+
+/* N(0,1) fill with the same Philox stream (initial image of the samplers, ddpm.py:763,800). */
+int b200dm_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, uint64_t elem_offset,
+                 void* stream);
+
+/* unnormalize_to_zero_to_one, ddpm.py:86-87 */
+int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolutions as implicit GEMM (ddpm.py:96,103,160,187,213-215,252-253,377,413).
+ *   mode 0: k x k, stride 1, 'same' padding (k = 1 or 3); input [B,H,W,Cin]
+ *   mode 1: pixel-unshuffle(2) + 1x1 == 2x2 stride-2 conv; input [B,2H,2W,Cin], 4 taps (p1,p2)
+ *   mode 2: transpose of mode 1 (its data gradient): input [B,H,W,Cin], output [B,2H,2W,Cout],
+ *           weight taps (p1,p2) of shape [Cout][Cin]
+ * Packed weights: [taps][Cout][Cin] in the activation dtype (Cin contiguous).
+ * y = conv(x) + bias (+ res) (+ y if accumulate).  impl: 0 = SIMT (any shape, fp32 or bf16),
+ * 1 = tcgen05/TMEM/TMA (bf16; Cin % 64 == 0, Cout % 64 == 0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dtype, mode, ksize, impl;
+  int32_t B, H, W; /* OUTPUT spatial size for modes 0/1; INPUT spatial size for mode 2 */
+  int32_t Cin, Cout;
+  const void* x;
+  int32_t x_ld;
+  const void* w;
+  const float* bias;
+  void* y;
+  int32_t y_ld;
+  const void* res;
+  int32_t res_ld;
+  int32_t accumulate;
+} b200dm_conv_desc;
+
+int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream);
+
+/* weight gradient of a mode-0/mode-1 conv:  dW[tap][co][ci] (+)= sum_pix dY[pix,co] * X[pix+tap,ci]
+ * (fp32, same packed order as the master weights).  Uses `ws` (fp32, ws_bytes) for split-K partials
+ * when needed.  impl as above. */
+typedef struct {
+  int32_t dtype, mode, ksize, impl;
+  int32_t B, H, W;
+  int32_t Cin, Cout;
+  const void* x;
+  int32_t x_ld;
+  const void* dy;
+  int32_t dy_ld;
+  float* dw;
+  int32_t accumulate;
+} b200dm_wgrad_desc;
+
+int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream);
+
+/* column sums: out[c] (+)= sum_rows x[row*ld + c]  (bias gradients) */
+int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t rows, int32_t C, float* out,
+                  int32_t accumulate, void* stream);
+
+/* init_conv 7x7, pad 3 (ddpm.py:304,437): NCHW fp32 in -> NHWC out; weight OIHW fp32. */
+int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* w, const float* bias, void* y,
+                         int32_t y_ld, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Cout,
+                         void* stream);
+int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void* dy, int32_t dy_ld, float* dw,
+                           int32_t B, int32_t C, int32_t H, int32_t W, int32_t Cout, void* stream);
+
+/* final_conv 1x1 Cin -> C (ddpm.py:422,471): NHWC in -> NCHW fp32 out; weight [C][Cin] fp32. */
+int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
+                          const float* bias, float* y, int32_t B, int32_t HW, int32_t Cin, int32_t C,
+                          void* stream);
+/* dx NHWC (dtype), dw/db fp32 accumulated into (dw, db must be zeroed or hold prior grads) */
+int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
+                          const float* dy, void* dx, int32_t dx_ld, float* dw, float* db, int32_t B,
+                          int32_t HW, int32_t Cin, int32_t C, void* stream);
+
+/* nearest x2 upsample (ddpm.py:95) and its gradient (2x2 sum). NHWC. */
+int b200dm_upsample2x_fwd(int32_t dtype, const void* x, int32_t x_ld, void* y, int32_t y_ld,
+                          int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int b200dm_upsample2x_bwd(int32_t dtype, const void* dy, int32_t dy_ld, void* dx, int32_t dx_ld,
+                          int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm(8) + FiLM + SiLU (+ residual)  — Block.forward ddpm.py:164-173, ResnetBlock :189-200
+ * ---------------------------------------------------------------------------------------------- */
+/* per-(sample, group) mean and rstd (eps 1e-5) of x [B,HW,C]; stats = fp32 [B][G][2] */
+int b200dm_gn_stats(int32_t dtype, const void* x, int32_t x_ld, float* stats, int32_t B, int32_t HW,
+                    int32_t C, int32_t G, float eps, void* stream);
+/* y = silu(((x-mean)*rstd*gamma+beta)*(1+scale)+shift) (+res).  film: fp32, scale at
+ * film[b*film_ld + c], shift at film[b*film_ld + C + c]; NULL => no FiLM. */
+int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* stats,
+                        const float* gamma, const float* beta, const float* film, int32_t film_ld,
+                        const void* res, int32_t res_ld, void* y, int32_t y_ld, int32_t B, int32_t HW,
+                        int32_t C, int32_t G, void* stream);
+/* backward, three launches inside:  (1) per-(b,c) sums of dz and dz*xnorm  (2) parameter / FiLM
+ * grads + group means  (3) dx.  sums: fp32 workspace [B][C][2]; gmeans: fp32 workspace [B][G][2].
+ * dgamma/dbeta accumulate (+=); dfilm (same addressing as film) is overwritten. */
+int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x, int32_t x_ld,
+                        const float* stats, const float* gamma, const float* beta, const float* film,
+                        int32_t film_ld, void* dx, int32_t dx_ld, float* dgamma, float* dbeta,
+                        float* dfilm, float* sums, float* gmeans, int32_t B, int32_t HW, int32_t C,
+                        int32_t G, void* stream);
+
+/* RMSNorm (ddpm.py:107-113): y = x / max(||x||_2, 1e-12) * g * sqrt(C) (+ res) */
+int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* g, const void* res,
+                       int32_t res_ld, void* y, int32_t y_ld, int64_t rows, int32_t C, void* stream);
+/* dx = rmsnorm'(dy) (+ res);  dg += ... */
+int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x, int32_t x_ld,
+                       const float* g, const void* res, int32_t res_ld, void* dx, int32_t dx_ld,
+                       float* dg, int64_t rows, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention cores; qkv is [B, n, 384] (q | k | v, each heads*32 channels, head-major), heads = 4.
+ * ---------------------------------------------------------------------------------------------- */
+/* LinearAttention core, ddpm.py:222-238.  mem_kv fp32 [2][4][32][4].  ctx: fp32 [B][4][32][32];
+ * kstat: fp32 [B][4][32][2] (max, sum of exp) saved for backward.  out [B,n,128]. */
+int b200dm_linattn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, const float* mem_kv,
+                       float* ctx, float* kstat, void* out, int32_t out_ld, int32_t B, int32_t n,
+                       void* stream);
+/* dctx: fp32 workspace [B][4][32][32]; dmem_kv accumulates (+=) */
+int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const void* qkv,
+                       int32_t qkv_ld, const float* mem_kv, const float* ctx, const float* kstat,
+                       float* dctx, void* dqkv, int32_t dqkv_ld, float* dmem_kv, int32_t B,
+                       int32_t n, void* stream);
+/* Attention + Attend.forward (math branch), ddpm.py:255-271, models/modules/attend.py:111-126.
+ * mem_kv fp32 [2][4][4][32]; n <= 64. */
+int b200dm_attn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, const float* mem_kv, void* out,
+                    int32_t out_ld, int32_t B, int32_t n, void* stream);
+int b200dm_attn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const void* qkv,
+                    int32_t qkv_ld, const float* mem_kv, void* dqkv, int32_t dqkv_ld,
+                    float* dmem_kv, int32_t B, int32_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Time embedding (ddpm.py:119-132, :328-333) and small fp32 linears (ddpm.py:179-183)
+ * ---------------------------------------------------------------------------------------------- */
+/* emb[b, :] = [sin(t*f_i) | cos(t*f_i)], f_i = exp(-i*ln(theta)/(dim/2-1)) */
+int b200dm_sinusoidal(const int64_t* t, float* emb, int32_t B, int32_t dim, float theta,
+                      void* stream);
+/* Y = act(X W^T + b); X [M,K], W [N,K], Y [M,N] fp32.  act: 0 none, 1 GELU(erf), 2 SiLU.
+ * pre (optional) receives the pre-activation. */
+int b200dm_linear_fwd(const float* X, const float* W, const float* b, float* Y, float* pre, int32_t M,
+                      int32_t N, int32_t K, int32_t act, void* stream);
+/* dPre = dY * act'(pre) (in place into dY when act != 0), dX = dPre W, dW += dPre^T X, db += colsum */
+int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* dY, float* dX,
+                      float* dW, float* db, int32_t M, int32_t N, int32_t K, int32_t act,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weight packing, optimiser, EMA
+ * ---------------------------------------------------------------------------------------------- */
+/* master fp32 [taps][Cout][Cin] -> fwd-packed (same order, dtype) and, if wt != NULL, the dgrad
+ * operand [taps][Cin][Cout] with taps reversed (mode 0) / kept (mode 1). */
+int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, int32_t taps,
+                            int32_t Cout, int32_t Cin, int32_t flip, void* stream);
+/* fused Adam over a flat fp32 arena (torch.optim.Adam semantics, ddpm.py:1053-1059):
+ * grad_scale multiplies g first (DDP mean).  step is the 1-based step count. */
+int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                     void* stream);
+/* ema = ema + (1-decay)*(online-ema)  (ema_pytorch lerp), or copy when decay == 0 */
+int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream);
+int b200dm_fill_f32(float* p, int64_t n, float value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DM_H */

@@ -1,0 +1,83 @@
+// C-ABI plumbing: error string, launch counter, capability probe, conv dispatch.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200dm {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return B200DM_ERR_CUDA;
+  }
+  return B200DM_OK;
+}
+
+int conv_fwd_simt(const b200dm_conv_desc* d, void* stream);
+int conv_wgrad_simt(const b200dm_wgrad_desc* d, void* stream);
+int conv_fwd_tc(const b200dm_conv_desc* d, void* stream);
+int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream);
+bool tc_supported();
+
+}  // namespace b200dm
+
+using namespace b200dm;
+
+extern "C" int b200dm_version(void) { return 100; }
+extern "C" const char* b200dm_last_error(void) { return g_err; }
+extern "C" int64_t b200dm_launch_count(void) { return g_launches; }
+extern "C" void b200dm_reset_launch_count(void) { g_launches = 0; }
+extern "C" int b200dm_tc_available(void) { return tc_supported() ? 1 : 0; }
+
+static int check_conv_common(int dtype, int mode, int ksize, int B, int H, int W, int Cin, int Cout) {
+  B200DM_REQUIRE(dtype == B200DM_F32 || dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "conv: dtype %d", dtype);
+  B200DM_REQUIRE(mode >= 0 && mode <= 2, B200DM_ERR_UNSUPPORTED, "conv: mode %d", mode);
+  B200DM_REQUIRE(mode != 0 || ksize == 1 || ksize == 3, B200DM_ERR_UNSUPPORTED, "conv: ksize %d (1 or 3)", ksize);
+  B200DM_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, B200DM_ERR_SHAPE,
+                 "conv: empty shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream) {
+  B200DM_REQUIRE(d != nullptr, B200DM_ERR_SHAPE, "conv_fwd: null descriptor");
+  int rc = check_conv_common(d->dtype, d->mode, d->ksize, d->B, d->H, d->W, d->Cin, d->Cout);
+  if (rc) return rc;
+  B200DM_REQUIRE(d->x && d->w && d->y, B200DM_ERR_SHAPE, "conv_fwd: null tensor pointer");
+  B200DM_REQUIRE(d->x_ld >= d->Cin && d->y_ld >= d->Cout, B200DM_ERR_SHAPE, "conv_fwd: ld smaller than channel count");
+  if (d->impl == 1) {
+    B200DM_REQUIRE(d->dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "conv_fwd(tc): bf16 only");
+    return conv_fwd_tc(d, stream);
+  }
+  B200DM_REQUIRE(d->impl == 0, B200DM_ERR_UNSUPPORTED, "conv_fwd: impl %d", d->impl);
+  return conv_fwd_simt(d, stream);
+}
+
+extern "C" int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream) {
+  B200DM_REQUIRE(d != nullptr, B200DM_ERR_SHAPE, "conv_wgrad: null descriptor");
+  int rc = check_conv_common(d->dtype, d->mode, d->ksize, d->B, d->H, d->W, d->Cin, d->Cout);
+  if (rc) return rc;
+  B200DM_REQUIRE(d->mode != 2, B200DM_ERR_UNSUPPORTED, "conv_wgrad: use mode 1 for the down/up-shuffle pair");
+  B200DM_REQUIRE(d->x && d->dy && d->dw, B200DM_ERR_SHAPE, "conv_wgrad: null tensor pointer");
+  if (!d->accumulate) {
+    int taps = d->mode == 0 ? d->ksize * d->ksize : 4;
+    rc = b200dm_fill_f32(d->dw, (int64_t)taps * d->Cout * d->Cin, 0.f, stream);
+    if (rc) return rc;
+  }
+  if (d->impl == 1) {
+    B200DM_REQUIRE(d->dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "conv_wgrad(tc): bf16 only");
+    return conv_wgrad_tc(d, stream);
+  }
+  B200DM_REQUIRE(d->impl == 0, B200DM_ERR_UNSUPPORTED, "conv_wgrad: impl %d", d->impl);
+  return conv_wgrad_simt(d, stream);
+}

@@ -1,0 +1,616 @@
+// CUDA-core implicit-GEMM convolutions: the fp32-mode path, and the path for shapes the tcgen05
+// kernel does not take (init 7x7 conv, final 1x1 conv to C channels).  fp32 accumulation always.
+// Reference ops replaced: nn.Conv2d at ddpm.py:96,103,160,187,213-215,252-253,304,377,413,422 and
+// their autograd data/weight gradients.
+#include "common.cuh"
+
+namespace b200dm {
+
+constexpr int BM = 64, BN = 64, BK = 16, PADM = 4;
+constexpr int kConvThreads = 256;
+
+struct ConvP {
+  int mode, ksize, B, H, W, Cin, Cout;  // H,W: output size (modes 0,1) / input size (mode 2)
+  int x_ld, y_ld, res_ld, accumulate;
+  int64_t M;  // number of GEMM rows (pixels of the iteration space)
+  int N;      // GEMM columns (Cout, or 4*Cout for mode 2)
+  int taps;
+};
+
+// Input pixel offset for GEMM row `p`, tap `tap`; returns -1 when the tap falls in the zero padding.
+__device__ __forceinline__ int64_t in_pixel(const ConvP& c, int64_t p, int tap) {
+  int ox = (int)(p % c.W);
+  int64_t q = p / c.W;
+  int oy = (int)(q % c.H);
+  int64_t b = q / c.H;
+  if (c.mode == 1) {  // 2x2 stride 2 over a [2H, 2W] input, tap = p1*2 + p2
+    int iy = 2 * oy + (tap >> 1), ix = 2 * ox + (tap & 1);
+    return (b * (2 * c.H) + iy) * (int64_t)(2 * c.W) + ix;
+  }
+  int pad = c.ksize >> 1;
+  int iy = oy + tap / c.ksize - pad, ix = ox + tap % c.ksize - pad;
+  if (iy < 0 || iy >= c.H || ix < 0 || ix >= c.W) return -1;
+  return (b * c.H + iy) * (int64_t)c.W + ix;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kConvThreads)
+conv_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ w,
+                 const float* __restrict__ bias, T* __restrict__ y, const T* __restrict__ res) {
+  __shared__ float As[BK][BM + PADM];
+  __shared__ float Bs[BK][BN + PADM];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // loader: one row, 4 consecutive k
+  const int ty = tid >> 4, tx = tid & 15;         // compute: 4x4 micro-tile
+  float acc[4][4] = {};
+
+  const int64_t prow = m0 + lrow;
+  const int wrow = n0 + lrow;  // weight row (GEMM column index)
+  // for mode 2 the GEMM column j = tap*Cout + co indexes the packed weight rows directly
+  const int kblocks = c.Cin / BK;
+  const int gtaps = (c.mode == 2) ? 1 : c.taps;
+
+  for (int tap = 0; tap < gtaps; ++tap) {
+    int64_t ipix = (prow < c.M) ? in_pixel(c, prow, tap) : -1;
+    const T* xrow = (ipix >= 0) ? x + ipix * c.x_ld : nullptr;
+    const T* wr = (wrow < c.N) ? w + ((int64_t)tap * c.N + wrow) * c.Cin : nullptr;
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int k0 = kb * BK + lk;
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (xrow) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = Elem<T>::ld(xrow + k0 + j);
+      }
+      if (wr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Elem<T>::ld(wr + k0 + j);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        As[lk + j][lrow] = a[j];
+        Bs[lk + j][lrow] = b[j];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t p = m0 + ty * 4 + i;
+    if (p >= c.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + tx * 4 + j;
+      if (col >= c.N) continue;
+      int co = col;
+      int64_t opix = p;
+      if (c.mode == 2) {  // scatter to the (2y+p1, 2x+p2) pixel of a [2H, 2W] output
+        int tap = col / c.Cout;
+        co = col - tap * c.Cout;
+        int ox = (int)(p % c.W);
+        int64_t q = p / c.W;
+        int oy = (int)(q % c.H);
+        int64_t b = q / c.H;
+        opix = (b * (2 * c.H) + 2 * oy + (tap >> 1)) * (int64_t)(2 * c.W) + 2 * ox + (tap & 1);
+      }
+      float v = acc[i][j];
+      if (bias) v += bias[co];
+      if (res) v += Elem<T>::ld(res + opix * c.res_ld + co);
+      T* yp = y + opix * c.y_ld + co;
+      if (c.accumulate) v += Elem<T>::ld(yp);
+      Elem<T>::st(yp, v);
+    }
+  }
+}
+
+// ---- weight gradient: dW[tap][co][ci] += sum_p dY[p,co] * X[in_pixel(p,tap), ci] -----------------
+template <typename T>
+__global__ void __launch_bounds__(kConvThreads)
+wgrad_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ dy, int dy_ld,
+                  float* __restrict__ dw, int splits) {
+  __shared__ float As[BK][BM + PADM];  // dY chunk: [pixel][co]
+  __shared__ float Bs[BK][BN + PADM];  // X chunk:  [pixel][ci]
+  const int tid = threadIdx.x;
+  const int co_tiles = (c.Cout + BM - 1) / BM;
+  const int co0 = (blockIdx.x % co_tiles) * BM;
+  const int ci0 = (blockIdx.x / co_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int split = blockIdx.z;
+  const int lrow = tid >> 4, lc = (tid & 15) * 4;  // loader: pixel row (16), 4 consecutive channels
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4] = {};
+
+  int64_t chunks = (c.M + BK - 1) / BK;
+  int64_t per = (chunks + splits - 1) / splits;
+  int64_t cbeg = split * per, cend = cbeg + per < chunks ? cbeg + per : chunks;
+  for (int64_t ch = cbeg; ch < cend; ++ch) {
+    int64_t p = ch * BK + lrow;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < c.M) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (co0 + lc + j < c.Cout) a[j] = Elem<T>::ld(dy + p * dy_ld + co0 + lc + j);
+      int64_t ipix = in_pixel(c, p, tap);
+      if (ipix >= 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ci0 + lc + j < c.Cin) b[j] = Elem<T>::ld(x + ipix * c.x_ld + ci0 + lc + j);
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lrow][lc]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(&Bs[lrow][lc]) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= c.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ci = ci0 + tx * 4 + j;
+      if (ci >= c.Cin) continue;
+      atomicAdd(dw + ((int64_t)tap * c.Cout + co) * c.Cin + ci, acc[i][j]);
+    }
+  }
+}
+
+// ---- column sums -------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, int ld, int64_t rows, int C,
+                              float* __restrict__ out, int64_t rows_per_block) {
+  __shared__ float red[4][64];
+  int c = blockIdx.x * 64 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) acc += Elem<T>::ld(x + r * ld + c);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float v = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(out + c, v);
+  }
+}
+
+// ---- init conv 7x7 (C -> Cout=64), NCHW fp32 in, NHWC out -----------------------------------------
+constexpr int IC_ROWS = 4;   // output rows per CTA
+constexpr int IC_SEG = 32;   // output columns per CTA
+template <typename T>
+__global__ void __launch_bounds__(256)
+init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                 const float* __restrict__ bias, T* __restrict__ y, int y_ld, int B, int C, int H,
+                 int W) {
+  extern __shared__ float sm[];
+  const int K = C * 49;
+  float* wsm = sm;                          // [K][64]
+  float* patch = sm + K * 64;               // [C][IC_ROWS+6][IC_SEG+6]
+  const int PW = IC_SEG + 6, PH = IC_ROWS + 6;
+  const int tid = threadIdx.x;
+  const int segs = (W + IC_SEG - 1) / IC_SEG;
+  const int seg = blockIdx.x % segs;
+  const int rowblk = blockIdx.x / segs;
+  const int b = blockIdx.y;
+  const int y0 = rowblk * IC_ROWS, x0 = seg * IC_SEG;
+  for (int i = tid; i < K * 64; i += 256) {
+    int co = i & 63, k = i >> 6;
+    wsm[i] = w[co * K + k];
+  }
+  for (int i = tid; i < C * PH * PW; i += 256) {
+    int px = i % PW, py = (i / PW) % PH, ch = i / (PW * PH);
+    int iy = y0 + py - 3, ix = x0 + px - 3;
+    patch[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                   ? x[(((int64_t)b * C + ch) * H + iy) * W + ix] : 0.f;
+  }
+  __syncthreads();
+  const int co = tid & 63, oct = tid >> 6;  // 4 octets of 8 pixels per row segment
+  const float bv = bias ? bias[co] : 0.f;
+  for (int r = 0; r < IC_ROWS; ++r) {
+    if (y0 + r >= H) break;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bv;
+    for (int ch = 0; ch < C; ++ch)
+      for (int ky = 0; ky < 7; ++ky) {
+        const float* pr = patch + (ch * PH + r + ky) * PW + oct * 8;
+        float pv[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) pv[i] = pr[i];
+        const float* wk = wsm + ((ch * 7 + ky) * 7) * 64 + co;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          float wv = wk[kx * 64];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv[i + kx], wv, acc[i]);
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int ox = x0 + oct * 8 + i;
+      if (ox < W) Elem<T>::st(y + (((int64_t)b * H + y0 + r) * W + ox) * y_ld + co, acc[i]);
+    }
+  }
+}
+
+// dW[co][c][ky][kx] += sum dY[b,y,x,co] * X[b,c,y+ky-3,x+kx-3]; one CTA per (b, row block)
+template <typename T>
+__global__ void __launch_bounds__(256)
+init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int dy_ld,
+                       float* __restrict__ dw, int B, int C, int H, int W) {
+  extern __shared__ float sm[];
+  const int PW = W + 6, PH = IC_ROWS + 6;
+  float* patch = sm;  // [C][PH][PW]
+  const int K = C * 49;
+  const int tid = threadIdx.x, co = tid & 63, q = tid >> 6;
+  const int b = blockIdx.y, y0 = blockIdx.x * IC_ROWS;
+  for (int i = tid; i < C * PH * PW; i += 256) {
+    int px = i % PW, py = (i / PW) % PH, ch = i / (PW * PH);
+    int iy = y0 + py - 3, ix = px - 3;
+    patch[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
+                   ? x[(((int64_t)b * C + ch) * H + iy) * W + ix] : 0.f;
+  }
+  __syncthreads();
+  constexpr int MAXK = 37;  // ceil(147 / 4); C <= 3
+  float acc[MAXK];
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) acc[i] = 0.f;
+  for (int r = 0; r < IC_ROWS && y0 + r < H; ++r)
+    for (int ox = 0; ox < W; ++ox) {
+      float g = Elem<T>::ld(dy + (((int64_t)b * H + y0 + r) * W + ox) * dy_ld + co);
+#pragma unroll
+      for (int i = 0; i < MAXK; ++i) {
+        int k = q + 4 * i;
+        if (k < K) {
+          int kx = k % 7, ky = (k / 7) % 7, ch = k / 49;
+          acc[i] = fmaf(g, patch[(ch * PH + r + ky) * PW + ox + kx], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) {
+    int k = q + 4 * i;
+    if (k < K) atomicAdd(dw + co * K + k, acc[i]);
+  }
+}
+
+// ---- final 1x1 conv (Cin -> C<=4), NHWC in, NCHW fp32 out ------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ y, int64_t total, int HW,
+                  int Cin, int C) {
+  extern __shared__ float wsm[];  // [C][Cin]
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* xr = x + p * x_ld;
+  for (int k = 0; k < Cin; k += 8) {
+    float v[8];
+    ld8(xr + k, v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c] = fmaf(v[j], wsm[c * Cin + k + j], acc[c]);
+      }
+  }
+  int64_t b = p / HW;
+  int pix = (int)(p - b * HW);
+  for (int c = 0; c < C; ++c) y[(b * C + c) * HW + pix] = acc[c] + (bias ? bias[c] : 0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+final_conv_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
+                     int dx_ld, int64_t total, int HW, int Cin, int C) {
+  extern __shared__ float wsm[];
+  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  int64_t b = p / HW;
+  int pix = (int)(p - b * HW);
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) g[c] = dy[(b * C + c) * HW + pix];
+  T* dr = dx + p * dx_ld;
+  for (int k = 0; k < Cin; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) s = fmaf(g[c], wsm[c * Cin + k + j], s);
+      v[j] = s;
+    }
+    st8(dr + k, v);
+  }
+}
+
+// dW[c][ci] += sum_p dy[b,c,p]*x[p,ci];  db[c] += sum dy.  blockDim = (Cin, 256/Cin)
+template <typename T>
+__global__ void final_conv_dw_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ dy,
+                                     float* __restrict__ dw, float* __restrict__ db, int64_t total,
+                                     int HW, int Cin, int C, int64_t per_block) {
+  extern __shared__ float red[];  // [blockDim.y][5][Cin]
+  const int ci = threadIdx.x, ly = threadIdx.y, ny = blockDim.y;
+  int64_t p0 = (int64_t)blockIdx.x * per_block;
+  int64_t p1 = p0 + per_block < total ? p0 + per_block : total;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t p = p0 + ly; p < p1; p += ny) {
+    int64_t b = p / HW;
+    int pix = (int)(p - b * HW);
+    float xv = Elem<T>::ld(x + p * x_ld + ci);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) {
+        float g = dy[(b * C + c) * HW + pix];
+        acc[c] = fmaf(g, xv, acc[c]);
+        accb[c] += g;
+      }
+  }
+  for (int c = 0; c < C; ++c) red[(ly * 4 + c) * Cin + ci] = acc[c];
+  __syncthreads();
+  if (ly == 0) {
+    for (int c = 0; c < C; ++c) {
+      float s = 0.f;
+      for (int j = 0; j < ny; ++j) s += red[(j * 4 + c) * Cin + ci];
+      atomicAdd(dw + c * Cin + ci, s);
+    }
+  }
+  // bias: every (ci == 0) lane holds the column sum of its pixel subset
+  if (ci == 0)
+    for (int c = 0; c < C; ++c) atomicAdd(db + c, accb[c]);
+}
+
+// ---- nearest x2 upsample and its gradient ------------------------------------------------------------
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld,
+                                    int64_t total8, int H, int W, int C8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    int64_t p = i / C8;  // output pixel over [B, 2H, 2W]
+    int ox = (int)(p % (2 * W));
+    int64_t q = p / (2 * W);
+    int oy = (int)(q % (2 * H));
+    int64_t b = q / (2 * H);
+    float v[8];
+    ld8(x + ((b * H + (oy >> 1)) * (int64_t)W + (ox >> 1)) * x_ld + c8 * 8, v);
+    st8(y + p * y_ld + c8 * 8, v);
+  }
+}
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, int dy_ld, T* __restrict__ dx,
+                                    int dx_ld, int64_t total8, int H, int W, int C8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    int64_t p = i / C8;  // input pixel over [B, H, W]
+    int ix = (int)(p % W);
+    int64_t q = p / W;
+    int iy = (int)(q % H);
+    int64_t b = q / H;
+    float s[8] = {};
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float v[8];
+      int64_t op = (b * (2 * H) + 2 * iy + (d >> 1)) * (int64_t)(2 * W) + 2 * ix + (d & 1);
+      ld8(dy + op * dy_ld + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += v[j];
+    }
+    st8(dx + p * dx_ld + c8 * 8, s);
+  }
+}
+
+template <typename T>
+static int launch_conv(const b200dm_conv_desc* d, cudaStream_t st) {
+  ConvP c{};
+  c.mode = d->mode; c.ksize = d->ksize; c.B = d->B; c.H = d->H; c.W = d->W;
+  c.Cin = d->Cin; c.Cout = d->Cout; c.x_ld = d->x_ld; c.y_ld = d->y_ld; c.res_ld = d->res_ld;
+  c.accumulate = d->accumulate;
+  c.M = (int64_t)d->B * d->H * d->W;
+  c.taps = d->mode == 0 ? d->ksize * d->ksize : 4;
+  c.N = d->mode == 2 ? 4 * d->Cout : d->Cout;
+  dim3 grid((unsigned)((c.M + BM - 1) / BM), (unsigned)((c.N + BN - 1) / BN));
+  conv_simt_kernel<T><<<grid, kConvThreads, 0, st>>>(c, (const T*)d->x, (const T*)d->w, d->bias,
+                                                      (T*)d->y, (const T*)d->res);
+  count_launch();
+  return check_launch("conv_simt");
+}
+
+int conv_fwd_simt(const b200dm_conv_desc* d, void* stream) {
+  B200DM_REQUIRE(d->Cin % BK == 0, B200DM_ERR_SHAPE, "conv(simt): Cin=%d must be a multiple of %d", d->Cin, BK);
+  if (d->dtype == B200DM_F32) return launch_conv<float>(d, (cudaStream_t)stream);
+  return launch_conv<__nv_bfloat16>(d, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int launch_wgrad(const b200dm_wgrad_desc* d, cudaStream_t st) {
+  ConvP c{};
+  c.mode = d->mode; c.ksize = d->ksize; c.B = d->B; c.H = d->H; c.W = d->W;
+  c.Cin = d->Cin; c.Cout = d->Cout; c.x_ld = d->x_ld;
+  c.M = (int64_t)d->B * d->H * d->W;
+  c.taps = d->mode == 0 ? d->ksize * d->ksize : 4;
+  c.N = d->Cout;
+  int tiles = ((c.Cout + BM - 1) / BM) * ((c.Cin + BN - 1) / BN);
+  int64_t chunks = (c.M + BK - 1) / BK;
+  int splits = (4 * num_sms() + tiles * c.taps - 1) / (tiles * c.taps);
+  if (splits > chunks / 8) splits = (int)(chunks / 8);
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  dim3 grid(tiles, c.taps, splits);
+  wgrad_simt_kernel<T><<<grid, kConvThreads, 0, st>>>(c, (const T*)d->x, (const T*)d->dy, d->dy_ld,
+                                                       d->dw, splits);
+  count_launch();
+  return check_launch("wgrad_simt");
+}
+
+int conv_wgrad_simt(const b200dm_wgrad_desc* d, void* stream) {
+  if (d->dtype == B200DM_F32) return launch_wgrad<float>(d, (cudaStream_t)stream);
+  return launch_wgrad<__nv_bfloat16>(d, (cudaStream_t)stream);
+}
+
+}  // namespace b200dm
+
+using namespace b200dm;
+
+extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t rows, int32_t C,
+                             float* out, int32_t accumulate, void* stream) {
+  B200DM_REQUIRE(rows > 0 && C > 0, B200DM_ERR_SHAPE, "colsum: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    int rc = b200dm_fill_f32(out, C, 0.f, stream);
+    if (rc) return rc;
+  }
+  int cblocks = (C + 63) / 64;
+  int64_t rblocks = (2 * num_sms() + cblocks - 1) / cblocks;
+  if (rblocks > (rows + 31) / 32) rblocks = (rows + 31) / 32;
+  if (rblocks < 1) rblocks = 1;
+  int64_t per = (rows + rblocks - 1) / rblocks;
+  dim3 grid(cblocks, (unsigned)rblocks), block(64, 4);
+  if (dtype == B200DM_F32)
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, rows, C, out, per);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, out, per);
+  count_launch();
+  return check_launch("colsum");
+}
+
+extern "C" int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* w, const float* bias,
+                                    void* y, int32_t y_ld, int32_t B, int32_t C, int32_t H, int32_t W,
+                                    int32_t Cout, void* stream) {
+  B200DM_REQUIRE(Cout == 64, B200DM_ERR_UNSUPPORTED, "init_conv: Cout=%d (only dim=64 is built)", Cout);
+  B200DM_REQUIRE(C >= 1 && C <= 3, B200DM_ERR_UNSUPPORTED, "init_conv: channels=%d (1..3 supported)", C);
+  B200DM_REQUIRE(W % 8 == 0 && H % 8 == 0, B200DM_ERR_SHAPE, "init_conv: H,W must be multiples of 8");
+  size_t smem = ((size_t)C * 49 * 64 + (size_t)C * (IC_ROWS + 6) * (IC_SEG + 6)) * sizeof(float);
+  int segs = (W + IC_SEG - 1) / IC_SEG;
+  dim3 grid(segs * ((H + IC_ROWS - 1) / IC_ROWS), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32) {
+    cudaFuncSetAttribute(init_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    init_conv_kernel<float><<<grid, 256, smem, st>>>(x, w, bias, (float*)y, y_ld, B, C, H, W);
+  } else {
+    cudaFuncSetAttribute(init_conv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    init_conv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, y_ld, B, C, H, W);
+  }
+  count_launch();
+  return check_launch("init_conv_fwd");
+}
+
+extern "C" int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void* dy, int32_t dy_ld,
+                                      float* dw, int32_t B, int32_t C, int32_t H, int32_t W,
+                                      int32_t Cout, void* stream) {
+  B200DM_REQUIRE(Cout == 64, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: Cout=%d (only dim=64 is built)", Cout);
+  B200DM_REQUIRE(C >= 1 && C <= 3, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: channels=%d", C);
+  size_t smem = (size_t)C * (IC_ROWS + 6) * (W + 6) * sizeof(float);
+  dim3 grid((H + IC_ROWS - 1) / IC_ROWS, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    init_conv_wgrad_kernel<float><<<grid, 256, smem, st>>>(x, (const float*)dy, dy_ld, dw, B, C, H, W);
+  else
+    init_conv_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, (const __nv_bfloat16*)dy, dy_ld, dw, B, C, H, W);
+  count_launch();
+  return check_launch("init_conv_wgrad");
+}
+
+extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
+                                     const float* bias, float* y, int32_t B, int32_t HW, int32_t Cin,
+                                     int32_t C, void* stream) {
+  B200DM_REQUIRE(C >= 1 && C <= 4 && Cin % 8 == 0, B200DM_ERR_UNSUPPORTED, "final_conv: C=%d Cin=%d", C, Cin);
+  int64_t total = (int64_t)B * HW;
+  size_t smem = (size_t)C * Cin * sizeof(float);
+  unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    final_conv_kernel<float><<<grid, 256, smem, st>>>((const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
+  else
+    final_conv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
+  count_launch();
+  return check_launch("final_conv_fwd");
+}
+
+extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
+                                     const float* dy, void* dx, int32_t dx_ld, float* dw, float* db,
+                                     int32_t B, int32_t HW, int32_t Cin, int32_t C, void* stream) {
+  B200DM_REQUIRE(C >= 1 && C <= 4 && Cin % 8 == 0 && Cin <= 256 && 256 % Cin == 0, B200DM_ERR_UNSUPPORTED,
+                 "final_conv_bwd: C=%d Cin=%d", C, Cin);
+  int64_t total = (int64_t)B * HW;
+  size_t smem = (size_t)C * Cin * sizeof(float);
+  unsigned grid = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  int ny = 256 / Cin;
+  int64_t nblk = 2 * num_sms();
+  if (nblk > (total + 63) / 64) nblk = (total + 63) / 64;
+  int64_t per = (total + nblk - 1) / nblk;
+  dim3 block2(Cin, ny);
+  size_t smem2 = (size_t)ny * 4 * Cin * sizeof(float);
+  if (dtype == B200DM_F32) {
+    final_conv_dx_kernel<float><<<grid, 256, smem, st>>>(w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
+    final_conv_dw_kernel<float><<<(unsigned)nblk, block2, smem2, st>>>((const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+  } else {
+    final_conv_dx_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
+    final_conv_dw_kernel<__nv_bfloat16><<<(unsigned)nblk, block2, smem2, st>>>((const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+  }
+  count_launch(2);
+  return check_launch("final_conv_bwd");
+}
+
+extern "C" int b200dm_upsample2x_fwd(int32_t dtype, const void* x, int32_t x_ld, void* y, int32_t y_ld,
+                                     int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  B200DM_REQUIRE(C % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0, B200DM_ERR_SHAPE, "upsample: C, ld must be multiples of 8");
+  int64_t total8 = (int64_t)B * 2 * H * 2 * W * (C / 8);
+  int64_t blocks = (total8 + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    upsample_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, x_ld, (float*)y, y_ld, total8, H, W, C / 8);
+  else
+    upsample_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, total8, H, W, C / 8);
+  count_launch();
+  return check_launch("upsample2x_fwd");
+}
+
+extern "C" int b200dm_upsample2x_bwd(int32_t dtype, const void* dy, int32_t dy_ld, void* dx,
+                                     int32_t dx_ld, int32_t B, int32_t H, int32_t W, int32_t C,
+                                     void* stream) {
+  B200DM_REQUIRE(C % 8 == 0 && dx_ld % 8 == 0 && dy_ld % 8 == 0, B200DM_ERR_SHAPE, "upsample_bwd: C, ld must be multiples of 8");
+  int64_t total8 = (int64_t)B * H * W * (C / 8);
+  int64_t blocks = (total8 + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    upsample_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, dy_ld, (float*)dx, dx_ld, total8, H, W, C / 8);
+  else
+    upsample_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)dx, dx_ld, total8, H, W, C / 8);
+  count_launch();
+  return check_launch("upsample2x_bwd");
+}

@@ -1,0 +1,540 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation).
+//
+//   D[128 pixels x N_TILE channels] = sum_{tap, 64-channel block}  A_tap[128 x 64] * W_tap[N_TILE x 64]^T
+//
+// A is never materialised (no im2col): each K-block is ONE 5-D TMA box over the NHWC activation whose
+// (w, h) start coordinate is shifted by the filter tap; out-of-image elements are zero-filled by the
+// TMA unit, which implements padding=1.  The pixel-unshuffle of Downsample (ddpm.py:100-104) is a
+// strided 5-D view of the same tensor, and torch.cat inputs are channel slices of a wider buffer
+// (x_ld).  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> +bias/+residual/+accumulate -> bf16 -> global).
+//
+// Serves the forward convs (ddpm.py:96,103,160,187,213-215,252-253,377,413) and, with the
+// tap-reversed/transposed weight pack, their data gradients.
+#include "tc_common.cuh"
+
+namespace b200dm {
+
+using namespace tc;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+bool tc_supported() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return major == 10 && get_encoder() != nullptr;
+}
+
+constexpr int TC_BM = 128;      // pixels per CTA tile  (UMMA M)
+constexpr int TC_BK = 64;       // channels per K-block (128 B of bf16 = one swizzle row)
+constexpr int TC_THREADS = 192;
+constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+
+struct TcParams {
+  int mode, ksize, taps, kblocks;  // kblocks = Cin / 64
+  int H, W, bh, bn;                // box geometry: bw == W
+  int Cout, Ncols;                 // Ncols = GEMM N (Cout, or 4*Cout in mode 2)
+  int x_ld_for_unshuffle;          // mode 1: channel-coordinate step of p2 (== x_ld)
+  long long M;                     // valid GEMM rows
+  __nv_bfloat16* y;
+  int y_ld;
+  const __nv_bfloat16* res;
+  int res_ld;
+  const float* bias;
+  int accumulate;
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  constexpr int B_STAGE_BYTES = N_TILE * TC_BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TMEM_COLS = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  // generic pointer to the TMEM-address slot
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n0 = blockIdx.y * N_TILE;
+  const int num_k = p.taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // tile origin: rows are (x + W*(y + bh*n)) over the box {W, bh, bn}
+      const long long first = (long long)m_tile * TC_BM;            // first pixel (linear, NHW order)
+      const int n_first = (int)(first / ((long long)p.H * p.W));
+      const int y_first = (int)((first / p.W) % p.H);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        const uint32_t a_dst = base + stage * STAGE_BYTES;
+        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+        if (p.mode == 1) {
+          // view (c' = p2*ld + c, ox, p1, oy, b)
+          tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld_for_unshuffle + kc * TC_BK, 0,
+                      tap >> 1, y_first, n_first);
+        } else {
+          const int pad = p.ksize >> 1;
+          const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
+          const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
+          tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+        }
+        tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * STAGE_BYTES;
+        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart; +32 B per 16-element K step
+          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);       // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const long long pix = (long long)m_tile * TC_BM + row;
+    const bool valid = pix < p.M;
+    long long opix = pix;
+    int co0 = n0;
+    if (p.mode == 2) {  // scatter to pixel (2y+p1, 2x+p2) of the [2H,2W] output; one tap per N tile
+      const int tap = n0 / p.Cout;
+      co0 = n0 - tap * p.Cout;
+      const int ox = (int)(pix % p.W);
+      const long long q = pix / p.W;
+      const int oy = (int)(q % p.H);
+      const long long b = q / p.H;
+      opix = (b * (2 * p.H) + 2 * oy + (tap >> 1)) * (long long)(2 * p.W) + 2 * ox + (tap & 1);
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    __nv_bfloat16* yrow = p.y + opix * p.y_ld + co0;
+    const __nv_bfloat16* rrow = p.res ? p.res + opix * p.res_ld + co0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < N_TILE; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (valid) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + co0 + c + j);
+        }
+        if (rrow) {
+          float t[8];
+          ld8(rrow + c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += t[j];
+          ld8(rrow + c + 8, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+        }
+        if (p.accumulate) {
+          float t[8];
+          ld8(yrow + c, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += t[j];
+          ld8(yrow + c + 8, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+        }
+        float lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
+        st8(yrow + c, lo);
+        st8(yrow + c + 8, hi);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn enc = get_encoder();
+  B200DM_REQUIRE(enc != nullptr, B200DM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable", what);
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
+                   strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200DM_REQUIRE(r == CUDA_SUCCESS, B200DM_ERR_CUDA,
+                 "%s: cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]",
+                 what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                 (unsigned long long)dims[2], rank > 3 ? (unsigned long long)dims[3] : 0ULL,
+                 rank > 4 ? (unsigned long long)dims[4] : 0ULL, box[0], box[1], box[2],
+                 rank > 3 ? box[3] : 0u, rank > 4 ? box[4] : 0u);
+  return B200DM_OK;
+}
+
+// Activation map shared by the forward/dgrad and wgrad kernels.  Box = {64 ch, W, bh, bn} pixels.
+int make_act_map(CUtensorMap* m, int mode, const void* x, int x_ld, int C, int B, int H, int W, int bh,
+                 int bn, const char* what) {
+  const cuuint64_t e = 2;  // bytes per element
+  if (mode == 1) {
+    // input [B, 2H, 2W, ld] viewed as (c' = p2*ld + c, ox, p1, oy, b)
+    cuuint64_t dims[5] = {(cuuint64_t)x_ld + C, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[4] = {2ull * x_ld * e, 2ull * W * x_ld * e, 4ull * W * x_ld * e,
+                         4ull * H * W * x_ld * e};
+    cuuint32_t box[5] = {TC_BK, (cuuint32_t)W, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+    return encode_map(m, x, 5, dims, str, box, what);
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 1};
+  cuuint64_t str[4] = {(cuuint64_t)x_ld * e, (cuuint64_t)W * x_ld * e, (cuuint64_t)H * W * x_ld * e,
+                       (cuuint64_t)B * H * W * x_ld * e};
+  cuuint32_t box[5] = {TC_BK, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  return encode_map(m, x, 5, dims, str, box, what);
+}
+
+int tile_geometry(int H, int W, int* bh, int* bn, const char* what) {
+  B200DM_REQUIRE(W >= 4 && W <= 128 && (W & (W - 1)) == 0, B200DM_ERR_UNSUPPORTED,
+                 "%s: W=%d must be a power of two in [4,128]", what, W);
+  int rows = TC_BM / W;  // image rows per tile if H is large enough
+  if (rows <= H) {
+    B200DM_REQUIRE(H % rows == 0, B200DM_ERR_UNSUPPORTED, "%s: H=%d not a multiple of %d", what, H, rows);
+    *bh = rows;
+    *bn = 1;
+  } else {
+    B200DM_REQUIRE(rows % H == 0, B200DM_ERR_UNSUPPORTED, "%s: H=%d does not divide %d", what, H, rows);
+    *bh = H;
+    *bn = rows / H;
+  }
+  return B200DM_OK;
+}
+
+template <int N_TILE, int STAGES>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles,
+                     int n_tiles, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  dim3 grid(m_tiles, n_tiles);
+  conv_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  count_launch();
+  return check_launch("conv_tc");
+}
+
+int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
+  B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_fwd(tc): needs an sm_100 device and a TMA-capable driver");
+  B200DM_REQUIRE(d->Cin % TC_BK == 0, B200DM_ERR_SHAPE, "conv_fwd(tc): Cin=%d must be a multiple of 64", d->Cin);
+  B200DM_REQUIRE(d->Cout % 64 == 0, B200DM_ERR_SHAPE, "conv_fwd(tc): Cout=%d must be a multiple of 64", d->Cout);
+  B200DM_REQUIRE(d->x_ld % 8 == 0 && d->y_ld % 8 == 0 && (!d->res || d->res_ld % 8 == 0), B200DM_ERR_SHAPE,
+                 "conv_fwd(tc): ld must be a multiple of 8 elements");
+  B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->y & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
+                     ((uintptr_t)d->res & 15) == 0,
+                 B200DM_ERR_SHAPE, "conv_fwd(tc): pointers must be 16-byte aligned");
+  const int ksize = d->mode == 0 ? d->ksize : 1;
+  int bh, bn;
+  int rc = tile_geometry(d->H, d->W, &bh, &bn, "conv_fwd(tc)");
+  if (rc) return rc;
+  TcParams p{};
+  p.mode = d->mode; p.ksize = ksize;
+  p.taps = d->mode == 0 ? ksize * ksize : (d->mode == 1 ? 4 : 1);
+  p.kblocks = d->Cin / TC_BK;
+  p.H = d->H; p.W = d->W; p.bh = bh; p.bn = bn;
+  p.Cout = d->Cout;
+  p.Ncols = d->mode == 2 ? 4 * d->Cout : d->Cout;
+  p.x_ld_for_unshuffle = d->x_ld;
+  p.M = (long long)d->B * d->H * d->W;
+  p.y = (__nv_bfloat16*)d->y; p.y_ld = d->y_ld;
+  p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
+  p.bias = d->bias; p.accumulate = d->accumulate;
+  const int m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+
+  // N tile: the widest tile that still yields about one CTA per SM
+  int n_tile = 64;
+  const int sms = num_sms();
+  if (d->Cout % 256 == 0 && (long long)m_tiles * (p.Ncols / 256) >= sms) n_tile = 256;
+  else if (d->Cout % 128 == 0 && (long long)m_tiles * (p.Ncols / 128) >= sms) n_tile = 128;
+
+  CUtensorMap tmA, tmB;
+  rc = make_act_map(&tmA, d->mode == 1 ? 1 : 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) A");
+  if (rc) return rc;
+  {
+    const int wt = d->mode == 2 ? 1 : p.taps;
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)p.Ncols, (cuuint64_t)wt};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)p.Ncols * d->Cin * 2};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)n_tile, 1};
+    rc = encode_map(&tmB, d->w, 3, dims, str, box, "conv_fwd(tc) B");
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_tiles = p.Ncols / n_tile;
+  if (n_tile == 256) return launch_tc<256, 4>(tmA, tmB, p, m_tiles, n_tiles, st);
+  if (n_tile == 128) return launch_tc<128, 3>(tmA, tmB, p, m_tiles, n_tiles, st);
+  return launch_tc<64, 4>(tmA, tmB, p, m_tiles, n_tiles, st);
+}
+
+
+// =====================================================================================================
+// Weight gradient:  dW[tap][co][ci] += sum_pixels dY[pix, co] * X[pix (+) tap, ci]
+// GEMM with M = co (128), N = ci (N_TILE), K = pixels.  Both operands are "MN-major" in shared memory:
+// a TMA box is [128 pixels][64 channels] (128-B swizzled rows), i.e. K runs over rows.  M = 128 spans
+// two such boxes (LBO = 16 KiB apart).  Split-K over pixel tiles; fp32 partials are reduced with
+// red.global.add into the (pre-zeroed or accumulating) master-gradient arena.
+// =====================================================================================================
+struct TcWgradParams {
+  int mode, ksize;
+  int H, W;
+  int Cout, Cin;
+  int x_ld;
+  int k_tiles;        // number of 128-pixel tiles
+  int splits;
+  float* dw;
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                const TcWgradParams p) {
+  constexpr int BOX_BYTES = TC_BM * TC_BK * 2;  // 16 KiB: [128 pixels][64 channels]
+  constexpr int NB = N_TILE / 64;
+  constexpr int STAGE_BYTES = (2 + NB) * BOX_BYTES;
+  constexpr int TMEM_COLS = N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * TC_BM, ci0 = blockIdx.y * N_TILE;
+  const int tap = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int per = (p.k_tiles + p.splits - 1) / p.splits;
+  const int kt0 = split * per, kt1 = min(kt0 + per, p.k_tiles);
+  const bool has_work = kt1 > kt0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int pad = p.ksize >> 1;
+      const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
+      const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        const long long first = (long long)kt * TC_BM;
+        const int n_first = (int)(first / ((long long)p.H * p.W));
+        const int y_first = (int)((first / p.W) % p.H);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        const uint32_t a_dst = base + stage * STAGE_BYTES;
+        const uint32_t b_dst = a_dst + 2 * BOX_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          tma_load_5d(a_dst + i * BOX_BYTES, &tmDY, full_bar(stage), co0 + 64 * i, 0, y_first, n_first, 0);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          if (p.mode == 1)
+            tma_load_5d(b_dst + j * BOX_BYTES, &tmX, full_bar(stage), (tap & 1) * p.x_ld + ci0 + 64 * j, 0,
+                        tap >> 1, y_first, n_first);
+          else
+            tma_load_5d(b_dst + j * BOX_BYTES, &tmX, full_bar(stage), ci0 + 64 * j, dx, y_first + dy,
+                        n_first, 0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && has_work) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = kt0; kt < kt1; ++kt) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t a_addr = base + stage * STAGE_BYTES;
+        const uint32_t b_addr = a_addr + 2 * BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BM / 16; ++k) {
+          // MN-major, SWIZZLE_128B: 16 pixels (K) per MMA = 2 groups of 8 rows, 1024 B apart (SBO);
+          // the next 64-channel slab of M/N lives one box further (LBO)
+          const uint64_t da = make_smem_desc(a_addr + k * 2048, BOX_BYTES, 1024);
+          const uint64_t db = make_smem_desc(b_addr + k * 2048, BOX_BYTES, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (has_work) {
+    const int quarter = warp & 3;
+    const int co = co0 + quarter * 32 + lane;
+    const bool valid = co < p.Cout;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float* drow = p.dw + ((long long)tap * p.Cout + co) * p.Cin + ci0;
+#pragma unroll 1
+    for (int c = 0; c < N_TILE; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int N_TILE, int STAGES>
+static int launch_wgrad_tc(const CUtensorMap& tmDY, const CUtensorMap& tmX, const TcWgradParams& p,
+                           dim3 grid, cudaStream_t st) {
+  constexpr int smem = STAGES * (2 + N_TILE / 64) * (TC_BM * TC_BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<N_TILE, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  wgrad_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmDY, tmX, p);
+  count_launch();
+  return check_launch("wgrad_tc");
+}
+
+int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
+  B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_wgrad(tc): needs an sm_100 device and a TMA-capable driver");
+  B200DM_REQUIRE(d->Cin % 64 == 0 && d->Cout % 64 == 0, B200DM_ERR_SHAPE,
+                 "conv_wgrad(tc): Cin=%d, Cout=%d must be multiples of 64", d->Cin, d->Cout);
+  B200DM_REQUIRE(d->x_ld % 8 == 0 && d->dy_ld % 8 == 0, B200DM_ERR_SHAPE, "conv_wgrad(tc): ld must be a multiple of 8");
+  B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0, B200DM_ERR_SHAPE,
+                 "conv_wgrad(tc): pointers must be 16-byte aligned");
+  int bh, bn;
+  int rc = tile_geometry(d->H, d->W, &bh, &bn, "conv_wgrad(tc)");
+  if (rc) return rc;
+  const int taps = d->mode == 0 ? d->ksize * d->ksize : 4;
+  TcWgradParams p{};
+  p.mode = d->mode; p.ksize = d->mode == 0 ? d->ksize : 1;
+  p.H = d->H; p.W = d->W; p.Cout = d->Cout; p.Cin = d->Cin; p.x_ld = d->x_ld;
+  const long long M = (long long)d->B * d->H * d->W;
+  p.k_tiles = (int)((M + TC_BM - 1) / TC_BM);
+  p.dw = d->dw;
+  const int n_tile = (d->Cin % 128 == 0) ? 128 : 64;
+  const int co_tiles = (d->Cout + TC_BM - 1) / TC_BM, ci_tiles = d->Cin / n_tile;
+  const int base_ctas = co_tiles * ci_tiles * taps;
+  int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
+  if (splits > p.k_tiles) splits = p.k_tiles;
+  if (splits < 1) splits = 1;
+  while (taps * splits > 65535) --splits;
+  p.splits = splits;
+
+  CUtensorMap tmDY, tmX;
+  rc = make_act_map(&tmDY, 0, d->dy, d->dy_ld, d->Cout, d->B, d->H, d->W, bh, bn, "conv_wgrad(tc) dY");
+  if (rc) return rc;
+  rc = make_act_map(&tmX, d->mode == 1 ? 1 : 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_wgrad(tc) X");
+  if (rc) return rc;
+  dim3 grid(co_tiles, ci_tiles, taps * splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_tile == 128) return launch_wgrad_tc<128, 3>(tmDY, tmX, p, grid, st);
+  return launch_wgrad_tc<64, 4>(tmDY, tmX, p, grid, st);
+}
+
+}  // namespace b200dm

@@ -1,0 +1,313 @@
+// Fused scheduler / loss kernels: q_sample, loss(+grad), DDIM step, DDPM step, Philox randn.
+// HBM-bound; one thread = 4 consecutive elements = one float4 per tensor = one Philox block.
+// Arithmetic mirrors the reference's op order (mul, mul, add — no FMA contraction) so the fp32
+// mode agrees with torch to the last bits.  Reference: models/generative/diffusion/ddpm.py
+// :673-694 (predict_*), :707-757 (model_predictions, p_sample), :812-827 (DDIM), :869-925.
+#include "common.cuh"
+
+namespace b200dm {
+
+constexpr int kElemThreads = 256;
+
+static inline int elem_grid(int64_t nvec) {
+  int64_t blocks = (nvec + kElemThreads - 1) / kElemThreads;
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p, int64_t i) {
+  return __ldg(reinterpret_cast<const float4*>(p) + i);
+}
+__device__ __forceinline__ void st4(float* p, int64_t i, float4 v) {
+  reinterpret_cast<float4*>(p)[i] = v;
+}
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.f), 1.f); }
+
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kElemThreads)
+q_sample_kernel(const float* __restrict__ img, const int64_t* __restrict__ t,
+                const float* __restrict__ noise, float* __restrict__ x_t,
+                float* __restrict__ noise_out, float* __restrict__ x0_out,
+                const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
+                int64_t nvec, int64_t chw4, int normalize, uint64_t seed, uint64_t stream_id,
+                uint64_t vec_offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / chw4);
+    int64_t tb = t[b];
+    float ca = __ldg(sqrt_ac + tb), cb = __ldg(sqrt_1mac + tb);
+    float4 x = ld4(img, i);
+    if (normalize) {
+      x.x = sub_(mul_(x.x, 2.f), 1.f); x.y = sub_(mul_(x.y, 2.f), 1.f);
+      x.z = sub_(mul_(x.z, 2.f), 1.f); x.w = sub_(mul_(x.w, 2.f), 1.f);
+    }
+    float4 e = noise ? ld4(noise, i) : Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id);
+    float4 o;
+    o.x = add_(mul_(ca, x.x), mul_(cb, e.x));
+    o.y = add_(mul_(ca, x.y), mul_(cb, e.y));
+    o.z = add_(mul_(ca, x.z), mul_(cb, e.z));
+    o.w = add_(mul_(ca, x.w), mul_(cb, e.w));
+    st4(x_t, i, o);
+    if (noise_out) st4(noise_out, i, e);
+    if (x0_out) st4(x0_out, i, x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float target_of(int objective, float x0, float e, float ca, float cb) {
+  if (objective == B200DM_PRED_NOISE) return e;
+  if (objective == B200DM_PRED_X0) return x0;
+  return sub_(mul_(ca, e), mul_(cb, x0));  // predict_v, ddpm.py:684-688
+}
+
+__global__ void __launch_bounds__(kElemThreads)
+loss_kernel(const float* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ noise,
+            const int64_t* __restrict__ t, const float* __restrict__ sqrt_ac,
+            const float* __restrict__ sqrt_1mac, const float* __restrict__ loss_weight,
+            float* __restrict__ loss_acc, float* __restrict__ d_out, int64_t nvec, int64_t chw4,
+            int objective, float inv_count) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / chw4);
+    int64_t tb = t[b];
+    float ca = __ldg(sqrt_ac + tb), cb = __ldg(sqrt_1mac + tb), w = __ldg(loss_weight + tb);
+    float4 o = ld4(out, i), x = ld4(x0, i), e = ld4(noise, i);
+    float4 d;
+    d.x = o.x - target_of(objective, x.x, e.x, ca, cb);
+    d.y = o.y - target_of(objective, x.y, e.y, ca, cb);
+    d.z = o.z - target_of(objective, x.z, e.z, ca, cb);
+    d.w = o.w - target_of(objective, x.w, e.w, ca, cb);
+    acc += w * (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w);
+    if (d_out) {
+      float s = 2.f * w * inv_count;
+      st4(d_out, i, make_float4(s * d.x, s * d.y, s * d.z, s * d.w));
+    }
+  }
+  __shared__ float red[kElemThreads / 32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kElemThreads / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(loss_acc, v * inv_count);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct StepCoef {
+  float sac, s1mac, sr, srm1;  // sqrt_alphas_cumprod[t], sqrt_one_minus..., sqrt_recip..., sqrt_recipm1...
+};
+
+// model_predictions (ddpm.py:707-734): x0 (optionally clamped) and eps re-derived from it.
+__device__ __forceinline__ void predict(int objective, const StepCoef& c, float x, float out,
+                                        bool clip, bool rederive, float& x0, float& eps) {
+  if (objective == B200DM_PRED_NOISE) {
+    eps = out;
+    x0 = sub_(mul_(c.sr, x), mul_(c.srm1, out));
+    if (clip) {
+      x0 = clamp1(x0);
+      if (rederive) eps = __fdiv_rn(sub_(mul_(c.sr, x), x0), c.srm1);
+    }
+  } else {
+    x0 = (objective == B200DM_PRED_X0) ? out : sub_(mul_(c.sac, x), mul_(c.s1mac, out));
+    if (clip) x0 = clamp1(x0);
+    eps = __fdiv_rn(sub_(mul_(c.sr, x), x0), c.srm1);
+  }
+}
+
+__global__ void __launch_bounds__(kElemThreads)
+ddim_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
+                 const float* __restrict__ noise, float* __restrict__ x_next,
+                 float* __restrict__ x0_out, StepCoef c, float sqrt_an, float cc, float sigma,
+                 int last, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
+                 uint64_t vec_offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = ld4(x_t, i), o = ld4(out, i);
+    float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, r[4], x0s[4];
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!last && sigma != 0.f) {
+      float4 z = noise ? ld4(noise, i) : Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id);
+      zs[0] = z.x; zs[1] = z.y; zs[2] = z.z; zs[3] = z.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x0, eps;
+      predict(objective, c, xs[k], os[k], true, true, x0, eps);
+      x0s[k] = x0;
+      // img = x_start*alpha_next.sqrt() + c*pred_noise + sigma*noise   (ddpm.py:827)
+      r[k] = last ? x0 : add_(add_(mul_(x0, sqrt_an), mul_(cc, eps)), mul_(sigma, zs[k]));
+    }
+    st4(x_next, i, make_float4(r[0], r[1], r[2], r[3]));
+    if (x0_out) st4(x0_out, i, make_float4(x0s[0], x0s[1], x0s[2], x0s[3]));
+  }
+}
+
+__global__ void __launch_bounds__(kElemThreads)
+ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
+                 const float* __restrict__ noise, float* __restrict__ x_prev,
+                 float* __restrict__ x0_out, StepCoef c, float coef1, float coef2, float noise_std,
+                 int add_noise, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
+                 uint64_t vec_offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = ld4(x_t, i), o = ld4(out, i);
+    float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, r[4], x0s[4];
+    float zs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (add_noise) {
+      float4 z = noise ? ld4(noise, i) : Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id);
+      zs[0] = z.x; zs[1] = z.y; zs[2] = z.z; zs[3] = z.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x0, eps;
+      // p_mean_variance: model_predictions without clipping, then x_start.clamp_(-1, 1)  (:736-746)
+      predict(objective, c, xs[k], os[k], false, false, x0, eps);
+      x0 = clamp1(x0);
+      x0s[k] = x0;
+      float mean = add_(mul_(coef1, x0), mul_(coef2, xs[k]));  // q_posterior :696-705
+      r[k] = add_noise ? add_(mean, mul_(noise_std, zs[k])) : mean;
+    }
+    st4(x_prev, i, make_float4(r[0], r[1], r[2], r[3]));
+    if (x0_out) st4(x0_out, i, make_float4(x0s[0], x0s[1], x0s[2], x0s[3]));
+  }
+}
+
+__global__ void __launch_bounds__(kElemThreads)
+randn_kernel(float* __restrict__ out, int64_t nvec, uint64_t seed, uint64_t stream_id,
+             uint64_t vec_offset) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x)
+    st4(out, i, Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id));
+}
+
+__global__ void __launch_bounds__(kElemThreads)
+unnormalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = ld4(x, i);
+    st4(y, i, make_float4(mul_(add_(v.x, 1.f), 0.5f), mul_(add_(v.y, 1.f), 0.5f),
+                          mul_(add_(v.z, 1.f), 0.5f), mul_(add_(v.w, 1.f), 0.5f)));
+  }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+}  // namespace b200dm
+
+using namespace b200dm;
+
+#define CHECK_VEC(n, what) \
+  B200DM_REQUIRE((n) > 0 && (n) % 4 == 0, B200DM_ERR_SHAPE, what ": element count %lld must be a positive multiple of 4", (long long)(n))
+#define CHECK_ALIGN16(p, what) \
+  B200DM_REQUIRE(((uintptr_t)(p) & 15) == 0, B200DM_ERR_SHAPE, what ": pointer not 16-byte aligned")
+
+extern "C" int b200dm_q_sample(const float* img, const int64_t* t, const float* noise, float* x_t,
+                               float* noise_out, float* x0_out, const float* sqrt_ac,
+                               const float* sqrt_1mac, int32_t B, int64_t chw, int32_t normalize,
+                               uint64_t seed, uint64_t stream_id, uint64_t elem_offset, void* stream) {
+  B200DM_REQUIRE(B > 0, B200DM_ERR_SHAPE, "q_sample: empty batch");
+  CHECK_VEC(chw, "q_sample");
+  B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "q_sample: elem_offset must be a multiple of 4");
+  CHECK_ALIGN16(img, "q_sample img"); CHECK_ALIGN16(x_t, "q_sample x_t");
+  CHECK_ALIGN16(noise, "q_sample noise"); CHECK_ALIGN16(noise_out, "q_sample noise_out");
+  CHECK_ALIGN16(x0_out, "q_sample x0_out");
+  int64_t nvec = (int64_t)B * chw / 4;
+  q_sample_kernel<<<elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream>>>(
+      img, t, noise, x_t, noise_out, x0_out, sqrt_ac, sqrt_1mac, nvec, chw / 4, normalize, seed,
+      stream_id, elem_offset / 4);
+  count_launch();
+  return check_launch("q_sample");
+}
+
+extern "C" int b200dm_loss_fwd_bwd(const float* model_out, const float* x0, const float* noise,
+                                   const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
+                                   const float* loss_weight, float* loss_acc, float* d_out, int32_t B,
+                                   int64_t chw, int32_t objective, void* stream) {
+  B200DM_REQUIRE(B > 0, B200DM_ERR_SHAPE, "loss: empty batch");
+  CHECK_VEC(chw, "loss");
+  B200DM_REQUIRE(objective >= 0 && objective <= 2, B200DM_ERR_UNSUPPORTED, "loss: unknown objective %d", objective);
+  CHECK_ALIGN16(model_out, "loss out"); CHECK_ALIGN16(x0, "loss x0"); CHECK_ALIGN16(noise, "loss noise");
+  CHECK_ALIGN16(d_out, "loss d_out");
+  int64_t nvec = (int64_t)B * chw / 4;
+  float inv_count = 1.f / ((float)B * (float)chw);
+  loss_kernel<<<elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream>>>(
+      model_out, x0, noise, t, sqrt_ac, sqrt_1mac, loss_weight, loss_acc, d_out, nvec, chw / 4,
+      objective, inv_count);
+  count_launch();
+  return check_launch("loss_fwd_bwd");
+}
+
+extern "C" int b200dm_ddim_step(const float* x_t, const float* model_out, const float* noise,
+                                float* x_next, float* x0_out, float c_sqrt_ac, float c_sqrt_1mac,
+                                float c_sqrt_recip, float c_sqrt_recipm1, float sqrt_alpha_next,
+                                float c, float sigma, int32_t last, int32_t objective, int64_t n,
+                                uint64_t seed, uint64_t stream_id, uint64_t elem_offset, void* stream) {
+  CHECK_VEC(n, "ddim_step");
+  B200DM_REQUIRE(objective >= 0 && objective <= 2, B200DM_ERR_UNSUPPORTED, "ddim_step: unknown objective %d", objective);
+  B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "ddim_step: elem_offset must be a multiple of 4");
+  CHECK_ALIGN16(x_t, "ddim x_t"); CHECK_ALIGN16(model_out, "ddim out"); CHECK_ALIGN16(x_next, "ddim x_next");
+  CHECK_ALIGN16(noise, "ddim noise"); CHECK_ALIGN16(x0_out, "ddim x0_out");
+  StepCoef sc{c_sqrt_ac, c_sqrt_1mac, c_sqrt_recip, c_sqrt_recipm1};
+  ddim_step_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(
+      x_t, model_out, noise, x_next, x0_out, sc, sqrt_alpha_next, c, sigma, last, objective, n / 4,
+      seed, stream_id, elem_offset / 4);
+  count_launch();
+  return check_launch("ddim_step");
+}
+
+extern "C" int b200dm_ddpm_step(const float* x_t, const float* model_out, const float* noise,
+                                float* x_prev, float* x0_out, float c_sqrt_ac, float c_sqrt_1mac,
+                                float c_sqrt_recip, float c_sqrt_recipm1, float coef1, float coef2,
+                                float noise_std, int32_t add_noise, int32_t objective, int64_t n,
+                                uint64_t seed, uint64_t stream_id, uint64_t elem_offset, void* stream) {
+  CHECK_VEC(n, "ddpm_step");
+  B200DM_REQUIRE(objective >= 0 && objective <= 2, B200DM_ERR_UNSUPPORTED, "ddpm_step: unknown objective %d", objective);
+  B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "ddpm_step: elem_offset must be a multiple of 4");
+  CHECK_ALIGN16(x_t, "ddpm x_t"); CHECK_ALIGN16(model_out, "ddpm out"); CHECK_ALIGN16(x_prev, "ddpm x_prev");
+  CHECK_ALIGN16(noise, "ddpm noise"); CHECK_ALIGN16(x0_out, "ddpm x0_out");
+  StepCoef sc{c_sqrt_ac, c_sqrt_1mac, c_sqrt_recip, c_sqrt_recipm1};
+  ddpm_step_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(
+      x_t, model_out, noise, x_prev, x0_out, sc, coef1, coef2, noise_std, add_noise, objective, n / 4,
+      seed, stream_id, elem_offset / 4);
+  count_launch();
+  return check_launch("ddpm_step");
+}
+
+extern "C" int b200dm_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id,
+                            uint64_t elem_offset, void* stream) {
+  CHECK_VEC(n, "randn");
+  B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "randn: elem_offset must be a multiple of 4");
+  CHECK_ALIGN16(out, "randn out");
+  randn_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(out, n / 4, seed, stream_id,
+                                                                           elem_offset / 4);
+  count_launch();
+  return check_launch("randn");
+}
+
+extern "C" int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream) {
+  CHECK_VEC(n, "unnormalize");
+  CHECK_ALIGN16(x, "unnormalize x"); CHECK_ALIGN16(y, "unnormalize y");
+  unnormalize_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(x, y, n / 4);
+  count_launch();
+  return check_launch("unnormalize");
+}
+
+extern "C" int b200dm_fill_f32(float* p, int64_t n, float value, void* stream) {
+  if (n <= 0) return B200DM_OK;
+  fill_kernel<<<elem_grid(n), kElemThreads, 0, (cudaStream_t)stream>>>(p, n, value);
+  count_launch();
+  return check_launch("fill_f32");
+}

@@ -1,0 +1,454 @@
+// GroupNorm(8)+FiLM+SiLU(+residual) forward/backward and RMSNorm forward/backward, NHWC.
+// Reference: Block.forward ddpm.py:164-173, ResnetBlock.forward :189-200, RMSNorm :107-113.
+// All statistics and arithmetic in fp32; tensors in the activation dtype.
+#include "common.cuh"
+
+namespace b200dm {
+
+// ---- GroupNorm statistics: one CTA per (sample, group), two passes (mean, then centred variance) ----
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const T* __restrict__ x, int ld, float* __restrict__ stats, int HW, int C, int G,
+                float eps) {
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int gs = C / G, vpp = gs / 8;  // 8-wide vectors per pixel within the group
+  const int64_t nvec = (int64_t)HW * vpp;
+  const T* base = x + (int64_t)b * HW * ld + g * gs;
+  __shared__ float red[8];
+  __shared__ float s_mean;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    int64_t p = i / vpp;
+    int v = (int)(i - p * vpp);
+    float f[8];
+    ld8(base + p * ld + v * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += f[j];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    s_mean = s / ((float)HW * (float)gs);
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.f;
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    int64_t p = i / vpp;
+    int v = (int)(i - p * vpp);
+    float f[8];
+    ld8(base + p * ld + v * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = f[j] - mean;
+      acc = fmaf(d, d, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    float var = s / ((float)HW * (float)gs);
+    stats[(b * G + g) * 2 + 0] = mean;
+    stats[(b * G + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// ---- apply: y = silu(((x-mean)*rstd*gamma+beta)*(1+scale)+shift) (+res) -------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_apply_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ film, int film_ld, const T* __restrict__ res,
+                    int res_ld, T* __restrict__ y, int y_ld, int64_t total8, int HW, int C, int G) {
+  const int C8 = C / 8, gs = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % C8) * 8;
+    int64_t p = i / C8;
+    int b = (int)(p / HW);
+    int g = c0 / gs;
+    float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+    float v[8], r[8];
+    ld8(x + p * x_ld + c0, v);
+    if (res) ld8(res + p * res_ld + c0, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float n = (v[j] - mean) * rstd * gamma[c0 + j] + beta[c0 + j];
+      if (film) n = n * (film[(int64_t)b * film_ld + c0 + j] + 1.f) + film[(int64_t)b * film_ld + C + c0 + j];
+      float o = silu_f(n);
+      v[j] = res ? o + r[j] : o;
+    }
+    st8(y + p * y_ld + c0, v);
+  }
+}
+
+// ---- backward pass 1: sums[b][c] = (sum_p dz, sum_p dz*xnorm) --------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
+                     const float* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
+                     float* __restrict__ sums, int HW, int C, int G, int pix_per_block) {
+  extern __shared__ float sred[];  // [lanes][C][2]
+  const int b = blockIdx.y;
+  const int C8 = C / 8, gs = C / G;
+  const int lanes = blockDim.x / C8;          // pixel lanes
+  const int cv = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int c0 = cv * 8;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  float s1[8] = {}, s2[8] = {};
+  if (lane < lanes) {
+    const int g = c0 / gs;
+    const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+    float ga[8], be[8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ga[j] = gamma[c0 + j];
+      be[j] = beta[c0 + j];
+      sc[j] = film ? film[(int64_t)b * film_ld + c0 + j] + 1.f : 1.f;
+      sh[j] = film ? film[(int64_t)b * film_ld + C + c0 + j] : 0.f;
+    }
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      int64_t row = (int64_t)b * HW + p;
+      float xv[8], gv[8];
+      ld8(x + row * x_ld + c0, xv);
+      ld8(dy + row * dy_ld + c0, gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float xn = (xv[j] - mean) * rstd;
+        float z = (xn * ga[j] + be[j]) * sc[j] + sh[j];
+        float dz = gv[j] * silu_grad_f(z);
+        s1[j] += dz;
+        s2[j] = fmaf(dz, xn, s2[j]);
+      }
+    }
+  }
+  if (lane < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sred[(lane * C + c0 + j) * 2] = s1[j];
+      sred[(lane * C + c0 + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += sred[l * C * 2 + i];
+    atomicAdd(sums + (int64_t)b * C * 2 + i, s);
+  }
+}
+
+// ---- backward pass 2: FiLM grads, group means, dgamma/dbeta; one CTA per sample ---------------------
+__global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ film,
+                                     int film_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float* __restrict__ dfilm, float* __restrict__ gmeans, int HW,
+                                     int C, int G) {
+  __shared__ float g1[64], g2[64];
+  const int b = blockIdx.x, gs = C / G;
+  if (threadIdx.x < G) g1[threadIdx.x] = g2[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float S1 = sums[((int64_t)b * C + c) * 2], S2 = sums[((int64_t)b * C + c) * 2 + 1];
+    float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+    float ga = gamma[c], be = beta[c];
+    if (dfilm) {
+      dfilm[(int64_t)b * film_ld + c] = ga * S2 + be * S1;  // d scale
+      dfilm[(int64_t)b * film_ld + C + c] = S1;             // d shift
+    }
+    atomicAdd(dgamma + c, sc * S2);
+    atomicAdd(dbeta + c, sc * S1);
+    float a = sc * ga;
+    atomicAdd(&g1[c / gs], a * S1);
+    atomicAdd(&g2[c / gs], a * S2);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float inv = 1.f / ((float)gs * (float)HW);
+    gmeans[(b * G + threadIdx.x) * 2] = g1[threadIdx.x] * inv;
+    gmeans[(b * G + threadIdx.x) * 2 + 1] = g2[threadIdx.x] * inv;
+  }
+}
+
+// ---- backward pass 3: dx = rstd*(a*dz - M1 - xnorm*M2) ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
+                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
+                    const float* __restrict__ gmeans, T* __restrict__ dx, int dx_ld, int64_t total8,
+                    int HW, int C, int G) {
+  const int C8 = C / 8, gs = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c0 = (int)(i % C8) * 8;
+    int64_t p = i / C8;
+    int b = (int)(p / HW);
+    int g = c0 / gs;
+    float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+    float M1 = gmeans[(b * G + g) * 2], M2 = gmeans[(b * G + g) * 2 + 1];
+    float xv[8], gv[8];
+    ld8(x + p * x_ld + c0, xv);
+    ld8(dy + p * dy_ld + c0, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ga = gamma[c0 + j], be = beta[c0 + j];
+      float sc = film ? film[(int64_t)b * film_ld + c0 + j] + 1.f : 1.f;
+      float sh = film ? film[(int64_t)b * film_ld + C + c0 + j] : 0.f;
+      float xn = (xv[j] - mean) * rstd;
+      float z = (xn * ga + be) * sc + sh;
+      float dz = gv[j] * silu_grad_f(z);
+      xv[j] = rstd * (sc * ga * dz - M1 - xn * M2);
+    }
+    st8(dx + p * dx_ld + c0, xv);
+  }
+}
+
+// ---- RMSNorm: one warp per row (pixel); C <= 512 ----------------------------------------------------
+constexpr int RMS_MAXV = 2;  // 8-wide vectors per lane (C <= 512)
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ g,
+                   const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int64_t rows,
+                   int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int C8 = C / 8;
+  const float sqrtC = sqrtf((float)C);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float v[RMS_MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < RMS_MAXV; ++k) {
+      int cv = lane + 32 * k;
+      if (cv < C8) {
+        ld8(x + r * x_ld + cv * 8, v[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(v[k][j], v[k][j], ss);
+      }
+    }
+    ss = warp_sum(ss);
+    float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int k = 0; k < RMS_MAXV; ++k) {
+      int cv = lane + 32 * k;
+      if (cv < C8) {
+        float o[8], rr[8];
+        if (res) ld8(res + r * res_ld + cv * 8, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = v[k][j] * rn * g[cv * 8 + j] * sqrtC;
+          if (res) o[j] += rr[j];
+        }
+        st8(y + r * y_ld + cv * 8, o);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
+                   const float* __restrict__ g, const T* __restrict__ res, int res_ld,
+                   T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int64_t rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int C8 = C / 8;
+  const float sqrtC = sqrtf((float)C);
+  float dgacc[RMS_MAXV][8] = {};
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float u[RMS_MAXV][8], gd[RMS_MAXV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < RMS_MAXV; ++k) {
+      int cv = lane + 32 * k;
+      if (cv < C8) {
+        ld8(x + r * x_ld + cv * 8, u[k]);
+        ld8(dy + r * dy_ld + cv * 8, gd[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
+      }
+    }
+    ss = warp_sum(ss);
+    float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < RMS_MAXV; ++k) {
+      int cv = lane + 32 * k;
+      if (cv < C8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          u[k][j] *= rn;                                    // unit vector
+          dgacc[k][j] = fmaf(gd[k][j], u[k][j], dgacc[k][j]);  // dg_c += dy_c*u_c (x sqrtC at the end)
+          gd[k][j] *= g[cv * 8 + j];                        // g .* dy
+          dot = fmaf(gd[k][j], u[k][j], dot);
+        }
+      }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int k = 0; k < RMS_MAXV; ++k) {
+      int cv = lane + 32 * k;
+      if (cv < C8) {
+        float o[8], rr[8];
+        if (res) ld8(res + r * res_ld + cv * 8, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rn * sqrtC * (gd[k][j] - u[k][j] * dot);
+          if (res) o[j] += rr[j];
+        }
+        st8(dx + r * dx_ld + cv * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RMS_MAXV; ++k) {
+    int cv = lane + 32 * k;
+    if (cv < C8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dg + cv * 8 + j, dgacc[k][j] * sqrtC);
+    }
+  }
+}
+
+static inline unsigned ew_grid(int64_t n) {
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
+  return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace b200dm
+
+using namespace b200dm;
+typedef __nv_bfloat16 bf16;
+
+#define GN_CHECKS(name)                                                                            \
+  B200DM_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0 && G <= 64 && C % G == 0 && (C / G) % 8 == 0,   \
+                 B200DM_ERR_SHAPE, name ": need C %% G == 0 and (C/G) %% 8 == 0 (C=%d G=%d)", C, G)
+
+extern "C" int b200dm_gn_stats(int32_t dtype, const void* x, int32_t x_ld, float* stats, int32_t B,
+                               int32_t HW, int32_t C, int32_t G, float eps, void* stream) {
+  GN_CHECKS("gn_stats");
+  B200DM_REQUIRE(x_ld % 8 == 0, B200DM_ERR_SHAPE, "gn_stats: ld must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    gn_stats_kernel<float><<<B * G, 256, 0, st>>>((const float*)x, x_ld, stats, HW, C, G, eps);
+  else
+    gn_stats_kernel<bf16><<<B * G, 256, 0, st>>>((const bf16*)x, x_ld, stats, HW, C, G, eps);
+  count_launch();
+  return check_launch("gn_stats");
+}
+
+extern "C" int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* stats,
+                                   const float* gamma, const float* beta, const float* film,
+                                   int32_t film_ld, const void* res, int32_t res_ld, void* y,
+                                   int32_t y_ld, int32_t B, int32_t HW, int32_t C, int32_t G,
+                                   void* stream) {
+  GN_CHECKS("gn_apply_fwd");
+  B200DM_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && (!res || res_ld % 8 == 0), B200DM_ERR_SHAPE,
+                 "gn_apply_fwd: ld must be a multiple of 8");
+  int64_t total8 = (int64_t)B * HW * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    gn_apply_fwd_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
+        (const float*)x, x_ld, stats, gamma, beta, film, film_ld, (const float*)res, res_ld, (float*)y,
+        y_ld, total8, HW, C, G);
+  else
+    gn_apply_fwd_kernel<bf16><<<ew_grid(total8), 256, 0, st>>>(
+        (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, (const bf16*)res, res_ld, (bf16*)y,
+        y_ld, total8, HW, C, G);
+  count_launch();
+  return check_launch("gn_apply_fwd");
+}
+
+extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x,
+                                   int32_t x_ld, const float* stats, const float* gamma,
+                                   const float* beta, const float* film, int32_t film_ld, void* dx,
+                                   int32_t dx_ld, float* dgamma, float* dbeta, float* dfilm,
+                                   float* sums, float* gmeans, int32_t B, int32_t HW, int32_t C,
+                                   int32_t G, void* stream) {
+  GN_CHECKS("gn_apply_bwd");
+  B200DM_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, B200DM_ERR_SHAPE,
+                 "gn_apply_bwd: ld must be a multiple of 8");
+  B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = b200dm_fill_f32(sums, (int64_t)B * C * 2, 0.f, stream);
+  if (rc) return rc;
+  const int C8 = C / 8;
+  int threads = 256;
+  if (C8 > threads) threads = C8;  // C <= 2048 -> <= 256 anyway
+  int lanes = threads / C8;
+  int chunks = (2 * num_sms() + B - 1) / B;
+  int maxchunks = (HW + lanes - 1) / lanes;
+  if (chunks > maxchunks) chunks = maxchunks;
+  if (chunks < 1) chunks = 1;
+  int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+  dim3 grid(chunks, B);
+  int64_t total8 = (int64_t)B * HW * C8;
+  if (dtype == B200DM_F32) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(gn_bwd_reduce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gn_bwd_reduce_kernel<float><<<grid, threads, smem, st>>>(
+        (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(gn_bwd_reduce_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gn_bwd_reduce_kernel<bf16><<<grid, threads, smem, st>>>(
+        (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
+  }
+  gn_bwd_params_kernel<<<B, 256, 0, st>>>(sums, gamma, beta, film, film_ld, dgamma, dbeta, dfilm,
+                                          gmeans, HW, C, G);
+  if (dtype == B200DM_F32)
+    gn_bwd_apply_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
+        (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,
+        (float*)dx, dx_ld, total8, HW, C, G);
+  else
+    gn_bwd_apply_kernel<bf16><<<ew_grid(total8), 256, 0, st>>>(
+        (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,
+        (bf16*)dx, dx_ld, total8, HW, C, G);
+  count_launch(3);
+  return check_launch("gn_apply_bwd");
+}
+
+extern "C" int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* g,
+                                  const void* res, int32_t res_ld, void* y, int32_t y_ld, int64_t rows,
+                                  int32_t C, void* stream) {
+  B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && y_ld % 8 == 0, B200DM_ERR_SHAPE,
+                 "rmsnorm_fwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned grid = ew_grid(rows * 32);
+  if (dtype == B200DM_F32)
+    rmsnorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C);
+  else
+    rmsnorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C);
+  count_launch();
+  return check_launch("rmsnorm_fwd");
+}
+
+extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x,
+                                  int32_t x_ld, const float* g, const void* res, int32_t res_ld,
+                                  void* dx, int32_t dx_ld, float* dg, int64_t rows, int32_t C,
+                                  void* stream) {
+  B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0,
+                 B200DM_ERR_SHAPE, "rmsnorm_bwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (rows + 7) / 8, cap = (int64_t)num_sms() * 4;
+  unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
+  if (dtype == B200DM_F32)
+    rmsnorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C);
+  else
+    rmsnorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C);
+  count_launch();
+  return check_launch("rmsnorm_bwd");
+}

@@ -1,0 +1,99 @@
+// Weight packing (fp32 master -> GEMM operand layouts), fused Adam, EMA lerp.
+// Reference: torch.optim.Adam configured at ddpm.py:1053-1059; ema_pytorch.EMA.update at :1047-1048.
+#include "common.cuh"
+
+namespace b200dm {
+
+// master w: [taps][Cout][Cin] fp32.  wf: same order in T.  wt: [taps'][Cin][Cout] in T with
+// taps' = flip ? taps-1-t : t  (the data-gradient operand: rotate the filter 180 deg, swap in/out).
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wt,
+                                   int taps, int Cout, int Cin, int flip) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const float* wsrc = w + (int64_t)t * Cout * Cin;
+  for (int r = ty; r < 32; r += 8) {
+    int co = co0 + r, ci = ci0 + tx;
+    float v = (co < Cout && ci < Cin) ? wsrc[(int64_t)co * Cin + ci] : 0.f;
+    tile[r][tx] = v;
+    if (wf && co < Cout && ci < Cin) Elem<T>::st(wf + ((int64_t)t * Cout + co) * Cin + ci, v);
+  }
+  __syncthreads();
+  if (wt) {
+    const int tt = flip ? taps - 1 - t : t;
+    for (int r = ty; r < 32; r += 8) {
+      int ci = ci0 + r, co = co0 + tx;
+      if (co < Cout && ci < Cin) Elem<T>::st(wt + ((int64_t)tt * Cin + ci) * Cout + co, tile[tx][r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
+            float weight_decay, float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    float mi = m[i], vi = v[i];
+    mi = mi + (1.f - beta1) * (gi - mi);          // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * beta2 + (1.f - beta2) * gi * gi;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ema_kernel(float* __restrict__ ema, const float* __restrict__ online, int64_t n, float w) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float e = ema[i];
+    ema[i] = e + w * (online[i] - e);  // ema.lerp_(online, 1 - decay)
+  }
+}
+
+}  // namespace b200dm
+
+using namespace b200dm;
+
+extern "C" int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, int32_t taps,
+                                       int32_t Cout, int32_t Cin, int32_t flip, void* stream) {
+  B200DM_REQUIRE(taps > 0 && Cout > 0 && Cin > 0, B200DM_ERR_SHAPE, "pack_conv_weight: bad shape");
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps), block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    pack_weight_kernel<float><<<grid, block, 0, st>>>(w, (float*)wf, (float*)wt, taps, Cout, Cin, flip);
+  else
+    pack_weight_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip);
+  count_launch();
+  return check_launch("pack_conv_weight");
+}
+
+extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                                float grad_scale, void* stream) {
+  B200DM_REQUIRE(n > 0 && step >= 1, B200DM_ERR_SHAPE, "adam_step: n=%lld step=%d", (long long)n, step);
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  float step_size = (float)((double)lr / bc1);
+  float bc2_sqrt = (float)sqrt(bc2);
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
+  adam_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+  count_launch();
+  return check_launch("adam_step");
+}
+
+extern "C" int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream) {
+  B200DM_REQUIRE(n > 0, B200DM_ERR_SHAPE, "ema_update: empty");
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
+  ema_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(ema, online, n, 1.f - decay);
+  count_launch();
+  return check_launch("ema_update");
+}

@@ -1,0 +1,594 @@
+"""GPU parity tests, one per kernel family, called through the C ABI (ctypes -> libb200dm.so) and
+checked against the torch-fp32 expression of the reference lines each kernel replaces
+(models/generative/diffusion/ddpm.py; the same expressions the oracle uses).
+
+Tolerances: fp32 kernels 1e-5..1e-4 relative (accumulation order only); bf16 kernels are compared with
+the fp32 expression evaluated on the bf16-rounded inputs, so the only differences are the fp32
+accumulation order and the final bf16 rounding of the output (rel-L2 <= 4e-3).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from b200dm import _lib as L
+from b200dm.tensor import View
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DT = {L.F32: torch.float32, L.BF16: torch.bfloat16}
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+def tol(dtype):
+    return 2e-5 if dtype == L.F32 else 4e-3
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def q(x, dtype):  # round to the storage dtype
+    return x.to(DT[dtype]).float()
+
+
+def nhwc(x_nchw, dtype, ld=None, off=0):
+    B, C, H, W = x_nchw.shape
+    v = View.zeros(B, H, W, C, DT[dtype], DEV, ld=ld, off=off)
+    v.buf.fill_(7.0)  # poison the padding channels
+    return v.from_nchw(x_nchw)
+
+
+# ------------------------------------------------------------------------------------------------
+# scheduler / loss kernels
+# ------------------------------------------------------------------------------------------------
+def _buffers(schedule="sigmoid", objective="pred_v"):
+    from b200dm.schedule import make_buffers
+    return {k: v.to(DEV) for k, v in make_buffers(1000, schedule, objective).items()}
+
+
+def test_q_sample_injected_noise_exact():
+    buf = _buffers()
+    B, C, S = 5, 3, 32
+    img, noise = torch.rand(B, C, S, S, device=DEV), rnd(B, C, S, S, seed=1)
+    t = torch.tensor([0, 999, 17, 500, 998], device=DEV)
+    xt, eo, x0 = (torch.empty_like(img) for _ in range(3))
+    L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), noise.data_ptr(), xt.data_ptr(), eo.data_ptr(),
+           x0.data_ptr(), buf["sqrt_alphas_cumprod"].data_ptr(),
+           buf["sqrt_one_minus_alphas_cumprod"].data_ptr(), B, C * S * S, 1, 0, 0, 0)
+    xs = img * 2 - 1
+    ref = (buf["sqrt_alphas_cumprod"][t].view(B, 1, 1, 1) * xs
+           + buf["sqrt_one_minus_alphas_cumprod"][t].view(B, 1, 1, 1) * noise)
+    assert torch.equal(x0, xs) and torch.equal(eo, noise)
+    assert (xt - ref).abs().max().item() <= 2.4e-7 * 4  # <= 1 ulp at |x| < 4 (FMA contraction in torch)
+
+
+def test_philox_noise_statistics_and_shard_invariance():
+    n = 1 << 22
+    a = torch.empty(n, device=DEV)
+    L.call("b200dm_randn", a.data_ptr(), n, 1234, 7, 0)
+    assert abs(a.mean().item()) < 3e-3 and abs(a.std().item() - 1) < 3e-3
+    assert abs((a ** 3).mean().item()) < 1e-2 and abs((a ** 4).mean().item() - 3) < 3e-2
+    # the same stream generated in two shards (elem_offset) is bit-identical
+    b = torch.empty(n, device=DEV)
+    h = n // 2
+    L.call("b200dm_randn", b.data_ptr(), h, 1234, 7, 0)
+    L.call("b200dm_randn", b.data_ptr() + 4 * h, h, 1234, 7, h)
+    assert torch.equal(a, b)
+    c = torch.empty(n, device=DEV)
+    L.call("b200dm_randn", c.data_ptr(), n, 1234, 8, 0)       # another stream id decorrelates
+    assert abs((a * c).mean().item()) < 3e-3
+    # q_sample without an injected noise pointer uses the same generator
+    buf = _buffers()
+    img = torch.rand(4, 3, 32, 32, device=DEV)
+    t = torch.tensor([10, 20, 30, 40], device=DEV)
+    xt, eo = torch.empty_like(img), torch.empty_like(img)
+    L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), None, xt.data_ptr(), eo.data_ptr(), None,
+           buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
+           4, 3 * 32 * 32, 1, 1234, 7, 0)
+    assert torch.equal(eo.flatten(), a[:eo.numel()])
+
+
+@pytest.mark.parametrize("objective", ["pred_noise", "pred_x0", "pred_v"])
+def test_loss_fwd_bwd(objective):
+    buf = _buffers(objective=objective)
+    B, C, S = 6, 3, 32
+    out = rnd(B, C, S, S, seed=2).requires_grad_(True)
+    x0, noise = rnd(B, C, S, S, seed=3), rnd(B, C, S, S, seed=4)
+    t = torch.tensor([0, 999, 17, 500, 998, 250], device=DEV)
+    sa = buf["sqrt_alphas_cumprod"][t].view(B, 1, 1, 1)
+    sb = buf["sqrt_one_minus_alphas_cumprod"][t].view(B, 1, 1, 1)
+    target = {"pred_noise": noise, "pred_x0": x0, "pred_v": sa * noise - sb * x0}[objective]
+    loss = (F.mse_loss(out, target, reduction="none").flatten(1).mean(1) * buf["loss_weight"][t]).mean()
+    loss.backward()
+    acc = torch.zeros(1, device=DEV)
+    dout = torch.empty_like(out)
+    L.call("b200dm_loss_fwd_bwd", out.data_ptr(), x0.data_ptr(), noise.data_ptr(), t.data_ptr(),
+           buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
+           buf["loss_weight"].data_ptr(), acc.data_ptr(), dout.data_ptr(), B, C * S * S,
+           L.OBJECTIVES[objective])
+    assert abs(acc.item() - loss.item()) <= 2e-6 * abs(loss.item()) + 1e-9
+    assert rel(dout, out.grad) < 1e-6
+
+
+@pytest.mark.parametrize("objective", ["pred_noise", "pred_x0", "pred_v"])
+@pytest.mark.parametrize("last,sigma", [(0, 0.0), (0, 0.3), (1, 0.0)])
+def test_ddim_step(objective, last, sigma):
+    buf = _buffers("linear", objective)
+    n = 2 * 3 * 32 * 32
+    x, out, z = rnd(n, seed=5), rnd(n, seed=6), rnd(n, seed=7)
+    t = 640
+    sac, s1m = buf["sqrt_alphas_cumprod"][t], buf["sqrt_one_minus_alphas_cumprod"][t]
+    sr, srm1 = buf["sqrt_recip_alphas_cumprod"][t], buf["sqrt_recipm1_alphas_cumprod"][t]
+    if objective == "pred_noise":
+        x0 = (sr * x - srm1 * out).clamp(-1, 1)
+    elif objective == "pred_x0":
+        x0 = out.clamp(-1, 1)
+    else:
+        x0 = (sac * x - s1m * out).clamp(-1, 1)
+    eps = (sr * x - x0) / srm1
+    san, c = 0.8, 0.55
+    ref = x0 if last else x0 * san + c * eps + sigma * z
+    xn, x0o = torch.empty_like(x), torch.empty_like(x)
+    L.call("b200dm_ddim_step", x.data_ptr(), out.data_ptr(), z.data_ptr(), xn.data_ptr(), x0o.data_ptr(),
+           sac.item(), s1m.item(), sr.item(), srm1.item(), san, c, sigma, last, L.OBJECTIVES[objective],
+           n, 0, 0, 0)
+    assert (x0o - x0).abs().max().item() < 1e-5
+    assert (xn - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("objective", ["pred_noise", "pred_x0", "pred_v"])
+@pytest.mark.parametrize("add_noise", [0, 1])
+def test_ddpm_step(objective, add_noise):
+    buf = _buffers("sigmoid", objective)
+    n = 2 * 3 * 32 * 32
+    x, out, z = rnd(n, seed=8), rnd(n, seed=9), rnd(n, seed=10)
+    t = 333
+    sac, s1m = buf["sqrt_alphas_cumprod"][t], buf["sqrt_one_minus_alphas_cumprod"][t]
+    sr, srm1 = buf["sqrt_recip_alphas_cumprod"][t], buf["sqrt_recipm1_alphas_cumprod"][t]
+    if objective == "pred_noise":
+        x0 = sr * x - srm1 * out
+    elif objective == "pred_x0":
+        x0 = out
+    else:
+        x0 = sac * x - s1m * out
+    x0 = x0.clamp(-1, 1)
+    c1, c2 = buf["posterior_mean_coef1"][t], buf["posterior_mean_coef2"][t]
+    std = (0.5 * buf["posterior_log_variance_clipped"][t]).exp()
+    ref = c1 * x0 + c2 * x + (std * z if add_noise else 0.0)
+    xp, x0o = torch.empty_like(x), torch.empty_like(x)
+    L.call("b200dm_ddpm_step", x.data_ptr(), out.data_ptr(), z.data_ptr(), xp.data_ptr(), x0o.data_ptr(),
+           sac.item(), s1m.item(), sr.item(), srm1.item(), c1.item(), c2.item(), std.item(), add_noise,
+           L.OBJECTIVES[objective], n, 0, 0, 0)
+    assert (x0o - x0).abs().max().item() < 1e-5 and (xp - ref).abs().max().item() < 1e-5
+
+
+def test_elementwise_argument_errors():
+    x = torch.zeros(6, device=DEV)
+    with pytest.raises(L.B200dmError):
+        L.call("b200dm_randn", x.data_ptr(), 6, 0, 0, 0)          # not a multiple of 4
+    with pytest.raises(L.B200dmError):
+        L.call("b200dm_unnormalize", x.data_ptr() + 4, x.data_ptr(), 4)  # misaligned
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+def pack_w(w_oihw, dtype, transpose=False, flip=False):
+    """OIHW fp32 -> [taps][Cout][Cin] (or the dgrad operand [taps'][Cin][Cout]) in the storage dtype."""
+    co, ci, kh, kw = w_oihw.shape
+    p = w_oihw.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+    if transpose:
+        p = p.transpose(1, 2)
+        if flip:
+            p = p.flip(0)
+    return p.contiguous().to(DT[dtype])
+
+
+def run_conv(dtype, impl, mode, ksize, xv, w_packed, bias, yv, Cin, Cout, H, W, res=None, accumulate=0):
+    d = L.ConvDesc(dtype=dtype, mode=mode, ksize=ksize, impl=impl, B=xv.B, H=H, W=W, Cin=Cin, Cout=Cout,
+                   x=xv.ptr, x_ld=xv.ld, w=w_packed.data_ptr(), bias=L.ptr(bias), y=yv.ptr, y_ld=yv.ld,
+                   res=None if res is None else res.ptr, res_ld=0 if res is None else res.ld,
+                   accumulate=accumulate)
+    L.call("b200dm_conv_fwd", d)
+
+
+CONV_CASES = [  # B, H, Cin, Cout, ksize
+    (2, 32, 64, 64, 3), (3, 16, 128, 128, 3), (2, 8, 192, 128, 3), (3, 4, 256, 512, 3),
+    (9, 4, 512, 512, 3), (2, 16, 64, 384, 1), (1, 64, 128, 64, 3), (5, 8, 384, 256, 1),
+]
+
+
+def _impls():
+    return [0, 1]
+
+
+def _skip_tc(impl, dtype):
+    if impl == 1:
+        if dtype != L.BF16:
+            pytest.skip("tcgen05 path is bf16 only")
+        assert L.load().b200dm_tc_available() == 1, "tcgen05 path unavailable on this GPU box"
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tc"])
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_same(impl, dtype, case):
+    _skip_tc(impl, dtype)
+    B, S, Cin, Cout, k = case
+    x = q(rnd(B, Cin, S, S, seed=11), dtype)
+    w = q(rnd(Cout, Cin, k, k, seed=12, scale=1 / math.sqrt(Cin * k * k)), dtype)
+    bias = rnd(Cout, seed=13)
+    ref = F.conv2d(x, w, bias, padding=k // 2)
+    xv = nhwc(x, dtype, ld=Cin + 64, off=32)            # channel slice of a wider (concat) buffer
+    yv = View.zeros(B, S, S, Cout, DT[dtype], DEV, ld=Cout + 8, off=8)
+    run_conv(dtype, impl, 0, k, xv, pack_w(w, dtype), bias, yv, Cin, Cout, S, S)
+    assert rel(yv.to_nchw(), ref) < tol(dtype)
+    # residual + accumulate epilogue
+    r = q(rnd(B, Cout, S, S, seed=14), dtype)
+    y0 = q(rnd(B, Cout, S, S, seed=15), dtype)
+    rv = nhwc(r, dtype)
+    yv.from_nchw(y0)
+    run_conv(dtype, impl, 0, k, xv, pack_w(w, dtype), None, yv, Cin, Cout, S, S, res=rv, accumulate=1)
+    ref2 = F.conv2d(x, w, None, padding=k // 2) + r + y0
+    assert rel(yv.to_nchw(), ref2) < tol(dtype)
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tc"])
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 32, 64, 64), (3, 16, 64, 128), (5, 8, 128, 256)])
+def test_conv_unshuffle_and_its_transpose(impl, dtype, case):
+    """Downsample (ddpm.py:100-104): 'b c (h p1) (w p2) -> b (c p1 p2) h w' + 1x1 conv == mode 1;
+    its data gradient == mode 2."""
+    _skip_tc(impl, dtype)
+    B, S, C, Cout = case          # input [B, C, S, S] -> output [B, Cout, S/2, S/2]
+    x = q(rnd(B, C, S, S, seed=21), dtype).requires_grad_(True)
+    w = q(rnd(Cout, 4 * C, 1, 1, seed=22, scale=1 / math.sqrt(4 * C)), dtype)
+    bias = rnd(Cout, seed=23)
+    xu = x.reshape(B, C, S // 2, 2, S // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 4 * C, S // 2, S // 2)
+    ref = F.conv2d(xu, w, bias)
+    # packed [tap = p1*2+p2][Cout][C] from W[Cout][c*4 + p1*2 + p2]
+    wp = w.reshape(Cout, C, 4).permute(2, 0, 1).contiguous()
+    xv = nhwc(x.detach(), dtype, ld=C + 64, off=0)
+    yv = View.zeros(B, S // 2, S // 2, Cout, DT[dtype], DEV)
+    run_conv(dtype, impl, 1, 1, xv, wp.to(DT[dtype]), bias, yv, C, Cout, S // 2, S // 2)
+    assert rel(yv.to_nchw(), ref) < tol(dtype)
+    # transpose: dX from dY
+    dy = q(rnd(B, Cout, S // 2, S // 2, seed=24), dtype)
+    ref.backward(dy)
+    wt = wp.transpose(1, 2).contiguous()         # [tap][C][Cout]: GEMM columns (tap, c), K = Cout
+    dyv = nhwc(dy, dtype)
+    dxv = View.zeros(B, S, S, C, DT[dtype], DEV, ld=C + 8, off=8)
+    run_conv(dtype, impl, 2, 1, dyv, wt.to(DT[dtype]), None, dxv, Cout, C, S // 2, S // 2)
+    assert rel(dxv.to_nchw(), x.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tc"])
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 32, 64, 64, 3), (3, 8, 128, 64, 3), (4, 4, 256, 128, 3),
+                                  (2, 16, 128, 192, 1)])
+def test_conv_dgrad_via_flipped_weights(impl, dtype, case):
+    _skip_tc(impl, dtype)
+    B, S, Cin, Cout, k = case
+    x = q(rnd(B, Cin, S, S, seed=31), dtype).requires_grad_(True)
+    w = q(rnd(Cout, Cin, k, k, seed=32, scale=1 / math.sqrt(Cin * k * k)), dtype)
+    dy = q(rnd(B, Cout, S, S, seed=33), dtype)
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    dyv = nhwc(dy, dtype)
+    dxv = View.zeros(B, S, S, Cin, DT[dtype], DEV)
+    run_conv(dtype, impl, 0, k, dyv, pack_w(w, dtype, transpose=True, flip=True), None, dxv, Cout, Cin, S, S)
+    assert rel(dxv.to_nchw(), x.grad) < tol(dtype)
+
+
+@pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tc"])
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 32, 64, 64, 3, 0), (3, 16, 128, 192, 3, 0), (9, 4, 256, 128, 3, 0),
+                                  (2, 8, 192, 64, 1, 0), (3, 16, 64, 128, 1, 1), (2, 64, 64, 64, 3, 0)])
+def test_conv_wgrad(impl, dtype, case):
+    _skip_tc(impl, dtype)
+    B, S, Cin, Cout, k, mode = case
+    if mode == 0:
+        x = q(rnd(B, Cin, S, S, seed=41), dtype)
+        w = rnd(Cout, Cin, k, k, seed=42).requires_grad_(True)
+        dy = q(rnd(B, Cout, S, S, seed=43), dtype)
+        F.conv2d(x, w, None, padding=k // 2).backward(dy)
+        ref = w.grad.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
+        xv, dyv, H = nhwc(x, dtype, ld=Cin + 8, off=8), nhwc(dy, dtype), S
+    else:  # unshuffle: x is [B, Cin, S, S], output spatial S/2
+        x = q(rnd(B, Cin, S, S, seed=41), dtype)
+        w = rnd(Cout, 4 * Cin, 1, 1, seed=42).requires_grad_(True)
+        dy = q(rnd(B, Cout, S // 2, S // 2, seed=43), dtype)
+        xu = x.reshape(B, Cin, S // 2, 2, S // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 4 * Cin, S // 2, S // 2)
+        F.conv2d(xu, w).backward(dy)
+        ref = w.grad.reshape(Cout, Cin, 4).permute(2, 0, 1)
+        xv, dyv, H = nhwc(x, dtype, ld=Cin + 8, off=0), nhwc(dy, dtype), S // 2
+    taps = ref.shape[0]
+    dw = torch.full((taps, Cout, Cin), 3.0, device=DEV)      # accumulate = 0 must overwrite
+    d = L.WgradDesc(dtype=dtype, mode=mode, ksize=k, impl=impl, B=B, H=H, W=H, Cin=Cin, Cout=Cout,
+                    x=xv.ptr, x_ld=xv.ld, dy=dyv.ptr, dy_ld=dyv.ld, dw=dw.data_ptr(), accumulate=0)
+    L.call("b200dm_conv_wgrad", d)
+    assert rel(dw, ref) < 2e-5 if dtype == L.F32 else rel(dw, ref) < 1e-4
+    d.accumulate = 1
+    L.call("b200dm_conv_wgrad", d)
+    assert rel(dw, 2 * ref) < 1e-4
+
+
+def test_conv_rejects_bad_shapes():
+    x = View.zeros(1, 8, 8, 24, torch.bfloat16, DEV)
+    w = torch.zeros(1, 64, 24, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(L.B200dmError):
+        run_conv(L.BF16, 1, 0, 1, x, w, None, View.zeros(1, 8, 8, 64, torch.bfloat16, DEV), 24, 64, 8, 8)
+    with pytest.raises(L.B200dmError):
+        run_conv(L.F32, 1, 0, 1, x, w, None, View.zeros(1, 8, 8, 64, torch.float32, DEV), 64, 64, 8, 8)
+    with pytest.raises(L.B200dmError):
+        run_conv(L.BF16, 0, 0, 5, x, w, None, View.zeros(1, 8, 8, 64, torch.bfloat16, DEV), 16, 64, 8, 8)
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("C,S,B", [(3, 32, 3), (1, 32, 2), (3, 64, 2)])
+def test_init_conv_fwd_and_wgrad(dtype, C, S, B):
+    x = rnd(B, C, S, S, seed=51)
+    w = rnd(64, C, 7, 7, seed=52, scale=0.1).requires_grad_(True)
+    bias = rnd(64, seed=53)
+    ref = F.conv2d(x, w, bias, padding=3)
+    yv = View.zeros(B, S, S, 64, DT[dtype], DEV, ld=128, off=64)
+    L.call("b200dm_init_conv_fwd", dtype, x.data_ptr(), w.data_ptr(), bias.data_ptr(), yv.ptr, yv.ld, B, C, S, S, 64)
+    assert rel(yv.to_nchw(), ref) < tol(dtype)
+    dy = q(rnd(B, 64, S, S, seed=54), dtype)
+    ref.backward(dy)
+    dw = torch.zeros_like(w)
+    dyv = nhwc(dy, dtype)
+    L.call("b200dm_init_conv_wgrad", dtype, x.data_ptr(), dyv.ptr, dyv.ld, dw.data_ptr(), B, C, S, S, 64)
+    assert rel(dw, w.grad) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("C", [1, 3])
+def test_final_conv_fwd_bwd(dtype, C):
+    B, S = 3, 16
+    x = q(rnd(B, 64, S, S, seed=61), dtype).requires_grad_(True)
+    w = rnd(C, 64, 1, 1, seed=62, scale=0.125).requires_grad_(True)
+    bias = rnd(C, seed=63).requires_grad_(True)
+    ref = F.conv2d(x, w, bias)
+    xv = nhwc(x.detach(), dtype, ld=72, off=8)
+    y = torch.empty(B, C, S, S, device=DEV)
+    L.call("b200dm_final_conv_fwd", dtype, xv.ptr, xv.ld, w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, S * S, 64, C)
+    assert rel(y, ref) < 2e-5
+    dy = rnd(B, C, S, S, seed=64)
+    ref.backward(dy)
+    dxv = View.zeros(B, S, S, 64, DT[dtype], DEV)
+    dw, db = torch.zeros(C, 64, device=DEV), torch.zeros(C, device=DEV)
+    L.call("b200dm_final_conv_bwd", dtype, xv.ptr, xv.ld, w.data_ptr(), dy.data_ptr(), dxv.ptr, dxv.ld,
+           dw.data_ptr(), db.data_ptr(), B, S * S, 64, C)
+    assert rel(dxv.to_nchw(), x.grad) < tol(dtype)
+    assert rel(dw, w.grad.view(C, 64)) < 2e-5 and rel(db, bias.grad) < 2e-5
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+def test_upsample_and_colsum(dtype):
+    B, S, Cc = 2, 8, 128
+    x = q(rnd(B, Cc, S, S, seed=71), dtype)
+    xv = nhwc(x, dtype, ld=Cc + 8, off=8)
+    yv = View.zeros(B, 2 * S, 2 * S, Cc, DT[dtype], DEV)
+    L.call("b200dm_upsample2x_fwd", dtype, xv.ptr, xv.ld, yv.ptr, yv.ld, B, S, S, Cc)
+    ref = x.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    assert torch.equal(yv.to_nchw(), ref)
+    dy = q(rnd(B, Cc, 2 * S, 2 * S, seed=72), dtype)
+    dyv = nhwc(dy, dtype)
+    dxv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
+    L.call("b200dm_upsample2x_bwd", dtype, dyv.ptr, dyv.ld, dxv.ptr, dxv.ld, B, S, S, Cc)
+    assert rel(dxv.to_nchw(), F.avg_pool2d(dy, 2) * 4) < tol(dtype)
+    out = torch.full((Cc,), 5.0, device=DEV)
+    L.call("b200dm_colsum", dtype, dyv.ptr, dyv.ld, B * 4 * S * S, Cc, out.data_ptr(), 0)
+    assert rel(out, dy.sum((0, 2, 3))) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# norms
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,S,Cc,film,res", [(3, 16, 64, True, False), (2, 8, 256, False, True),
+                                             (2, 32, 128, True, True), (5, 4, 512, False, False)])
+def test_groupnorm_film_silu_fwd_bwd(dtype, B, S, Cc, film, res):
+    G = 8
+    x = (q(rnd(B, Cc, S, S, seed=81) + 0.5, dtype)).requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(Cc, seed=82)).requires_grad_(True)
+    beta = (0.1 * rnd(Cc, seed=83)).requires_grad_(True)
+    fm = rnd(B, 2 * Cc + 6, seed=84, scale=0.3).requires_grad_(True) if film else None
+    r = q(rnd(B, Cc, S, S, seed=85), dtype) if res else None
+    h = F.group_norm(x, G, gamma, beta, eps=1e-5)
+    if film:
+        sc, sh = fm[:, 3:3 + Cc], fm[:, 3 + Cc:3 + 2 * Cc]
+        h = h * (sc[:, :, None, None] + 1) + sh[:, :, None, None]
+    ref = F.silu(h) + (r if res else 0)
+    xv = nhwc(x.detach(), dtype, ld=Cc + 8, off=8)
+    stats = torch.empty(B, G, 2, device=DEV)
+    L.call("b200dm_gn_stats", dtype, xv.ptr, xv.ld, stats.data_ptr(), B, S * S, Cc, G, 1e-5)
+    xs = x.detach().reshape(B, G, -1)
+    assert rel(stats[..., 0], xs.mean(-1)) < 1e-5
+    assert rel(stats[..., 1], (xs.var(-1, unbiased=False) + 1e-5).rsqrt()) < 1e-5
+    yv = View.zeros(B, S, S, Cc, DT[dtype], DEV, ld=2 * Cc, off=Cc)
+    rv = nhwc(r, dtype) if res else None
+    fptr = fm.detach().data_ptr() + 3 * 4 if film else None
+    L.call("b200dm_gn_apply_fwd", dtype, xv.ptr, xv.ld, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           fptr, 2 * Cc + 6, None if rv is None else rv.ptr, 0 if rv is None else rv.ld, yv.ptr, yv.ld,
+           B, S * S, Cc, G)
+    assert rel(yv.to_nchw(), ref) < tol(dtype)
+    # backward
+    dy = q(rnd(B, Cc, S, S, seed=86), dtype)
+    ref.backward(dy)
+    dyv = nhwc(dy, dtype)
+    dxv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
+    dgamma, dbeta = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
+    dfilm = torch.zeros(B, 2 * Cc + 6, device=DEV)
+    sums, gmeans = torch.empty(B, Cc, 2, device=DEV), torch.empty(B, G, 2, device=DEV)
+    L.call("b200dm_gn_apply_bwd", dtype, dyv.ptr, dyv.ld, xv.ptr, xv.ld, stats.data_ptr(), gamma.data_ptr(),
+           beta.data_ptr(), fptr, 2 * Cc + 6, dxv.ptr, dxv.ld, dgamma.data_ptr(), dbeta.data_ptr(),
+           dfilm.data_ptr() + 3 * 4 if film else None, sums.data_ptr(), gmeans.data_ptr(), B, S * S, Cc, G)
+    assert rel(dxv.to_nchw(), x.grad) < (1e-4 if dtype == L.F32 else 6e-3)
+    assert rel(dgamma, gamma.grad) < 1e-4 and rel(dbeta, beta.grad) < 1e-4
+    if film:
+        assert rel(dfilm, fm.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("Cc,res", [(64, False), (128, True), (256, True), (512, False)])
+def test_rmsnorm_fwd_bwd(dtype, Cc, res):
+    B, S = 3, 8
+    x = q(rnd(B, Cc, S, S, seed=91), dtype).requires_grad_(True)
+    g = (1 + 0.1 * rnd(1, Cc, 1, 1, seed=92)).requires_grad_(True)
+    r = q(rnd(B, Cc, S, S, seed=93), dtype) if res else None
+    ref = F.normalize(x, dim=1) * g * (Cc ** 0.5) + (r if res else 0)
+    xv = nhwc(x.detach(), dtype, ld=Cc + 8, off=0)
+    yv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
+    rv = nhwc(r, dtype) if res else None
+    L.call("b200dm_rmsnorm_fwd", dtype, xv.ptr, xv.ld, g.data_ptr(), None if rv is None else rv.ptr,
+           0 if rv is None else rv.ld, yv.ptr, yv.ld, B * S * S, Cc)
+    assert rel(yv.to_nchw(), ref) < tol(dtype)
+    dy = q(rnd(B, Cc, S, S, seed=94), dtype)
+    ref.backward(dy)
+    dyv = nhwc(dy, dtype)
+    dxv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
+    dg = torch.zeros(Cc, device=DEV)
+    L.call("b200dm_rmsnorm_bwd", dtype, dyv.ptr, dyv.ld, xv.ptr, xv.ld, g.data_ptr(),
+           None if rv is None else rv.ptr, 0 if rv is None else rv.ld, dxv.ptr, dxv.ld, dg.data_ptr(),
+           B * S * S, Cc)
+    expect_dx = x.grad + (r if res else 0)     # `res` of the backward kernel is an additive gradient
+    assert rel(dxv.to_nchw(), expect_dx) < tol(dtype)
+    assert rel(dg, g.grad.flatten()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _lin_attn_ref(qkv, mem):  # qkv [B, 384, n] fp32; mem [2,4,32,4]   (ddpm.py:222-238)
+    B, _, n = qkv.shape
+    qh, kh, vh = (t.reshape(B, 4, 32, n) for t in qkv.chunk(3, dim=1))
+    k = torch.cat((mem[0][None].expand(B, -1, -1, -1), kh), dim=-1)
+    v = torch.cat((mem[1][None].expand(B, -1, -1, -1), vh), dim=-1)
+    qs = qh.softmax(dim=-2) * (32 ** -0.5)
+    ks = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", ks, v)
+    return torch.einsum("bhde,bhdn->bhen", ctx, qs).reshape(B, 128, n)
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,S", [(2, 8), (3, 16), (1, 64)])
+def test_linear_attention_fwd_bwd(dtype, B, S):
+    n = S * S
+    qkv = q(rnd(B, 384, S, S, seed=101), dtype).requires_grad_(True)
+    mem = rnd(2, 4, 32, 4, seed=102).requires_grad_(True)
+    ref = _lin_attn_ref(qkv.flatten(2), mem)
+    qv = nhwc(qkv.detach(), dtype)
+    ctx, kstat = torch.empty(B, 4, 32, 32, device=DEV), torch.empty(B, 4, 32, 2, device=DEV)
+    ov = View.zeros(B, S, S, 128, DT[dtype], DEV)
+    L.call("b200dm_linattn_fwd", dtype, qv.ptr, qv.ld, mem.data_ptr(), ctx.data_ptr(), kstat.data_ptr(),
+           ov.ptr, ov.ld, B, n)
+    assert rel(ov.to_nchw().flatten(2), ref) < tol(dtype)
+    do = q(rnd(B, 128, S, S, seed=103), dtype)
+    ref.backward(do.flatten(2))
+    dov = nhwc(do, dtype)
+    dqv = View.zeros(B, S, S, 384, DT[dtype], DEV)
+    dctx, dmem = torch.empty(B, 4, 32, 32, device=DEV), torch.zeros(2, 4, 32, 4, device=DEV)
+    L.call("b200dm_linattn_bwd", dtype, dov.ptr, dov.ld, qv.ptr, qv.ld, mem.data_ptr(), ctx.data_ptr(),
+           kstat.data_ptr(), dctx.data_ptr(), dqv.ptr, dqv.ld, dmem.data_ptr(), B, n)
+    assert rel(dqv.to_nchw(), qkv.grad) < (1e-4 if dtype == L.F32 else 6e-3)
+    assert rel(dmem, mem.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("B,S", [(3, 4), (2, 8)])
+def test_full_attention_fwd_bwd(dtype, B, S):
+    n = S * S
+    qkv = q(rnd(B, 384, S, S, seed=111), dtype).requires_grad_(True)
+    mem = rnd(2, 4, 4, 32, seed=112).requires_grad_(True)
+    qh, kh, vh = (t.reshape(B, 4, 32, n).transpose(-1, -2) for t in qkv.flatten(2).chunk(3, dim=1))
+    k = torch.cat((mem[0][None].expand(B, -1, -1, -1), kh), dim=-2)
+    v = torch.cat((mem[1][None].expand(B, -1, -1, -1), vh), dim=-2)
+    attn = (torch.einsum("bhid,bhjd->bhij", qh, k) * 32 ** -0.5).softmax(-1)
+    ref = torch.einsum("bhij,bhjd->bhid", attn, v).transpose(-1, -2).reshape(B, 128, S, S)
+    qv = nhwc(qkv.detach(), dtype)
+    ov = View.zeros(B, S, S, 128, DT[dtype], DEV)
+    L.call("b200dm_attn_fwd", dtype, qv.ptr, qv.ld, mem.data_ptr(), ov.ptr, ov.ld, B, n)
+    assert rel(ov.to_nchw(), ref) < tol(dtype)
+    do = q(rnd(B, 128, S, S, seed=113), dtype)
+    ref.backward(do)
+    dov = nhwc(do, dtype)
+    dqv = View.zeros(B, S, S, 384, DT[dtype], DEV)
+    dmem = torch.zeros(2, 4, 4, 32, device=DEV)
+    L.call("b200dm_attn_bwd", dtype, dov.ptr, dov.ld, qv.ptr, qv.ld, mem.data_ptr(), dqv.ptr, dqv.ld,
+           dmem.data_ptr(), B, n)
+    assert rel(dqv.to_nchw(), qkv.grad) < (1e-4 if dtype == L.F32 else 6e-3)
+    assert rel(dmem, mem.grad) < 1e-4
+    with pytest.raises(L.B200dmError):       # 16x16 softmax attention never occurs
+        L.call("b200dm_attn_fwd", dtype, qv.ptr, qv.ld, mem.data_ptr(), ov.ptr, ov.ld, B, 256)
+
+
+# ------------------------------------------------------------------------------------------------
+# time embedding, linears, optimiser
+# ------------------------------------------------------------------------------------------------
+def test_sinusoidal_and_linears():
+    B = 37
+    t = torch.randint(0, 1000, (B,), device=DEV)
+    emb = torch.empty(B, 64, device=DEV)
+    L.call("b200dm_sinusoidal", t.data_ptr(), emb.data_ptr(), B, 64, 10000.0)
+    half = 32
+    fr = torch.exp(torch.arange(half, device=DEV) * -(math.log(10000) / (half - 1)))
+    a = t[:, None] * fr[None, :]
+    assert (emb - torch.cat((a.sin(), a.cos()), -1)).abs().max().item() < 2e-4  # argument up to ~1e3 rad
+    for act, fn in ((0, lambda v: v), (1, F.gelu), (2, F.silu)):
+        M, N, K = B, 200, 64
+        X = rnd(M, K, seed=121).requires_grad_(True)
+        W = rnd(N, K, seed=122, scale=0.1).requires_grad_(True)
+        b = rnd(N, seed=123).requires_grad_(True)
+        ref = fn(F.linear(X, W, b))
+        Y, pre = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+        L.call("b200dm_linear_fwd", X.data_ptr(), W.data_ptr(), b.data_ptr(), Y.data_ptr(), pre.data_ptr(), M, N, K, act)
+        assert rel(Y, ref) < 1e-5
+        dY = rnd(M, N, seed=124)
+        ref.backward(dY)
+        dX = torch.empty(M, K, device=DEV)
+        dW, db = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+        g = dY.clone()
+        L.call("b200dm_linear_bwd", X.data_ptr(), W.data_ptr(), pre.data_ptr(), g.data_ptr(), dX.data_ptr(),
+               dW.data_ptr(), db.data_ptr(), M, N, K, act)
+        assert rel(dX, X.grad) < 1e-5 and rel(dW, W.grad) < 1e-5 and rel(db, b.grad) < 1e-5
+    # the wide FiLM projection shape: M = batch, N = 8064, K = 256 (split-K dX path)
+    M, N, K = 16, 8064, 256
+    X, W, dY = rnd(M, K, seed=125), rnd(N, K, seed=126, scale=0.05), rnd(M, N, seed=127)
+    dX = torch.empty(M, K, device=DEV)
+    L.call("b200dm_linear_bwd", X.data_ptr(), W.data_ptr(), None, dY.data_ptr(), dX.data_ptr(), None, None, M, N, K, 0)
+    assert rel(dX, dY @ W) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+def test_pack_conv_weight(dtype):
+    w = rnd(96, 160, 3, 3, seed=131)
+    master = w.permute(2, 3, 0, 1).reshape(9, 96, 160).contiguous()
+    wf = torch.empty(9, 96, 160, dtype=DT[dtype], device=DEV)
+    wt = torch.empty(9, 160, 96, dtype=DT[dtype], device=DEV)
+    L.call("b200dm_pack_conv_weight", dtype, master.data_ptr(), wf.data_ptr(), wt.data_ptr(), 9, 96, 160, 1)
+    assert torch.equal(wf, pack_w(w, dtype)) and torch.equal(wt, pack_w(w, dtype, transpose=True, flip=True))
+
+
+def test_adam_matches_torch_and_ema():
+    n = 100003
+    p0, g = rnd(n, seed=141), rnd(n, seed=142)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=2e-5, betas=(0.9, 0.99))
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        ref.grad = g * step
+        opt.step()
+        gs = (g * step * 2).contiguous()
+        L.call("b200dm_adam_step", p.data_ptr(), gs.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2e-5, 0.9, 0.99,
+               1e-8, 0.0, step, 0.5)
+    assert (p - ref.detach()).abs().max().item() < 1e-7
+    ema = p0.clone()
+    L.call("b200dm_ema_update", ema.data_ptr(), p.data_ptr(), n, 0.995)
+    assert (ema - torch.lerp(p0, p, 0.005)).abs().max().item() < 1e-7
