@@ -139,6 +139,10 @@ typedef struct {
   int32_t dy_ld;
   float* dw;
   int32_t accumulate;
+  /* element strides of dw: dw[tap*s_tap + co*s_co + ci*s_ci]; all 0 => tap-major packed
+   * (s_tap = Cout*Cin, s_co = Cin, s_ci = 1).  The pixel-unshuffle conv keeps the reference layout
+   * [Cout][c*4 + tap] (s_tap = 1, s_co = 4*Cin, s_ci = 4). */
+  int64_t s_tap, s_co, s_ci;
 } b200dm_wgrad_desc;
 
 int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream);
@@ -237,10 +241,11 @@ int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* d
 /* ------------------------------------------------------------------------------------------------
  * Weight packing, optimiser, EMA
  * ---------------------------------------------------------------------------------------------- */
-/* master fp32 [taps][Cout][Cin] -> fwd-packed (same order, dtype) and, if wt != NULL, the dgrad
- * operand [taps][Cin][Cout] with taps reversed (mode 0) / kept (mode 1). */
+/* master fp32 w[tap*s_tap + co*s_co + ci*s_ci] -> fwd-packed [taps][Cout][Cin] (dtype) and, if
+ * wt != NULL, the dgrad operand [taps][Cin][Cout] with taps reversed when flip != 0. */
 int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, int32_t taps,
-                            int32_t Cout, int32_t Cin, int32_t flip, void* stream);
+                            int32_t Cout, int32_t Cin, int32_t flip, int64_t s_tap, int64_t s_co,
+                            int64_t s_ci, void* stream);
 /* fused Adam over a flat fp32 arena (torch.optim.Adam semantics, ddpm.py:1053-1059):
  * grad_scale multiplies g first (DDP mean).  step is the 1-based step count. */
 int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

@@ -43,6 +43,7 @@ class WgradDesc(C.Structure):
         ("dy", C.c_void_p), ("dy_ld", C.c_int32),
         ("dw", C.c_void_p),
         ("accumulate", C.c_int32),
+        ("s_tap", C.c_int64), ("s_co", C.c_int64), ("s_ci", C.c_int64),
     ]
 
 
@@ -78,7 +79,7 @@ PROTOTYPES = {
     "b200dm_sinusoidal": [_P, _P, _I, _I, _F, _P],
     "b200dm_linear_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200dm_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "b200dm_pack_conv_weight": [_I, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200dm_pack_conv_weight": [_I, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _P],
     "b200dm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "b200dm_ema_update": [_P, _P, _L, _F, _P],
     "b200dm_fill_f32": [_P, _L, _F, _P],

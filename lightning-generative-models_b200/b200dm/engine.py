@@ -1,0 +1,393 @@
+"""Static launch plan of the B200 Unet forward / backward.
+
+`Plan` turns one (batch, size, training?) configuration of the reference's `Unet.forward`
+(models/generative/diffusion/ddpm.py:428-471) into a fixed list of C-ABI kernel launches over
+pre-allocated NHWC buffers, plus the mirrored backward list (the reference gets its backward from
+autograd through ~9,000 ATen calls; here it is ~400 launches, CUDA-graph capturable: no allocation,
+no host sync, no shape-dependent control flow at run time).
+
+Data-flow decisions:
+  * torch.cat never runs: producers write into channel slices of the consumer's concat buffer;
+  * every gradient accumulation is an epilogue flag (accumulate / residual pointer) of the kernel that
+    produces the contribution, so there are no stand-alone add kernels;
+  * FiLM projections of all 19 ResnetBlocks are one GEMM.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional
+
+import torch
+
+from . import _lib as L
+from .params import HIDDEN, ParamArena
+from .tensor import View
+
+GROUPS = 8
+GN_EPS = 1e-5
+
+
+class WeightPack:
+    """GEMM-operand copies of the conv weights in the activation dtype: forward [taps][Cout][Cin] and
+    data-gradient [taps'][Cin][Cout] (taps reversed for k x k convs)."""
+
+    def __init__(self, arena: ParamArena, dt: int, with_dgrad: bool):
+        self.arena, self.dt = arena, dt
+        tdt = torch.bfloat16 if dt == L.BF16 else torch.float32
+        self.fwd, self.tr = {}, {}
+        total = sum(ci.taps * ci.cout * ci.cin for ci in arena.convs.values())
+        dev = arena.flat.device
+        self.fbuf = torch.empty(total, dtype=tdt, device=dev)
+        self.tbuf = torch.empty(total, dtype=tdt, device=dev) if with_dgrad else None
+        off = 0
+        for nm, ci in arena.convs.items():
+            n = ci.taps * ci.cout * ci.cin
+            self.fwd[nm] = self.fbuf[off:off + n]
+            if with_dgrad:
+                self.tr[nm] = self.tbuf[off:off + n]
+            off += n
+        self.version = -1
+
+    def refresh(self, force: bool = False):
+        """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
+        v = self.arena.flat._version
+        if not force and v == self.version:
+            return
+        for nm, ci in self.arena.convs.items():
+            if ci.master_packed:
+                s_tap, s_co, s_ci = ci.cout * ci.cin, ci.cin, 1
+            else:                       # reference layout [Cout][c*4 + tap]
+                s_tap, s_co, s_ci = 1, 4 * ci.cin, 4
+            L.call("b200dm_pack_conv_weight", self.dt, self.arena.ptr(nm + ".weight"),
+                   self.fwd[nm].data_ptr(), self.tr[nm].data_ptr() if self.tbuf is not None else None,
+                   ci.taps, ci.cout, ci.cin, 1 if ci.mode == 0 else 0, s_tap, s_co, s_ci)
+        self.version = v
+
+
+class Plan:
+    def __init__(self, arena: ParamArena, pack: WeightPack, B: int, S: int, dt: int, training: bool,
+                 use_tc: bool):
+        assert S % 8 == 0, "H, W must be divisible by 8"
+        self.arena, self.pack = arena, pack
+        self.B, self.S, self.dt, self.training, self.use_tc = B, S, dt, training, use_tc
+        self.dev = arena.flat.device
+        self.tdt = torch.bfloat16 if dt == L.BF16 else torch.float32
+        self.fwd: List[Callable[[int], None]] = []
+        self.bwd_groups: List[List[Callable[[int], None]]] = []
+        self._cur_bwd: Optional[List[Callable[[int], None]]] = None
+        self._keep = []              # ctypes structs / tensors referenced by raw pointers
+        self._scratch = {}
+        self.lib = L.load()
+        self.nbytes = 0
+        dim, ch = arena.dim, arena.channels
+        self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
+        self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
+        self.out = torch.zeros(B, ch, S, S, device=self.dev)
+        self.d_out = torch.zeros(B, ch, S, S, device=self.dev) if training else None
+        self._build(dim, ch)
+        self.bwd: List[Callable[[int], None]] = [op for g in reversed(self.bwd_groups) for op in g]
+
+    # ---- allocation -------------------------------------------------------------------------------
+    def buf(self, H, C, dtype=None) -> View:
+        dtype = self.tdt if dtype is None else dtype
+        t = torch.zeros(self.B, H, H, C, dtype=dtype, device=self.dev)
+        self.nbytes += t.numel() * t.element_size()
+        return View(t)
+
+    def scratch(self, key, H, C) -> View:
+        """Backward scratch shared by all units of the same geometry (backward is sequential)."""
+        k = (key, H, C)
+        if k not in self._scratch:
+            self._scratch[k] = self.buf(H, C)
+        return self._scratch[k]
+
+    def f32(self, *shape) -> torch.Tensor:
+        t = torch.zeros(*shape, dtype=torch.float32, device=self.dev)
+        self.nbytes += t.numel() * 4
+        self._keep.append(t)
+        return t
+
+    # ---- op emission --------------------------------------------------------------------------------
+    def _emit(self, lst, name, *args):
+        fn = getattr(self.lib, name)
+        self._keep.append(args)
+
+        def op(stream, fn=fn, args=args, name=name):
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise L.B200dmError(f"{name} failed with code {rc}: {L.last_error()}")
+        lst.append(op)
+
+    def F(self, name, *args):
+        self._emit(self.fwd, name, *args)
+
+    def Bk(self, name, *args):
+        if self.training:
+            self._emit(self._cur_bwd, name, *args)
+
+    def begin_unit(self):
+        self._cur_bwd = []
+        self.bwd_groups.append(self._cur_bwd)
+
+    def _impl(self, cin, cout):
+        return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
+
+    def conv_fwd(self, lst_fn, nm, x: View, y: View, *, dgrad=False, res: Optional[View] = None,
+                 accumulate=0, bias=True):
+        """Forward conv `nm` (x -> y), or with dgrad=True its data gradient (x = dY, y = dX)."""
+        ci = self.arena.convs[nm]
+        if not dgrad:
+            mode, cin, cout, H = ci.mode, ci.cin, ci.cout, y.H
+            w = self.pack.fwd[nm].data_ptr()
+            b = self.arena.ptr(nm + ".bias") if (ci.bias and bias) else None
+        else:
+            mode = 0 if ci.mode == 0 else 2
+            cin, cout, H = ci.cout, ci.cin, x.H
+            w = self.pack.tr[nm].data_ptr()
+            b = None
+        assert x.C == cin and y.C == cout, (nm, x.C, cin, y.C, cout)
+        d = L.ConvDesc(dtype=self.dt, mode=mode, ksize=ci.ksize if ci.mode == 0 else 1,
+                       impl=self._impl(cin, cout), B=self.B, H=H, W=H, Cin=cin, Cout=cout,
+                       x=x.ptr, x_ld=x.ld, w=w, bias=b, y=y.ptr, y_ld=y.ld,
+                       res=None if res is None else res.ptr, res_ld=0 if res is None else res.ld,
+                       accumulate=accumulate)
+        lst_fn("b200dm_conv_fwd", C.byref(d))
+        self._keep.append(d)
+
+    def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None):
+        """wgrad + bias grad + (optional) dgrad of conv `nm` whose forward was x -> y, given dy."""
+        if not self.training:
+            return
+        ci = self.arena.convs[nm]
+        H = dy.H
+        if ci.master_packed:
+            s_tap, s_co, s_ci = ci.cout * ci.cin, ci.cin, 1
+        else:
+            s_tap, s_co, s_ci = 1, 4 * ci.cin, 4
+        d = L.WgradDesc(dtype=self.dt, mode=ci.mode, ksize=ci.ksize if ci.mode == 0 else 1,
+                        impl=self._impl(ci.cin, ci.cout), B=self.B, H=H, W=H, Cin=ci.cin, Cout=ci.cout,
+                        x=x.ptr, x_ld=x.ld, dy=dy.ptr, dy_ld=dy.ld, dw=self.arena.gptr(nm + ".weight"),
+                        accumulate=1, s_tap=s_tap, s_co=s_co, s_ci=s_ci)
+        self.Bk("b200dm_conv_wgrad", C.byref(d))
+        self._keep.append(d)
+        if ci.bias:
+            self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
+                    self.arena.gptr(nm + ".bias"), 1)
+        if dx is not None:
+            self.conv_fwd(self.Bk, nm, dy, dx, dgrad=True, res=dx_res, accumulate=dx_acc)
+
+    # ---- composite units -----------------------------------------------------------------------------
+    def resblock(self, nm, x: View, out: View, gx: Optional[View], gout: Optional[View], gx_prior: bool):
+        a = self.arena
+        cin, cout = a.blocks[nm]
+        H, HW = x.H, x.H * x.H
+        has_res_conv = cin != cout
+        self.begin_unit()
+        c1, h1, c2 = self.buf(H, cout), self.buf(H, cout), self.buf(H, cout)
+        st1, st2 = self.f32(self.B, GROUPS, 2), self.f32(self.B, GROUPS, 2)
+        film_ptr = self.film.data_ptr() + 4 * a.film_off[nm]
+        b1, b2 = nm + ".block1", nm + ".block2"
+        self.conv_fwd(self.F, b1 + ".proj", x, c1)
+        self.F("b200dm_gn_stats", self.dt, c1.ptr, c1.ld, st1.data_ptr(), self.B, HW, cout, GROUPS, GN_EPS)
+        self.F("b200dm_gn_apply_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
+               a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout, GROUPS)
+        self.conv_fwd(self.F, b2 + ".proj", h1, c2)
+        self.F("b200dm_gn_stats", self.dt, c2.ptr, c2.ld, st2.data_ptr(), self.B, HW, cout, GROUPS, GN_EPS)
+        if has_res_conv:
+            rc = self.buf(H, cout)
+            self.conv_fwd(self.F, nm + ".res_conv", x, rc)
+            res = rc
+        else:
+            res = x
+        self.F("b200dm_gn_apply_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
+               a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS)
+        if not self.training:
+            return
+        dc, gh1 = self.scratch("dc", H, cout), self.scratch("gh1", H, cout)
+        dfilm_ptr = self.dfilm.data_ptr() + 4 * a.film_off[nm]
+        # block2: GN/SiLU backward -> dc ; conv2 backward -> gh1
+        self.Bk("b200dm_gn_apply_bwd", self.dt, gout.ptr, gout.ld, c2.ptr, c2.ld, st2.data_ptr(),
+                a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, dc.ptr, dc.ld,
+                a.gptr(b2 + ".norm.weight"), a.gptr(b2 + ".norm.bias"), None, self.sums.data_ptr(),
+                self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
+        self.conv_bwd(b2 + ".proj", h1, dc, gh1)
+        # block1: GN/FiLM/SiLU backward -> dc ; conv1 backward -> gx (+ identity-skip gradient)
+        self.Bk("b200dm_gn_apply_bwd", self.dt, gh1.ptr, gh1.ld, c1.ptr, c1.ld, st1.data_ptr(),
+                a.ptr(b1 + ".norm.weight"), a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, dc.ptr, dc.ld,
+                a.gptr(b1 + ".norm.weight"), a.gptr(b1 + ".norm.bias"), dfilm_ptr, self.sums.data_ptr(),
+                self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
+        self.conv_bwd(b1 + ".proj", x, dc, gx, dx_acc=1 if gx_prior else 0,
+                      dx_res=None if has_res_conv else gout)
+        if has_res_conv:
+            self.conv_bwd(nm + ".res_conv", x, gout, gx, dx_acc=1)
+
+    def attention(self, nm, x: View, out: View, gx: Optional[View], gout: Optional[View], full: bool):
+        a = self.arena
+        Cc, H = x.C, x.H
+        n, rows = H * H, self.B * H * H
+        self.begin_unit()
+        xn, qkv, ao = self.buf(H, Cc), self.buf(H, 3 * HIDDEN), self.buf(H, HIDDEN)
+        self.F("b200dm_rmsnorm_fwd", self.dt, x.ptr, x.ld, a.ptr(nm + ".norm.g"), None, 0, xn.ptr, xn.ld, rows, Cc)
+        self.conv_fwd(self.F, nm + ".to_qkv", xn, qkv)
+        if full:
+            self.F("b200dm_attn_fwd", self.dt, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"), ao.ptr, ao.ld, self.B, n)
+            self.conv_fwd(self.F, nm + ".to_out", ao, out, res=x)
+        else:
+            ctx, kstat = self.f32(self.B, 4, 32, 32), self.f32(self.B, 4, 32, 2)
+            to = self.buf(H, Cc)
+            self.F("b200dm_linattn_fwd", self.dt, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"), ctx.data_ptr(),
+                   kstat.data_ptr(), ao.ptr, ao.ld, self.B, n)
+            self.conv_fwd(self.F, nm + ".to_out.0", ao, to)
+            self.F("b200dm_rmsnorm_fwd", self.dt, to.ptr, to.ld, a.ptr(nm + ".to_out.1.g"), x.ptr, x.ld,
+                   out.ptr, out.ld, rows, Cc)
+        if not self.training:
+            return
+        dao, dqkv, dxn = self.scratch("dao", H, HIDDEN), self.scratch("dqkv", H, 3 * HIDDEN), self.scratch("dxn", H, Cc)
+        if full:
+            self.conv_bwd(nm + ".to_out", ao, gout, dao)
+            self.Bk("b200dm_attn_bwd", self.dt, dao.ptr, dao.ld, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"),
+                    dqkv.ptr, dqkv.ld, a.gptr(nm + ".mem_kv"), self.B, n)
+        else:
+            dto = self.scratch("dto", H, Cc)
+            self.Bk("b200dm_rmsnorm_bwd", self.dt, gout.ptr, gout.ld, to.ptr, to.ld, a.ptr(nm + ".to_out.1.g"),
+                    None, 0, dto.ptr, dto.ld, a.gptr(nm + ".to_out.1.g"), rows, Cc)
+            self.conv_bwd(nm + ".to_out.0", ao, dto, dao)
+            self.Bk("b200dm_linattn_bwd", self.dt, dao.ptr, dao.ld, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"),
+                    ctx.data_ptr(), kstat.data_ptr(), self.dctx.data_ptr(), dqkv.ptr, dqkv.ld,
+                    a.gptr(nm + ".mem_kv"), self.B, n)
+        self.conv_bwd(nm + ".to_qkv", xn, dqkv, dxn)
+        # gx = rmsnorm'(dxn) + gout   (the `attn(x) + x` skip, ddpm.py:449,455,464)
+        self.Bk("b200dm_rmsnorm_bwd", self.dt, dxn.ptr, dxn.ld, x.ptr, x.ld, a.ptr(nm + ".norm.g"),
+                gout.ptr, gout.ld, gx.ptr, gx.ld, a.gptr(nm + ".norm.g"), rows, Cc)
+
+    def plain_conv(self, nm, x: View, out: View, gx, gout, gx_prior: bool):
+        self.begin_unit()
+        self.conv_fwd(self.F, nm, x, out)
+        if self.training:
+            self.conv_bwd(nm, x, gout, gx, dx_acc=1 if gx_prior else 0)
+
+    def upsample_conv(self, nm, x: View, out: View, gx, gout):
+        self.begin_unit()
+        xu = self.buf(2 * x.H, x.C)
+        self.F("b200dm_upsample2x_fwd", self.dt, x.ptr, x.ld, xu.ptr, xu.ld, self.B, x.H, x.H, x.C)
+        self.conv_fwd(self.F, nm, xu, out)
+        if self.training:
+            gxu = self.scratch("gxu", 2 * x.H, x.C)
+            self.conv_bwd(nm, xu, gout, gxu)
+            self.Bk("b200dm_upsample2x_bwd", self.dt, gxu.ptr, gxu.ld, gx.ptr, gx.ld, self.B, x.H, x.H, x.C)
+
+    # ---- the network -----------------------------------------------------------------------------------
+    def _build(self, dim, ch):
+        a, B, S, tr = self.arena, self.B, self.S, self.training
+        dims = [dim, dim, 2 * dim, 4 * dim, 8 * dim]
+        td = a.time_dim
+        # time embedding + all FiLM projections (ddpm.py:440, :191-194)
+        self.emb, self.pre1, self.h = self.f32(B, dim), self.f32(B, td), self.f32(B, td)
+        self.pre3, self.tact = self.f32(B, td), self.f32(B, td)
+        self.film = self.f32(B, a.film_cols)
+        if tr:
+            self.dfilm, self.dtact, self.dh = self.f32(B, a.film_cols), self.f32(B, td), self.f32(B, td)
+            self.sums, self.gmeans = self.f32(B, 8 * dim, 2), self.f32(B, GROUPS, 2)
+            self.dctx = self.f32(B, 4, 32, 32)
+        self.begin_unit()
+        self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0)
+        self.F("b200dm_linear_fwd", self.emb.data_ptr(), a.ptr("time_mlp.1.weight"), a.ptr("time_mlp.1.bias"),
+               self.h.data_ptr(), self.pre1.data_ptr(), B, td, dim, 1)
+        self.F("b200dm_linear_fwd", self.h.data_ptr(), a.ptr("time_mlp.3.weight"), a.ptr("time_mlp.3.bias"),
+               self.tact.data_ptr(), self.pre3.data_ptr(), B, td, td, 2)
+        self.F("b200dm_linear_fwd", self.tact.data_ptr(), a.film_weight_ptr, a.film_bias_ptr,
+               self.film.data_ptr(), None, B, a.film_cols, td, 0)
+        if tr:  # runs LAST in backward (dfilm is complete once every block has run)
+            self.Bk("b200dm_linear_bwd", self.tact.data_ptr(), a.film_weight_ptr, None, self.dfilm.data_ptr(),
+                    self.dtact.data_ptr(), a.film_weight_gptr, a.film_bias_gptr, B, a.film_cols, td, 0)
+            self.Bk("b200dm_linear_bwd", self.h.data_ptr(), a.ptr("time_mlp.3.weight"), self.pre3.data_ptr(),
+                    self.dtact.data_ptr(), self.dh.data_ptr(), a.gptr("time_mlp.3.weight"),
+                    a.gptr("time_mlp.3.bias"), B, td, td, 2)
+            self.Bk("b200dm_linear_bwd", self.emb.data_ptr(), a.ptr("time_mlp.1.weight"), self.pre1.data_ptr(),
+                    self.dh.data_ptr(), None, a.gptr("time_mlp.1.weight"), a.gptr("time_mlp.1.bias"),
+                    B, td, dim, 1)
+
+        res = [S, S // 2, S // 4, S // 8]
+        G = (lambda H, Cc: self.buf(H, Cc)) if tr else (lambda H, Cc: None)
+        # concat buffers of the up path, [x_up | skip]; level i of the down path feeds up level 3-i
+        catB, catA, gcatB, gcatA = {}, {}, {}, {}
+        for i in range(4):
+            d_in, d_out = dims[i], dims[i + 1]
+            catB[i], catA[i] = self.buf(res[i], d_out + d_in), self.buf(res[i], d_out + d_in)
+            gcatB[i], gcatA[i] = G(res[i], d_out + d_in), G(res[i], d_out + d_in)
+        catF, gcatF = self.buf(S, 2 * dim), G(S, 2 * dim)
+        sl = (lambda g, off, Cc: None if g is None else g.slice(off, Cc))
+
+        # init conv -> r (= second half of the final concat), ddpm.py:437-438, :468
+        self.begin_unit()
+        r, gr = catF.slice(dim, dim), sl(gcatF, dim, dim)
+        self.F("b200dm_init_conv_fwd", self.dt, self.x_in.data_ptr(), a.ptr("init_conv.weight"),
+               a.ptr("init_conv.bias"), r.ptr, r.ld, B, ch, S, S, dim)
+        if tr:
+            self.Bk("b200dm_init_conv_wgrad", self.dt, self.x_in.data_ptr(), gr.ptr, gr.ld,
+                    a.gptr("init_conv.weight"), B, ch, S, S, dim)
+            self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
+
+        x, gx = r, gr
+        x_prior = True        # gcatF[dim:] also receives the final block's gradient first
+        for i in range(4):
+            d_in, d_out, H = dims[i], dims[i + 1], res[i]
+            last = i == 3
+            x1, gx1 = catA[i].slice(d_out, d_in), sl(gcatA[i], d_out, d_in)
+            self.resblock(f"downs.{i}.0", x, x1, gx, gx1, gx_prior=x_prior)
+            x2, gx2 = self.buf(H, d_in), G(H, d_in)
+            self.resblock(f"downs.{i}.1", x1, x2, gx1, gx2, gx_prior=True)
+            x3, gx3 = catB[i].slice(d_out, d_in), sl(gcatB[i], d_out, d_in)
+            self.attention(f"downs.{i}.2", x2, x3, gx2, gx3, full=last)
+            Hn = H if last else H // 2
+            x4 = View(torch.zeros(B, Hn, Hn, d_out, dtype=self.tdt, device=self.dev))
+            gx4 = View(torch.zeros(B, Hn, Hn, d_out, dtype=self.tdt, device=self.dev)) if tr else None
+            self.plain_conv(f"downs.{i}.3" if last else f"downs.{i}.3.1", x3, x4, gx3, gx4, gx_prior=True)
+            x, gx, x_prior = x4, gx4, False
+
+        mid = dims[4]
+        Hm = res[3]
+        m1, gm1 = self.buf(Hm, mid), G(Hm, mid)
+        self.resblock("mid_block1", x, m1, gx, gm1, gx_prior=False)
+        m2, gm2 = self.buf(Hm, mid), G(Hm, mid)
+        self.attention("mid_attn", m1, m2, gm1, gm2, full=True)
+        u0, gu0 = catB[3].slice(0, mid), sl(gcatB[3], 0, mid)
+        self.resblock("mid_block2", m2, u0, gm2, gu0, gx_prior=False)
+
+        for j in range(4):
+            i = 3 - j
+            d_in, d_out, H = dims[i], dims[i + 1], res[i]
+            last = j == 3
+            u1, gu1 = catA[i].slice(0, d_out), sl(gcatA[i], 0, d_out)
+            self.resblock(f"ups.{j}.0", catB[i], u1, gcatB[i], gu1, gx_prior=False)
+            u2, gu2 = self.buf(H, d_out), G(H, d_out)
+            self.resblock(f"ups.{j}.1", catA[i], u2, gcatA[i], gu2, gx_prior=False)
+            u3, gu3 = self.buf(H, d_out), G(H, d_out)
+            self.attention(f"ups.{j}.2", u2, u3, gu2, gu3, full=(j == 0))
+            if last:
+                nxt, gnxt = catF.slice(0, dim), sl(gcatF, 0, dim)
+                self.plain_conv(f"ups.{j}.3", u3, nxt, gu3, gnxt, gx_prior=False)
+            else:
+                nxt, gnxt = catB[i - 1].slice(0, d_in), sl(gcatB[i - 1], 0, d_in)
+                self.upsample_conv(f"ups.{j}.3.1", u3, nxt, gu3, gnxt)
+
+        yb, gy = self.buf(S, dim), G(S, dim)
+        self.resblock("final_res_block", catF, yb, gcatF, gy, gx_prior=False)
+        self.begin_unit()
+        self.F("b200dm_final_conv_fwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
+               a.ptr("final_conv.bias"), self.out.data_ptr(), B, S * S, dim, ch)
+        if tr:
+            self.Bk("b200dm_final_conv_bwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
+                    self.d_out.data_ptr(), gy.ptr, gy.ld, a.gptr("final_conv.weight"),
+                    a.gptr("final_conv.bias"), B, S * S, dim, ch)
+
+    # ---- execution --------------------------------------------------------------------------------------
+    def run_forward(self):
+        st = L.stream_ptr()
+        for op in self.fwd:
+            op(st)
+
+    def run_backward(self):
+        st = L.stream_ptr()
+        for op in self.bwd:
+            op(st)

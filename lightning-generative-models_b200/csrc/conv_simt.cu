@@ -121,7 +121,7 @@ conv_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ w,
 template <typename T>
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ dy, int dy_ld,
-                  float* __restrict__ dw, int splits) {
+                  float* __restrict__ dw, int splits, long long s_tap, long long s_co, long long s_ci) {
   __shared__ float As[BK][BM + PADM];  // dY chunk: [pixel][co]
   __shared__ float Bs[BK][BN + PADM];  // X chunk:  [pixel][ci]
   const int tid = threadIdx.x;
@@ -174,7 +174,7 @@ wgrad_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ dy, in
     for (int j = 0; j < 4; ++j) {
       int ci = ci0 + tx * 4 + j;
       if (ci >= c.Cin) continue;
-      atomicAdd(dw + ((int64_t)tap * c.Cout + co) * c.Cin + ci, acc[i][j]);
+      atomicAdd(dw + (int64_t)tap * s_tap + (int64_t)co * s_co + (int64_t)ci * s_ci, acc[i][j]);
     }
   }
 }
@@ -468,8 +468,10 @@ static int launch_wgrad(const b200dm_wgrad_desc* d, cudaStream_t st) {
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   dim3 grid(tiles, c.taps, splits);
+  long long s_tap = d->s_tap, s_co = d->s_co, s_ci = d->s_ci;
+  if (s_tap == 0 && s_co == 0 && s_ci == 0) { s_tap = (long long)c.Cout * c.Cin; s_co = c.Cin; s_ci = 1; }
   wgrad_simt_kernel<T><<<grid, kConvThreads, 0, st>>>(c, (const T*)d->x, (const T*)d->dy, d->dy_ld,
-                                                       d->dw, splits);
+                                                       d->dw, splits, s_tap, s_co, s_ci);
   count_launch();
   return check_launch("wgrad_simt");
 }

@@ -361,6 +361,7 @@ struct TcWgradParams {
   int k_tiles;        // number of 128-pixel tiles
   int splits;
   float* dw;
+  long long s_tap, s_co, s_ci;
 };
 
 template <int N_TILE, int STAGES>
@@ -463,7 +464,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     const bool valid = co < p.Cout;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    float* drow = p.dw + ((long long)tap * p.Cout + co) * p.Cin + ci0;
+    float* drow = p.dw + (long long)tap * p.s_tap + (long long)co * p.s_co + (long long)ci0 * p.s_ci;
 #pragma unroll 1
     for (int c = 0; c < N_TILE; c += 16) {
       uint32_t r[16];
@@ -471,7 +472,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+        for (int j = 0; j < 16; ++j) atomicAdd(drow + (long long)(c + j) * p.s_ci, __uint_as_float(r[j]));
       }
     }
   }
@@ -517,6 +518,8 @@ int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
   const long long M = (long long)d->B * d->H * d->W;
   p.k_tiles = (int)((M + TC_BM - 1) / TC_BM);
   p.dw = d->dw;
+  p.s_tap = d->s_tap; p.s_co = d->s_co; p.s_ci = d->s_ci;
+  if (p.s_tap == 0 && p.s_co == 0 && p.s_ci == 0) { p.s_tap = (long long)d->Cout * d->Cin; p.s_co = d->Cin; p.s_ci = 1; }
   const int n_tile = (d->Cin % 128 == 0) ? 128 : 64;
   const int co_tiles = (d->Cout + TC_BM - 1) / TC_BM, ci_tiles = d->Cin / n_tile;
   const int base_ctas = co_tiles * ci_tiles * taps;

@@ -8,15 +8,16 @@ namespace b200dm {
 // taps' = flip ? taps-1-t : t  (the data-gradient operand: rotate the filter 180 deg, swap in/out).
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wt,
-                                   int taps, int Cout, int Cin, int flip) {
+                                   int taps, int Cout, int Cin, int flip, long long s_tap,
+                                   long long s_co, long long s_ci) {
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
-  const float* wsrc = w + (int64_t)t * Cout * Cin;
+  const float* wsrc = w + (int64_t)t * s_tap;
   for (int r = ty; r < 32; r += 8) {
     int co = co0 + r, ci = ci0 + tx;
-    float v = (co < Cout && ci < Cin) ? wsrc[(int64_t)co * Cin + ci] : 0.f;
+    float v = (co < Cout && ci < Cin) ? wsrc[(int64_t)co * s_co + (int64_t)ci * s_ci] : 0.f;
     tile[r][tx] = v;
     if (wf && co < Cout && ci < Cin) Elem<T>::st(wf + ((int64_t)t * Cout + co) * Cin + ci, v);
   }
@@ -63,14 +64,16 @@ ema_kernel(float* __restrict__ ema, const float* __restrict__ online, int64_t n,
 using namespace b200dm;
 
 extern "C" int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, int32_t taps,
-                                       int32_t Cout, int32_t Cin, int32_t flip, void* stream) {
+                                       int32_t Cout, int32_t Cin, int32_t flip, int64_t s_tap,
+                                       int64_t s_co, int64_t s_ci, void* stream) {
   B200DM_REQUIRE(taps > 0 && Cout > 0 && Cin > 0, B200DM_ERR_SHAPE, "pack_conv_weight: bad shape");
+  if (s_tap == 0 && s_co == 0 && s_ci == 0) { s_tap = (int64_t)Cout * Cin; s_co = Cin; s_ci = 1; }
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    pack_weight_kernel<float><<<grid, block, 0, st>>>(w, (float*)wf, (float*)wt, taps, Cout, Cin, flip);
+    pack_weight_kernel<float><<<grid, block, 0, st>>>(w, (float*)wf, (float*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
   else
-    pack_weight_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip);
+    pack_weight_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
   count_launch();
   return check_launch("pack_conv_weight");
 }

@@ -17,6 +17,9 @@ from b200dm.tensor import View
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+# the torch expressions below are the fp32 yardstick: keep cuDNN/cuBLAS from silently using TF32
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 DT = {L.F32: torch.float32, L.BF16: torch.bfloat16}
 
 
@@ -572,7 +575,7 @@ def test_pack_conv_weight(dtype):
     master = w.permute(2, 3, 0, 1).reshape(9, 96, 160).contiguous()
     wf = torch.empty(9, 96, 160, dtype=DT[dtype], device=DEV)
     wt = torch.empty(9, 160, 96, dtype=DT[dtype], device=DEV)
-    L.call("b200dm_pack_conv_weight", dtype, master.data_ptr(), wf.data_ptr(), wt.data_ptr(), 9, 96, 160, 1)
+    L.call("b200dm_pack_conv_weight", dtype, master.data_ptr(), wf.data_ptr(), wt.data_ptr(), 9, 96, 160, 1, 0, 0, 0)
     assert torch.equal(wf, pack_w(w, dtype)) and torch.equal(wt, pack_w(w, dtype, transpose=True, flip=True))
 
 
