@@ -73,6 +73,8 @@ class Plan:
         self.dev = arena.flat.device
         self.tdt = torch.bfloat16 if dt == L.BF16 else torch.float32
         self.fwd: List[Callable[[int], None]] = []
+        self.fwd_names: List[str] = []
+        self.fwd_flops: List[float] = []
         self.bwd_groups: List[List[Callable[[int], None]]] = []
         self._cur_bwd: Optional[List[Callable[[int], None]]] = None
         self._keep = []              # ctypes structs / tensors referenced by raw pointers
@@ -86,6 +88,10 @@ class Plan:
         self.d_out = torch.zeros(B, ch, S, S, device=self.dev) if training else None
         self._build(dim, ch)
         self.bwd: List[Callable[[int], None]] = [op for g in reversed(self.bwd_groups) for op in g]
+        self.bwd_names = [op.kname for op in self.bwd]
+        self.bwd_flops = [op.flops for op in self.bwd]
+        self.fwd_names = [op.kname for op in self.fwd]
+        self.fwd_flops = [op.flops for op in self.fwd]
 
     # ---- allocation -------------------------------------------------------------------------------
     def buf(self, H, C, dtype=None) -> View:
@@ -108,7 +114,7 @@ class Plan:
         return t
 
     # ---- op emission --------------------------------------------------------------------------------
-    def _emit(self, lst, name, *args):
+    def _emit(self, lst, name, *args, kname=None, flops=0.0):
         fn = getattr(self.lib, name)
         self._keep.append(args)
 
@@ -116,14 +122,16 @@ class Plan:
             rc = fn(*args, stream)
             if rc != 0:
                 raise L.B200dmError(f"{name} failed with code {rc}: {L.last_error()}")
+        op.kname = kname or name.replace("b200dm_", "")     # kernel family (bench.py per-kernel table)
+        op.flops = flops                                    # algorithmic FLOPs of this launch
         lst.append(op)
 
-    def F(self, name, *args):
-        self._emit(self.fwd, name, *args)
+    def F(self, name, *args, **kw):
+        self._emit(self.fwd, name, *args, **kw)
 
-    def Bk(self, name, *args):
+    def Bk(self, name, *args, **kw):
         if self.training:
-            self._emit(self._cur_bwd, name, *args)
+            self._emit(self._cur_bwd, name, *args, **kw)
 
     def begin_unit(self):
         self._cur_bwd = []
@@ -151,7 +159,10 @@ class Plan:
                        x=x.ptr, x_ld=x.ld, w=w, bias=b, y=y.ptr, y_ld=y.ld,
                        res=None if res is None else res.ptr, res_ld=0 if res is None else res.ld,
                        accumulate=accumulate)
-        lst_fn("b200dm_conv_fwd", C.byref(d))
+        taps = ci.taps
+        flops = 2.0 * self.B * H * H * cout * cin * taps
+        fam = ("conv_tc" if d.impl == 1 else "conv_simt") + ("_dgrad" if dgrad else "_fwd")
+        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops)
         self._keep.append(d)
 
     def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None):
@@ -168,7 +179,8 @@ class Plan:
                         impl=self._impl(ci.cin, ci.cout), B=self.B, H=H, W=H, Cin=ci.cin, Cout=ci.cout,
                         x=x.ptr, x_ld=x.ld, dy=dy.ptr, dy_ld=dy.ld, dw=self.arena.gptr(nm + ".weight"),
                         accumulate=1, s_tap=s_tap, s_co=s_co, s_ci=s_ci)
-        self.Bk("b200dm_conv_wgrad", C.byref(d))
+        self.Bk("b200dm_conv_wgrad", C.byref(d), kname="wgrad_tc" if d.impl == 1 else "wgrad_simt",
+                flops=2.0 * self.B * H * H * ci.cout * ci.cin * ci.taps)
         self._keep.append(d)
         if ci.bias:
             self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
