@@ -82,6 +82,7 @@ class Plan:
         self.lib = L.load()
         self.nbytes = 0
         dim, ch = arena.dim, arena.channels
+        self._keep.append(pack)
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
         self.out = torch.zeros(B, ch, S, S, device=self.dev)
@@ -98,6 +99,7 @@ class Plan:
         dtype = self.tdt if dtype is None else dtype
         t = torch.zeros(self.B, H, H, C, dtype=dtype, device=self.dev)
         self.nbytes += t.numel() * t.element_size()
+        self._keep.append(t)          # ops hold raw pointers only: the plan owns every buffer
         return View(t)
 
     def scratch(self, key, H, C) -> View:
@@ -352,8 +354,7 @@ class Plan:
             x3, gx3 = catB[i].slice(d_out, d_in), sl(gcatB[i], d_out, d_in)
             self.attention(f"downs.{i}.2", x2, x3, gx2, gx3, full=last)
             Hn = H if last else H // 2
-            x4 = View(torch.zeros(B, Hn, Hn, d_out, dtype=self.tdt, device=self.dev))
-            gx4 = View(torch.zeros(B, Hn, Hn, d_out, dtype=self.tdt, device=self.dev)) if tr else None
+            x4, gx4 = self.buf(Hn, d_out), G(Hn, d_out)
             self.plain_conv(f"downs.{i}.3" if last else f"downs.{i}.3.1", x3, x4, gx3, gx4, gx_prior=True)
             x, gx, x_prior = x4, gx4, False
 
