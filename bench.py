@@ -48,7 +48,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
@@ -57,7 +57,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -65,7 +65,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this (and under load) are reported."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -75,19 +79,25 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, sm_all, mx, reasons = [], [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, r in self.rows:
             try:
-                sm.append(float(r[0]))
                 mx = float(r[1])
+                sm_all.append(float(r[0]))
+                if ts < t_mark:
+                    continue
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
+                if float(r[7]) >= 50:            # under load
+                    sm.append(float(r[0]))
             except (ValueError, IndexError):
                 continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = sm if sm else sm_all
+        return {"sm_mhz": statistics.median(use) if use else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples_under_load": len(sm), "samples": len(sm_all)}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -325,15 +335,16 @@ def main():
         step_device(0)
         torch.cuda.synchronize()
         launches_per_step = int(L.load().b200dm_launch_count())
-        for i in range(W):
-            step_device(i)
         clocks = ClockSampler(local)
         clocks.start()
+        for i in range(W):
+            step_device(i)
+        clocks.mark()
         ms = timed(step_device, K)
-        clk = clocks.stop()
         for i in range(2):
             step_e2e(i)
         ms_e2e = timed(step_e2e, K)
+        clk = clocks.stop()
         imgs = B * world * K
         value, e2e_value = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
         h2d, d2h = B * 3 * S * S * 4, 4
@@ -363,13 +374,14 @@ def main():
         step_device(0)
         torch.cuda.synchronize()
         launches_per_step = int(L.load().b200dm_launch_count())
-        for i in range(max(1, min(W, 2))):
-            step_device(i)
         clocks = ClockSampler(local)
         clocks.start()
+        for i in range(max(1, min(W, 2))):
+            step_device(i)
+        clocks.mark()
         ms = timed(step_device, K)
-        clk = clocks.stop()
         ms_e2e = timed(step_e2e, K)
+        clk = clocks.stop()
         imgs = DDIM_B * K
         value, e2e_value = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
         h2d, d2h = 0, B * 3 * S * S * 4

@@ -42,7 +42,7 @@ extern "C" {
 
 int b200dm_version(void);
 const char* b200dm_last_error(void);
-/* number of kernels launched by this library on the calling thread since the last reset */
+/* number of kernels launched by this library (all threads of the process) since the last reset */
 int64_t b200dm_launch_count(void);
 void b200dm_reset_launch_count(void);
 /* 1 if the tcgen05/TMA path can be used on the current device (sm_100), else 0 */

@@ -1,12 +1,14 @@
 // C-ABI plumbing: error string, launch counter, capability probe, conv dispatch.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace b200dm {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -36,7 +38,7 @@ using namespace b200dm;
 
 extern "C" int b200dm_version(void) { return 100; }
 extern "C" const char* b200dm_last_error(void) { return g_err; }
-extern "C" int64_t b200dm_launch_count(void) { return g_launches; }
+extern "C" int64_t b200dm_launch_count(void) { return g_launches.load(); }
 extern "C" void b200dm_reset_launch_count(void) { g_launches = 0; }
 extern "C" int b200dm_tc_available(void) { return tc_supported() ? 1 : 0; }
 

@@ -311,13 +311,23 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
       }
     }
   }
+  // dg: reduce the 8 warps of the CTA in shared memory, then one atomic per channel per CTA
+  __shared__ float dgs[8][512];
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < RMS_MAXV; ++k) {
     int cv = lane + 32 * k;
     if (cv < C8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dg + cv * 8 + j, dgacc[k][j] * sqrtC);
+      for (int j = 0; j < 8; ++j) dgs[wib][cv * 8 + j] = dgacc[k][j];
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += dgs[w][c];
+    atomicAdd(dg + c, s * sqrtC);
   }
 }
 
