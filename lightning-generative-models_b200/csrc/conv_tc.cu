@@ -49,53 +49,69 @@ bool tc_supported() {
 
 constexpr int TC_BM = 128;      // pixels per CTA tile  (UMMA M)
 constexpr int TC_BK = 64;       // channels per K-block (128 B of bf16 = one swizzle row)
-constexpr int TC_THREADS = 192;
-constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+constexpr int TC_EPI_WARPS = 8; // two warps per TMEM lane quarter (each takes half of the columns)
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int WG_THREADS = 192;                      // wgrad kernel: 4 epilogue warps
+constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 2;     // 16 KiB
+constexpr int OUT_STAGE_BYTES = TC_BM * 64 * 2;      // 16 KiB: [128 rows][64 bf16], 128-B swizzled
 
 struct TcParams {
   int mode, ksize, taps, kblocks;  // kblocks = Cin / 64
   int H, W, bh, bn;                // box geometry: bw == W
   int Cout, Ncols;                 // Ncols = GEMM N (Cout, or 4*Cout in mode 2)
-  int x_ld_for_unshuffle;          // mode 1: channel-coordinate step of p2 (== x_ld)
+  int x_ld, y_ld;
+  int m_tiles, n_tiles;
   long long M;                     // valid GEMM rows
-  __nv_bfloat16* y;
-  int y_ld;
+  const __nv_bfloat16* y_read;     // accumulate source (== output tensor) or nullptr
   const __nv_bfloat16* res;
   int res_ld;
   const float* bias;
-  int accumulate;
 };
 
+// Persistent, warp-specialised implicit-GEMM convolution.  Each CTA walks tiles
+// (tile = blockIdx.x + i*gridDim.x, N fastest so CTAs running together share the activation tile in L2):
+//   warp 0      TMA producer : STAGES-deep ring of {A box 128x64, W box N_TILEx64}, runs ahead across tiles
+//   warp 1      MMA issuer   : 4 x tcgen05.mma (128 x N_TILE x 16) per K-block into one of TWO TMEM
+//                              accumulators, so tile i+1 accumulates while tile i is being drained
+//   warps 2..9  epilogue     : tcgen05.ld -> +bias (+residual / +previous value) -> bf16 -> swizzled smem
+//                              staging -> TMA store (coalesced 128-B rows, clipped at the tensor edge)
 template <int N_TILE, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcParams p) {
+               const __grid_constant__ CUtensorMap tmY, const TcParams p) {
   constexpr int B_STAGE_BYTES = N_TILE * TC_BK * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  constexpr int TMEM_COLS = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
+  constexpr int SUBTILES = N_TILE / 64;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  const uint32_t out_stage = base + STAGES * STAGE_BYTES;        // 2 x 16 KiB staging for TMA stores
+  const uint32_t bar_base = out_stage + 2 * OUT_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
-  // generic pointer to the TMEM-address slot
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* out_stage_ptr = smem_raw + (out_stage - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n0 = blockIdx.y * N_TILE;
   const int num_k = p.taps * p.kblocks;
+  const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), TC_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -107,114 +123,159 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // tile origin: rows are (x + W*(y + bh*n)) over the box {W, bh, bn}
-      const long long first = (long long)m_tile * TC_BM;            // first pixel (linear, NHW order)
-      const int n_first = (int)(first / ((long long)p.H * p.W));
-      const int y_first = (int)((first / p.W) % p.H);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-        const uint32_t a_dst = base + stage * STAGE_BYTES;
-        const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-        if (p.mode == 1) {
-          // view (c' = p2*ld + c, ox, p1, oy, b)
-          tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld_for_unshuffle + kc * TC_BK, 0,
-                      tap >> 1, y_first, n_first);
-        } else {
-          const int pad = p.ksize >> 1;
-          const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
-          const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
-          tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+        const long long first = (long long)m_tile * TC_BM;  // first pixel (linear NHW order)
+        const int n_first = (int)(first / ((long long)p.H * p.W));
+        const int y_first = (int)((first / p.W) % p.H);
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t a_dst = base + stage * STAGE_BYTES;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          if (p.mode == 1) {
+            // unshuffle view (c' = p2*ld + c, ox, p1, oy, b)
+            tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld + kc * TC_BK, 0, tap >> 1, y_first,
+                        n_first);
+          } else {
+            const int pad = p.ksize >> 1;
+            const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
+            const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
+            tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+          }
+          tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = base + stage * STAGE_BYTES;
-        const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = base + stage * STAGE_BYTES;
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart; +32 B per 16-element K step
-          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart; +32 B per 16-element K step
+            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        umma_commit(tmem_full_bar(acc));  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
       }
-      umma_commit(tmem_full_bar);       // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which 32 of the 64 sub-tile columns
     const int row = quarter * 32 + lane;
-    const long long pix = (long long)m_tile * TC_BM + row;
-    const bool valid = pix < p.M;
-    long long opix = pix;
-    int co0 = n0;
-    if (p.mode == 2) {  // scatter to pixel (2y+p1, 2x+p2) of the [2H,2W] output; one tap per N tile
-      const int tap = n0 / p.Cout;
-      co0 = n0 - tap * p.Cout;
-      const int ox = (int)(pix % p.W);
-      const long long q = pix / p.W;
-      const int oy = (int)(q % p.H);
-      const long long b = q / p.H;
-      opix = (b * (2 * p.H) + 2 * oy + (tap >> 1)) * (long long)(2 * p.W) + 2 * ox + (tap & 1);
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    __nv_bfloat16* yrow = p.y + opix * p.y_ld + co0;
-    const __nv_bfloat16* rrow = p.res ? p.res + opix * p.res_ld + co0 : nullptr;
+    const bool store_thread = (threadIdx.x == 64);
+    int acc = 0, sbuf = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      const long long first = (long long)m_tile * TC_BM;
+      const int n_first = (int)(first / ((long long)p.H * p.W));
+      const int y_first = (int)((first / p.W) % p.H);
+      const long long pix = first + row;
+      const bool valid = pix < p.M;
+      long long opix = pix;
+      int co0 = n0, tap2 = 0;
+      if (p.mode == 2) {  // output pixel (2y+p1, 2x+p2) of the [2H,2W] tensor; one tap per N tile
+        tap2 = n0 / p.Cout;
+        co0 = n0 - tap2 * p.Cout;
+        const int ox = (int)(pix % p.W);
+        const long long q = pix / p.W;
+        const int oy = (int)(q % p.H);
+        const long long b = q / p.H;
+        opix = (b * (2 * p.H) + 2 * oy + (tap2 >> 1)) * (long long)(2 * p.W) + 2 * ox + (tap2 & 1);
+      }
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < N_TILE; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      if (valid) {
-        float v[16];
+      for (int s = 0; s < SUBTILES; ++s) {
+        uint32_t r[32];
+        const int c = s * 64 + half * 32;     // column offset inside the N tile
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
+        tmem_ld_wait();
+        if (s == SUBTILES - 1) {              // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + co0 + c + j);
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co0 + c + j);
         }
-        if (rrow) {
-          float t[8];
-          ld8(rrow + c, t);
+        if (valid && p.res) {
+          const __nv_bfloat16* rr = p.res + opix * p.res_ld + co0 + c;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += t[j];
-          ld8(rrow + c + 8, t);
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            ld8(rr + g * 8, t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+          }
         }
-        if (p.accumulate) {
-          float t[8];
-          ld8(yrow + c, t);
+        if (valid && p.y_read) {
+          const __nv_bfloat16* yr = p.y_read + opix * p.y_ld + co0 + c;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += t[j];
-          ld8(yrow + c + 8, t);
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            ld8(yr + g * 8, t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[8 + j] += t[j];
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+          }
         }
-        float lo[8], hi[8];
+        // staging buffer `sbuf` was last used two sub-tiles ago: its TMA store must have read it
+        if (store_thread) tma_store_wait_read<1>();
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
+        uint8_t* srow = out_stage_ptr + sbuf * OUT_STAGE_BYTES + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { lo[j] = v[j]; hi[j] = v[8 + j]; }
-        st8(yrow + c, lo);
-        st8(yrow + c + 8, hi);
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+          const int chunk = (half * 4 + g) ^ (row & 7);   // 128-B swizzle: 16-B chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(srow + chunk * 16) = u;
+        }
+        fence_proxy_async();                  // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(2, 32 * TC_EPI_WARPS);
+        if (store_thread) {
+          const uint32_t src = out_stage + sbuf * OUT_STAGE_BYTES;
+          if (p.mode == 2)
+            tma_store_5d(&tmY, src, (tap2 & 1) * p.y_ld + co0 + s * 64, 0, tap2 >> 1, y_first, n_first);
+          else
+            tma_store_5d(&tmY, src, co0 + s * 64, 0, y_first, n_first, 0);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
+    if (store_thread) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -278,9 +339,9 @@ int tile_geometry(int H, int W, int* bh, int* bn, const char* what) {
 }
 
 template <int N_TILE, int STAGES>
-static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int m_tiles,
-                     int n_tiles, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 1024 + 256;
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                     const TcParams& p, cudaStream_t st) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, STAGES>,
@@ -288,8 +349,9 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPar
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid(m_tiles, n_tiles);
-  conv_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p);
   count_launch();
   return check_launch("conv_tc");
 }
@@ -314,21 +376,33 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   p.H = d->H; p.W = d->W; p.bh = bh; p.bn = bn;
   p.Cout = d->Cout;
   p.Ncols = d->mode == 2 ? 4 * d->Cout : d->Cout;
-  p.x_ld_for_unshuffle = d->x_ld;
+  p.x_ld = d->x_ld; p.y_ld = d->y_ld;
   p.M = (long long)d->B * d->H * d->W;
-  p.y = (__nv_bfloat16*)d->y; p.y_ld = d->y_ld;
+  p.y_read = d->accumulate ? (const __nv_bfloat16*)d->y : nullptr;
   p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
-  p.bias = d->bias; p.accumulate = d->accumulate;
-  const int m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  p.bias = d->bias;
+  p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
 
-  // N tile: the widest tile that still yields about one CTA per SM
-  int n_tile = 64;
+  // N tile: maximise (MMA efficiency of the tile shape) x (fill of the last wave of the persistent grid)
   const int sms = num_sms();
-  if (d->Cout % 256 == 0 && (long long)m_tiles * (p.Ncols / 256) >= sms) n_tile = 256;
-  else if (d->Cout % 128 == 0 && (long long)m_tiles * (p.Ncols / 128) >= sms) n_tile = 128;
+  int n_tile = 64;
+  double best = -1.0;
+  const int cand[3] = {256, 128, 64};
+  const double eff[3] = {1.0, 0.85, 0.6};
+  for (int i = 0; i < 3; ++i) {
+    if (d->Cout % cand[i]) continue;
+    const long long tiles = (long long)p.m_tiles * (p.Ncols / cand[i]);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double score = eff[i] * (double)tiles / (double)(waves * sms);
+    if (score > best) { best = score; n_tile = cand[i]; }
+  }
+  p.n_tiles = p.Ncols / n_tile;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   rc = make_act_map(&tmA, d->mode == 1 ? 1 : 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) A");
+  if (rc) return rc;
+  // output: NHWC tensor (modes 0/1) or the unshuffle view of the [2H,2W] tensor (mode 2)
+  rc = make_act_map(&tmY, d->mode == 2 ? 1 : 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) Y");
   if (rc) return rc;
   {
     const int wt = d->mode == 2 ? 1 : p.taps;
@@ -339,12 +413,10 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int n_tiles = p.Ncols / n_tile;
-  if (n_tile == 256) return launch_tc<256, 4>(tmA, tmB, p, m_tiles, n_tiles, st);
-  if (n_tile == 128) return launch_tc<128, 3>(tmA, tmB, p, m_tiles, n_tiles, st);
-  return launch_tc<64, 4>(tmA, tmB, p, m_tiles, n_tiles, st);
+  if (n_tile == 256) return launch_tc<256, 3>(tmA, tmB, tmY, p, st);
+  if (n_tile == 128) return launch_tc<128, 5>(tmA, tmB, tmY, p, st);
+  return launch_tc<64, 6>(tmA, tmB, tmY, p, st);
 }
-
 
 // =====================================================================================================
 // Weight gradient:  dW[tap][co][ci] += sum_pixels dY[pix, co] * X[pix (+) tap, ci]
@@ -365,7 +437,7 @@ struct TcWgradParams {
 };
 
 template <int N_TILE, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(WG_THREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                 const TcWgradParams p) {
   constexpr int BOX_BYTES = TC_BM * TC_BK * 2;  // 16 KiB: [128 pixels][64 channels]
@@ -496,7 +568,7 @@ static int launch_wgrad_tc(const CUtensorMap& tmDY, const CUtensorMap& tmX, cons
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  wgrad_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmDY, tmX, p);
+  wgrad_tc_kernel<N_TILE, STAGES><<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, p);
   count_launch();
   return check_launch("wgrad_tc");
 }
