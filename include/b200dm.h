@@ -185,14 +185,16 @@ int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, const float*
                         const float* gamma, const float* beta, const float* film, int32_t film_ld,
                         const void* res, int32_t res_ld, void* y, int32_t y_ld, int32_t B, int32_t HW,
                         int32_t C, int32_t G, void* stream);
-/* backward, three launches inside:  (1) per-(b,c) sums of dz and dz*xnorm  (2) parameter / FiLM
- * grads + group means  (3) dx.  sums: fp32 workspace [B][C][2]; gmeans: fp32 workspace [B][G][2].
- * dgamma/dbeta accumulate (+=); dfilm (same addressing as film) is overwritten. */
+/* backward, three launches inside:  (1) per-(b,c) sums of dz, dz*xnorm and x  (2) parameter / FiLM
+ * grads + group means (+ the bias gradient of the conv that produced x, if dbias != NULL: the pixel
+ * sum of dx follows in closed form from the sums)  (3) dx.  sums: fp32 workspace [B][C][3];
+ * gmeans: fp32 workspace [B][G][2].  dgamma/dbeta/dbias accumulate (+=); dfilm (same addressing as
+ * film) is overwritten. */
 int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x, int32_t x_ld,
                         const float* stats, const float* gamma, const float* beta, const float* film,
                         int32_t film_ld, void* dx, int32_t dx_ld, float* dgamma, float* dbeta,
-                        float* dfilm, float* sums, float* gmeans, int32_t B, int32_t HW, int32_t C,
-                        int32_t G, void* stream);
+                        float* dfilm, float* dbias, float* sums, float* gmeans, int32_t B, int32_t HW,
+                        int32_t C, int32_t G, void* stream);
 
 /* RMSNorm (ddpm.py:107-113): y = x / max(||x||_2, 1e-12) * g * sqrt(C) (+ res) */
 int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* g, const void* res,

@@ -68,7 +68,7 @@ PROTOTYPES = {
     "b200dm_upsample2x_bwd": [_I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_gn_stats": [_I, _P, _I, _P, _I, _I, _I, _I, _F, _P],
     "b200dm_gn_apply_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
-    "b200dm_gn_apply_bwd": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P,
+    "b200dm_gn_apply_bwd": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P,
                             _I, _I, _I, _I, _P],
     "b200dm_rmsnorm_fwd": [_I, _P, _I, _P, _P, _I, _P, _I, _L, _I, _P],
     "b200dm_rmsnorm_bwd": [_I, _P, _I, _P, _I, _P, _P, _I, _P, _I, _P, _L, _I, _P],

@@ -167,7 +167,8 @@ class Plan:
         lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops)
         self._keep.append(d)
 
-    def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None):
+    def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None,
+                 bias_grad=True):
         """wgrad + bias grad + (optional) dgrad of conv `nm` whose forward was x -> y, given dy."""
         if not self.training:
             return
@@ -184,7 +185,7 @@ class Plan:
         self.Bk("b200dm_conv_wgrad", C.byref(d), kname="wgrad_tc" if d.impl == 1 else "wgrad_simt",
                 flops=2.0 * self.B * H * H * ci.cout * ci.cin * ci.taps)
         self._keep.append(d)
-        if ci.bias:
+        if ci.bias and bias_grad:
             self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
                     self.arena.gptr(nm + ".bias"), 1)
         if dx is not None:
@@ -222,16 +223,16 @@ class Plan:
         # block2: GN/SiLU backward -> dc ; conv2 backward -> gh1
         self.Bk("b200dm_gn_apply_bwd", self.dt, gout.ptr, gout.ld, c2.ptr, c2.ld, st2.data_ptr(),
                 a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, dc.ptr, dc.ld,
-                a.gptr(b2 + ".norm.weight"), a.gptr(b2 + ".norm.bias"), None, self.sums.data_ptr(),
-                self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
-        self.conv_bwd(b2 + ".proj", h1, dc, gh1)
+                a.gptr(b2 + ".norm.weight"), a.gptr(b2 + ".norm.bias"), None, a.gptr(b2 + ".proj.bias"),
+                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
+        self.conv_bwd(b2 + ".proj", h1, dc, gh1, bias_grad=False)
         # block1: GN/FiLM/SiLU backward -> dc ; conv1 backward -> gx (+ identity-skip gradient)
         self.Bk("b200dm_gn_apply_bwd", self.dt, gh1.ptr, gh1.ld, c1.ptr, c1.ld, st1.data_ptr(),
                 a.ptr(b1 + ".norm.weight"), a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, dc.ptr, dc.ld,
-                a.gptr(b1 + ".norm.weight"), a.gptr(b1 + ".norm.bias"), dfilm_ptr, self.sums.data_ptr(),
-                self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
+                a.gptr(b1 + ".norm.weight"), a.gptr(b1 + ".norm.bias"), dfilm_ptr, a.gptr(b1 + ".proj.bias"),
+                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
         self.conv_bwd(b1 + ".proj", x, dc, gx, dx_acc=1 if gx_prior else 0,
-                      dx_res=None if has_res_conv else gout)
+                      dx_res=None if has_res_conv else gout, bias_grad=False)
         if has_res_conv:
             self.conv_bwd(nm + ".res_conv", x, gout, gx, dx_acc=1)
 
@@ -301,7 +302,7 @@ class Plan:
         self.film = self.f32(B, a.film_cols)
         if tr:
             self.dfilm, self.dtact, self.dh = self.f32(B, a.film_cols), self.f32(B, td), self.f32(B, td)
-            self.sums, self.gmeans = self.f32(B, 8 * dim, 2), self.f32(B, GROUPS, 2)
+            self.sums, self.gmeans = self.f32(B, 8 * dim, 3), self.f32(B, GROUPS, 2)
             self.dctx = self.f32(B, 4, 32, 32)
         self.begin_unit()
         self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0)

@@ -89,14 +89,14 @@ gn_apply_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__
   }
 }
 
-// ---- backward pass 1: sums[b][c] = (sum_p dz, sum_p dz*xnorm) --------------------------------------
+// ---- backward pass 1: sums[b][c] = (sum_p dz, sum_p dz*xnorm, sum_p x) ---------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                      const float* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                      float* __restrict__ sums, int HW, int C, int G, int pix_per_block) {
-  extern __shared__ float sred[];  // [lanes][C][2]
+  extern __shared__ float sred[];  // [lanes][C][3]
   const int b = blockIdx.y;
   const int C8 = C / 8, gs = C / G;
   const int lanes = blockDim.x / C8;          // pixel lanes
@@ -104,7 +104,7 @@ gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
   const int c0 = cv * 8;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
-  float s1[8] = {}, s2[8] = {};
+  float s1[8] = {}, s2[8] = {}, s0[8] = {};
   if (lane < lanes) {
     const int g = c0 / gs;
     const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
@@ -128,36 +128,39 @@ gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
         float dz = gv[j] * silu_grad_f(z);
         s1[j] += dz;
         s2[j] = fmaf(dz, xn, s2[j]);
+        s0[j] += xv[j];
       }
     }
   }
   if (lane < lanes) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sred[(lane * C + c0 + j) * 2] = s1[j];
-      sred[(lane * C + c0 + j) * 2 + 1] = s2[j];
+      sred[(lane * C + c0 + j) * 3] = s1[j];
+      sred[(lane * C + c0 + j) * 3 + 1] = s2[j];
+      sred[(lane * C + c0 + j) * 3 + 2] = s0[j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += sred[l * C * 2 + i];
-    atomicAdd(sums + (int64_t)b * C * 2 + i, s);
+    for (int l = 0; l < lanes; ++l) s += sred[l * C * 3 + i];
+    atomicAdd(sums + (int64_t)b * C * 3 + i, s);
   }
 }
 
 // ---- backward pass 2: FiLM grads, group means, dgamma/dbeta; one CTA per sample ---------------------
-__global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, const float* __restrict__ film,
-                                     int film_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ dfilm, float* __restrict__ gmeans, int HW,
-                                     int C, int G) {
+__global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ film, int film_ld,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                     float* __restrict__ dfilm, float* __restrict__ dbias,
+                                     float* __restrict__ gmeans, int HW, int C, int G) {
   __shared__ float g1[64], g2[64];
   const int b = blockIdx.x, gs = C / G;
   if (threadIdx.x < G) g1[threadIdx.x] = g2[threadIdx.x] = 0.f;
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float S1 = sums[((int64_t)b * C + c) * 2], S2 = sums[((int64_t)b * C + c) * 2 + 1];
+    float S1 = sums[((int64_t)b * C + c) * 3], S2 = sums[((int64_t)b * C + c) * 3 + 1];
     float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
     float ga = gamma[c], be = beta[c];
     if (dfilm) {
@@ -171,10 +174,24 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float
     atomicAdd(&g2[c / gs], a * S2);
   }
   __syncthreads();
+  const float inv = 1.f / ((float)gs * (float)HW);
   if (threadIdx.x < G) {
-    float inv = 1.f / ((float)gs * (float)HW);
     gmeans[(b * G + threadIdx.x) * 2] = g1[threadIdx.x] * inv;
     gmeans[(b * G + threadIdx.x) * 2 + 1] = g2[threadIdx.x] * inv;
+  }
+  if (dbias) {
+    // bias gradient of the producing conv = sum over pixels of dx = rstd*(a*dz - M1 - xn*M2):
+    //   sum_p dx[b,p,c] = rstd * (a*S1 - HW*M1 - M2 * sum_p xn),  sum_p xn = (S0 - HW*mean) * rstd
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / gs;
+      const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+      const float S1 = sums[((int64_t)b * C + c) * 3], S0 = sums[((int64_t)b * C + c) * 3 + 2];
+      const float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+      const float a = sc * gamma[c];
+      const float M1 = g1[g] * inv, M2 = g2[g] * inv;
+      const float sum_xn = (S0 - (float)HW * mean) * rstd;
+      atomicAdd(dbias + c, rstd * (a * S1 - (float)HW * M1 - M2 * sum_xn));
+    }
   }
 }
 
@@ -384,14 +401,14 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
                                    int32_t x_ld, const float* stats, const float* gamma,
                                    const float* beta, const float* film, int32_t film_ld, void* dx,
                                    int32_t dx_ld, float* dgamma, float* dbeta, float* dfilm,
-                                   float* sums, float* gmeans, int32_t B, int32_t HW, int32_t C,
-                                   int32_t G, void* stream) {
+                                   float* dbias, float* sums, float* gmeans, int32_t B, int32_t HW,
+                                   int32_t C, int32_t G, void* stream) {
   GN_CHECKS("gn_apply_bwd");
   B200DM_REQUIRE(x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0, B200DM_ERR_SHAPE,
                  "gn_apply_bwd: ld must be a multiple of 8");
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = b200dm_fill_f32(sums, (int64_t)B * C * 2, 0.f, stream);
+  int rc = b200dm_fill_f32(sums, (int64_t)B * C * 3, 0.f, stream);
   if (rc) return rc;
   const int C8 = C / 8;
   int threads = 256;
@@ -403,7 +420,7 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   if (chunks < 1) chunks = 1;
   int ppb = (HW + chunks - 1) / chunks;
   chunks = (HW + ppb - 1) / ppb;
-  size_t smem = (size_t)lanes * C * 2 * sizeof(float);
+  size_t smem = (size_t)lanes * C * 3 * sizeof(float);
   dim3 grid(chunks, B);
   int64_t total8 = (int64_t)B * HW * C8;
   if (dtype == B200DM_F32) {
@@ -417,8 +434,8 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     gn_bwd_reduce_kernel<bf16><<<grid, threads, smem, st>>>(
         (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
   }
-  gn_bwd_params_kernel<<<B, 256, 0, st>>>(sums, gamma, beta, film, film_ld, dgamma, dbeta, dfilm,
-                                          gmeans, HW, C, G);
+  gn_bwd_params_kernel<<<B, 256, 0, st>>>(sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm,
+                                          dbias, gmeans, HW, C, G);
   if (dtype == B200DM_F32)
     gn_bwd_apply_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
         (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,

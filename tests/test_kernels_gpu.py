@@ -429,10 +429,15 @@ def test_groupnorm_film_silu_fwd_bwd(dtype, B, S, Cc, film, res):
     dxv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
     dgamma, dbeta = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     dfilm = torch.zeros(B, 2 * Cc + 6, device=DEV)
-    sums, gmeans = torch.empty(B, Cc, 2, device=DEV), torch.empty(B, G, 2, device=DEV)
+    sums, gmeans = torch.empty(B, Cc, 3, device=DEV), torch.empty(B, G, 2, device=DEV)
+    dbias = torch.zeros(Cc, device=DEV)
     L.call("b200dm_gn_apply_bwd", dtype, dyv.ptr, dyv.ld, xv.ptr, xv.ld, stats.data_ptr(), gamma.data_ptr(),
            beta.data_ptr(), fptr, 2 * Cc + 6, dxv.ptr, dxv.ld, dgamma.data_ptr(), dbeta.data_ptr(),
-           dfilm.data_ptr() + 3 * 4 if film else None, sums.data_ptr(), gmeans.data_ptr(), B, S * S, Cc, G)
+           dfilm.data_ptr() + 3 * 4 if film else None, dbias.data_ptr(), sums.data_ptr(), gmeans.data_ptr(),
+           B, S * S, Cc, G)
+    # closed-form bias gradient of the producing conv == pixel/batch sum of dx
+    ref_db = x.grad.sum((0, 2, 3))
+    assert (dbias - ref_db).abs().max().item() <= 2e-4 * max(1.0, x.grad.abs().sum((0, 2, 3)).max().item())
     assert rel(dxv.to_nchw(), x.grad) < (1e-4 if dtype == L.F32 else 6e-3)
     assert rel(dgamma, gamma.grad) < 1e-4 and rel(dbeta, beta.grad) < 1e-4
     if film:
