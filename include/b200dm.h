@@ -187,9 +187,11 @@ int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, const float*
                         int32_t C, int32_t G, void* stream);
 /* backward, three launches inside:  (1) per-(b,c) sums of dz, dz*xnorm and x  (2) parameter / FiLM
  * grads + group means (+ the bias gradient of the conv that produced x, if dbias != NULL: the pixel
- * sum of dx follows in closed form from the sums)  (3) dx.  sums: fp32 workspace [B][C][3];
+ * sum of dx follows in closed form from the sums)  (3) dx.  sums: fp32 workspace of
+ * b200dm_gn_bwd_ws_floats(B, HW, C) floats (per-CTA partials, reduced deterministically);
  * gmeans: fp32 workspace [B][G][2].  dgamma/dbeta/dbias accumulate (+=); dfilm (same addressing as
  * film) is overwritten. */
+int64_t b200dm_gn_bwd_ws_floats(int32_t B, int32_t HW, int32_t C);
 int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x, int32_t x_ld,
                         const float* stats, const float* gamma, const float* beta, const float* film,
                         int32_t film_ld, void* dx, int32_t dx_ld, float* dgamma, float* dbeta,

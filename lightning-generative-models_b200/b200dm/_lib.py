@@ -88,6 +88,7 @@ _SPECIAL = {
     "b200dm_version": ([], C.c_int),
     "b200dm_last_error": ([], C.c_char_p),
     "b200dm_launch_count": ([], C.c_int64),
+    "b200dm_gn_bwd_ws_floats": ([_I, _I, _I], C.c_int64),
     "b200dm_reset_launch_count": ([], None),
     "b200dm_tc_available": ([], C.c_int),
 }

@@ -302,7 +302,9 @@ class Plan:
         self.film = self.f32(B, a.film_cols)
         if tr:
             self.dfilm, self.dtact, self.dh = self.f32(B, a.film_cols), self.f32(B, td), self.f32(B, td)
-            self.sums, self.gmeans = self.f32(B, 8 * dim, 3), self.f32(B, GROUPS, 2)
+            ws = max(self.lib.b200dm_gn_bwd_ws_floats(B, (S >> lv) ** 2, cc)
+                     for lv in range(4) for cc in (dim << lv, dim << min(lv + 1, 3), dim))
+            self.sums, self.gmeans = self.f32(int(ws)), self.f32(B, GROUPS, 2)
             self.dctx = self.f32(B, 4, 32, 32)
         self.begin_unit()
         self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0)

@@ -198,31 +198,35 @@ __global__ void colsum_kernel(const T* __restrict__ x, int ld, int64_t rows, int
   }
 }
 
-// vectorised variant: one thread = 8 channels (16 B of bf16 / 32 B of fp32) of a strided subset of rows
+// vectorised variant: one thread = 8 channels (16 B of bf16 / 32 B of fp32) of a strided subset of rows.
+// 256 threads = VL vector lanes x (256 / VL) row lanes, VL = min(C/8, 64) rounded up to a power of two.
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum8_kernel(const T* __restrict__ x, int ld, int64_t rows, int C8, float* __restrict__ out,
-               int64_t rows_per_block) {
-  __shared__ float red[4][64][8];
-  const int cv = blockIdx.x * 64 + threadIdx.x;  // 8-channel vector index
+               int64_t rows_per_block, int VL) {
+  __shared__ float red[256][8];
+  const int vl = threadIdx.x % VL, rl = threadIdx.x / VL, RL = 256 / VL;
+  const int cv = blockIdx.x * VL + vl;  // 8-channel vector index
   int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float acc[8] = {};
   if (cv < C8)
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
+    for (int64_t r = r0 + rl; r < r1; r += RL) {
       float v[8];
       ld8(x + r * ld + cv * 8, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
   __syncthreads();
-  if (threadIdx.y == 0 && cv < C8) {
+  if (rl == 0 && cv < C8) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      atomicAdd(out + cv * 8 + j, red[0][threadIdx.x][j] + red[1][threadIdx.x][j] + red[2][threadIdx.x][j] +
-                                      red[3][threadIdx.x][j]);
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < RL; ++k) s += red[k * VL + vl][j];
+      atomicAdd(out + cv * 8 + j, s);
+    }
   }
 }
 
@@ -286,23 +290,35 @@ init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
 }
 
 // dW[co][c][ky][kx] += sum dY[b,y,x,co] * X[b,c,y+ky-3,x+kx-3].  Persistent CTAs walk (sample, row-block)
-// items and keep the 64 x (C*49) partial sums in registers; one atomic flush per CTA at the end.
+// items; thread = 4 output channels x up to 10 filter taps (register micro-tile: 40 FMA per 11 smem
+// loads); one atomic flush per CTA at the end.
 template <typename T>
 __global__ void __launch_bounds__(256)
 init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int dy_ld,
                        float* __restrict__ dw, int B, int C, int H, int W) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int PW = W + 6, PH = IC_ROWS + 6;
-  float* patch = sm;                       // [C][PH][PW]
-  float* gsm = sm + C * PH * PW;           // [IC_ROWS][W][64] output gradients of the item
+  float* gsm = sm;                            // [IC_ROWS][W][64] output gradients of the item
+  float* patch = sm + IC_ROWS * W * 64;       // [C][PH][PW]
   const int K = C * 49;
-  const int tid = threadIdx.x, co = tid & 63, q = tid >> 6;
+  const int tid = threadIdx.x, co0 = (tid & 15) * 4, kq = tid >> 4;
   const int rowblocks = (H + IC_ROWS - 1) / IC_ROWS;
   const int items = B * rowblocks;
-  constexpr int MAXK = 37;  // ceil(147 / 4); C <= 3
-  float acc[MAXK];
+  constexpr int MAXK = 10;  // ceil(147 / 16); C <= 3
+  int koff[MAXK];           // patch offset of tap k relative to the output pixel
 #pragma unroll
-  for (int i = 0; i < MAXK; ++i) acc[i] = 0.f;
+  for (int i = 0; i < MAXK; ++i) {
+    int k = kq + 16 * i;
+    if (k < K) {
+      int kx = k % 7, ky = (k / 7) % 7, ch = k / 49;
+      koff[i] = (ch * PH + ky) * PW + kx;
+    } else {
+      koff[i] = -1;
+    }
+  }
+  float acc[MAXK][4];
+#pragma unroll
+  for (int i = 0; i < MAXK; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / rowblocks, y0 = (item - b * rowblocks) * IC_ROWS;
     __syncthreads();
@@ -319,21 +335,27 @@ init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, in
     __syncthreads();
     for (int r = 0; r < IC_ROWS; ++r)
       for (int ox = 0; ox < W; ++ox) {
-        const float g = gsm[(r * W + ox) * 64 + co];
+        const float4 g = *reinterpret_cast<const float4*>(&gsm[(r * W + ox) * 64 + co0]);
+        const float* pb = patch + r * PW + ox;
 #pragma unroll
         for (int i = 0; i < MAXK; ++i) {
-          int k = q + 4 * i;
-          if (k < K) {
-            int kx = k % 7, ky = (k / 7) % 7, ch = k / 49;
-            acc[i] = fmaf(g, patch[(ch * PH + r + ky) * PW + ox + kx], acc[i]);
+          if (koff[i] >= 0) {
+            const float pv = pb[koff[i]];
+            acc[i][0] = fmaf(g.x, pv, acc[i][0]);
+            acc[i][1] = fmaf(g.y, pv, acc[i][1]);
+            acc[i][2] = fmaf(g.z, pv, acc[i][2]);
+            acc[i][3] = fmaf(g.w, pv, acc[i][3]);
           }
         }
       }
   }
 #pragma unroll
   for (int i = 0; i < MAXK; ++i) {
-    int k = q + 4 * i;
-    if (k < K) atomicAdd(dw + co * K + k, acc[i]);
+    int k = kq + 16 * i;
+    if (k < K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(dw + (co0 + j) * K + k, acc[i][j]);
+    }
   }
 }
 
@@ -534,16 +556,19 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
   }
   if (C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x & 15) == 0) {
     const int C8 = C / 8;
-    int cb = (C8 + 63) / 64;
-    int64_t rb = (2 * num_sms() + cb - 1) / cb;
-    if (rb > (rows + 15) / 16) rb = (rows + 15) / 16;
+    int VL = 1;
+    while (VL < C8 && VL < 64) VL <<= 1;
+    int cb = (C8 + VL - 1) / VL;
+    int64_t rb = (4 * num_sms() + cb - 1) / cb;
+    const int RL = 256 / VL;
+    if (rb > (rows + 4 * RL - 1) / (4 * RL)) rb = (rows + 4 * RL - 1) / (4 * RL);
     if (rb < 1) rb = 1;
     int64_t per8 = (rows + rb - 1) / rb;
-    dim3 grid8(cb, (unsigned)rb), block8(64, 4);
+    dim3 grid8(cb, (unsigned)rb);
     if (dtype == B200DM_F32)
-      colsum8_kernel<float><<<grid8, block8, 0, st>>>((const float*)x, ld, rows, C8, out, per8);
+      colsum8_kernel<float><<<grid8, 256, 0, st>>>((const float*)x, ld, rows, C8, out, per8, VL);
     else
-      colsum8_kernel<__nv_bfloat16><<<grid8, block8, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C8, out, per8);
+      colsum8_kernel<__nv_bfloat16><<<grid8, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C8, out, per8, VL);
     count_launch();
     return check_launch("colsum8");
   }

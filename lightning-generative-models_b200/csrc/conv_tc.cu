@@ -543,8 +543,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
       if (valid) {
+        if (p.s_ci == 1) {   // contiguous along ci: 16-byte vector reductions (4x fewer L2 atomic ops)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(drow + (long long)(c + j) * p.s_ci, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c + j),
+                         "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                         "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(drow + (long long)(c + j) * p.s_ci, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -595,7 +604,7 @@ int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
   const int n_tile = (d->Cin % 128 == 0) ? 128 : 64;
   const int co_tiles = (d->Cout + TC_BM - 1) / TC_BM, ci_tiles = d->Cin / n_tile;
   const int base_ctas = co_tiles * ci_tiles * taps;
-  int splits = (2 * num_sms() + base_ctas - 1) / base_ctas;
+  int splits = (num_sms() + base_ctas / 2) / base_ctas;   // about one wave of CTAs
   if (splits > p.k_tiles) splits = p.k_tiles;
   if (splits < 1) splits = 1;
   while (taps * splits > 65535) --splits;

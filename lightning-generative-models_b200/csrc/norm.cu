@@ -141,10 +141,12 @@ gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
     }
   }
   __syncthreads();
+  // deterministic: each CTA writes its own partial [b][chunk][c][3]; pass 2 sums the chunks
+  float* part = sums + ((int64_t)b * gridDim.x + blockIdx.x) * C * 3;
   for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += sred[l * C * 3 + i];
-    atomicAdd(sums + (int64_t)b * C * 3 + i, s);
+    part[i] = s;
   }
 }
 
@@ -154,13 +156,19 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float
                                      const float* __restrict__ film, int film_ld,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      float* __restrict__ dfilm, float* __restrict__ dbias,
-                                     float* __restrict__ gmeans, int HW, int C, int G) {
+                                     float* __restrict__ gmeans, int HW, int C, int G, int chunks) {
   __shared__ float g1[64], g2[64];
+  extern __shared__ float tot[];   // [C][3] chunk-summed
   const int b = blockIdx.x, gs = C / G;
   if (threadIdx.x < G) g1[threadIdx.x] = g2[threadIdx.x] = 0.f;
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += sums[((int64_t)b * chunks + k) * C * 3 + i];
+    tot[i] = s;
+  }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float S1 = sums[((int64_t)b * C + c) * 3], S2 = sums[((int64_t)b * C + c) * 3 + 1];
+    float S1 = tot[c * 3], S2 = tot[c * 3 + 1];
     float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
     float ga = gamma[c], be = beta[c];
     if (dfilm) {
@@ -185,7 +193,7 @@ __global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / gs;
       const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
-      const float S1 = sums[((int64_t)b * C + c) * 3], S0 = sums[((int64_t)b * C + c) * 3 + 2];
+      const float S1 = tot[c * 3], S0 = tot[c * 3 + 2];
       const float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
       const float a = sc * gamma[c];
       const float M1 = g1[g] * inv, M2 = g2[g] * inv;
@@ -397,6 +405,24 @@ extern "C" int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, c
   return check_launch("gn_apply_fwd");
 }
 
+static int gn_bwd_chunks(int B, int HW, int C) {
+  const int C8 = C / 8;
+  int threads = 256;
+  if (C8 > threads) threads = C8;
+  int lanes = threads / C8;
+  int chunks = (2 * num_sms() + B - 1) / B;
+  int maxchunks = (HW + lanes - 1) / lanes;
+  if (chunks > maxchunks) chunks = maxchunks;
+  if (chunks < 1) chunks = 1;
+  int ppb = (HW + chunks - 1) / chunks;
+  return (HW + ppb - 1) / ppb;
+}
+
+extern "C" int64_t b200dm_gn_bwd_ws_floats(int32_t B, int32_t HW, int32_t C) {
+  if (B <= 0 || HW <= 0 || C <= 0 || C % 8) return 0;
+  return (int64_t)B * gn_bwd_chunks(B, HW, C) * C * 3;
+}
+
 extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void* x,
                                    int32_t x_ld, const float* stats, const float* gamma,
                                    const float* beta, const float* film, int32_t film_ld, void* dx,
@@ -408,8 +434,6 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
                  "gn_apply_bwd: ld must be a multiple of 8");
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = b200dm_fill_f32(sums, (int64_t)B * C * 3, 0.f, stream);
-  if (rc) return rc;
   const int C8 = C / 8;
   int threads = 256;
   if (C8 > threads) threads = C8;  // C <= 2048 -> <= 256 anyway
@@ -434,8 +458,8 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     gn_bwd_reduce_kernel<bf16><<<grid, threads, smem, st>>>(
         (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
   }
-  gn_bwd_params_kernel<<<B, 256, 0, st>>>(sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm,
-                                          dbias, gmeans, HW, C, G);
+  gn_bwd_params_kernel<<<B, 256, (size_t)C * 3 * sizeof(float), st>>>(
+      sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm, dbias, gmeans, HW, C, G, chunks);
   if (dtype == B200DM_F32)
     gn_bwd_apply_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
         (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,

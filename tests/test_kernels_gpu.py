@@ -429,7 +429,8 @@ def test_groupnorm_film_silu_fwd_bwd(dtype, B, S, Cc, film, res):
     dxv = View.zeros(B, S, S, Cc, DT[dtype], DEV)
     dgamma, dbeta = torch.zeros(Cc, device=DEV), torch.zeros(Cc, device=DEV)
     dfilm = torch.zeros(B, 2 * Cc + 6, device=DEV)
-    sums, gmeans = torch.empty(B, Cc, 3, device=DEV), torch.empty(B, G, 2, device=DEV)
+    sums = torch.empty(L.load().b200dm_gn_bwd_ws_floats(B, S * S, Cc), device=DEV)
+    gmeans = torch.empty(B, G, 2, device=DEV)
     dbias = torch.zeros(Cc, device=DEV)
     L.call("b200dm_gn_apply_bwd", dtype, dyv.ptr, dyv.ld, xv.ptr, xv.ld, stats.data_ptr(), gamma.data_ptr(),
            beta.data_ptr(), fptr, 2 * Cc + 6, dxv.ptr, dxv.ld, dgamma.data_ptr(), dbeta.data_ptr(),
