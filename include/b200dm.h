@@ -214,7 +214,8 @@ int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, const void*
 int b200dm_linattn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, const float* mem_kv,
                        float* ctx, float* kstat, void* out, int32_t out_ld, int32_t B, int32_t n,
                        void* stream);
-/* dctx: fp32 workspace [B][4][32][32]; dmem_kv accumulates (+=) */
+/* dctx: fp32 workspace [B][4][33][32] (the 32x32 context gradient plus one row of per-d dot products);
+ * dmem_kv accumulates (+=) */
 int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const void* qkv,
                        int32_t qkv_ld, const float* mem_kv, const float* ctx, const float* kstat,
                        float* dctx, void* dqkv, int32_t dqkv_ld, float* dmem_kv, int32_t B,
@@ -250,6 +251,18 @@ int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* d
 int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, int32_t taps,
                             int32_t Cout, int32_t Cin, int32_t flip, int64_t s_tap, int64_t s_co,
                             int64_t s_ci, void* stream);
+/* the same for every conv of the network in one launch.  `table` is a DEVICE array of entries; entry i
+ * owns the CTAs [tile_begin, tile_begin + taps*tiles_co*tiles_ci) with tiles_* = ceil(C* / 32). */
+typedef struct {
+  const float* w;
+  void* wf;
+  void* wt;
+  int32_t taps, Cout, Cin, flip;
+  int64_t s_tap, s_co, s_ci;
+  int32_t tile_begin, tiles_ci, tiles_co, reserved;
+} b200dm_pack_entry;
+int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack_entry* table, int32_t n_entries,
+                                     int32_t total_tiles, void* stream);
 /* fused Adam over a flat fp32 arena (torch.optim.Adam semantics, ddpm.py:1053-1059):
  * grad_scale multiplies g first (DDP mean).  step is the 1-based step count. */
 int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

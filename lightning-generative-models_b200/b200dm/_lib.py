@@ -47,6 +47,15 @@ class WgradDesc(C.Structure):
     ]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("wf", C.c_void_p), ("wt", C.c_void_p),
+        ("taps", C.c_int32), ("Cout", C.c_int32), ("Cin", C.c_int32), ("flip", C.c_int32),
+        ("s_tap", C.c_int64), ("s_co", C.c_int64), ("s_ci", C.c_int64),
+        ("tile_begin", C.c_int32), ("tiles_ci", C.c_int32), ("tiles_co", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 _P, _I, _L, _F, _U = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
 # name -> argtypes (restype is int unless listed in _SPECIAL)
@@ -80,6 +89,7 @@ PROTOTYPES = {
     "b200dm_linear_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200dm_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200dm_pack_conv_weight": [_I, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _P],
+    "b200dm_pack_conv_weights_batched": [_I, _P, _I, _I, _P],
     "b200dm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "b200dm_ema_update": [_P, _P, _L, _F, _P],
     "b200dm_fill_f32": [_P, _L, _F, _P],

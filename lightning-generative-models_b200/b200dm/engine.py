@@ -47,20 +47,33 @@ class WeightPack:
                 self.tr[nm] = self.tbuf[off:off + n]
             off += n
         self.version = -1
+        # device table for the one-launch batched pack
+        entries = (L.PackEntry * len(arena.convs))()
+        tile = 0
+        for i, (nm, ci) in enumerate(arena.convs.items()):
+            if ci.master_packed:
+                s_tap, s_co, s_ci = ci.cout * ci.cin, ci.cin, 1
+            else:                       # reference layout [Cout][c*4 + tap]
+                s_tap, s_co, s_ci = 1, 4 * ci.cin, 4
+            e = entries[i]
+            e.w, e.wf = arena.ptr(nm + ".weight"), self.fwd[nm].data_ptr()
+            e.wt = self.tr[nm].data_ptr() if with_dgrad else None
+            e.taps, e.Cout, e.Cin, e.flip = ci.taps, ci.cout, ci.cin, 1 if ci.mode == 0 else 0
+            e.s_tap, e.s_co, e.s_ci = s_tap, s_co, s_ci
+            e.tiles_ci, e.tiles_co = (ci.cin + 31) // 32, (ci.cout + 31) // 32
+            e.tile_begin = tile
+            tile += ci.taps * e.tiles_ci * e.tiles_co
+        self.n_entries, self.total_tiles = len(arena.convs), tile
+        raw = bytes(entries)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
 
     def refresh(self, force: bool = False):
         """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
         v = self.arena.flat._version
         if not force and v == self.version:
             return
-        for nm, ci in self.arena.convs.items():
-            if ci.master_packed:
-                s_tap, s_co, s_ci = ci.cout * ci.cin, ci.cin, 1
-            else:                       # reference layout [Cout][c*4 + tap]
-                s_tap, s_co, s_ci = 1, 4 * ci.cin, 4
-            L.call("b200dm_pack_conv_weight", self.dt, self.arena.ptr(nm + ".weight"),
-                   self.fwd[nm].data_ptr(), self.tr[nm].data_ptr() if self.tbuf is not None else None,
-                   ci.taps, ci.cout, ci.cin, 1 if ci.mode == 0 else 0, s_tap, s_co, s_ci)
+        L.call("b200dm_pack_conv_weights_batched", self.dt, self.table.data_ptr(), self.n_entries,
+               self.total_tiles)
         self.version = v
 
 
@@ -305,7 +318,7 @@ class Plan:
             ws = max(self.lib.b200dm_gn_bwd_ws_floats(B, (S >> lv) ** 2, cc)
                      for lv in range(4) for cc in (dim << lv, dim << min(lv + 1, 3), dim))
             self.sums, self.gmeans = self.f32(int(ws)), self.f32(B, GROUPS, 2)
-            self.dctx = self.f32(B, 4, 32, 32)
+            self.dctx = self.f32(B, 4, 33, 32)
         self.begin_unit()
         self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0)
         self.F("b200dm_linear_fwd", self.emb.data_ptr(), a.ptr("time_mlp.1.weight"), a.ptr("time_mlp.1.bias"),

@@ -13,6 +13,7 @@ constexpr float kScale = 0.17677669529663687f;  // 32^-0.5
 // All four kernels work on 64-pixel chunks staged in shared memory and compute the 32x32 products as
 // register micro-tiles (4x4 or 2x4 per thread) instead of one-value-per-lane shuffles.
 constexpr int LA_CHUNK = 64;
+constexpr int LA_CPB = 4;   // chunks per CTA in the per-pixel kernels (amortises the 32x32 operand loads)
 
 // vectorised tile load: 256 threads, thread = (pixel = tid/4, 8 channels = (tid%4)*8)
 template <typename T>
@@ -157,7 +158,10 @@ linattn_out_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ 
   __shared__ __align__(16) float Q_s[LA_CHUNK][DH];  // scale * softmax(q)
   for (int i = tid; i < DH * DH; i += 256) C_s[i >> 5][i & 31] = ctx[(int64_t)bh * DH * DH + i];
   const int pix = tid >> 2, part = tid & 3;
-  const int j0 = blockIdx.x * LA_CHUNK;
+  for (int cc = 0; cc < LA_CPB; ++cc) {
+  const int j0 = (blockIdx.x * LA_CPB + cc) * LA_CHUNK;
+  if (j0 >= n) break;
+  __syncthreads();
   {
     float v[8];
     la_load8(qkv + (int64_t)b * n * ld + h * DH, ld, j0 + pix, n, part, v);
@@ -187,6 +191,7 @@ linattn_out_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ 
       for (int i = 0; i < 4; ++i) Elem<T>::st(o + i, a[i]);
     }
   }
+  }  // chunk loop
 }
 
 // Backward kernel C: per (b,h): dq for every pixel and dctx[d][e] = sum_j qs[d,j]*dout[e,j]
@@ -266,9 +271,18 @@ linattn_bwd_q_kernel(const T* __restrict__ dout, int dout_ld, const T* __restric
     *reinterpret_cast<float4*>(&red[grp][d0 + i][e0]) =
         make_float4(acc[i][0] * kScale, acc[i][1] * kScale, acc[i][2] * kScale, acc[i][3] * kScale);
   __syncthreads();
+  float* dws = dctx + (int64_t)bh * (DH + 1) * DH;     // [33][32]: dctx rows, then Dd
   for (int i = tid; i < DH * DH; i += 256) {
     const int d = i >> 5, e = i & 31;
-    dctx[(int64_t)bh * DH * DH + i] = red[0][d][e] + red[1][d][e] + red[2][d][e] + red[3][d][e];
+    const float v = red[0][d][e] + red[1][d][e] + red[2][d][e] + red[3][d][e];
+    dws[i] = v;
+    red[0][d][e] = v * CT_s[e][d];                      // dctx[d][e]*ctx[d][e]
+  }
+  __syncthreads();
+  if (tid < DH) {
+    float a = 0.f;
+    for (int e = 0; e < DH; ++e) a += red[0][tid][(e + tid) & 31];
+    dws[DH * DH + tid] = a;
   }
 }
 
@@ -286,24 +300,23 @@ linattn_bwd_kv_kernel(const T* __restrict__ qkv, int ld, const float* __restrict
   __shared__ __align__(16) float KS_s[LA_CHUNK][DH];  // softmax_j(k)[d, pixel]
   __shared__ __align__(16) float V_s[LA_CHUNK][DH];
   __shared__ float Dd[DH], kmx[DH], kinv[DH];
+  const float* dws = dctx + (int64_t)bh * (DH + 1) * DH;
   for (int i = tid; i < DH * DH; i += 256) {
-    const float v = dctx[(int64_t)bh * DH * DH + i];
+    const float v = dws[i];
     D_s[i >> 5][i & 31] = v;
     DT_s[i & 31][i >> 5] = v;
   }
   if (tid < DH) {
     kmx[tid] = kstat[((int64_t)bh * DH + tid) * 2];
     kinv[tid] = 1.f / kstat[((int64_t)bh * DH + tid) * 2 + 1];
-  }
-  __syncthreads();
-  if (tid < DH) {   // Dd[d] = sum_e dctx[d][e]*ctx[d][e]
-    float a = 0.f;
-    for (int e = 0; e < DH; ++e) a = fmaf(D_s[tid][e], ctx[((int64_t)bh * DH + tid) * DH + e], a);
-    Dd[tid] = a;
+    Dd[tid] = dws[DH * DH + tid];
   }
   const int pix = tid >> 2, part = tid & 3;
   const int total = n + NMEM;
-  const int c0 = blockIdx.x * LA_CHUNK;  // global index: [0,NMEM) memory, then pixels
+  for (int cc = 0; cc < LA_CPB; ++cc) {
+  const int c0 = (blockIdx.x * LA_CPB + cc) * LA_CHUNK;  // global index: [0,NMEM) memory, then pixels
+  if (c0 >= total) break;
+  __syncthreads();
   {
     const int j = c0 + pix;
     float kv[8], vv[8];
@@ -367,6 +380,7 @@ linattn_bwd_kv_kernel(const T* __restrict__ qkv, int ld, const float* __restrict
       }
     }
   }
+  }  // chunk loop
 }
 
 // ================================ full softmax attention (n <= 64) ==================================
@@ -521,7 +535,7 @@ extern "C" int b200dm_linattn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld
   B200DM_REQUIRE(B > 0 && n > 0, B200DM_ERR_SHAPE, "linattn_fwd: empty input");
   cudaStream_t st = (cudaStream_t)stream;
   B200DM_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0, B200DM_ERR_SHAPE, "linattn_fwd: qkv must be 16-byte aligned, ld %% 8 == 0");
-  dim3 g2((n + LA_CHUNK - 1) / LA_CHUNK, B * HEADS);
+  dim3 g2((n + LA_CHUNK * LA_CPB - 1) / (LA_CHUNK * LA_CPB), B * HEADS);
   if (dtype == B200DM_F32) {
     linattn_ctx_kernel<float><<<B * HEADS, 256, 0, st>>>((const float*)qkv, qkv_ld, mem_kv, ctx, kstat, n);
     linattn_out_kernel<float><<<g2, 256, 0, st>>>((const float*)qkv, qkv_ld, ctx, (float*)out, out_ld, n);
@@ -541,7 +555,7 @@ extern "C" int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_
   cudaStream_t st = (cudaStream_t)stream;
   B200DM_REQUIRE(qkv_ld % 8 == 0 && dout_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dout & 15) == 0,
                  B200DM_ERR_SHAPE, "linattn_bwd: tensors must be 16-byte aligned, ld %% 8 == 0");
-  dim3 g2((n + NMEM + LA_CHUNK - 1) / LA_CHUNK, B * HEADS);
+  dim3 g2((n + NMEM + LA_CHUNK * LA_CPB - 1) / (LA_CHUNK * LA_CPB), B * HEADS);
   if (dtype == B200DM_F32) {
     linattn_bwd_q_kernel<float><<<B * HEADS, 256, 0, st>>>((const float*)dout, dout_ld, (const float*)qkv, qkv_ld, ctx, dctx, (float*)dqkv, dqkv_ld, n);
     linattn_bwd_kv_kernel<float><<<g2, 256, 0, st>>>((const float*)qkv, qkv_ld, mem_kv, ctx, kstat, dctx, (float*)dqkv, dqkv_ld, dmem_kv, n);

@@ -559,7 +559,7 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
     int VL = 1;
     while (VL < C8 && VL < 64) VL <<= 1;
     int cb = (C8 + VL - 1) / VL;
-    int64_t rb = (4 * num_sms() + cb - 1) / cb;
+    int64_t rb = (num_sms() + cb - 1) / cb;   // few CTAs: the final atomics hit only C/32 cache lines
     const int RL = 256 / VL;
     if (rb > (rows + 4 * RL - 1) / (4 * RL)) rb = (rows + 4 * RL - 1) / (4 * RL);
     if (rb < 1) rb = 1;

@@ -151,54 +151,82 @@ gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
 }
 
 // ---- backward pass 2: FiLM grads, group means, dgamma/dbeta; one CTA per sample ---------------------
-__global__ void gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ film, int film_ld,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                     float* __restrict__ dfilm, float* __restrict__ dbias,
-                                     float* __restrict__ gmeans, int HW, int C, int G, int chunks) {
-  __shared__ float g1[64], g2[64];
-  extern __shared__ float tot[];   // [C][3] chunk-summed
-  const int b = blockIdx.x, gs = C / G;
-  if (threadIdx.x < G) g1[threadIdx.x] = g2[threadIdx.x] = 0.f;
-  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += sums[((int64_t)b * chunks + k) * C * 3 + i];
-    tot[i] = s;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float S1 = tot[c * 3], S2 = tot[c * 3 + 1];
-    float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
-    float ga = gamma[c], be = beta[c];
-    if (dfilm) {
-      dfilm[(int64_t)b * film_ld + c] = ga * S2 + be * S1;  // d scale
-      dfilm[(int64_t)b * film_ld + C + c] = S1;             // d shift
-    }
-    atomicAdd(dgamma + c, sc * S2);
-    atomicAdd(dbeta + c, sc * S1);
-    float a = sc * ga;
-    atomicAdd(&g1[c / gs], a * S1);
-    atomicAdd(&g2[c / gs], a * S2);
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(256)
+gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ film, int film_ld, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dfilm, float* __restrict__ dbias,
+                     float* __restrict__ gmeans, int B, int HW, int C, int G, int chunks) {
+  // one CTA per group: thread = (channel of the group, sample lane); every parameter gradient of the
+  // group's channels is reduced over the batch inside the CTA -> plain (+=) stores, no global atomics
+  extern __shared__ float sh[];            // tot[gs][3] per sample lane, then reductions
+  const int g = blockIdx.x, gs = C / G;
+  const int cl = threadIdx.x % gs, bl = threadIdx.x / gs, BL = blockDim.x / gs;
+  const int c = g * gs + cl;
+  float* accg = sh;                        // [BL][gs][3] : dgamma, dbeta, dbias partials
+  float* gsum = sh + BL * gs * 3;          // [BL][2] group sums of the current sample per lane
+  const float ga = gamma[c], be = beta[c];
   const float inv = 1.f / ((float)gs * (float)HW);
-  if (threadIdx.x < G) {
-    gmeans[(b * G + threadIdx.x) * 2] = g1[threadIdx.x] * inv;
-    gmeans[(b * G + threadIdx.x) * 2 + 1] = g2[threadIdx.x] * inv;
-  }
-  if (dbias) {
-    // bias gradient of the producing conv = sum over pixels of dx = rstd*(a*dz - M1 - xn*M2):
-    //   sum_p dx[b,p,c] = rstd * (a*S1 - HW*M1 - M2 * sum_p xn),  sum_p xn = (S0 - HW*mean) * rstd
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / gs;
+  float a_dg = 0.f, a_db = 0.f, a_dbias = 0.f;
+  // gridDim.y slices of the batch: at most 4 sample-lane iterations per CTA
+  const int per = (B + gridDim.y - 1) / gridDim.y;
+  const int bbeg = blockIdx.y * per, bend = min(bbeg + per, B);
+  for (int b0 = bbeg; b0 < bend; b0 += BL) {
+    const int b = b0 + bl < bend ? b0 + bl : B;     // B = "no sample"
+    float S1 = 0.f, S2 = 0.f, S0 = 0.f, sc = 1.f;
+    if (b < B) {
+      for (int k = 0; k < chunks; ++k) {
+        const float* p = sums + (((int64_t)b * chunks + k) * C + c) * 3;
+        S1 += p[0]; S2 += p[1]; S0 += p[2];
+      }
+      sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+      if (dfilm) {
+        dfilm[(int64_t)b * film_ld + c] = ga * S2 + be * S1;  // d scale
+        dfilm[(int64_t)b * film_ld + C + c] = S1;             // d shift
+      }
+    }
+    const float a = sc * ga;
+    // group sums over the gs channels of this sample lane
+    __syncthreads();
+    if (cl == 0) { gsum[bl * 2] = 0.f; gsum[bl * 2 + 1] = 0.f; }
+    __syncthreads();
+    atomicAdd(&gsum[bl * 2], a * S1);
+    atomicAdd(&gsum[bl * 2 + 1], a * S2);
+    __syncthreads();
+    if (b < B) {
+      const float M1 = gsum[bl * 2] * inv, M2 = gsum[bl * 2 + 1] * inv;
+      if (cl == 0) {
+        gmeans[(b * G + g) * 2] = M1;
+        gmeans[(b * G + g) * 2 + 1] = M2;
+      }
+      a_dg += sc * S2;
+      a_db += sc * S1;
+      // sum_p dx[b,p,c] = rstd*(a*S1 - HW*M1 - M2*sum_p xn),  sum_p xn = (S0 - HW*mean)*rstd
       const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
-      const float S1 = tot[c * 3], S0 = tot[c * 3 + 2];
-      const float sc = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
-      const float a = sc * gamma[c];
-      const float M1 = g1[g] * inv, M2 = g2[g] * inv;
       const float sum_xn = (S0 - (float)HW * mean) * rstd;
-      atomicAdd(dbias + c, rstd * (a * S1 - (float)HW * M1 - M2 * sum_xn));
+      a_dbias += rstd * (a * S1 - (float)HW * M1 - M2 * sum_xn);
+    }
+  }
+  __syncthreads();
+  accg[(bl * gs + cl) * 3] = a_dg;
+  accg[(bl * gs + cl) * 3 + 1] = a_db;
+  accg[(bl * gs + cl) * 3 + 2] = a_dbias;
+  __syncthreads();
+  if (bl == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < BL; ++k) {
+      t0 += accg[(k * gs + cl) * 3];
+      t1 += accg[(k * gs + cl) * 3 + 1];
+      t2 += accg[(k * gs + cl) * 3 + 2];
+    }
+    if (gridDim.y == 1) {
+      dgamma[c] += t0;
+      dbeta[c] += t1;
+      if (dbias) dbias[c] += t2;
+    } else {
+      atomicAdd(dgamma + c, t0);
+      atomicAdd(dbeta + c, t1);
+      if (dbias) atomicAdd(dbias + c, t2);
     }
   }
 }
@@ -237,36 +265,45 @@ gn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x
   }
 }
 
-// ---- RMSNorm: one warp per row (pixel); C <= 512 ----------------------------------------------------
+// ---- RMSNorm: a row (pixel) is handled by L = min(32, C/8) lanes, 32/L rows per warp; C <= 512 ----------
 constexpr int RMS_MAXV = 2;  // 8-wide vectors per lane (C <= 512)
+
+__device__ __forceinline__ float seg_sum(float v, int L) {   // sum over aligned groups of L lanes
+  for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ g,
                    const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int64_t rows,
-                   int C) {
+                   int C, int L) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L, rpw = 32 / L;      // row slot inside the warp, lane in the row
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
-  for (int64_t r = warp; r < rows; r += nwarps) {
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
     float v[RMS_MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = lane + 32 * k;
-      if (cv < C8) {
+      int cv = sl + L * k;
+      if (ok && cv < C8) {
         ld8(x + r * x_ld + cv * 8, v[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss = fmaf(v[k][j], v[k][j], ss);
       }
     }
-    ss = warp_sum(ss);
+    ss = seg_sum(ss, L);
     float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
     for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = lane + 32 * k;
-      if (cv < C8) {
+      int cv = sl + L * k;
+      if (ok && cv < C8) {
         float o[8], rr[8];
         if (res) ld8(res + r * res_ld + cv * 8, rr);
 #pragma unroll
@@ -284,47 +321,50 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                    const float* __restrict__ g, const T* __restrict__ res, int res_ld,
-                   T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int64_t rows, int C) {
+                   T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int64_t rows, int C, int L) {
   const int lane = threadIdx.x & 31;
+  const int sub = lane / L, sl = lane % L, rpw = 32 / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
   float dgacc[RMS_MAXV][8] = {};
-  for (int64_t r = warp; r < rows; r += nwarps) {
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
     float u[RMS_MAXV][8], gd[RMS_MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = lane + 32 * k;
-      if (cv < C8) {
+      int cv = sl + L * k;
+      if (ok && cv < C8) {
         ld8(x + r * x_ld + cv * 8, u[k]);
         ld8(dy + r * dy_ld + cv * 8, gd[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
       }
     }
-    ss = warp_sum(ss);
+    ss = seg_sum(ss, L);
     float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = lane + 32 * k;
-      if (cv < C8) {
+      int cv = sl + L * k;
+      if (ok && cv < C8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          u[k][j] *= rn;                                    // unit vector
+          u[k][j] *= rn;                                       // unit vector
           dgacc[k][j] = fmaf(gd[k][j], u[k][j], dgacc[k][j]);  // dg_c += dy_c*u_c (x sqrtC at the end)
-          gd[k][j] *= g[cv * 8 + j];                        // g .* dy
+          gd[k][j] *= g[cv * 8 + j];                           // g .* dy
           dot = fmaf(gd[k][j], u[k][j], dot);
         }
       }
     }
-    dot = warp_sum(dot);
+    dot = seg_sum(dot, L);
 #pragma unroll
     for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = lane + 32 * k;
-      if (cv < C8) {
+      int cv = sl + L * k;
+      if (ok && cv < C8) {
         float o[8], rr[8];
         if (res) ld8(res + r * res_ld + cv * 8, rr);
 #pragma unroll
@@ -336,24 +376,20 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
       }
     }
   }
-  // dg: reduce the 8 warps of the CTA in shared memory, then one atomic per channel per CTA
-  __shared__ float dgs[8][512];
-  const int wib = threadIdx.x >> 5;
+  // dg: reduce all (warp, row-slot) partials of the CTA in shared memory, one atomic per channel per CTA
+  __shared__ float dgs[512];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dgs[c] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < RMS_MAXV; ++k) {
-    int cv = lane + 32 * k;
+    int cv = sl + L * k;
     if (cv < C8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dgs[wib][cv * 8 + j] = dgacc[k][j];
+      for (int j = 0; j < 8; ++j) atomicAdd(&dgs[cv * 8 + j], dgacc[k][j]);
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) s += dgs[w][c];
-    atomicAdd(dg + c, s * sqrtC);
-  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dg + c, dgs[c] * sqrtC);
 }
 
 static inline unsigned ew_grid(int64_t n) {
@@ -458,8 +494,14 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     gn_bwd_reduce_kernel<bf16><<<grid, threads, smem, st>>>(
         (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
   }
-  gn_bwd_params_kernel<<<B, 256, (size_t)C * 3 * sizeof(float), st>>>(
-      sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm, dbias, gmeans, HW, C, G, chunks);
+  {
+    const int gs = C / G;
+    B200DM_REQUIRE(gs <= 256 && 256 % gs == 0, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: group size %d", gs);
+    const int BL = 256 / gs;
+    dim3 pgrid(G, (B + 4 * BL - 1) / (4 * BL));
+    gn_bwd_params_kernel<<<pgrid, 256, (size_t)(BL * gs * 3 + BL * 2) * sizeof(float), st>>>(
+        sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm, dbias, gmeans, B, HW, C, G, chunks);
+  }
   if (dtype == B200DM_F32)
     gn_bwd_apply_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
         (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,
@@ -478,11 +520,13 @@ extern "C" int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, co
   B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && y_ld % 8 == 0, B200DM_ERR_SHAPE,
                  "rmsnorm_fwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned grid = ew_grid(rows * 32);
+  int L = 1;
+  while (L < C / 8 && L < 32) L <<= 1;
+  unsigned grid = ew_grid(rows * L);
   if (dtype == B200DM_F32)
-    rmsnorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C);
+    rmsnorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
   else
-    rmsnorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C);
+    rmsnorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
   count_launch();
   return check_launch("rmsnorm_fwd");
 }
@@ -494,12 +538,14 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0,
                  B200DM_ERR_SHAPE, "rmsnorm_bwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = (rows + 7) / 8, cap = (int64_t)num_sms() * 4;
+  int L = 1;
+  while (L < C / 8 && L < 32) L <<= 1;
+  int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: dg atomics share C/32 lines
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   if (dtype == B200DM_F32)
-    rmsnorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C);
+    rmsnorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C, L);
   else
-    rmsnorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C);
+    rmsnorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C, L);
   count_launch();
   return check_launch("rmsnorm_bwd");
 }

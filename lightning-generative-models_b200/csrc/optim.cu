@@ -31,6 +31,43 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+// All conv weights of the network in ONE launch: `table` lists the tensors, each CTA finds its
+// (tensor, tap, 32x32 tile) by binary search over the tile prefix sums.
+template <typename T>
+__global__ void pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n - 1;
+  const int bid = blockIdx.x;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (table[mid].tile_begin <= bid) lo = mid; else hi = mid - 1;
+  }
+  const b200dm_pack_entry e = table[lo];
+  int local = bid - e.tile_begin;
+  const int per_tap = e.tiles_ci * e.tiles_co;
+  const int t = local / per_tap;
+  local -= t * per_tap;
+  const int ci0 = (local % e.tiles_ci) * 32, co0 = (local / e.tiles_ci) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const float* wsrc = e.w + (int64_t)t * e.s_tap;
+  T* wf = (T*)e.wf;
+  T* wt = (T*)e.wt;
+  for (int r = ty; r < 32; r += 8) {
+    int co = co0 + r, ci = ci0 + tx;
+    float v = (co < e.Cout && ci < e.Cin) ? wsrc[(int64_t)co * e.s_co + (int64_t)ci * e.s_ci] : 0.f;
+    tile[r][tx] = v;
+    if (wf && co < e.Cout && ci < e.Cin) Elem<T>::st(wf + ((int64_t)t * e.Cout + co) * e.Cin + ci, v);
+  }
+  __syncthreads();
+  if (wt) {
+    const int tt = e.flip ? e.taps - 1 - t : t;
+    for (int r = ty; r < 32; r += 8) {
+      int ci = ci0 + r, co = co0 + tx;
+      if (co < e.Cout && ci < e.Cin) Elem<T>::st(wt + ((int64_t)tt * e.Cin + ci) * e.Cout + co, tile[tx][r]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
@@ -76,6 +113,19 @@ extern "C" int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, 
     pack_weight_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
   count_launch();
   return check_launch("pack_conv_weight");
+}
+
+extern "C" int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack_entry* table,
+                                                int32_t n_entries, int32_t total_tiles, void* stream) {
+  B200DM_REQUIRE(table && n_entries > 0 && total_tiles > 0, B200DM_ERR_SHAPE, "pack_conv_weights_batched: empty table");
+  dim3 block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    pack_weights_batched_kernel<float><<<total_tiles, block, 0, st>>>(table, n_entries);
+  else
+    pack_weights_batched_kernel<__nv_bfloat16><<<total_tiles, block, 0, st>>>(table, n_entries);
+  count_launch();
+  return check_launch("pack_conv_weights_batched");
 }
 
 extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,

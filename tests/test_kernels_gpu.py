@@ -503,7 +503,7 @@ def test_linear_attention_fwd_bwd(dtype, B, S):
     ref.backward(do.flatten(2))
     dov = nhwc(do, dtype)
     dqv = View.zeros(B, S, S, 384, DT[dtype], DEV)
-    dctx, dmem = torch.empty(B, 4, 32, 32, device=DEV), torch.zeros(2, 4, 32, 4, device=DEV)
+    dctx, dmem = torch.empty(B, 4, 33, 32, device=DEV), torch.zeros(2, 4, 32, 4, device=DEV)
     L.call("b200dm_linattn_bwd", dtype, dov.ptr, dov.ld, qv.ptr, qv.ld, mem.data_ptr(), ctx.data_ptr(),
            kstat.data_ptr(), dctx.data_ptr(), dqv.ptr, dqv.ld, dmem.data_ptr(), B, n)
     assert rel(dqv.to_nchw(), qkv.grad) < (1e-4 if dtype == L.F32 else 6e-3)
@@ -601,3 +601,24 @@ def test_adam_matches_torch_and_ema():
     ema = p0.clone()
     L.call("b200dm_ema_update", ema.data_ptr(), p.data_ptr(), n, 0.995)
     assert (ema - torch.lerp(p0, p, 0.005)).abs().max().item() < 1e-7
+
+
+def test_batched_weight_pack_matches_reference_layouts():
+    """WeightPack (one launch for all 73 GEMM convs) against per-tensor torch permutations, including the
+    pixel-unshuffle conv that keeps the reference [Cout, 4C] master layout."""
+    from b200dm.engine import WeightPack
+    from b200dm.params import ParamArena
+    arena = ParamArena(64, 3, DEV)
+    g = torch.Generator().manual_seed(5)
+    arena.flat.copy_(torch.randn(arena.flat.numel(), generator=g))
+    pk = WeightPack(arena, L.BF16, with_dgrad=True)
+    pk.refresh(force=True)
+    for nm, ci in arena.convs.items():
+        w = arena.views[nm + ".weight"]                      # logical reference shape
+        if ci.mode == 0:
+            assert torch.equal(pk.fwd[nm].view(ci.taps, ci.cout, ci.cin), pack_w(w, L.BF16)), nm
+            assert torch.equal(pk.tr[nm].view(ci.taps, ci.cin, ci.cout), pack_w(w, L.BF16, True, True)), nm
+        else:
+            wp = w.reshape(ci.cout, ci.cin, 4).permute(2, 0, 1).contiguous().to(torch.bfloat16)
+            assert torch.equal(pk.fwd[nm].view(4, ci.cout, ci.cin), wp), nm
+            assert torch.equal(pk.tr[nm].view(4, ci.cin, ci.cout), wp.transpose(1, 2).contiguous()), nm
