@@ -11,6 +11,8 @@
 //
 // Serves the forward convs (ddpm.py:96,103,160,187,213-215,252-253,377,413) and, with the
 // tap-reversed/transposed weight pack, their data gradients.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace b200dm {
@@ -286,6 +288,243 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =====================================================================================================
+// 3x3 convolution with an on-chip halo: the implicit GEMM above re-reads the activation tile once per
+// filter tap (9x) through L2, which is what bounds it (measured ~6.5 TB/s L2->SM).  Here a tile is
+// 8 x 16 output pixels; ONE TMA box {64 ch, 16 cols, 18 rows} brings the tile plus its 1-pixel halo into
+// shared memory (row pitch 16 pixels so that image rows stay 8-row-group aligned), and the nine taps are
+// nine *views* of that buffer: the UMMA A descriptor starts (dx + 16*dy) rows into the buffer, uses a
+// stride of 2048 B between 8-row groups (= next image row) and base_offset = dx so the 128-B swizzle
+// phase of the shifted rows matches what the TMA unit wrote.  For 64->64 layers the whole 3x3 weight
+// (72 KiB) stays resident in shared memory for the life of the persistent CTA.
+// =====================================================================================================
+constexpr int HALO_W = 16, HALO_H = 18;
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;  // 36 KiB per 64-channel block
+
+struct TcHaloParams {
+  int kblocks;                 // Cin / 64
+  int H, W, tiles_x, tiles_y;  // 8x16 tiles per image
+  int Cout, y_ld;
+  int m_tiles, n_tiles;
+  const __nv_bfloat16* y_read;
+  const __nv_bfloat16* res;
+  int res_ld;
+  const float* bias;
+  int bo_mode;                 // debug: 1 = base_offset = dx (documented), 0 = always 0
+};
+
+template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const TcHaloParams p) {
+  constexpr int B_BYTES = N_TILE * TC_BK * 2;
+  constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
+  constexpr int SUBTILES = N_TILE / 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + A_BUFS * HALO_BYTES;
+  const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
+  const uint32_t out_stage = b_base + b_slots * B_BYTES;
+  const uint32_t bar_base = out_stage + 2 * OUT_STAGE_BYTES;
+  auto afull = [&](int a) { return bar_base + 8u * a; };
+  auto aempty = [&](int a) { return bar_base + 8u * (A_BUFS + a); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * A_BUFS + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * A_BUFS + B_STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 + a); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* out_stage_ptr = smem_raw + (out_stage - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+    for (int a = 0; a < A_BUFS; ++a) { mbar_init(afull(a), 1); mbar_init(aempty(a), 1); }
+    for (int s2 = 0; s2 < B_STAGES; ++s2) { mbar_init(bfull(s2), 1); mbar_init(bempty(s2), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), TC_EPI_WARPS); }
+    mbar_init(bres_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      if (B_RESIDENT) {   // the whole [9][N_TILE][Cin] weight, once
+        mbar_expect_tx(bres_bar, (uint32_t)(9 * p.kblocks * B_BYTES));
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kc = 0; kc < p.kblocks; ++kc)
+            tma_load_3d(b_base + (tap * p.kblocks + kc) * B_BYTES, &tmB, bres_bar, kc * TC_BK, 0, tap);
+      }
+      int ab = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+        const int b = m_tile / tiles_per_img, rem = m_tile - b * tiles_per_img;
+        const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(aempty(ab), aph ^ 1u);
+          mbar_expect_tx(afull(ab), HALO_BYTES);
+          tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
+          if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
+          if (!B_RESIDENT) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bempty(bs), bph ^ 1u);
+              mbar_expect_tx(bfull(bs), B_BYTES);
+              tma_load_3d(b_base + bs * B_BYTES, &tmB, bfull(bs), kc * TC_BK, n0, tap);
+              if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+      int ab = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      if (B_RESIDENT) mbar_wait(bres_bar, 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(afull(ab), aph);
+          tc_fence_after();
+          const uint32_t a_buf = a_base + ab * HALO_BYTES;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            uint32_t b_addr;
+            if (B_RESIDENT) {
+              b_addr = b_base + (tap * p.kblocks + kc) * B_BYTES;
+            } else {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+              b_addr = b_base + bs * B_BYTES;
+            }
+            // tap window: rows (tx + dx) + 16*(ty + dy) of the halo buffer; 8-row groups = image rows
+            const uint32_t a_start = a_buf + (uint32_t)(dx + HALO_W * dy) * 128u;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              const uint64_t da = make_smem_desc(a_start + k * 32, 16, HALO_W * 128, p.bo_mode ? (uint32_t)dx : 0u);
+              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            if (!B_RESIDENT) {
+              umma_commit(bempty(bs));
+              if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+            }
+          }
+          umma_commit(aempty(ab));
+          if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
+        }
+        umma_commit(tmem_full_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const int tx = row & 7, ty = row >> 3;
+    const bool store_thread = (threadIdx.x == 64);
+    int acc = 0, sbuf = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      const int b = m_tile / tiles_per_img, rem = m_tile - b * tiles_per_img;
+      const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
+      const long long opix = ((long long)b * p.H + y0 + ty) * p.W + x0 + tx;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int s2 = 0; s2 < SUBTILES; ++s2) {
+        uint32_t r[32];
+        const int c = s2 * 64 + half * 32;
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
+        tmem_ld_wait();
+        if (s2 == SUBTILES - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c + j);
+        }
+        if (p.res) {
+          const __nv_bfloat16* rr = p.res + opix * p.res_ld + n0 + c;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            ld8(rr + g * 8, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+          }
+        }
+        if (p.y_read) {
+          const __nv_bfloat16* yr = p.y_read + opix * p.y_ld + n0 + c;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float t[8];
+            ld8(yr + g * 8, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+          }
+        }
+        if (store_thread) tma_store_wait_read<1>();
+        named_bar_sync(1, 32 * TC_EPI_WARPS);
+        uint8_t* srow = out_stage_ptr + sbuf * OUT_STAGE_BYTES + row * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+          const int chunk = (half * 4 + g) ^ (row & 7);
+          *reinterpret_cast<uint4*>(srow + chunk * 16) = u;
+        }
+        fence_proxy_async();
+        named_bar_sync(2, 32 * TC_EPI_WARPS);
+        if (store_thread) {
+          tma_store_5d(&tmY, out_stage + sbuf * OUT_STAGE_BYTES, n0 + s2 * 64, x0, y0, b, 0);
+          tma_store_commit();
+        }
+        sbuf ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (store_thread) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
   EncodeTiledFn enc = get_encoder();
@@ -356,6 +595,89 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   return check_launch("conv_tc");
 }
 
+template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                       const TcHaloParams& p, cudaStream_t st) {
+  const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
+  const int smem = A_BUFS * HALO_BYTES + b_slots * (N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 512;
+  B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv3x3_halo: %d B of shared memory", smem);
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv3x3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv3x3_halo_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p);
+  count_launch();
+  return check_launch("conv3x3_halo");
+}
+
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200DM_NO_HALO");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// 3x3 'same' conv on images of at least 16x16: halo kernel
+static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
+  TcHaloParams p{};
+  p.kblocks = d->Cin / TC_BK;
+  p.H = d->H; p.W = d->W; p.tiles_x = d->W / 8; p.tiles_y = d->H / 16;
+  p.Cout = d->Cout; p.y_ld = d->y_ld;
+  p.m_tiles = d->B * p.tiles_x * p.tiles_y;
+  p.y_read = d->accumulate ? (const __nv_bfloat16*)d->y : nullptr;
+  p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
+  p.bias = d->bias;
+  {
+    const char* e = getenv("B200DM_HALO_BO");
+    p.bo_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int sms = num_sms();
+  int n_tile = 64;
+  if (d->Cout % 128 == 0) {
+    // N = 128 unless that leaves most of the machine idle
+    const long long t128 = (long long)p.m_tiles * (d->Cout / 128);
+    if (t128 >= sms / 2) n_tile = 128;
+  }
+  p.n_tiles = d->Cout / n_tile;
+  const bool resident = (d->Cout == 64 && d->Cin == 64);
+
+  CUtensorMap tmA, tmB, tmY;
+  const cuuint64_t e = 2;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)d->x_ld * e, (cuuint64_t)d->W * d->x_ld * e,
+                         (cuuint64_t)d->H * d->W * d->x_ld * e, (cuuint64_t)d->B * d->H * d->W * d->x_ld * e};
+    cuuint32_t box[5] = {TC_BK, HALO_W, HALO_H, 1, 1};
+    int rc = encode_map(&tmA, d->x, 5, dims, str, box, "conv3x3_halo A");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)d->y_ld * e, (cuuint64_t)d->W * d->y_ld * e,
+                         (cuuint64_t)d->H * d->W * d->y_ld * e, (cuuint64_t)d->B * d->H * d->W * d->y_ld * e};
+    cuuint32_t box[5] = {64, 8, 16, 1, 1};
+    int rc = encode_map(&tmY, d->y, 5, dims, str, box, "conv3x3_halo Y");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout, 9};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout * d->Cin * 2};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)n_tile, 1};
+    int rc = encode_map(&tmB, d->w, 3, dims, str, box, "conv3x3_halo B");
+    if (rc) return rc;
+  }
+  if (resident) return launch_halo<64, 3, 1, true>(tmA, tmB, tmY, p, st);
+  if (n_tile == 128) return launch_halo<128, 2, 6, false>(tmA, tmB, tmY, p, st);
+  return launch_halo<64, 3, 6, false>(tmA, tmB, tmY, p, st);
+}
+
 int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_fwd(tc): needs an sm_100 device and a TMA-capable driver");
   B200DM_REQUIRE(d->Cin % TC_BK == 0, B200DM_ERR_SHAPE, "conv_fwd(tc): Cin=%d must be a multiple of 64", d->Cin);
@@ -366,6 +688,8 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
                      ((uintptr_t)d->res & 15) == 0,
                  B200DM_ERR_SHAPE, "conv_fwd(tc): pointers must be 16-byte aligned");
   const int ksize = d->mode == 0 ? d->ksize : 1;
+  if (d->mode == 0 && ksize == 3 && d->W >= 16 && d->W % 8 == 0 && d->H % 16 == 0 && halo_enabled())
+    return conv3x3_halo(d, (cudaStream_t)stream);
   int bh, bn;
   int rc = tile_geometry(d->H, d->W, &bh, &bn, "conv_fwd(tc)");
   if (rc) return rc;

@@ -156,8 +156,11 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ---- UMMA descriptors (cute/arch/mma_sm100_desc.hpp bit layout) --------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle:
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
+// [49,52) base offset = (start address >> 7) & 7 when the start is not aligned to the 1024-B swizzle
+// pattern (used by the halo kernel, whose tap windows start at arbitrary 128-B rows of the staged tile)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t base_offset = 0) {
+  uint64_t d = (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
