@@ -294,8 +294,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 8 x 16 output pixels; ONE TMA box {64 ch, 16 cols, 18 rows} brings the tile plus its 1-pixel halo into
 // shared memory (row pitch 16 pixels so that image rows stay 8-row-group aligned), and the nine taps are
 // nine *views* of that buffer: the UMMA A descriptor starts (dx + 16*dy) rows into the buffer, uses a
-// stride of 2048 B between 8-row groups (= next image row) and base_offset = dx so the 128-B swizzle
-// phase of the shifted rows matches what the TMA unit wrote.  For 64->64 layers the whole 3x3 weight
+// stride of 2048 B between 8-row groups (= next image row); the 128-B swizzle phase follows the absolute
+// shared-memory address (measured), so the shifted rows read back exactly what the TMA unit wrote.  For 64->64 layers the whole 3x3 weight
 // (72 KiB) stays resident in shared memory for the life of the persistent CTA.
 // =====================================================================================================
 constexpr int HALO_W = 16, HALO_H = 18;
@@ -635,8 +635,12 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
   p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
   p.bias = d->bias;
   {
+    // MEASURED on B200 (scripts/halo_debug.py): the tensor core derives the 128-B swizzle phase from the
+    // absolute shared-memory address bits [7,10), exactly like the TMA unit that wrote the tile, so a
+    // window that starts at an arbitrary 128-B row needs base_offset = 0.  Setting the "documented"
+    // (start >> 7) & 7 corrupts every dx != 0 tap.  B200DM_HALO_BO=1 re-enables it for experiments.
     const char* e = getenv("B200DM_HALO_BO");
-    p.bo_mode = (e && e[0] == '0') ? 0 : 1;
+    p.bo_mode = (e && e[0] == '1') ? 1 : 0;
   }
   const int sms = num_sms();
   int n_tile = 64;
