@@ -301,11 +301,11 @@ def main():
                      device=dev)
         model.train()
         unet = model.ema.model.model
-        if dist is not None:                                   # identical initial weights (DDP broadcast)
-            dist.broadcast(unet.arena.flat, 0)
-            model.ema.ema_model.model.arena.flat.copy_(unet.arena.flat)
         opt = model.configure_optimizers()
-        opt.grad_scale = 1.0 / world
+        if dist is not None:       # DDP semantics: broadcast rank 0's weights, bucketed all-reduce overlapped with backward
+            sync = unet.enable_data_parallel()
+            model.ema.ema_model.model.arena.flat.copy_(unet.arena.flat)
+            opt.grad_scale = sync.grad_scale
         g = torch.Generator().manual_seed(10 + rank)
         host = [torch.rand(B, 3, S, S, generator=g).pin_memory() for _ in range(4)]
         labels = torch.zeros(B, dtype=torch.long, device=dev)
@@ -315,9 +315,7 @@ def main():
         def step_core(data):
             opt.zero_grad()
             loss = model.training_step((data, labels))
-            loss.backward()
-            if dist is not None:
-                dist.all_reduce(unet.arena.gflat)              # sum; FusedAdam scales by 1/world
+            loss.backward()                                    # includes the overlapped gradient all-reduce
             opt.step()
             model.on_train_batch_end(None, None, 0)
             return loss

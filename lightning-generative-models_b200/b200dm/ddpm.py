@@ -165,4 +165,13 @@ class DDPM(_Base):
 
     def configure_optimizers(self):
         h = self.hparams_
-        return FusedAdam(self.ema.model.model, lr=h.lr, betas=h.betas)
+        opt = FusedAdam(self.ema.model.model, lr=h.lr, betas=h.betas)
+        # the reference relies on Lightning's DDPStrategy when several GPUs are used
+        # (utils/lightning_utils.py:41-43): same semantics here when torch.distributed is initialised
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            unet = self.ema.model.model
+            sync = unet.grad_sync or unet.enable_data_parallel()
+            self.ema.copy_params_from_model_to_ema()
+            opt.grad_scale = sync.grad_scale
+        return opt

@@ -90,6 +90,8 @@ class Plan:
         self.fwd_flops: List[float] = []
         self.bwd_groups: List[List[Callable[[int], None]]] = []
         self._cur_bwd: Optional[List[Callable[[int], None]]] = None
+        self._region = "head"        # which gradient bucket the current unit's parameters belong to
+        self.unit_regions: List[str] = []
         self._keep = []              # ctypes structs / tensors referenced by raw pointers
         self._scratch = {}
         self.lib = L.load()
@@ -102,6 +104,14 @@ class Plan:
         self.d_out = torch.zeros(B, ch, S, S, device=self.dev) if training else None
         self._build(dim, ch)
         self.bwd: List[Callable[[int], None]] = [op for g in reversed(self.bwd_groups) for op in g]
+        # backward segments in gradient-bucket order (b200dm.distributed.buckets): after segment i has run,
+        # bucket i of the gradient arena is final and can be all-reduced while the rest of backward runs
+        self.bwd_segments: List[List[Callable[[int], None]]] = []
+        for region in ("final", "ups", "mid", "downs", "head"):
+            seg = [op for g, r in zip(reversed(self.bwd_groups), reversed(self.unit_regions)) if r == region
+                   for op in g]
+            self.bwd_segments.append(seg)
+        assert sum(len(sg) for sg in self.bwd_segments) == len(self.bwd)
         self.bwd_names = [op.kname for op in self.bwd]
         self.bwd_flops = [op.flops for op in self.bwd]
         self.fwd_names = [op.kname for op in self.fwd]
@@ -151,6 +161,7 @@ class Plan:
     def begin_unit(self):
         self._cur_bwd = []
         self.bwd_groups.append(self._cur_bwd)
+        self.unit_regions.append(self._region)
 
     def _impl(self, cin, cout):
         return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
@@ -360,6 +371,7 @@ class Plan:
 
         x, gx = r, gr
         x_prior = True        # gcatF[dim:] also receives the final block's gradient first
+        self._region = "downs"
         for i in range(4):
             d_in, d_out, H = dims[i], dims[i + 1], res[i]
             last = i == 3
@@ -376,6 +388,7 @@ class Plan:
 
         mid = dims[4]
         Hm = res[3]
+        self._region = "mid"
         m1, gm1 = self.buf(Hm, mid), G(Hm, mid)
         self.resblock("mid_block1", x, m1, gx, gm1, gx_prior=False)
         m2, gm2 = self.buf(Hm, mid), G(Hm, mid)
@@ -383,6 +396,7 @@ class Plan:
         u0, gu0 = catB[3].slice(0, mid), sl(gcatB[3], 0, mid)
         self.resblock("mid_block2", m2, u0, gm2, gu0, gx_prior=False)
 
+        self._region = "ups"
         for j in range(4):
             i = 3 - j
             d_in, d_out, H = dims[i], dims[i + 1], res[i]
@@ -400,6 +414,7 @@ class Plan:
                 nxt, gnxt = catB[i - 1].slice(0, d_in), sl(gcatB[i - 1], 0, d_in)
                 self.upsample_conv(f"ups.{j}.3.1", u3, nxt, gu3, gnxt)
 
+        self._region = "final"
         yb, gy = self.buf(S, dim), G(S, dim)
         self.resblock("final_res_block", catF, yb, gcatF, gy, gx_prior=False)
         self.begin_unit()
@@ -419,4 +434,9 @@ class Plan:
     def run_backward(self):
         st = L.stream_ptr()
         for op in self.bwd:
+            op(st)
+
+    def run_backward_segment(self, i: int):
+        st = L.stream_ptr()
+        for op in self.bwd_segments[i]:
             op(st)

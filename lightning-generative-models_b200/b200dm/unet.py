@@ -99,6 +99,7 @@ class Unet(nn.Module):
         self._cuda_graph = (env != "0") if cuda_graph is None else cuda_graph
         self._pack: Optional[WeightPack] = None
         self._plans: Dict[tuple, Plan] = {}
+        self.grad_sync = None        # b200dm.distributed.GradSync when training data-parallel
 
     # ---- reference surface ----------------------------------------------------------------------------
     @property
@@ -217,17 +218,39 @@ class Unet(nn.Module):
                 plan.run_forward()
             plan.graph_fwd = g
 
+    def enable_data_parallel(self, group=None):
+        """Overlap the gradient all-reduce with backward (DDP semantics; see b200dm.distributed)."""
+        from .distributed import GradSync, broadcast_parameters
+        broadcast_parameters(self.arena, 0, group)
+        self.grad_sync = GradSync(self.arena, group)
+        return self.grad_sync
+
     def run_plan_backward(self, plan: Plan):
+        """Backward launches, one segment per gradient bucket; each bucket's all-reduce is enqueued on the
+        communication stream as soon as its segment has been issued."""
+        sync = self.grad_sync
+        nseg = len(plan.bwd_segments)
         if self._cuda_graph and plan.graph_bwd is not None:
-            plan.graph_bwd.replay()
-            return
-        plan.run_backward()
-        if self._cuda_graph and plan.warm >= 2 and not torch.cuda.is_current_stream_capturing():
-            # capture for the following steps (stream capture records the launches, it does not run them)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                plan.run_backward()
-            plan.graph_bwd = g
+            for i in range(nseg):
+                plan.graph_bwd[i].replay()
+                if sync is not None:
+                    sync.reduce_bucket(i)
+        else:
+            for i in range(nseg):
+                plan.run_backward_segment(i)
+                if sync is not None:
+                    sync.reduce_bucket(i)
+            if self._cuda_graph and plan.warm >= 2 and not torch.cuda.is_current_stream_capturing():
+                # capture for the following steps (stream capture records the launches, it does not run them)
+                graphs = []
+                for i in range(nseg):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        plan.run_backward_segment(i)
+                    graphs.append(g)
+                plan.graph_bwd = graphs
+        if sync is not None:
+            sync.finish()
 
     def _backward(self, plan: Plan, grad_out: torch.Tensor):
         first = next(iter(self._params.values()))
