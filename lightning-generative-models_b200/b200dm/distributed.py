@@ -47,24 +47,24 @@ def buckets(arena) -> List[Tuple[int, int]]:
         offs = [(arena.offset[n], arena.offset[n] + arena._numel(n)) for n in names if pred(n)]
         return min(o[0] for o in offs), max(o[1] for o in offs)
 
-    regions = [
-        span(lambda n: n.startswith("final_") and ".mlp.1." not in n),
-        span(lambda n: n.startswith("ups.") and ".mlp.1." not in n),
-        span(lambda n: n.startswith("mid_") and ".mlp.1." not in n),
-        span(lambda n: n.startswith("downs.") and ".mlp.1." not in n),
-        # stem, time MLP and the concatenated FiLM projections are finished last
-        (0, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1]),
-    ]
-    # make the regions tile the arena exactly (alignment padding goes to the following bucket)
-    regions = sorted(regions)
-    out, prev = [], 0
-    for b, e in regions:
-        out.append((prev, e))
+    named = {
+        "final": span(lambda n: n.startswith("final_") and ".mlp.1." not in n),
+        "ups": span(lambda n: n.startswith("ups.") and ".mlp.1." not in n),
+        "mid": span(lambda n: n.startswith("mid_") and ".mlp.1." not in n),
+        "downs": span(lambda n: n.startswith("downs.") and ".mlp.1." not in n),
+        # stem, time MLP and the concatenated FiLM projections (arena head) are finished last
+        "head": (0, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1]),
+    }
+    # make the regions tile the arena exactly (alignment padding goes to the following region)
+    by_mem = sorted(named.items(), key=lambda kv: kv[1][0])
+    tiled, prev = {}, 0
+    for k, (b, e) in by_mem:
+        tiled[k] = (prev, e)
         prev = e
-    out[-1] = (out[-1][0], arena.numel)
-    # backward order = reverse memory order of the four main regions, head last
-    head, rest = out[0], out[1:]
-    return list(reversed(rest)) + [head]
+    last = by_mem[-1][0]
+    tiled[last] = (tiled[last][0], arena.numel)
+    # order in which Plan.bwd_segments completes them
+    return [tiled[k] for k in ("final", "ups", "mid", "downs", "head")]
 
 
 class GradSync:
