@@ -185,7 +185,16 @@ int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, const float*
                         const float* gamma, const float* beta, const float* film, int32_t film_ld,
                         const void* res, int32_t res_ld, void* y, int32_t y_ld, int32_t B, int32_t HW,
                         int32_t C, int32_t G, void* stream);
-/* backward, three launches inside:  (1) per-(b,c) sums of dz, dz*xnorm and x  (2) parameter / FiLM
+/* stats + apply in ONE launch: a thread-block cluster per sample reduces (sum, sum of squares) through
+ * distributed shared memory, writes stats [B][G][2] = (mean, rstd) for the backward pass and applies the
+ * norm while the chunk is still in L2.  C <= 512; other shapes take the two-launch path internally. */
+int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* stats, const float* gamma,
+                  const float* beta, const float* film, int32_t film_ld, const void* res, int32_t res_ld,
+                  void* y, int32_t y_ld, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
+                  void* stream);
+/* backward.  C <= 512: one cluster launch per call (per-channel sums exchanged through distributed shared
+ * memory; dgamma/dbeta/dbias reduced over the batch with fp32 atomics; sums/gmeans unused).  Otherwise
+ * three launches inside:  (1) per-(b,c) sums of dz, dz*xnorm and x  (2) parameter / FiLM
  * grads + group means (+ the bias gradient of the conv that produced x, if dbias != NULL: the pixel
  * sum of dx follows in closed form from the sums)  (3) dx.  sums: fp32 workspace of
  * b200dm_gn_bwd_ws_floats(B, HW, C) floats (per-CTA partials, reduced deterministically);
@@ -242,6 +251,12 @@ int b200dm_linear_fwd(const float* X, const float* W, const float* b, float* Y, 
 int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* dY, float* dX,
                       float* dW, float* db, int32_t M, int32_t N, int32_t K, int32_t act,
                       void* stream);
+
+/* Diagnostic (scripts/umma_rate.py): cycles for `iters` x 8 tcgen05.mma (M=128, N=n_tile, K=16) issued by one
+ * thread per CTA on resident shared-memory operands; mode 0 = K-major SW128, 1 = shifted halo view,
+ * 2 = MN-major (wgrad).  out_cycles: int64 [ctas]. */
+int b200dm_debug_umma_rate(int32_t n_tile, int32_t iters, int32_t mode, int32_t ctas, long long* out_cycles,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Weight packing, optimiser, EMA

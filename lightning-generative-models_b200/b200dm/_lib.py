@@ -76,6 +76,7 @@ PROTOTYPES = {
     "b200dm_upsample2x_fwd": [_I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_upsample2x_bwd": [_I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_gn_stats": [_I, _P, _I, _P, _I, _I, _I, _I, _F, _P],
+    "b200dm_gn_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "b200dm_gn_apply_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_gn_apply_bwd": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P,
                             _I, _I, _I, _I, _P],
@@ -93,6 +94,7 @@ PROTOTYPES = {
     "b200dm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "b200dm_ema_update": [_P, _P, _L, _F, _P],
     "b200dm_fill_f32": [_P, _L, _F, _P],
+    "b200dm_debug_umma_rate": [_I, _I, _I, _I, _P, _P],
 }
 _SPECIAL = {
     "b200dm_version": ([], C.c_int),

@@ -227,19 +227,19 @@ class Plan:
         film_ptr = self.film.data_ptr() + 4 * a.film_off[nm]
         b1, b2 = nm + ".block1", nm + ".block2"
         self.conv_fwd(self.F, b1 + ".proj", x, c1)
-        self.F("b200dm_gn_stats", self.dt, c1.ptr, c1.ld, st1.data_ptr(), self.B, HW, cout, GROUPS, GN_EPS)
-        self.F("b200dm_gn_apply_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
-               a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout, GROUPS)
+        self.F("b200dm_gn_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
+               a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout, GROUPS,
+               GN_EPS)
         self.conv_fwd(self.F, b2 + ".proj", h1, c2)
-        self.F("b200dm_gn_stats", self.dt, c2.ptr, c2.ld, st2.data_ptr(), self.B, HW, cout, GROUPS, GN_EPS)
         if has_res_conv:
             rc = self.buf(H, cout)
             self.conv_fwd(self.F, nm + ".res_conv", x, rc)
             res = rc
         else:
             res = x
-        self.F("b200dm_gn_apply_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
-               a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS)
+        self.F("b200dm_gn_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
+               a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS,
+               GN_EPS)
         if not self.training:
             return
         dc, gh1 = self.scratch("dc", H, cout), self.scratch("gh1", H, cout)

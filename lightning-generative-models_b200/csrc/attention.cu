@@ -2,7 +2,11 @@
 //   LinearAttention   ddpm.py:222-238   (softmax over d for q, over n+4 for k; 32x32 context per head)
 //   Attention/Attend  ddpm.py:255-271, models/modules/attend.py:111-126 (n <= 64, 4 memory kv)
 // Everything inside a (sample, head) is fp32; tensors are in the activation dtype.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200dm {
 
@@ -383,6 +387,946 @@ linattn_bwd_kv_kernel(const T* __restrict__ qkv, int ld, const float* __restrict
   }  // chunk loop
 }
 
+// =====================================================================================================
+// Cluster-fused LinearAttention: ONE launch per direction.  A cluster of CL CTAs owns one (sample, head);
+// each CTA handles a contiguous pixel range.  The 32x32 context (forward) / its gradient (backward) is
+// reduced across the cluster through distributed shared memory, so q/k/v (and dout) are streamed from HBM
+// exactly once and nothing but the final context/statistics (saved for backward) goes through global
+// memory.  Global loads of the next 64-pixel chunk are issued before the current chunk is processed
+// (register double buffering) — the previous kernels exposed one DRAM round trip per chunk.
+// =====================================================================================================
+template <typename T> struct LaRaw;
+template <> struct LaRaw<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct LaRaw<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { u = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(__nv_bfloat16* p, const float (&v)[4]) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h[0] = __floats2bfloat162_rn(v[0], v[1]);
+  h[1] = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+struct LaFwdSmem {
+  float P[LA_CHUNK][DH];       // exp(k - m_loc) of the current chunk / scale*softmax(q) in the output phase
+  float V[LA_CHUNK][DH];
+  float red[4][DH][DH];        // per pixel-quarter partial contexts; also the max reduction scratch
+  float ctx_loc[DH][DH];       // this CTA's un-normalised partial context   (read by the cluster peers)
+  float m_loc[DH], l_loc[DH];  // its running max and exp-sum per key channel (read by the cluster peers)
+  float ctx[DH][DH];           // merged, normalised context
+  float ps[4][DH];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+linattn_fwd_cluster_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
+                           float* __restrict__ ctx_out, float* __restrict__ kstat, T* __restrict__ out,
+                           int out_ld, int n) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
+  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char la_smem_raw[];
+  LaFwdSmem& s = *reinterpret_cast<LaFwdSmem*>(la_smem_raw);
+  const T* qbase = qkv + (int64_t)b * n * ld + h * DH;
+  const T* kbase = qbase + HID;
+  const T* vbase = qbase + 2 * HID;
+  const float* mk = mem_kv + (0 * HEADS + h) * DH * NMEM;  // [d][m]
+  const float* mv = mem_kv + (1 * HEADS + h) * DH * NMEM;  // [e][m]
+  // pixel range of this CTA (whole 64-pixel chunks); rank 0 also owns the NMEM memory keys
+  const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  const int cpr = (chunks + CL - 1) / CL;
+  const int p0 = min(rank * cpr * LA_CHUNK, n), p1 = min((rank + 1) * cpr * LA_CHUNK, n);
+  const int pix = tid >> 2, part = tid & 3;
+  // ---- phase 1a: local max of k over the range (4 independent loads in flight per thread)
+  {
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int j = p0 + pix; j < p1; j += 4 * LA_CHUNK) {
+      LaRaw<T> raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u * LA_CHUNK < p1) raw[u].load(kbase + (int64_t)(j + u * LA_CHUNK) * ld + part * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u * LA_CHUNK < p1) {
+          float v[8];
+          raw[u].unpack(v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+        }
+      }
+    }
+    float* mred = &s.red[0][0][0];                   // [64 pixel lanes][32]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mred[pix * DH + part * 8 + i] = m[i];
+    __syncthreads();
+    if (tid < DH) {
+      float mm = -INFINITY;
+      for (int i = 0; i < 64; ++i) mm = fmaxf(mm, mred[i * DH + tid]);
+      if (rank == 0)
+        for (int i = 0; i < NMEM; ++i) mm = fmaxf(mm, mk[tid * NMEM + i]);
+      s.m_loc[tid] = mm;
+    }
+    __syncthreads();
+  }
+  // ---- phase 1b: partial context; thread = (pixel quarter, 4 d x 4 e micro-tile)
+  const int grp = tid >> 6, tt = tid & 63;
+  const int d0 = (tt >> 3) * 4, e0 = (tt & 7) * 4;
+  {
+    float acc[4][4] = {}, psum[4] = {0.f, 0.f, 0.f, 0.f};
+    // local index space: rank 0 -> [0,NMEM) memory then its pixels; other ranks -> pixels only
+    const int lead = rank == 0 ? NMEM : 0;
+    const int total = (p1 - p0) + lead;
+    LaRaw<T> rk, rv;
+    auto fetch = [&](int c0) {
+      const int j = c0 + pix - lead;                  // pixel offset inside the range (negative: memory key)
+      if (j >= 0 && j < p1 - p0) {
+        rk.load(kbase + (int64_t)(p0 + j) * ld + part * 8);
+        rv.load(vbase + (int64_t)(p0 + j) * ld + part * 8);
+      } else {
+        rk.zero();
+        rv.zero();
+      }
+    };
+    if (total > 0) fetch(0);
+    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+      float kv[8], vv[8];
+      rk.unpack(kv);
+      rv.unpack(vv);
+      const int jl = c0 + pix;                        // local index of this thread's row
+      if (jl < lead) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kv[i] = mk[(part * 8 + i) * NMEM + jl];
+          vv[i] = mv[(part * 8 + i) * NMEM + jl];
+        }
+      }
+      if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);   // next chunk's loads fly during this chunk's math
+      const bool ok = jl < total;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s.P[pix][part * 8 + i] = ok ? __expf(kv[i] - s.m_loc[part * 8 + i]) : 0.f;
+        s.V[pix][part * 8 + i] = ok ? vv[i] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int jj = grp * 16; jj < grp * 16 + 16; ++jj) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&s.P[jj][d0]);
+        const float4 v4 = *reinterpret_cast<const float4*>(&s.V[jj][e0]);
+        const float pa[4] = {p4.x, p4.y, p4.z, p4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          psum[i] += pa[i];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(pa[i], va[k], acc[i][k]);
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(&s.red[grp][d0 + i][e0]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if ((tt & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s.ps[grp][d0 + i] = psum[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < DH * DH; i += 256) {
+      const int d = i >> 5, e = i & 31;
+      s.ctx_loc[d][e] = s.red[0][d][e] + s.red[1][d][e] + s.red[2][d][e] + s.red[3][d][e];
+      if (e == 0) s.l_loc[d] = s.ps[0][d] + s.ps[1][d] + s.ps[2][d] + s.ps[3][d];
+    }
+  }
+  cluster.sync();
+  // ---- merge the CL partial softmax states (every CTA computes the full context it needs)
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float M = -INFINITY;
+    for (int r = 0; r < CL; ++r) M = fmaxf(M, cluster.map_shared_rank(&s.m_loc[0], r)[d]);
+    float L = 0.f, a = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float w = __expf(cluster.map_shared_rank(&s.m_loc[0], r)[d] - M);
+      L = fmaf(cluster.map_shared_rank(&s.l_loc[0], r)[d], w, L);
+      a = fmaf(cluster.map_shared_rank(&s.ctx_loc[0][0], r)[i], w, a);
+    }
+    const float c = a / L;
+    s.ctx[d][e] = c;
+    if (rank == 0) {
+      ctx_out[(int64_t)bh * DH * DH + i] = c;
+      if (e == 0) {
+        kstat[((int64_t)bh * DH + d) * 2] = M;
+        kstat[((int64_t)bh * DH + d) * 2 + 1] = L;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: out[j, e] = sum_d ctx[d][e] * scale * softmax_d(q[j, :])[d]  for the own pixels
+  {
+    LaRaw<T> rq;
+    auto fetchq = [&](int j0) {
+      if (j0 + pix < p1) rq.load(qbase + (int64_t)(j0 + pix) * ld + part * 8);
+      else rq.zero();
+    };
+    if (p0 < p1) fetchq(p0);
+    const int pp = tid >> 3, eo = (tid & 7) * 4;
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+      float v[8];
+      rq.unpack(v);
+      if (j0 + LA_CHUNK < p1) fetchq(j0 + LA_CHUNK);
+      softmax32_quad(v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s.P[pix][part * 8 + i] = v[i] * kScale;
+      __syncthreads();
+      float a0[4] = {}, a1[4] = {};
+#pragma unroll 8
+      for (int d = 0; d < DH; ++d) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&s.ctx[d][eo]);
+        const float q0 = s.P[2 * pp][d], q1 = s.P[2 * pp + 1][d];
+        a0[0] = fmaf(c4.x, q0, a0[0]); a0[1] = fmaf(c4.y, q0, a0[1]);
+        a0[2] = fmaf(c4.z, q0, a0[2]); a0[3] = fmaf(c4.w, q0, a0[3]);
+        a1[0] = fmaf(c4.x, q1, a1[0]); a1[1] = fmaf(c4.y, q1, a1[1]);
+        a1[2] = fmaf(c4.z, q1, a1[2]); a1[3] = fmaf(c4.w, q1, a1[3]);
+      }
+      if (j0 + 2 * pp < p1) st4(out + ((int64_t)b * n + j0 + 2 * pp) * out_ld + h * DH + eo, a0);
+      if (j0 + 2 * pp + 1 < p1) st4(out + ((int64_t)b * n + j0 + 2 * pp + 1) * out_ld + h * DH + eo, a1);
+      __syncthreads();
+    }
+  }
+  cluster.sync();     // peers may still be reading this CTA's partials
+}
+
+struct LaBwdSmem {
+  float CT[DH][DH];            // ctx transposed: CT[e][d]
+  float A[LA_CHUNK][DH];       // softmax(q) in phase 1, softmax_n(k) in phase 2
+  float Bm[LA_CHUNK][DH];      // dout in phase 1, v in phase 2
+  float red[4][DH][DH];
+  float dctx_loc[DH][DH];      // this CTA's partial d(context)   (read by the cluster peers)
+  float D[DH][DH];             // merged dctx[d][e]
+  float DT[DH][DH];            // merged dctx^T
+  float Dd[DH], kmx[DH], kinv[DH];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+linattn_bwd_cluster_kernel(const T* __restrict__ dout, int dout_ld, const T* __restrict__ qkv, int ld,
+                           const float* __restrict__ mem_kv, const float* __restrict__ ctx,
+                           const float* __restrict__ kstat, T* __restrict__ dqkv, int dld,
+                           float* __restrict__ dmem_kv, int n) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
+  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char la_smem_raw[];
+  LaBwdSmem& s = *reinterpret_cast<LaBwdSmem*>(la_smem_raw);
+  const T* qbase = qkv + (int64_t)b * n * ld + h * DH;
+  const T* kbase = qbase + HID;
+  const T* vbase = qbase + 2 * HID;
+  const T* gbase = dout + (int64_t)b * n * dout_ld + h * DH;
+  T* dqbase = dqkv + (int64_t)b * n * dld + h * DH;
+  const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  const int cpr = (chunks + CL - 1) / CL;
+  const int p0 = min(rank * cpr * LA_CHUNK, n), p1 = min((rank + 1) * cpr * LA_CHUNK, n);
+  for (int i = tid; i < DH * DH; i += 256) s.CT[i & 31][i >> 5] = ctx[(int64_t)bh * DH * DH + i];
+  if (tid < DH) {
+    s.kmx[tid] = kstat[((int64_t)bh * DH + tid) * 2];
+    s.kinv[tid] = 1.f / kstat[((int64_t)bh * DH + tid) * 2 + 1];
+  }
+  const int pix = tid >> 2, part = tid & 3;
+  const int grp = tid >> 6, tt = tid & 63;
+  const int d0 = (tt >> 3) * 4, e0 = (tt & 7) * 4;
+  const int pp = tid >> 3, c4 = (tid & 7) * 4;          // pixel pair, 4 channels
+  // ---- phase 1: dq for the own pixels, partial dctx[d][e] = sum_j scale*softmax(q)[j,d]*dout[j,e]
+  {
+    float acc[4][4] = {};
+    LaRaw<T> rq, rg;
+    auto fetch = [&](int j0) {
+      if (j0 + pix < p1) {
+        rq.load(qbase + (int64_t)(j0 + pix) * ld + part * 8);
+        rg.load(gbase + (int64_t)(j0 + pix) * dout_ld + part * 8);
+      } else {
+        rq.zero();
+        rg.zero();
+      }
+    };
+    if (p0 < p1) fetch(p0);
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+      float v[8], g[8];
+      rq.unpack(v);
+      rg.unpack(g);
+      if (j0 + LA_CHUNK < p1) fetch(j0 + LA_CHUNK);
+      softmax32_quad(v);
+      const bool ok = j0 + pix < p1;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s.A[pix][part * 8 + i] = ok ? v[i] : 0.f;
+        s.Bm[pix][part * 8 + i] = g[i];
+      }
+      __syncthreads();
+      // dqs[pixel][d] = sum_e ctx[d][e] * dout[pixel][e]; two pixels x four d per thread
+      float s0[4] = {}, s1[4] = {};
+#pragma unroll 8
+      for (int e = 0; e < DH; ++e) {
+        const float4 cc = *reinterpret_cast<const float4*>(&s.CT[e][c4]);
+        const float g0 = s.Bm[2 * pp][e], g1 = s.Bm[2 * pp + 1][e];
+        s0[0] = fmaf(cc.x, g0, s0[0]); s0[1] = fmaf(cc.y, g0, s0[1]);
+        s0[2] = fmaf(cc.z, g0, s0[2]); s0[3] = fmaf(cc.w, g0, s0[3]);
+        s1[0] = fmaf(cc.x, g1, s1[0]); s1[1] = fmaf(cc.y, g1, s1[1]);
+        s1[2] = fmaf(cc.z, g1, s1[2]); s1[3] = fmaf(cc.w, g1, s1[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float* sr = r ? s1 : s0;
+        const float4 p4 = *reinterpret_cast<const float4*>(&s.A[2 * pp + r][c4]);
+        const float pa[4] = {p4.x, p4.y, p4.z, p4.w};
+        float t = pa[0] * sr[0] + pa[1] * sr[1] + pa[2] * sr[2] + pa[3] * sr[3];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);   // the 8 lanes of a pixel pair cover the 32 d's
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+        const int j = j0 + 2 * pp + r;
+        if (j < p1) {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = kScale * pa[i] * (sr[i] - t);
+          st4(dqbase + (int64_t)j * dld + c4, o);
+        }
+      }
+#pragma unroll 4
+      for (int jj = grp * 16; jj < grp * 16 + 16; ++jj) {
+        const float4 p4 = *reinterpret_cast<const float4*>(&s.A[jj][d0]);
+        const float4 v4 = *reinterpret_cast<const float4*>(&s.Bm[jj][e0]);
+        const float pa[4] = {p4.x, p4.y, p4.z, p4.w}, va[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(pa[i], va[k], acc[i][k]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(&s.red[grp][d0 + i][e0]) =
+          make_float4(acc[i][0] * kScale, acc[i][1] * kScale, acc[i][2] * kScale, acc[i][3] * kScale);
+    __syncthreads();
+    for (int i = tid; i < DH * DH; i += 256) {
+      const int d = i >> 5, e = i & 31;
+      s.dctx_loc[d][e] = s.red[0][d][e] + s.red[1][d][e] + s.red[2][d][e] + s.red[3][d][e];
+    }
+  }
+  cluster.sync();
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float a = 0.f;
+    for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(&s.dctx_loc[0][0], r)[i];
+    s.D[d][e] = a;
+    s.DT[e][d] = a;
+    s.red[0][d][e] = a * s.CT[e][d];                    // dctx[d][e]*ctx[d][e]
+  }
+  __syncthreads();
+  if (tid < DH) {
+    float a = 0.f;
+    for (int e = 0; e < DH; ++e) a += s.red[0][tid][(e + tid) & 31];
+    s.Dd[tid] = a;
+  }
+  // ---- phase 2: dk, dv for the own pixels (+ the memory keys on rank 0)
+  {
+    const int lead = rank == 0 ? NMEM : 0;
+    const int total = (p1 - p0) + lead;
+    LaRaw<T> rk, rv;
+    auto fetch = [&](int c0) {
+      const int j = c0 + pix - lead;
+      if (j >= 0 && j < p1 - p0) {
+        rk.load(kbase + (int64_t)(p0 + j) * ld + part * 8);
+        rv.load(vbase + (int64_t)(p0 + j) * ld + part * 8);
+      } else {
+        rk.zero();
+        rv.zero();
+      }
+    };
+    if (total > 0) fetch(0);
+    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+      float kv[8], vv[8];
+      rk.unpack(kv);
+      rv.unpack(vv);
+      const int jl = c0 + pix;
+      if (jl < lead) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kv[i] = mem_kv[((0 * HEADS + h) * DH + part * 8 + i) * NMEM + jl];
+          vv[i] = mem_kv[((1 * HEADS + h) * DH + part * 8 + i) * NMEM + jl];
+        }
+      }
+      if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);
+      const bool ok = jl < total;
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int d = part * 8 + i;
+        s.A[pix][d] = ok ? __expf(kv[i] - s.kmx[d]) * s.kinv[d] : 0.f;
+        s.Bm[pix][d] = ok ? vv[i] : 0.f;
+      }
+      __syncthreads();
+      float dv0[4] = {}, dv1[4] = {}, dk0[4] = {}, dk1[4] = {};
+#pragma unroll 8
+      for (int k = 0; k < DH; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&s.D[k][c4]);    // dctx[d=k][e..]
+        const float4 b4 = *reinterpret_cast<const float4*>(&s.DT[k][c4]);   // dctx[d..][e=k]
+        const float ks0 = s.A[2 * pp][k], ks1 = s.A[2 * pp + 1][k];
+        const float v0 = s.Bm[2 * pp][k], v1 = s.Bm[2 * pp + 1][k];
+        dv0[0] = fmaf(a4.x, ks0, dv0[0]); dv0[1] = fmaf(a4.y, ks0, dv0[1]);
+        dv0[2] = fmaf(a4.z, ks0, dv0[2]); dv0[3] = fmaf(a4.w, ks0, dv0[3]);
+        dv1[0] = fmaf(a4.x, ks1, dv1[0]); dv1[1] = fmaf(a4.y, ks1, dv1[1]);
+        dv1[2] = fmaf(a4.z, ks1, dv1[2]); dv1[3] = fmaf(a4.w, ks1, dv1[3]);
+        dk0[0] = fmaf(b4.x, v0, dk0[0]); dk0[1] = fmaf(b4.y, v0, dk0[1]);
+        dk0[2] = fmaf(b4.z, v0, dk0[2]); dk0[3] = fmaf(b4.w, v0, dk0[3]);
+        dk1[0] = fmaf(b4.x, v1, dk1[0]); dk1[1] = fmaf(b4.y, v1, dk1[1]);
+        dk1[2] = fmaf(b4.z, v1, dk1[2]); dk1[3] = fmaf(b4.w, v1, dk1[3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int jr = c0 + 2 * pp + r;                 // local index
+        if (jr >= total) continue;
+        const float* dks = r ? dk1 : dk0;
+        const float* dv = r ? dv1 : dv0;
+        float dk[4], dvv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dk[i] = s.A[2 * pp + r][c4 + i] * (dks[i] - s.Dd[c4 + i]);
+          dvv[i] = dv[i];
+        }
+        if (jr < lead) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            atomicAdd(dmem_kv + ((0 * HEADS + h) * DH + c4 + i) * NMEM + jr, dk[i]);
+            atomicAdd(dmem_kv + ((1 * HEADS + h) * DH + c4 + i) * NMEM + jr, dvv[i]);
+          }
+        } else {
+          T* o = dqbase + (int64_t)(p0 + jr - lead) * dld + c4;
+          st4(o + HID, dk);
+          st4(o + 2 * HID, dvv);
+        }
+      }
+    }
+  }
+  cluster.sync();
+}
+
+// =====================================================================================================
+// bf16 path: the same cluster algorithm with the four 32-wide contractions on tensor cores
+// (mma.sync.m16n8k16, bf16 operands staged in shared memory, fp32 accumulation).  The fp32 SIMT version
+// above issues ~400 instructions per thread per 64-pixel chunk and is instruction-bound; this version is
+// HBM-bound.  (tcgen05 needs M >= 64 per instruction; the per-head problems are 32x32xn, so the warp-level
+// MMA is the fitting tensor instruction here — <1% of the network's FLOPs.)
+// Operand rounding to bf16 matches the reference's autocast einsum (ddpm.py:232-237 under bf16-mixed).
+// =====================================================================================================
+constexpr int LP = 40;   // row pitch (bf16 elements) of the staged operand tiles: 80 B -> conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+typedef __nv_bfloat16 lbf;
+
+// acc[32 x 32 tile of this warp: rows mt*16.., cols nt*8..] += A^T B over the 64 staged rows.
+//   A, B: [64][LP] bf16 (row = pixel).  warp w: mt = w >> 2, nt = w & 3.
+__device__ __forceinline__ void mma_atb(const lbf* A, const lbf* B, float (&acc)[4], int warp, int lane) {
+  const int mt = warp >> 2, nt = warp & 3;
+  const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4], b[2];
+    ldsm_x4_t(a, (uint32_t)__cvta_generic_to_shared(A + (ks * 16 + (mi >> 1) * 8 + r) * LP + mt * 16 + (mi & 1) * 8));
+    ldsm_x2_t(b, (uint32_t)__cvta_generic_to_shared(B + (ks * 16 + (mi & 1) * 8 + r) * LP + nt * 8));
+    mma_bf16_16816(acc, a, b);
+  }
+}
+// acc[j][n] = sum_k X[j][k] * W(k, n) for 64 rows j, 32 k, 32 n.  warp w: rows (w >> 1)*16.., n-tiles
+// (w & 1)*2 + {0,1}.  W_KN = true: W stored [k][LP] (row = k); false: W stored [n][LP] (row = n).
+template <bool W_KN>
+__device__ __forceinline__ void mma_xw(const lbf* X, const lbf* W, float (&acc)[2][4], int warp, int lane) {
+  const int mt = warp >> 1, nt0 = (warp & 1) * 2;
+  const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, (uint32_t)__cvta_generic_to_shared(X + (mt * 16 + (mi & 1) * 8 + r) * LP + ks * 16 + (mi >> 1) * 8));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      uint32_t b[2];
+      const int n0 = (nt0 + t) * 8;
+      if (W_KN) ldsm_x2_t(b, (uint32_t)__cvta_generic_to_shared(W + (ks * 16 + (mi & 1) * 8 + r) * LP + n0));
+      else ldsm_x2(b, (uint32_t)__cvta_generic_to_shared(W + (n0 + r) * LP + ks * 16 + (mi & 1) * 8));
+      mma_bf16_16816(acc[t], a, b);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+struct LaFwdTc {
+  lbf Kb[LA_CHUNK][LP];        // exp(k - m_loc) / scale*softmax(q) in the output phase
+  lbf Vb[LA_CHUNK][LP];        // v / output staging in the output phase
+  lbf Cb[DH][LP];              // merged context, bf16, [d][e]
+  float mred[LA_CHUNK][DH];    // reduction scratch (max, exp sums)
+  float ctx_loc[DH][DH];       // partial context (read by the cluster peers)
+  float m_loc[DH], l_loc[DH];
+};
+
+__global__ void __launch_bounds__(256)
+linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
+                      float* __restrict__ ctx_out, float* __restrict__ kstat, lbf* __restrict__ out,
+                      int out_ld, int n) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  __shared__ __align__(16) LaFwdTc s;
+  const lbf* qbase = qkv + (int64_t)b * n * ld + h * DH;
+  const lbf* kbase = qbase + HID;
+  const lbf* vbase = qbase + 2 * HID;
+  const float* mk = mem_kv + (0 * HEADS + h) * DH * NMEM;  // [d][m]
+  const float* mv = mem_kv + (1 * HEADS + h) * DH * NMEM;  // [e][m]
+  const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  const int cpr = (chunks + CL - 1) / CL;
+  const int p0 = min(rank * cpr * LA_CHUNK, n), p1 = min((rank + 1) * cpr * LA_CHUNK, n);
+  const int pix = tid >> 2, part = tid & 3;
+  // ---- phase 1a: local max of k
+  {
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int j = p0 + pix; j < p1; j += 4 * LA_CHUNK) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u * LA_CHUNK < p1) raw[u] = *reinterpret_cast<const uint4*>(kbase + (int64_t)(j + u * LA_CHUNK) * ld + part * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j + u * LA_CHUNK < p1) {
+          float v[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.mred[pix][part * 8 + i] = m[i];
+    __syncthreads();
+    if (tid < DH) {
+      float mm = -INFINITY;
+      for (int i = 0; i < LA_CHUNK; ++i) mm = fmaxf(mm, s.mred[i][tid]);
+      if (rank == 0)
+        for (int i = 0; i < NMEM; ++i) mm = fmaxf(mm, mk[tid * NMEM + i]);
+      s.m_loc[tid] = mm;
+    }
+    __syncthreads();
+  }
+  // ---- phase 1b: partial context on tensor cores
+  {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, psum[8] = {};
+    const int lead = rank == 0 ? NMEM : 0;
+    const int total = (p1 - p0) + lead;
+    float mloc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mloc[i] = s.m_loc[part * 8 + i];
+    uint4 rk = make_uint4(0, 0, 0, 0), rv = rk;
+    auto fetch = [&](int c0) {
+      const int j = c0 + pix - lead;
+      if (j >= 0 && j < p1 - p0) {
+        rk = *reinterpret_cast<const uint4*>(kbase + (int64_t)(p0 + j) * ld + part * 8);
+        rv = *reinterpret_cast<const uint4*>(vbase + (int64_t)(p0 + j) * ld + part * 8);
+      } else {
+        rk = make_uint4(0, 0, 0, 0);
+        rv = rk;
+      }
+    };
+    if (total > 0) fetch(0);
+    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+      float kv[8];
+      unpack8(rk, kv);
+      uint4 vraw = rv;
+      const int jl = c0 + pix;
+      if (jl < lead) {
+        float vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kv[i] = mk[(part * 8 + i) * NMEM + jl];
+          vv[i] = mv[(part * 8 + i) * NMEM + jl];
+        }
+        vraw = pack8(vv);
+      }
+      if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);
+      const bool ok = jl < total;
+      float pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = ok ? __expf(kv[i] - mloc[i]) : 0.f;
+      const uint4 praw = pack8(pv);
+      unpack8(praw, pv);                               // sum what the tensor core will see
+#pragma unroll
+      for (int i = 0; i < 8; ++i) psum[i] += pv[i];
+      *reinterpret_cast<uint4*>(&s.Kb[pix][part * 8]) = praw;
+      *reinterpret_cast<uint4*>(&s.Vb[pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      mma_atb(&s.Kb[0][0], &s.Vb[0][0], acc, warp, lane);
+      __syncthreads();
+    }
+    {
+      const int mt = warp >> 2, nt = warp & 3, row = lane >> 2, col = 2 * (lane & 3);
+      s.ctx_loc[mt * 16 + row][nt * 8 + col] = acc[0];
+      s.ctx_loc[mt * 16 + row][nt * 8 + col + 1] = acc[1];
+      s.ctx_loc[mt * 16 + row + 8][nt * 8 + col] = acc[2];
+      s.ctx_loc[mt * 16 + row + 8][nt * 8 + col + 1] = acc[3];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.mred[pix][part * 8 + i] = psum[i];
+    __syncthreads();
+    if (tid < DH) {
+      float a = 0.f;
+      for (int i = 0; i < LA_CHUNK; ++i) a += s.mred[i][tid];
+      s.l_loc[tid] = a;
+    }
+  }
+  cluster.sync();
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float M = -INFINITY;
+    for (int r = 0; r < CL; ++r) M = fmaxf(M, cluster.map_shared_rank(&s.m_loc[0], r)[d]);
+    float Lsum = 0.f, a = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float w = __expf(cluster.map_shared_rank(&s.m_loc[0], r)[d] - M);
+      Lsum = fmaf(cluster.map_shared_rank(&s.l_loc[0], r)[d], w, Lsum);
+      a = fmaf(cluster.map_shared_rank(&s.ctx_loc[0][0], r)[i], w, a);
+    }
+    const float c = a / Lsum;
+    s.Cb[d][e] = __float2bfloat16_rn(c);
+    if (rank == 0) {
+      ctx_out[(int64_t)bh * DH * DH + i] = c;
+      if (e == 0) {
+        kstat[((int64_t)bh * DH + d) * 2] = M;
+        kstat[((int64_t)bh * DH + d) * 2 + 1] = Lsum;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: out = (scale * softmax_d(q)) @ ctx for the own pixels
+  {
+    uint4 rq = make_uint4(0, 0, 0, 0);
+    auto fetchq = [&](int j0) {
+      if (j0 + pix < p1) rq = *reinterpret_cast<const uint4*>(qbase + (int64_t)(j0 + pix) * ld + part * 8);
+      else rq = make_uint4(0, 0, 0, 0);
+    };
+    if (p0 < p1) fetchq(p0);
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+      float v[8];
+      unpack8(rq, v);
+      if (j0 + LA_CHUNK < p1) fetchq(j0 + LA_CHUNK);
+      softmax32_quad(v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= kScale;
+      *reinterpret_cast<uint4*>(&s.Kb[pix][part * 8]) = pack8(v);
+      __syncthreads();
+      float acc[2][4] = {};
+      mma_xw<true>(&s.Kb[0][0], &s.Cb[0][0], acc, warp, lane);
+      {
+        const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[mt * 16 + row][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][0], acc[t][1]);
+          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[mt * 16 + row + 8][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][2], acc[t][3]);
+        }
+      }
+      __syncthreads();
+      if (j0 + pix < p1)
+        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + j0 + pix) * out_ld + h * DH + part * 8) =
+            *reinterpret_cast<const uint4*>(&s.Vb[pix][part * 8]);
+    }
+  }
+  cluster.sync();
+}
+
+struct LaBwdTc {
+  lbf Ab[LA_CHUNK][LP];        // softmax(q) (phase 1) / softmax_n(k) (phase 2)
+  lbf Bb[LA_CHUNK][LP];        // dout (phase 1) / v (phase 2)
+  lbf Cb[DH][LP];              // ctx, bf16, [d][e]
+  lbf Db[DH][LP];              // merged dctx, bf16, [d][e]
+  lbf Ob[LA_CHUNK][LP];        // dv staging
+  float F[LA_CHUNK][DH + 1];   // fp32 product staging (dqs / dks)
+  float dctx_loc[DH][DH];      // partial dctx (read by the cluster peers)
+  float D[DH][DH];             // merged dctx * ctx scratch
+  float Dd[DH], kmx[DH], kinv[DH];
+};
+
+__global__ void __launch_bounds__(256)
+linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __restrict__ qkv, int ld,
+                      const float* __restrict__ mem_kv, const float* __restrict__ ctx,
+                      const float* __restrict__ kstat, lbf* __restrict__ dqkv, int dld,
+                      float* __restrict__ dmem_kv, int n) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  extern __shared__ __align__(16) unsigned char la_smem_raw[];
+  LaBwdTc& s = *reinterpret_cast<LaBwdTc*>(la_smem_raw);
+  const lbf* qbase = qkv + (int64_t)b * n * ld + h * DH;
+  const lbf* kbase = qbase + HID;
+  const lbf* vbase = qbase + 2 * HID;
+  const lbf* gbase = dout + (int64_t)b * n * dout_ld + h * DH;
+  lbf* dqbase = dqkv + (int64_t)b * n * dld + h * DH;
+  const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  const int cpr = (chunks + CL - 1) / CL;
+  const int p0 = min(rank * cpr * LA_CHUNK, n), p1 = min((rank + 1) * cpr * LA_CHUNK, n);
+  for (int i = tid; i < DH * DH; i += 256) s.Cb[i >> 5][i & 31] = __float2bfloat16_rn(ctx[(int64_t)bh * DH * DH + i]);
+  if (tid < DH) {
+    s.kmx[tid] = kstat[((int64_t)bh * DH + tid) * 2];
+    s.kinv[tid] = 1.f / kstat[((int64_t)bh * DH + tid) * 2 + 1];
+  }
+  const int pix = tid >> 2, part = tid & 3;
+  // ---- phase 1: dq for the own pixels; partial dctx = P^T dout
+  {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 rq = make_uint4(0, 0, 0, 0), rg = rq;
+    auto fetch = [&](int j0) {
+      if (j0 + pix < p1) {
+        rq = *reinterpret_cast<const uint4*>(qbase + (int64_t)(j0 + pix) * ld + part * 8);
+        rg = *reinterpret_cast<const uint4*>(gbase + (int64_t)(j0 + pix) * dout_ld + part * 8);
+      } else {
+        rq = make_uint4(0, 0, 0, 0);
+        rg = rq;
+      }
+    };
+    if (p0 < p1) fetch(p0);
+    __syncthreads();
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+      float pv[8];
+      unpack8(rq, pv);
+      const uint4 graw = rg;
+      const bool ok = j0 + pix < p1;
+      if (j0 + LA_CHUNK < p1) fetch(j0 + LA_CHUNK);
+      softmax32_quad(pv);
+      if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pv[i] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(&s.Ab[pix][part * 8]) = pack8(pv);
+      *reinterpret_cast<uint4*>(&s.Bb[pix][part * 8]) = graw;
+      __syncthreads();
+      // dqs[j][d] = sum_e dout[j][e] * ctx[d][e]   (W stored [n = d][k = e])
+      float dqs[2][4] = {};
+      mma_xw<false>(&s.Bb[0][0], &s.Cb[0][0], dqs, warp, lane);
+      {
+        const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          s.F[mt * 16 + row][(nt0 + t) * 8 + col] = dqs[t][0];
+          s.F[mt * 16 + row][(nt0 + t) * 8 + col + 1] = dqs[t][1];
+          s.F[mt * 16 + row + 8][(nt0 + t) * 8 + col] = dqs[t][2];
+          s.F[mt * 16 + row + 8][(nt0 + t) * 8 + col + 1] = dqs[t][3];
+        }
+      }
+      mma_atb(&s.Ab[0][0], &s.Bb[0][0], acc, warp, lane);     // dctx += P^T dout
+      __syncthreads();
+      {
+        float t = 0.f, dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dv[i] = s.F[pix][part * 8 + i];
+          t = fmaf(pv[i], dv[i], t);
+        }
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = kScale * pv[i] * (dv[i] - t);
+        if (ok) *reinterpret_cast<uint4*>(dqbase + (int64_t)(j0 + pix) * dld + part * 8) = pack8(dv);
+      }
+      __syncthreads();
+    }
+    {
+      const int mt = warp >> 2, nt = warp & 3, row = lane >> 2, col = 2 * (lane & 3);
+      s.dctx_loc[mt * 16 + row][nt * 8 + col] = acc[0] * kScale;
+      s.dctx_loc[mt * 16 + row][nt * 8 + col + 1] = acc[1] * kScale;
+      s.dctx_loc[mt * 16 + row + 8][nt * 8 + col] = acc[2] * kScale;
+      s.dctx_loc[mt * 16 + row + 8][nt * 8 + col + 1] = acc[3] * kScale;
+    }
+  }
+  cluster.sync();
+  for (int i = tid; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float a = 0.f;
+    for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(&s.dctx_loc[0][0], r)[i];
+    s.Db[d][e] = __float2bfloat16_rn(a);
+    s.D[d][e] = a * ctx[(int64_t)bh * DH * DH + i];          // dctx[d][e]*ctx[d][e]
+  }
+  __syncthreads();
+  if (tid < DH) {
+    float a = 0.f;
+    for (int e = 0; e < DH; ++e) a += s.D[tid][(e + tid) & 31];
+    s.Dd[tid] = a;
+  }
+  __syncthreads();
+  // ---- phase 2: dk, dv for the own pixels (+ the memory keys on rank 0)
+  {
+    const int lead = rank == 0 ? NMEM : 0;
+    const int total = (p1 - p0) + lead;
+    float kmx[8], kinv[8], Dd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      kmx[i] = s.kmx[part * 8 + i];
+      kinv[i] = s.kinv[part * 8 + i];
+      Dd[i] = s.Dd[part * 8 + i];
+    }
+    uint4 rk = make_uint4(0, 0, 0, 0), rv = rk;
+    auto fetch = [&](int c0) {
+      const int j = c0 + pix - lead;
+      if (j >= 0 && j < p1 - p0) {
+        rk = *reinterpret_cast<const uint4*>(kbase + (int64_t)(p0 + j) * ld + part * 8);
+        rv = *reinterpret_cast<const uint4*>(vbase + (int64_t)(p0 + j) * ld + part * 8);
+      } else {
+        rk = make_uint4(0, 0, 0, 0);
+        rv = rk;
+      }
+    };
+    if (total > 0) fetch(0);
+    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+      float ks[8];
+      unpack8(rk, ks);
+      uint4 vraw = rv;
+      const int jl = c0 + pix;
+      if (jl < lead) {
+        float vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ks[i] = mem_kv[((0 * HEADS + h) * DH + part * 8 + i) * NMEM + jl];
+          vv[i] = mem_kv[((1 * HEADS + h) * DH + part * 8 + i) * NMEM + jl];
+        }
+        vraw = pack8(vv);
+      }
+      if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);
+      const bool ok = jl < total;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ks[i] = ok ? __expf(ks[i] - kmx[i]) * kinv[i] : 0.f;
+      *reinterpret_cast<uint4*>(&s.Ab[pix][part * 8]) = pack8(ks);
+      *reinterpret_cast<uint4*>(&s.Bb[pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      float dvv[2][4] = {}, dks[2][4] = {};
+      mma_xw<true>(&s.Ab[0][0], &s.Db[0][0], dvv, warp, lane);    // dv[j][e] = sum_d ks[j][d] dctx[d][e]
+      mma_xw<false>(&s.Bb[0][0], &s.Db[0][0], dks, warp, lane);   // dks[j][d] = sum_e v[j][e] dctx[d][e]
+      {
+        const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int c = (nt0 + t) * 8 + col;
+          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[mt * 16 + row][c]) = __floats2bfloat162_rn(dvv[t][0], dvv[t][1]);
+          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[mt * 16 + row + 8][c]) = __floats2bfloat162_rn(dvv[t][2], dvv[t][3]);
+          s.F[mt * 16 + row][c] = dks[t][0];
+          s.F[mt * 16 + row][c + 1] = dks[t][1];
+          s.F[mt * 16 + row + 8][c] = dks[t][2];
+          s.F[mt * 16 + row + 8][c + 1] = dks[t][3];
+        }
+      }
+      __syncthreads();
+      if (ok) {
+        float dk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dk[i] = ks[i] * (s.F[pix][part * 8 + i] - Dd[i]);
+        if (jl < lead) {
+          float dvf[8];
+          unpack8(*reinterpret_cast<const uint4*>(&s.Ob[pix][part * 8]), dvf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            atomicAdd(dmem_kv + ((0 * HEADS + h) * DH + part * 8 + i) * NMEM + jl, dk[i]);
+            atomicAdd(dmem_kv + ((1 * HEADS + h) * DH + part * 8 + i) * NMEM + jl, dvf[i]);
+          }
+        } else {
+          lbf* o = dqbase + (int64_t)(p0 + jl - lead) * dld + part * 8;
+          *reinterpret_cast<uint4*>(o + HID) = pack8(dk);
+          *reinterpret_cast<uint4*>(o + 2 * HID) = *reinterpret_cast<const uint4*>(&s.Ob[pix][part * 8]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  cluster.sync();
+}
+
+// cluster size for n pixels: at most 8 CTAs per (sample, head), at least one 64-pixel chunk each
+static int la_cluster_size(int n) {
+  const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  return chunks >= 8 ? 8 : (chunks < 1 ? 1 : chunks);
+}
+
+template <typename K, typename... Args>
+static cudaError_t la_launch_cluster(K kernel, dim3 grid, int cl, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ================================ full softmax attention (n <= 64) ==================================
 constexpr int FA_MAXN = 64, FA_MAXKV = FA_MAXN + NMEM;
 struct FaSmem {
@@ -535,13 +1479,22 @@ extern "C" int b200dm_linattn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld
   B200DM_REQUIRE(B > 0 && n > 0, B200DM_ERR_SHAPE, "linattn_fwd: empty input");
   cudaStream_t st = (cudaStream_t)stream;
   B200DM_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0, B200DM_ERR_SHAPE, "linattn_fwd: qkv must be 16-byte aligned, ld %% 8 == 0");
-  dim3 g2((n + LA_CHUNK * LA_CPB - 1) / (LA_CHUNK * LA_CPB), B * HEADS);
-  if (dtype == B200DM_F32) {
-    linattn_ctx_kernel<float><<<B * HEADS, 256, 0, st>>>((const float*)qkv, qkv_ld, mem_kv, ctx, kstat, n);
-    linattn_out_kernel<float><<<g2, 256, 0, st>>>((const float*)qkv, qkv_ld, ctx, (float*)out, out_ld, n);
-  } else {
-    linattn_ctx_kernel<bf16><<<B * HEADS, 256, 0, st>>>((const bf16*)qkv, qkv_ld, mem_kv, ctx, kstat, n);
-    linattn_out_kernel<bf16><<<g2, 256, 0, st>>>((const bf16*)qkv, qkv_ld, ctx, (bf16*)out, out_ld, n);
+  {
+    const int cl = la_cluster_size(n);
+    dim3 grid(cl, B * HEADS);
+    cudaError_t e;
+    if (dtype == B200DM_F32) {
+      const size_t smem = sizeof(LaFwdSmem);
+      cudaFuncSetAttribute(linattn_fwd_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = la_launch_cluster(linattn_fwd_cluster_kernel<float>, grid, cl, smem, st, (const float*)qkv, (int)qkv_ld,
+                            mem_kv, ctx, kstat, (float*)out, (int)out_ld, (int)n);
+    } else {
+      e = la_launch_cluster(linattn_fwd_tc_kernel, grid, cl, 0, st, (const bf16*)qkv, (int)qkv_ld, mem_kv, ctx,
+                            kstat, (bf16*)out, (int)out_ld, (int)n);
+    }
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "linattn_fwd: launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return check_launch("linattn_fwd");
   }
   count_launch(2);
   return check_launch("linattn_fwd");
@@ -555,13 +1508,27 @@ extern "C" int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_
   cudaStream_t st = (cudaStream_t)stream;
   B200DM_REQUIRE(qkv_ld % 8 == 0 && dout_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)dout & 15) == 0,
                  B200DM_ERR_SHAPE, "linattn_bwd: tensors must be 16-byte aligned, ld %% 8 == 0");
-  dim3 g2((n + NMEM + LA_CHUNK * LA_CPB - 1) / (LA_CHUNK * LA_CPB), B * HEADS);
-  if (dtype == B200DM_F32) {
-    linattn_bwd_q_kernel<float><<<B * HEADS, 256, 0, st>>>((const float*)dout, dout_ld, (const float*)qkv, qkv_ld, ctx, dctx, (float*)dqkv, dqkv_ld, n);
-    linattn_bwd_kv_kernel<float><<<g2, 256, 0, st>>>((const float*)qkv, qkv_ld, mem_kv, ctx, kstat, dctx, (float*)dqkv, dqkv_ld, dmem_kv, n);
-  } else {
-    linattn_bwd_q_kernel<bf16><<<B * HEADS, 256, 0, st>>>((const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, ctx, dctx, (bf16*)dqkv, dqkv_ld, n);
-    linattn_bwd_kv_kernel<bf16><<<g2, 256, 0, st>>>((const bf16*)qkv, qkv_ld, mem_kv, ctx, kstat, dctx, (bf16*)dqkv, dqkv_ld, dmem_kv, n);
+  {
+    (void)dctx;
+    const int cl = la_cluster_size(n);
+    dim3 grid(cl, B * HEADS);
+    cudaError_t e;
+    if (dtype == B200DM_F32) {
+      const size_t smem = sizeof(LaBwdSmem);
+      cudaFuncSetAttribute(linattn_bwd_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = la_launch_cluster(linattn_bwd_cluster_kernel<float>, grid, cl, smem, st, (const float*)dout, (int)dout_ld,
+                            (const float*)qkv, (int)qkv_ld, mem_kv, ctx, kstat, (float*)dqkv, (int)dqkv_ld, dmem_kv,
+                            (int)n);
+    } else {
+      const size_t smem = sizeof(LaBwdTc);
+      cudaFuncSetAttribute(linattn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = la_launch_cluster(linattn_bwd_tc_kernel, grid, cl, smem, st, (const bf16*)dout, (int)dout_ld,
+                            (const bf16*)qkv, (int)qkv_ld, mem_kv, ctx, kstat, (bf16*)dqkv, (int)dqkv_ld, dmem_kv,
+                            (int)n);
+    }
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "linattn_bwd: launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return check_launch("linattn_bwd");
   }
   count_launch(2);
   return check_launch("linattn_bwd");

@@ -154,34 +154,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+    // ===================== MMA issuer =====================
+    // warp-uniform loop, one elected lane issues; descriptor = per-stage base + compile-time k offset
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+    // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart; +32 B per 16-element K step
+    const uint64_t a_desc0 = make_smem_desc(base, 16, 1024);
+    const uint64_t b_desc0 = make_smem_desc(base + A_STAGE_BYTES, 16, 1024);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+    const bool leader = elect_one();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = base + stage * STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+        if (leader) {
+          const uint32_t so = (uint32_t)stage * (STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // K-major, SWIZZLE_128B: 8-row groups are 1024 B apart; +32 B per 16-element K step
-            const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_lohi(d_tmem, a_lo0 + so + (uint32_t)((k * 32) >> 4), a_hi,
+                           b_lo0 + so + (uint32_t)((k * 32) >> 4), b_hi, idesc, (k > 0) ? 1u : (kb > 0 ? 1u : 0u));
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full_bar(acc));  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(tmem_full_bar(acc));  // accumulator complete
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -310,7 +313,7 @@ struct TcHaloParams {
   const __nv_bfloat16* res;
   int res_ld;
   const float* bias;
-  int bo_mode;                 // debug: 1 = base_offset = dx (documented), 0 = always 0
+  int dbg;                     // B200DM_HALO_DEBUG bit 0: skip epilogue stores, 1: skip A loads, 2: skip MMAs
 };
 
 template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
@@ -340,7 +343,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* out_stage_ptr = smem_raw + (out_stage - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  if (p.dbg & 8) return;
+  const int num_tiles = (p.dbg & 16) ? 0 : p.m_tiles * p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
@@ -362,7 +366,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (B_RESIDENT) {   // the whole [9][N_TILE][Cin] weight, once
+      if (B_RESIDENT && !(p.dbg & 32)) {   // the whole [9][N_TILE][Cin] weight, once
         mbar_expect_tx(bres_bar, (uint32_t)(9 * p.kblocks * B_BYTES));
         for (int tap = 0; tap < 9; ++tap)
           for (int kc = 0; kc < p.kblocks; ++kc)
@@ -376,8 +380,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
         for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(aempty(ab), aph ^ 1u);
-          mbar_expect_tx(afull(ab), HALO_BYTES);
-          tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
+          if (p.dbg & 2) {
+            mbar_arrive(afull(ab));
+          } else {
+            mbar_expect_tx(afull(ab), HALO_BYTES);
+            tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
+          }
           if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
           if (!B_RESIDENT) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -391,51 +399,65 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
-      int ab = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, acc_phase = 0;
-      if (B_RESIDENT) mbar_wait(bres_bar, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+    // ===================== MMA issuer =====================
+    // The whole warp walks the loop (warp-uniform control flow and operands, so ptxas keeps the descriptors in
+    // uniform registers); one elected lane issues.  Descriptors: base (lo, hi) per operand buffer + a
+    // compile-time constant per (tap, k-step) added to the start-address field.
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc(a_base, 16, HALO_W * 128);
+    const uint64_t b_desc0 = make_smem_desc(b_base, 16, 1024);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+    const bool leader = elect_one();
+    int ab = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0;
+    if (B_RESIDENT && !(p.dbg & 32)) mbar_wait(bres_bar, 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      for (int kc = 0; kc < p.kblocks; ++kc) {
+        mbar_wait(afull(ab), aph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
-        for (int kc = 0; kc < p.kblocks; ++kc) {
-          mbar_wait(afull(ab), aph);
-          tc_fence_after();
-          const uint32_t a_buf = a_base + ab * HALO_BYTES;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            uint32_t b_addr;
-            if (B_RESIDENT) {
-              b_addr = b_base + (tap * p.kblocks + kc) * B_BYTES;
-            } else {
-              mbar_wait(bfull(bs), bph);
-              tc_fence_after();
-              b_addr = b_base + bs * B_BYTES;
-            }
-            // tap window: rows (tx + dx) + 16*(ty + dy) of the halo buffer; 8-row groups = image rows
-            const uint32_t a_start = a_buf + (uint32_t)(dx + HALO_W * dy) * 128u;
+        const uint32_t a_lo = a_lo0 + (uint32_t)ab * (HALO_BYTES >> 4);
+        if (B_RESIDENT) {
+          if (leader && !(p.dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_start + k * 32, 16, HALO_W * 128, p.bo_mode ? (uint32_t)dx : 0u);
-              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(d_tmem, da, db, idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
-            if (!B_RESIDENT) {
-              umma_commit(bempty(bs));
-              if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const uint32_t b_lo = b_lo0 + (uint32_t)(tap * p.kblocks + kc) * (B_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4), a_hi,
+                               b_lo + (uint32_t)((k * 32) >> 4), b_hi, idesc,
+                               (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
             }
           }
-          umma_commit(aempty(ab));
-          if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            // tap window: rows (tx + dx) + 16*(ty + dy) of the halo buffer; 8-row groups = image rows
+            const int dy = tap / 3, dx = tap - dy * 3;
+            mbar_wait(bfull(bs), bph);
+            tc_fence_after();
+            const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_BYTES >> 4);
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k)
+                umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4), a_hi,
+                               b_lo + (uint32_t)((k * 32) >> 4), b_hi, idesc,
+                               (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
+              umma_commit(bempty(bs));
+            }
+            if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+          }
         }
-        umma_commit(tmem_full_bar(acc));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (leader) umma_commit(aempty(ab));
+        if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
       }
+      if (leader) umma_commit(tmem_full_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
@@ -464,6 +486,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
+        if (p.dbg & 1) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -637,10 +660,9 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
   {
     // MEASURED on B200 (scripts/halo_debug.py): the tensor core derives the 128-B swizzle phase from the
     // absolute shared-memory address bits [7,10), exactly like the TMA unit that wrote the tile, so a
-    // window that starts at an arbitrary 128-B row needs base_offset = 0.  Setting the "documented"
-    // (start >> 7) & 7 corrupts every dx != 0 tap.  B200DM_HALO_BO=1 re-enables it for experiments.
-    const char* e = getenv("B200DM_HALO_BO");
-    p.bo_mode = (e && e[0] == '1') ? 1 : 0;
+    // window that starts at an arbitrary 128-B row needs base_offset = 0 in the UMMA descriptor.
+    const char* e = getenv("B200DM_HALO_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
   }
   const int sms = num_sms();
   int n_tile = 64;
@@ -836,27 +858,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && has_work) {
+    if (has_work) {
       constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 1, 1);
+      // MN-major, SWIZZLE_128B: 16 pixels (K) per MMA = 2 groups of 8 rows, 1024 B apart (SBO);
+      // the next 64-channel slab of M/N lives one box further (LBO)
+      const uint64_t a_desc0 = make_smem_desc(base, BOX_BYTES, 1024);
+      const uint64_t b_desc0 = make_smem_desc(base + 2 * BOX_BYTES, BOX_BYTES, 1024);
+      const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = kt0; kt < kt1; ++kt) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t a_addr = base + stage * STAGE_BYTES;
-        const uint32_t b_addr = a_addr + 2 * BOX_BYTES;
+        if (leader) {
+          const uint32_t so = (uint32_t)stage * (STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < TC_BM / 16; ++k) {
-          // MN-major, SWIZZLE_128B: 16 pixels (K) per MMA = 2 groups of 8 rows, 1024 B apart (SBO);
-          // the next 64-channel slab of M/N lives one box further (LBO)
-          const uint64_t da = make_smem_desc(a_addr + k * 2048, BOX_BYTES, 1024);
-          const uint64_t db = make_smem_desc(b_addr + k * 2048, BOX_BYTES, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < TC_BM / 16; ++k)
+            umma_bf16_lohi(tmem_base, a_lo0 + so + (uint32_t)((k * 2048) >> 4), a_hi,
+                           b_lo0 + so + (uint32_t)((k * 2048) >> 4), b_hi, idesc,
+                           (k > 0) ? 1u : (kt > kt0 ? 1u : 0u));
+          umma_commit(empty_bar(stage));
         }
-        umma_commit(empty_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tmem_full_bar);
+      if (leader) umma_commit(tmem_full_bar);
     }
   } else if (has_work) {
     const int quarter = warp & 3;
@@ -950,3 +977,76 @@ int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
 }
 
 }  // namespace b200dm
+
+// =====================================================================================================
+// Diagnostic: issue rate of tcgen05.mma (M=128, N in {64,128,256}, K=16) on resident shared-memory
+// operands, no TMA, no epilogue — the ceiling the conv kernels' main loops are measured against
+// (scripts/umma_rate.py).  mode 0: K-major SW128 operands as in conv_tc_kernel; mode 1: A window shifted by
+// one 128-B row with a 2048-B group stride as in conv3x3_halo_kernel; mode 2: MN-major as in wgrad.
+// =====================================================================================================
+namespace b200dm {
+template <int N_TILE>
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base, b_base = base + 64 * 1024;     // 64 KiB A region, up to 32 KiB B region
+  const uint32_t bar = b_base + 64 * 1024, tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x * 16; i < 128 * 1024; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)) + i) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = mode == 2 ? make_idesc_bf16(TC_BM, N_TILE, 1, 1) : make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+    const uint64_t a_desc0 = mode == 2 ? make_smem_desc(a_base, 16384, 1024)
+                                       : make_smem_desc(a_base + (mode == 1 ? 128 : 0), 16, mode == 1 ? 2048 : 1024);
+    const uint64_t b_desc0 = mode == 2 ? make_smem_desc(b_base, 16384, 1024) : make_smem_desc(b_base, 16, 1024);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo = (uint32_t)a_desc0, b_lo = (uint32_t)b_desc0;
+    const long long t0 = clock64();
+    if (leader) {
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t off = mode == 2 ? (uint32_t)((k * 2048) >> 4) : (uint32_t)(((k & 3) * 32 + (k >> 2) * 16384) >> 4);
+          umma_bf16_lohi(tmem_base, a_lo + off, a_hi, b_lo + off, b_hi, idesc, (it | k) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (leader && out_cycles) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+}  // namespace b200dm
+
+extern "C" int b200dm_debug_umma_rate(int32_t n_tile, int32_t iters, int32_t mode, int32_t ctas, long long* out_cycles,
+                                      void* stream) {
+  using namespace b200dm;
+  const int smem = 128 * 1024 + 1024 + 64;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_RATE(N)                                                                                       \
+  do {                                                                                                       \
+    cudaFuncSetAttribute(umma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);            \
+    umma_rate_kernel<N><<<ctas, 128, smem, st>>>(iters, mode, out_cycles);                                   \
+  } while (0)
+  if (n_tile == 64) LAUNCH_RATE(64);
+  else if (n_tile == 128) LAUNCH_RATE(128);
+  else if (n_tile == 256) LAUNCH_RATE(256);
+  else { set_error("debug_umma_rate: n_tile must be 64, 128 or 256"); return B200DM_ERR_UNSUPPORTED; }
+#undef LAUNCH_RATE
+  return check_launch("debug_umma_rate");
+}

@@ -1,7 +1,11 @@
 // GroupNorm(8)+FiLM+SiLU(+residual) forward/backward and RMSNorm forward/backward, NHWC.
 // Reference: Block.forward ddpm.py:164-173, ResnetBlock.forward :189-200, RMSNorm :107-113.
 // All statistics and arithmetic in fp32; tensors in the activation dtype.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace b200dm {
 
@@ -265,6 +269,350 @@ gn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x
   }
 }
 
+// =====================================================================================================
+// Cluster-fused GroupNorm: ONE launch per norm in each direction.  A thread-block cluster of CL CTAs owns
+// one sample; every CTA streams its pixel chunk once from HBM for the reductions, the partial sums are
+// exchanged through distributed shared memory (cluster.sync), and the chunk is streamed a second time
+// (L2/L1 hits: it was read microseconds earlier by the same SM) to produce the output.  Replaces the
+// stats -> apply (forward) and reduce -> params -> apply (backward) launch chains.
+//   thread = (8-channel vector cv = tid % C8, pixel lane = tid / C8); all per-channel coefficients are folded
+//   into two registers per channel before the pixel loop, so the loop body has no divisions or lookups.
+// =====================================================================================================
+constexpr int GNC_THREADS = 256;
+constexpr int GNC_MAXC = 512;          // channels handled by the cluster kernels (C8 <= 64 -> >= 4 pixel lanes)
+
+__device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
+// raw 8-element vectors: issue the loads of several pixels first, convert afterwards (memory-level parallelism)
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GNC_THREADS)
+gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
+                      T* __restrict__ y, int y_ld, int HW, int C, int G, float eps, int write_stats) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int C8 = C >> 3, gs8 = C8 / G;                 // 8-wide vectors per group
+  const int lanes = GNC_THREADS / C8;
+  const int cv = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int c0 = cv * 8, g = cv / gs8;
+  const int ppb = (HW + CL - 1) / CL;
+  const int p0 = rank * ppb, p1 = min(p0 + ppb, HW);
+  __shared__ float part[GNC_THREADS][2];
+  __shared__ float gpart[64][2];                       // this CTA's per-group (sum, sumsq): read by the peers
+  __shared__ float gstat[64][2];                       // (mean, rstd) per group
+  const T* xp = x + (int64_t)b * HW * x_ld + c0;
+  // ---- phase 1: per-group sum / sum of squares of the chunk
+  float s = 0.f, ss = 0.f;
+  for (int p = p0 + lane; p < p1; p += 4 * lanes) {
+    Raw8<T> raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u * lanes < p1) raw[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * lanes < p1) {
+        float v[8];
+        raw[u].unpack(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s += v[j];
+          ss = fmaf(v[j], v[j], ss);
+        }
+      }
+    }
+  }
+  part[threadIdx.x][0] = s;
+  part[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < 2 * G) {
+    const int gg = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l)
+      for (int v = 0; v < gs8; ++v) a += part[l * C8 + gg * gs8 + v][k];
+    gpart[gg][k] = a;
+  }
+  cluster.sync();
+  if (threadIdx.x < G) {
+    float a = 0.f, q = 0.f;
+    for (int r = 0; r < CL; ++r) {
+      const float* rp = cluster.map_shared_rank(&gpart[0][0], r);
+      a += rp[threadIdx.x * 2];
+      q += rp[threadIdx.x * 2 + 1];
+    }
+    const float inv = 1.f / ((float)HW * (float)(C / G));
+    const float mean = a * inv;
+    const float var = fmaxf(q * inv - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    gstat[threadIdx.x][0] = mean;
+    gstat[threadIdx.x][1] = rstd;
+    if (rank == 0 && write_stats) {
+      stats[(b * G + threadIdx.x) * 2] = mean;
+      stats[(b * G + threadIdx.x) * 2 + 1] = rstd;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: y = silu(A*x + Bc) (+ res)
+  float A[8], Bc[8];
+  {
+    const float mean = gstat[g][0], rstd = gstat[g][1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ga = gamma[c0 + j] * rstd;
+      float be = beta[c0 + j] - mean * ga;
+      if (film) {
+        const float sc = film[(int64_t)b * film_ld + c0 + j] + 1.f;
+        const float sh = film[(int64_t)b * film_ld + C + c0 + j];
+        ga *= sc;
+        be = be * sc + sh;
+      }
+      A[j] = ga;
+      Bc[j] = be;
+    }
+  }
+  const T* rp = res ? res + (int64_t)b * HW * res_ld + c0 : nullptr;
+  T* yp = y + (int64_t)b * HW * y_ld + c0;
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
+    Raw8<T> rx[2], rr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        float v[8], r[8];
+        rx[u].unpack(v);
+        if (rp) rr[u].unpack(r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(A[j], v[j], Bc[j]);
+          const float o = z * fast_sigmoid(z);
+          v[j] = rp ? o + r[j] : o;
+        }
+        st8(yp + (int64_t)(p + u * lanes) * y_ld, v);
+      }
+    }
+  }
+  cluster.sync();        // peers may still be reading this CTA's gpart
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GNC_THREADS, 3)
+gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
+                      const float* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
+                      T* __restrict__ dx, int dx_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                      float* __restrict__ dfilm, float* __restrict__ dbias, int HW, int C, int G) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int C8 = C >> 3, gs8 = C8 / G, gs = C / G;
+  const int lanes = GNC_THREADS / C8;
+  const int cv = threadIdx.x % C8, lane = threadIdx.x / C8;
+  const int c0 = cv * 8, g = cv / gs8;
+  const int ppb = (HW + CL - 1) / CL;
+  const int p0 = rank * ppb, p1 = min(p0 + ppb, HW);
+  __shared__ float red[GNC_THREADS * 8 * 3];           // [lanes][C][3], 24 KiB
+  __shared__ float cpart[GNC_MAXC * 3];                // this CTA's per-channel (S1, S2, S0): read by the peers
+  __shared__ float ctot[GNC_MAXC * 3];                 // cluster totals
+  __shared__ float gm[64][2];                          // (M1, M2) per group
+  const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+  float A[8], Bc[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float ga = gamma[c0 + j] * rstd;
+    float be = beta[c0 + j] - mean * ga;
+    sc[j] = 1.f;
+    if (film) {
+      sc[j] = film[(int64_t)b * film_ld + c0 + j] + 1.f;
+      const float sh = film[(int64_t)b * film_ld + C + c0 + j];
+      ga *= sc[j];
+      be = be * sc[j] + sh;
+    }
+    A[j] = ga;
+    Bc[j] = be;
+  }
+  const T* xp = x + (int64_t)b * HW * x_ld + c0;
+  const T* gp = dy + (int64_t)b * HW * dy_ld + c0;
+  // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk)
+  float s1[8] = {}, s2[8] = {}, s0[8] = {};
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
+    Raw8<T> rx[2], rg[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        rg[u].load(gp + (int64_t)(p + u * lanes) * dy_ld);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        float xv[8], gv[8];
+        rx[u].unpack(xv);
+        rg[u].unpack(gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(A[j], xv[j], Bc[j]);
+          const float sg = fast_sigmoid(z);
+          const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
+          const float xn = (xv[j] - mean) * rstd;
+          s1[j] += dz;
+          s2[j] = fmaf(dz, xn, s2[j]);
+          s0[j] += xv[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float* r = red + ((lane * C + c0 + j) * 3);
+    r[0] = s1[j];
+    r[1] = s2[j];
+    r[2] = s0[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 3; i += GNC_THREADS) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += red[l * C * 3 + i];
+    cpart[i] = a;
+  }
+  cluster.sync();
+  for (int i = threadIdx.x; i < C * 3; i += GNC_THREADS) {
+    float a = 0.f;
+    for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(&cpart[0], r)[i];
+    ctot[i] = a;
+  }
+  __syncthreads();
+  // group means of a*S1 and a*S2 (a = scale * gamma)
+  if (threadIdx.x < 2 * G) {
+    const int gg = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float a = 0.f;
+    for (int c = gg * gs; c < (gg + 1) * gs; ++c) {
+      const float scl = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+      a += scl * gamma[c] * ctot[c * 3 + k];
+    }
+    gm[gg][k] = a / ((float)gs * (float)HW);
+  }
+  __syncthreads();
+  // parameter gradients (one CTA of the cluster): batch reduction through fp32 atomics
+  if (rank == 0) {
+    for (int c = threadIdx.x; c < C; c += GNC_THREADS) {
+      const int gg = c / gs;
+      const float S1 = ctot[c * 3], S2 = ctot[c * 3 + 1], S0 = ctot[c * 3 + 2];
+      const float ga = gamma[c], be = beta[c];
+      const float scl = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+      if (dfilm) {
+        dfilm[(int64_t)b * film_ld + c] = ga * S2 + be * S1;
+        dfilm[(int64_t)b * film_ld + C + c] = S1;
+      }
+      atomicAdd(dgamma + c, scl * S2);
+      atomicAdd(dbeta + c, scl * S1);
+      if (dbias) {
+        const float mu = stats[(b * G + gg) * 2], rs = stats[(b * G + gg) * 2 + 1];
+        const float sum_xn = (S0 - (float)HW * mu) * rs;
+        atomicAdd(dbias + c, rs * (scl * ga * S1 - (float)HW * gm[gg][0] - gm[gg][1] * sum_xn));
+      }
+    }
+  }
+  // ---- phase 2: dx = P*dz + Q + R*x,  P = rstd*scale*gamma, R = -rstd^2*M2, Q = -rstd*M1 - R*mean
+  const float M1 = gm[g][0], M2 = gm[g][1];
+  const float R = -rstd * rstd * M2, Q = -rstd * M1 - R * mean;
+  float P[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) P[j] = rstd * sc[j] * gamma[c0 + j];
+  T* dp = dx + (int64_t)b * HW * dx_ld + c0;
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
+    Raw8<T> rx[2], rg[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        rg[u].load(gp + (int64_t)(p + u * lanes) * dy_ld);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        float xv[8], gv[8];
+        rx[u].unpack(xv);
+        rg[u].unpack(gv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = fmaf(A[j], xv[j], Bc[j]);
+          const float sg = fast_sigmoid(z);
+          const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
+          xv[j] = fmaf(P[j], dz, fmaf(R, xv[j], Q));
+        }
+        st8(dp + (int64_t)(p + u * lanes) * dx_ld, xv);
+      }
+    }
+  }
+  cluster.sync();
+}
+
+// cluster size: as many CTAs per sample as still fit on the machine in ONE wave (a second, partial wave costs
+// more than the smaller chunks save), each chunk at least two passes of the pixel lanes; any size 1..8.
+static int gn_cluster_size(int B, int HW, int C, int ctas_per_sm) {
+  const int lanes = GNC_THREADS / (C / 8);
+  const long long slots = (long long)num_sms() * ctas_per_sm;
+  int cl = (int)(slots / B);
+  if (cl > 8) cl = 8;
+  while (cl > 1 && HW / cl < 2 * lanes) --cl;
+  return cl < 1 ? 1 : cl;
+}
+static bool gn_cluster_ok(int C, int G) {
+  const int C8 = C / 8;
+  return C <= GNC_MAXC && GNC_THREADS % C8 == 0 && C8 % G == 0 && G <= 64;
+}
+
+template <typename K, typename... Args>
+static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GNC_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- RMSNorm: a row (pixel) is handled by L = min(32, C/8) lanes, 32/L rows per warp; C <= 512 ----------
 constexpr int RMS_MAXV = 2;  // 8-wide vectors per lane (C <= 512)
 
@@ -441,6 +789,37 @@ extern "C" int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, c
   return check_launch("gn_apply_fwd");
 }
 
+extern "C" int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* stats, const float* gamma,
+                             const float* beta, const float* film, int32_t film_ld, const void* res,
+                             int32_t res_ld, void* y, int32_t y_ld, int32_t B, int32_t HW, int32_t C,
+                             int32_t G, float eps, void* stream) {
+  GN_CHECKS("gn_fwd");
+  B200DM_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && (!res || res_ld % 8 == 0), B200DM_ERR_SHAPE,
+                 "gn_fwd: ld must be a multiple of 8");
+  B200DM_REQUIRE(stats != nullptr, B200DM_ERR_SHAPE, "gn_fwd: stats output is required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!gn_cluster_ok(C, G)) {      // shapes outside the cluster kernel: the two-launch path
+    int rc = b200dm_gn_stats(dtype, x, x_ld, stats, B, HW, C, G, eps, stream);
+    if (rc) return rc;
+    return b200dm_gn_apply_fwd(dtype, x, x_ld, stats, gamma, beta, film, film_ld, res, res_ld, y, y_ld, B,
+                               HW, C, G, stream);
+  }
+  const int cl = gn_cluster_size(B, HW, C, 4);
+  dim3 grid(cl, B);
+  cudaError_t e;
+  if (dtype == B200DM_F32)
+    e = launch_cluster(gn_fwd_cluster_kernel<float>, grid, cl, st, (const float*)x, (int)x_ld, stats, gamma,
+                       beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld,
+                       (int)HW, (int)C, (int)G, eps, 1);
+  else
+    e = launch_cluster(gn_fwd_cluster_kernel<bf16>, grid, cl, st, (const bf16*)x, (int)x_ld, stats, gamma,
+                       beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW,
+                       (int)C, (int)G, eps, 1);
+  B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_fwd: launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return check_launch("gn_fwd");
+}
+
 static int gn_bwd_chunks(int B, int HW, int C) {
   const int C8 = C / 8;
   int threads = 256;
@@ -470,6 +849,22 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
                  "gn_apply_bwd: ld must be a multiple of 8");
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
+  if (gn_cluster_ok(C, G)) {
+    const int cl = gn_cluster_size(B, HW, C, 3);
+    dim3 grid(cl, B);
+    cudaError_t e;
+    if (dtype == B200DM_F32)
+      e = launch_cluster(gn_bwd_cluster_kernel<float>, grid, cl, st, (const float*)dy, (int)dy_ld,
+                         (const float*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (float*)dx,
+                         (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
+    else
+      e = launch_cluster(gn_bwd_cluster_kernel<bf16>, grid, cl, st, (const bf16*)dy, (int)dy_ld,
+                         (const bf16*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (bf16*)dx,
+                         (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
+    count_launch();
+    return check_launch("gn_apply_bwd");
+  }
   const int C8 = C / 8;
   int threads = 256;
   if (C8 > threads) threads = C8;  // C <= 2048 -> <= 256 anyway

@@ -124,6 +124,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same MMA with the two shared-memory descriptors given as (lo, hi) 32-bit halves.  Only the start-address
+// field (bits [0,14) of lo, in 16-byte units) changes between the MMAs of a tile, so the issuing thread keeps
+// `hi` and the base `lo` in registers and adds a compile-time constant per MMA: the issue loop is then a few
+// integer instructions per tcgen05.mma instead of a full descriptor rebuild (measured: the rebuild made the
+// single issuing thread, not the tensor pipe, the bottleneck for N=64 tiles, whose MMAs take only 32 cycles).
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -422,6 +422,14 @@ def test_groupnorm_film_silu_fwd_bwd(dtype, B, S, Cc, film, res):
            fptr, 2 * Cc + 6, None if rv is None else rv.ptr, 0 if rv is None else rv.ld, yv.ptr, yv.ld,
            B, S * S, Cc, G)
     assert rel(yv.to_nchw(), ref) < tol(dtype)
+    # one-launch cluster kernel (statistics + apply): same outputs, same statistics
+    stats2 = torch.zeros(B, G, 2, device=DEV)
+    yv2 = View.zeros(B, S, S, Cc, DT[dtype], DEV, ld=2 * Cc, off=Cc)
+    L.call("b200dm_gn_fwd", dtype, xv.ptr, xv.ld, stats2.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+           fptr, 2 * Cc + 6, None if rv is None else rv.ptr, 0 if rv is None else rv.ld, yv2.ptr, yv2.ld,
+           B, S * S, Cc, G, 1e-5)
+    assert rel(stats2, stats) < 2e-5
+    assert rel(yv2.to_nchw(), ref) < tol(dtype)
     # backward
     dy = q(rnd(B, Cc, S, S, seed=86), dtype)
     ref.backward(dy)
@@ -507,7 +515,9 @@ def test_linear_attention_fwd_bwd(dtype, B, S):
     L.call("b200dm_linattn_bwd", dtype, dov.ptr, dov.ld, qv.ptr, qv.ld, mem.data_ptr(), ctx.data_ptr(),
            kstat.data_ptr(), dctx.data_ptr(), dqv.ptr, dqv.ld, dmem.data_ptr(), B, n)
     assert rel(dqv.to_nchw(), qkv.grad) < (1e-4 if dtype == L.F32 else 6e-3)
-    assert rel(dmem, mem.grad) < 1e-4
+    # bf16 mode runs the 32x32 contractions on tensor cores with bf16 operands (as the reference's autocast
+    # einsum does), so the memory-kv gradient carries operand rounding; fp32 mode stays at 1e-4
+    assert rel(dmem, mem.grad) < (1e-4 if dtype == L.F32 else 5e-3)
 
 
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
