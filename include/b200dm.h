@@ -139,6 +139,7 @@ typedef struct {
   int32_t dy_ld;
   float* dw;
   int32_t accumulate;
+  int32_t cin_valid; /* tcgen05 path: columns ci >= cin_valid are padding and are skipped (0 = all Cin) */
   /* element strides of dw: dw[tap*s_tap + co*s_co + ci*s_ci]; all 0 => tap-major packed
    * (s_tap = Cout*Cin, s_co = Cin, s_ci = 1).  The pixel-unshuffle conv keeps the reference layout
    * [Cout][c*4 + tap] (s_tap = 1, s_co = 4*Cin, s_ci = 4). */
@@ -152,6 +153,13 @@ int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t rows, int32_
                   int32_t accumulate, void* stream);
 
 /* init_conv 7x7, pad 3 (ddpm.py:304,437): NCHW fp32 in -> NHWC out; weight OIHW fp32. */
+/* Stem on tensor cores (bf16): P [B*H*W][KP] bf16 = im2col of the 7x7 patches of x (NCHW fp32), columns in the
+ * OIHW order of init_conv.weight, zero-padded to KP (multiple of 64); wp [Cout][KP] bf16 = zero-padded weight
+ * rows.  conv_fwd (mode 0, ksize 1, Cin = KP) over P is then the 7x7 conv and conv_wgrad (cin_valid = C*49,
+ * s_co = C*49) its weight gradient. */
+int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, void* stream);
+int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream);
+
 int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* w, const float* bias, void* y,
                          int32_t y_ld, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Cout,
                          void* stream);

@@ -42,7 +42,7 @@ class WgradDesc(C.Structure):
         ("x", C.c_void_p), ("x_ld", C.c_int32),
         ("dy", C.c_void_p), ("dy_ld", C.c_int32),
         ("dw", C.c_void_p),
-        ("accumulate", C.c_int32),
+        ("accumulate", C.c_int32), ("cin_valid", C.c_int32),
         ("s_tap", C.c_int64), ("s_co", C.c_int64), ("s_ci", C.c_int64),
     ]
 
@@ -69,6 +69,8 @@ PROTOTYPES = {
     "b200dm_conv_fwd": [C.POINTER(ConvDesc), _P],
     "b200dm_conv_wgrad": [C.POINTER(WgradDesc), _P],
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
+    "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "b200dm_pack_stem_weight": [_P, _P, _I, _I, _I, _P],
     "b200dm_init_conv_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200dm_init_conv_wgrad": [_I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_final_conv_fwd": [_I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],

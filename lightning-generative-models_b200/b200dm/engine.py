@@ -47,6 +47,10 @@ class WeightPack:
                 self.tr[nm] = self.tbuf[off:off + n]
             off += n
         self.version = -1
+        # stem (7x7, C -> dim) as a GEMM over im2col patches: zero-padded bf16 weight rows [dim][KP]
+        self.stem_k = arena.channels * 49
+        self.stem_kp = (self.stem_k + 63) // 64 * 64
+        self.stem = torch.zeros(arena.dim * self.stem_kp, dtype=tdt, device=dev) if dt == L.BF16 else None
         # device table for the one-launch batched pack
         entries = (L.PackEntry * len(arena.convs))()
         tile = 0
@@ -74,6 +78,9 @@ class WeightPack:
             return
         L.call("b200dm_pack_conv_weights_batched", self.dt, self.table.data_ptr(), self.n_entries,
                self.total_tiles)
+        if self.stem is not None:
+            L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
+                   self.arena.dim, self.stem_k, self.stem_kp)
         self.version = v
 
 
@@ -362,12 +369,30 @@ class Plan:
         # init conv -> r (= second half of the final concat), ddpm.py:437-438, :468
         self.begin_unit()
         r, gr = catF.slice(dim, dim), sl(gcatF, dim, dim)
-        self.F("b200dm_init_conv_fwd", self.dt, self.x_in.data_ptr(), a.ptr("init_conv.weight"),
-               a.ptr("init_conv.bias"), r.ptr, r.ld, B, ch, S, S, dim)
-        if tr:
-            self.Bk("b200dm_init_conv_wgrad", self.dt, self.x_in.data_ptr(), gr.ptr, gr.ld,
-                    a.gptr("init_conv.weight"), B, ch, S, S, dim)
-            self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
+        if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None:
+            # stem on the tensor cores: im2col patches (kept for the weight gradient) + 1x1 GEMM conv
+            KP, K = self.pack.stem_kp, self.pack.stem_k
+            P = self.buf(S, KP)
+            self.F("b200dm_im2col7", self.x_in.data_ptr(), P.ptr, B, ch, S, S, KP)
+            d = L.ConvDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim, x=P.ptr,
+                           x_ld=P.ld, w=self.pack.stem.data_ptr(), bias=a.ptr("init_conv.bias"), y=r.ptr,
+                           y_ld=r.ld, res=None, res_ld=0, accumulate=0)
+            self.F("b200dm_conv_fwd", C.byref(d), kname="conv_tc_fwd", flops=2.0 * B * S * S * dim * K)
+            self._keep.append(d)
+            if tr:
+                wd = L.WgradDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim,
+                                 x=P.ptr, x_ld=P.ld, dy=gr.ptr, dy_ld=gr.ld, dw=a.gptr("init_conv.weight"),
+                                 accumulate=1, cin_valid=K, s_tap=dim * K, s_co=K, s_ci=1)
+                self.Bk("b200dm_conv_wgrad", C.byref(wd), kname="wgrad_tc", flops=2.0 * B * S * S * dim * K)
+                self._keep.append(wd)
+                self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
+        else:
+            self.F("b200dm_init_conv_fwd", self.dt, self.x_in.data_ptr(), a.ptr("init_conv.weight"),
+                   a.ptr("init_conv.bias"), r.ptr, r.ld, B, ch, S, S, dim)
+            if tr:
+                self.Bk("b200dm_init_conv_wgrad", self.dt, self.x_in.data_ptr(), gr.ptr, gr.ld,
+                        a.gptr("init_conv.weight"), B, ch, S, S, dim)
+                self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
 
         x, gx = r, gr
         x_prior = True        # gcatF[dim:] also receives the final block's gradient first

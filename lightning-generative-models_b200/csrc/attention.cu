@@ -918,11 +918,37 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   }
 }
 
+// column reduction over the 64 pixel lanes: thread (pix = tid >> 2, part = tid & 3) holds 8 channels;
+// result[32] = op over all pixels.  scratch: [8 warps][32].
+template <bool MAX>
+__device__ __forceinline__ void la_col_reduce(float (&v)[8], float (*scratch)[DH], float* result, int tid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v[i], o);
+      v[i] = MAX ? fmaxf(v[i], t) : v[i] + t;
+    }
+  }
+  if ((tid & 31) < 4) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) scratch[tid >> 5][(tid & 3) * 8 + i] = v[i];
+  }
+  __syncthreads();
+  if (tid < DH) {
+    float r = scratch[0][tid];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) r = MAX ? fmaxf(r, scratch[w][tid]) : r + scratch[w][tid];
+    result[tid] = r;
+  }
+  __syncthreads();
+}
+
 struct LaFwdTc {
   lbf Kb[LA_CHUNK][LP];        // exp(k - m_loc) / scale*softmax(q) in the output phase
   lbf Vb[LA_CHUNK][LP];        // v / output staging in the output phase
   lbf Cb[DH][LP];              // merged context, bf16, [d][e]
-  float mred[LA_CHUNK][DH];    // reduction scratch (max, exp sums)
+  float mred[8][DH];           // reduction scratch (max, exp sums)
   float ctx_loc[DH][DH];       // partial context (read by the cluster peers)
   float m_loc[DH], l_loc[DH];
 };
@@ -965,17 +991,11 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
         }
       }
     }
+    if (rank == 0 && pix < NMEM) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s.mred[pix][part * 8 + i] = m[i];
-    __syncthreads();
-    if (tid < DH) {
-      float mm = -INFINITY;
-      for (int i = 0; i < LA_CHUNK; ++i) mm = fmaxf(mm, s.mred[i][tid]);
-      if (rank == 0)
-        for (int i = 0; i < NMEM; ++i) mm = fmaxf(mm, mk[tid * NMEM + i]);
-      s.m_loc[tid] = mm;
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], mk[(part * 8 + i) * NMEM + pix]);
     }
-    __syncthreads();
+    la_col_reduce<true>(m, s.mred, s.m_loc, tid);
   }
   // ---- phase 1b: partial context on tensor cores
   {
@@ -1033,14 +1053,7 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
       s.ctx_loc[mt * 16 + row + 8][nt * 8 + col] = acc[2];
       s.ctx_loc[mt * 16 + row + 8][nt * 8 + col + 1] = acc[3];
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s.mred[pix][part * 8 + i] = psum[i];
-    __syncthreads();
-    if (tid < DH) {
-      float a = 0.f;
-      for (int i = 0; i < LA_CHUNK; ++i) a += s.mred[i][tid];
-      s.l_loc[tid] = a;
-    }
+    la_col_reduce<false>(psum, s.mred, s.l_loc, tid);
   }
   cluster.sync();
   for (int i = tid; i < DH * DH; i += 256) {
@@ -1304,10 +1317,14 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
   cluster.sync();
 }
 
-// cluster size for n pixels: at most 8 CTAs per (sample, head), at least one 64-pixel chunk each
-static int la_cluster_size(int n) {
+// cluster size for n pixels: about two waves of CTAs on the machine (each CTA has a fixed cost of two
+// reductions and two cluster barriers, so more, smaller CTAs lose), at most 8, at least one chunk each
+static int la_cluster_size(int BH, int n) {
   const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
-  return chunks >= 8 ? 8 : (chunks < 1 ? 1 : chunks);
+  int cl = (int)((2LL * num_sms() * 4 + BH / 2) / BH);
+  if (cl > 8) cl = 8;
+  if (cl > chunks) cl = chunks;
+  return cl < 1 ? 1 : cl;
 }
 
 template <typename K, typename... Args>
@@ -1480,7 +1497,7 @@ extern "C" int b200dm_linattn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld
   cudaStream_t st = (cudaStream_t)stream;
   B200DM_REQUIRE(qkv_ld % 8 == 0 && ((uintptr_t)qkv & 15) == 0, B200DM_ERR_SHAPE, "linattn_fwd: qkv must be 16-byte aligned, ld %% 8 == 0");
   {
-    const int cl = la_cluster_size(n);
+    const int cl = la_cluster_size(B * HEADS, n);
     dim3 grid(cl, B * HEADS);
     cudaError_t e;
     if (dtype == B200DM_F32) {
@@ -1510,7 +1527,7 @@ extern "C" int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_
                  B200DM_ERR_SHAPE, "linattn_bwd: tensors must be 16-byte aligned, ld %% 8 == 0");
   {
     (void)dctx;
-    const int cl = la_cluster_size(n);
+    const int cl = la_cluster_size(B * HEADS, n);
     dim3 grid(cl, B * HEADS);
     cudaError_t e;
     if (dtype == B200DM_F32) {

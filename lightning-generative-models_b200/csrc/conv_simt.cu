@@ -211,11 +211,20 @@ colsum8_kernel(const T* __restrict__ x, int ld, int64_t rows, int C8, float* __r
   int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   float acc[8] = {};
   if (cv < C8)
-    for (int64_t r = r0 + rl; r < r1; r += RL) {
-      float v[8];
-      ld8(x + r * ld + cv * 8, v);
+    for (int64_t r = r0 + rl; r < r1; r += 8 * RL) {   // eight independent loads in flight per thread
+      float v[8][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int u = 0; u < 8; ++u) {
+        if (r + u * RL < r1) {
+          ld8(x + (r + u * RL) * ld + cv * 8, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[j] += ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) + ((v[4][j] + v[5][j]) + (v[6][j] + v[7][j]));
     }
 #pragma unroll
   for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
@@ -559,7 +568,7 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
     int VL = 1;
     while (VL < C8 && VL < 64) VL <<= 1;
     int cb = (C8 + VL - 1) / VL;
-    int64_t rb = (num_sms() + cb - 1) / cb;   // few CTAs: the final atomics hit only C/32 cache lines
+    int64_t rb = (num_sms() + cb - 1) / cb;   // one wave: the final atomics of every CTA hit the same C addresses
     const int RL = 256 / VL;
     if (rb > (rows + 4 * RL - 1) / (4 * RL)) rb = (rows + 4 * RL - 1) / (4 * RL);
     if (rb < 1) rb = 1;
@@ -584,6 +593,68 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
     colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, out, per);
   count_launch();
   return check_launch("colsum");
+}
+
+// ---- stem on tensor cores: im2col of the 7x7 patches + zero-padded weight rows -------------------------------
+// P[pix][k] = x[b, ch, y + ky - 3, x + kx - 3], k = (ch*7 + ky)*7 + kx (the OIHW order of the master weight),
+// columns [C*49, KP) are zero.  The 7x7 conv (ddpm.py:304) then IS a 1x1 conv with Cin = KP over P, and its
+// weight gradient a plain wgrad over P — both run on the tcgen05 kernels.
+namespace b200dm {
+// block = (KP/8 vector lanes, 8 pixels): no per-thread division for the vector index, 32-bit pixel math
+__global__ void im2col7_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, unsigned npix, int C, int H,
+                               int W, int KP) {
+  const int K = C * 49;
+  const int v = threadIdx.x;
+  int kch[8], kdy[8], kdx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    const int ch = k / 49, r = k - ch * 49, ky = r / 7;
+    kch[j] = k < K ? ch : -1;
+    kdy[j] = ky - 3;
+    kdx[j] = r - ky * 7 - 3;
+  }
+  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += gridDim.x * blockDim.y) {
+    const unsigned ox = pix % (unsigned)W, t = pix / (unsigned)W;
+    const unsigned oy = t % (unsigned)H, b = t / (unsigned)H;
+    const float* xb = x + (size_t)b * C * H * W;
+    float val[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int iy = (int)oy + kdy[j], ix = (int)ox + kdx[j];
+      val[j] = (kch[j] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (kch[j] * H + iy) * W + ix) : 0.f;
+    }
+    st8(P + (size_t)pix * KP + v * 8, val);
+  }
+}
+__global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int K, int KP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cout * KP) {
+    const int co = i / KP, k = i - co * KP;
+    wp[i] = __float2bfloat16_rn(k < K ? w[co * K + k] : 0.f);
+  }
+}
+}  // namespace b200dm
+
+extern "C" int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP,
+                              void* stream) {
+  B200DM_REQUIRE(B > 0 && C >= 1 && C * 49 <= KP && KP % 64 == 0 && ((uintptr_t)P & 15) == 0, B200DM_ERR_SHAPE,
+                 "im2col7: need C*49 <= KP, KP %% 64 == 0 (C=%d KP=%d)", C, KP);
+  B200DM_REQUIRE((int64_t)B * H * W < (1LL << 31) && KP / 8 <= 128, B200DM_ERR_UNSUPPORTED, "im2col7: tensor too large");
+  const unsigned npix = (unsigned)((int64_t)B * H * W);
+  dim3 block(KP / 8, 8);
+  unsigned blocks = (npix + 7) / 8, cap = (unsigned)b200dm::num_sms() * 16;
+  b200dm::im2col7_kernel<<<blocks > cap ? cap : blocks, block, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)P, npix, C, H, W, KP);
+  b200dm::count_launch();
+  return b200dm::check_launch("im2col7");
+}
+
+extern "C" int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream) {
+  B200DM_REQUIRE(Cout > 0 && K > 0 && K <= KP, B200DM_ERR_SHAPE, "pack_stem_weight: K=%d KP=%d", K, KP);
+  b200dm::pack_stem_kernel<<<(Cout * KP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, K, KP);
+  b200dm::count_launch();
+  return b200dm::check_launch("pack_stem_weight");
 }
 
 extern "C" int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* w, const float* bias,

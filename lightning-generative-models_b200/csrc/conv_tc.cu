@@ -784,6 +784,8 @@ struct TcWgradParams {
   int splits;
   float* dw;
   long long s_tap, s_co, s_ci;
+  int cin_valid;      // columns ci >= cin_valid are padding (stem im2col) and are not written
+  int vec_ok;         // 16-byte vector reductions allowed (alignment of every row start)
 };
 
 template <int N_TILE, int STAGES>
@@ -898,7 +900,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
       if (valid) {
-        if (p.s_ci == 1) {   // contiguous along ci: 16-byte vector reductions (4x fewer L2 atomic ops)
+        if (p.vec_ok) {      // contiguous along ci: 16-byte vector reductions (4x fewer L2 atomic ops)
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c + j),
@@ -907,7 +909,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                          : "memory");
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(drow + (long long)(c + j) * p.s_ci, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j)
+            if (ci0 + c + j < p.cin_valid) atomicAdd(drow + (long long)(c + j) * p.s_ci, __uint_as_float(r[j]));
         }
       }
     }
@@ -956,6 +959,9 @@ int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
   p.dw = d->dw;
   p.s_tap = d->s_tap; p.s_co = d->s_co; p.s_ci = d->s_ci;
   if (p.s_tap == 0 && p.s_co == 0 && p.s_ci == 0) { p.s_tap = (long long)d->Cout * d->Cin; p.s_co = d->Cin; p.s_ci = 1; }
+  p.cin_valid = (d->cin_valid > 0 && d->cin_valid < d->Cin) ? d->cin_valid : d->Cin;
+  p.vec_ok = (p.s_ci == 1 && p.s_co % 4 == 0 && p.s_tap % 4 == 0 && p.cin_valid == d->Cin &&
+              ((uintptr_t)d->dw & 15) == 0) ? 1 : 0;
   const int n_tile = (d->Cin % 128 == 0) ? 128 : 64;
   const int co_tiles = (d->Cout + TC_BM - 1) / TC_BM, ci_tiles = d->Cin / n_tile;
   const int base_ctas = co_tiles * ci_tiles * taps;

@@ -309,7 +309,10 @@ template <> struct Raw8<__nv_bfloat16> {
   }
 };
 
-template <typename T>
+// STAGE: the chunk's raw vectors are parked in (dynamic) shared memory during phase 1 and phase 2 reads them
+// from there instead of going back to L2 (chunk bytes = ceil(HW/CL) * C * sizeof(T), <= GNC_STAGE_MAX).
+constexpr int GNC_STAGE_MAX = 40 * 1024;
+template <typename T, bool STAGE>
 __global__ void __launch_bounds__(GNC_THREADS)
 gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -328,6 +331,8 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   __shared__ float gpart[64][2];                       // this CTA's per-group (sum, sumsq): read by the peers
   __shared__ float gstat[64][2];                       // (mean, rstd) per group
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
+  extern __shared__ __align__(16) unsigned char gn_stage_raw[];
+  Raw8<T>* stage = reinterpret_cast<Raw8<T>*>(gn_stage_raw);     // [pixel of the chunk][C8]
   // ---- phase 1: per-group sum / sum of squares of the chunk
   float s = 0.f, ss = 0.f;
   for (int p = p0 + lane; p < p1; p += 4 * lanes) {
@@ -340,6 +345,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
       if (p + u * lanes < p1) {
         float v[8];
         raw[u].unpack(v);
+        if (STAGE) stage[(p + u * lanes - p0) * C8 + cv] = raw[u];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s += v[j];
@@ -403,7 +409,8 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
-        rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        if (STAGE) rx[u] = stage[(p + u * lanes - p0) * C8 + cv];
+        else rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
         if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
       }
     }
@@ -597,11 +604,11 @@ static bool gn_cluster_ok(int C, int G) {
 }
 
 template <typename K, typename... Args>
-static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, cudaStream_t st, Args... args) {
+static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(GNC_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -806,15 +813,18 @@ extern "C" int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* 
   }
   const int cl = gn_cluster_size(B, HW, C, 4);
   dim3 grid(cl, B);
+  const size_t chunk_bytes = (size_t)((HW + cl - 1) / cl) * C * (dtype == B200DM_F32 ? 4 : 2);
+  const bool stage = chunk_bytes <= (size_t)GNC_STAGE_MAX;
+  const size_t smem = stage ? chunk_bytes : 0;
   cudaError_t e;
+#define GN_FWD_LAUNCH(TT, ST)                                                                                 \
+  launch_cluster(gn_fwd_cluster_kernel<TT, ST>, grid, cl, smem, st, (const TT*)x, (int)x_ld, stats, gamma, beta, \
+                 film, (int)film_ld, (const TT*)res, (int)res_ld, (TT*)y, (int)y_ld, (int)HW, (int)C, (int)G, eps, 1)
   if (dtype == B200DM_F32)
-    e = launch_cluster(gn_fwd_cluster_kernel<float>, grid, cl, st, (const float*)x, (int)x_ld, stats, gamma,
-                       beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld,
-                       (int)HW, (int)C, (int)G, eps, 1);
+    e = stage ? GN_FWD_LAUNCH(float, true) : GN_FWD_LAUNCH(float, false);
   else
-    e = launch_cluster(gn_fwd_cluster_kernel<bf16>, grid, cl, st, (const bf16*)x, (int)x_ld, stats, gamma,
-                       beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW,
-                       (int)C, (int)G, eps, 1);
+    e = stage ? GN_FWD_LAUNCH(bf16, true) : GN_FWD_LAUNCH(bf16, false);
+#undef GN_FWD_LAUNCH
   B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_fwd: launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("gn_fwd");
@@ -854,11 +864,11 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     dim3 grid(cl, B);
     cudaError_t e;
     if (dtype == B200DM_F32)
-      e = launch_cluster(gn_bwd_cluster_kernel<float>, grid, cl, st, (const float*)dy, (int)dy_ld,
+      e = launch_cluster(gn_bwd_cluster_kernel<float>, grid, cl, 0, st, (const float*)dy, (int)dy_ld,
                          (const float*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (float*)dx,
                          (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
     else
-      e = launch_cluster(gn_bwd_cluster_kernel<bf16>, grid, cl, st, (const bf16*)dy, (int)dy_ld,
+      e = launch_cluster(gn_bwd_cluster_kernel<bf16>, grid, cl, 0, st, (const bf16*)dy, (int)dy_ld,
                          (const bf16*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (bf16*)dx,
                          (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
@@ -935,7 +945,7 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   cudaStream_t st = (cudaStream_t)stream;
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
-  int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: dg atomics share C/32 lines
+  int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   if (dtype == B200DM_F32)
     rmsnorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C, L);

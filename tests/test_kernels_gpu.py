@@ -350,6 +350,43 @@ def test_init_conv_fwd_and_wgrad(dtype, C, S, B):
     assert rel(dw, w.grad) < 2e-5
 
 
+@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 16, 5)])
+def test_stem_on_tensor_cores_im2col_gemm_and_wgrad(C, S, B):
+    """7x7 stem as im2col + tcgen05 1x1 GEMM, and its weight gradient through conv_wgrad(cin_valid)."""
+    if not L.load().b200dm_tc_available():
+        pytest.skip("needs the tcgen05 path")
+    K, KP = C * 49, (C * 49 + 63) // 64 * 64
+    x = rnd(B, C, S, S, seed=71)
+    w = rnd(64, C, 7, 7, seed=72, scale=0.1)
+    bias = rnd(64, seed=73, scale=0.1)
+    P = torch.full((B * S * S, KP), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.call("b200dm_im2col7", x.data_ptr(), P.data_ptr(), B, C, S, S, KP)
+    ref_cols = F.unfold(q(x, L.BF16), 7, padding=3).transpose(1, 2).reshape(B * S * S, K)
+    assert torch.equal(P[:, :K].float(), ref_cols) and P[:, K:].abs().max().item() == 0
+    wp = torch.empty(64, KP, dtype=torch.bfloat16, device=DEV)
+    L.call("b200dm_pack_stem_weight", w.data_ptr(), wp.data_ptr(), 64, K, KP)
+    assert torch.equal(wp[:, :K].float(), q(w.reshape(64, K), L.BF16)) and wp[:, K:].abs().max().item() == 0
+    yv = View.zeros(B, S, S, 64, torch.bfloat16, DEV, ld=128, off=64)
+    d = L.ConvDesc(dtype=L.BF16, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=64, x=P.data_ptr(), x_ld=KP,
+                   w=wp.data_ptr(), bias=bias.data_ptr(), y=yv.ptr, y_ld=yv.ld, res=None, res_ld=0, accumulate=0)
+    L.call("b200dm_conv_fwd", d)
+    ref = F.conv2d(q(x, L.BF16), q(w, L.BF16), bias, padding=3)
+    assert rel(yv.to_nchw(), ref) < tol(L.BF16)
+    dy = q(rnd(B, 64, S, S, seed=74), L.BF16)
+    dyv = nhwc(dy, L.BF16)
+    dw = torch.zeros(64, C, 7, 7, device=DEV)
+    guard = dw.clone()
+    wd = L.WgradDesc(dtype=L.BF16, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=64, x=P.data_ptr(), x_ld=KP,
+                     dy=dyv.ptr, dy_ld=dyv.ld, dw=dw.data_ptr(), accumulate=1, cin_valid=K, s_tap=64 * K, s_co=K,
+                     s_ci=1)
+    L.call("b200dm_conv_wgrad", wd)
+    xr = q(x, L.BF16).requires_grad_(False)
+    wr = torch.zeros(64, C, 7, 7, device=DEV, requires_grad=True)
+    F.conv2d(xr, wr, None, padding=3).backward(dy)
+    assert rel(dw, wr.grad) < 2e-3
+    del guard
+
+
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("C", [1, 3])
 def test_final_conv_fwd_bwd(dtype, C):
