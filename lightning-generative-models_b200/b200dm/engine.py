@@ -105,6 +105,9 @@ class Plan:
         self.nbytes = 0
         dim, ch = arena.dim, arena.channels
         self._keep.append(pack)
+        import os
+        self.side_enabled = training and os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
+        self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
         self.out = torch.zeros(B, ch, S, S, device=self.dev)
@@ -146,7 +149,7 @@ class Plan:
         return t
 
     # ---- op emission --------------------------------------------------------------------------------
-    def _emit(self, lst, name, *args, kname=None, flops=0.0):
+    def _emit(self, lst, name, *args, kname=None, flops=0.0, side=False, reads=(), writes=()):
         fn = getattr(self.lib, name)
         self._keep.append(args)
 
@@ -156,6 +159,12 @@ class Plan:
                 raise L.B200dmError(f"{name} failed with code {rc}: {L.last_error()}")
         op.kname = kname or name.replace("b200dm_", "")     # kernel family (bench.py per-kernel table)
         op.flops = flops                                    # algorithmic FLOPs of this launch
+        # side = parameter-gradient work (wgrad, bias column sums) that nothing in the backward chain waits
+        # for: it runs on the plan's second stream.  reads (side ops) / writes (main ops) name the buffers
+        # whose reuse must be ordered across the two streams (write-after-read on shared scratch).
+        op.side = side
+        op.reads = frozenset(v.buf.data_ptr() for v in reads if v is not None)
+        op.writes = frozenset(v.buf.data_ptr() for v in writes if v is not None)
         lst.append(op)
 
     def F(self, name, *args, **kw):
@@ -195,7 +204,7 @@ class Plan:
         taps = ci.taps
         flops = 2.0 * self.B * H * H * cout * cin * taps
         fam = ("conv_tc" if d.impl == 1 else "conv_simt") + ("_dgrad" if dgrad else "_fwd")
-        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops)
+        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops, writes=(y,))
         self._keep.append(d)
 
     def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None,
@@ -214,11 +223,11 @@ class Plan:
                         x=x.ptr, x_ld=x.ld, dy=dy.ptr, dy_ld=dy.ld, dw=self.arena.gptr(nm + ".weight"),
                         accumulate=1, s_tap=s_tap, s_co=s_co, s_ci=s_ci)
         self.Bk("b200dm_conv_wgrad", C.byref(d), kname="wgrad_tc" if d.impl == 1 else "wgrad_simt",
-                flops=2.0 * self.B * H * H * ci.cout * ci.cin * ci.taps)
+                flops=2.0 * self.B * H * H * ci.cout * ci.cin * ci.taps, side=True, reads=(x, dy))
         self._keep.append(d)
         if ci.bias and bias_grad:
             self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
-                    self.arena.gptr(nm + ".bias"), 1)
+                    self.arena.gptr(nm + ".bias"), 1, side=True, reads=(dy,))
         if dx is not None:
             self.conv_fwd(self.Bk, nm, dy, dx, dgrad=True, res=dx_res, accumulate=dx_acc)
 
@@ -249,19 +258,21 @@ class Plan:
                GN_EPS)
         if not self.training:
             return
-        dc, gh1 = self.scratch("dc", H, cout), self.scratch("gh1", H, cout)
+        # dc2 / dc1: separate scratch for the two norm gradients, so block1's norm backward does not have to wait
+        # for block2's weight gradient (second stream) to finish reading its operand
+        dc2, dc, gh1 = self.scratch("dc2", H, cout), self.scratch("dc", H, cout), self.scratch("gh1", H, cout)
         dfilm_ptr = self.dfilm.data_ptr() + 4 * a.film_off[nm]
-        # block2: GN/SiLU backward -> dc ; conv2 backward -> gh1
+        # block2: GN/SiLU backward -> dc2 ; conv2 backward -> gh1
         self.Bk("b200dm_gn_apply_bwd", self.dt, gout.ptr, gout.ld, c2.ptr, c2.ld, st2.data_ptr(),
-                a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, dc.ptr, dc.ld,
+                a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, dc2.ptr, dc2.ld,
                 a.gptr(b2 + ".norm.weight"), a.gptr(b2 + ".norm.bias"), None, a.gptr(b2 + ".proj.bias"),
-                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
-        self.conv_bwd(b2 + ".proj", h1, dc, gh1, bias_grad=False)
+                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS, writes=(dc2,))
+        self.conv_bwd(b2 + ".proj", h1, dc2, gh1, bias_grad=False)
         # block1: GN/FiLM/SiLU backward -> dc ; conv1 backward -> gx (+ identity-skip gradient)
         self.Bk("b200dm_gn_apply_bwd", self.dt, gh1.ptr, gh1.ld, c1.ptr, c1.ld, st1.data_ptr(),
                 a.ptr(b1 + ".norm.weight"), a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, dc.ptr, dc.ld,
                 a.gptr(b1 + ".norm.weight"), a.gptr(b1 + ".norm.bias"), dfilm_ptr, a.gptr(b1 + ".proj.bias"),
-                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS)
+                self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS, writes=(dc,))
         self.conv_bwd(b1 + ".proj", x, dc, gx, dx_acc=1 if gx_prior else 0,
                       dx_res=None if has_res_conv else gout, bias_grad=False)
         if has_res_conv:
@@ -292,19 +303,19 @@ class Plan:
         if full:
             self.conv_bwd(nm + ".to_out", ao, gout, dao)
             self.Bk("b200dm_attn_bwd", self.dt, dao.ptr, dao.ld, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"),
-                    dqkv.ptr, dqkv.ld, a.gptr(nm + ".mem_kv"), self.B, n)
+                    dqkv.ptr, dqkv.ld, a.gptr(nm + ".mem_kv"), self.B, n, writes=(dqkv,))
         else:
             dto = self.scratch("dto", H, Cc)
             self.Bk("b200dm_rmsnorm_bwd", self.dt, gout.ptr, gout.ld, to.ptr, to.ld, a.ptr(nm + ".to_out.1.g"),
-                    None, 0, dto.ptr, dto.ld, a.gptr(nm + ".to_out.1.g"), rows, Cc)
+                    None, 0, dto.ptr, dto.ld, a.gptr(nm + ".to_out.1.g"), rows, Cc, writes=(dto,))
             self.conv_bwd(nm + ".to_out.0", ao, dto, dao)
             self.Bk("b200dm_linattn_bwd", self.dt, dao.ptr, dao.ld, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"),
                     ctx.data_ptr(), kstat.data_ptr(), self.dctx.data_ptr(), dqkv.ptr, dqkv.ld,
-                    a.gptr(nm + ".mem_kv"), self.B, n)
+                    a.gptr(nm + ".mem_kv"), self.B, n, writes=(dqkv,))
         self.conv_bwd(nm + ".to_qkv", xn, dqkv, dxn)
         # gx = rmsnorm'(dxn) + gout   (the `attn(x) + x` skip, ddpm.py:449,455,464)
         self.Bk("b200dm_rmsnorm_bwd", self.dt, dxn.ptr, dxn.ld, x.ptr, x.ld, a.ptr(nm + ".norm.g"),
-                gout.ptr, gout.ld, gx.ptr, gx.ld, a.gptr(nm + ".norm.g"), rows, Cc)
+                gout.ptr, gout.ld, gx.ptr, gx.ld, a.gptr(nm + ".norm.g"), rows, Cc, writes=(gx,))
 
     def plain_conv(self, nm, x: View, out: View, gx, gout, gx_prior: bool):
         self.begin_unit()
@@ -320,7 +331,8 @@ class Plan:
         if self.training:
             gxu = self.scratch("gxu", 2 * x.H, x.C)
             self.conv_bwd(nm, xu, gout, gxu)
-            self.Bk("b200dm_upsample2x_bwd", self.dt, gxu.ptr, gxu.ld, gx.ptr, gx.ld, self.B, x.H, x.H, x.C)
+            self.Bk("b200dm_upsample2x_bwd", self.dt, gxu.ptr, gxu.ld, gx.ptr, gx.ld, self.B, x.H, x.H, x.C,
+                    writes=(gx,))
 
     # ---- the network -----------------------------------------------------------------------------------
     def _build(self, dim, ch):
@@ -383,9 +395,11 @@ class Plan:
                 wd = L.WgradDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim,
                                  x=P.ptr, x_ld=P.ld, dy=gr.ptr, dy_ld=gr.ld, dw=a.gptr("init_conv.weight"),
                                  accumulate=1, cin_valid=K, s_tap=dim * K, s_co=K, s_ci=1)
-                self.Bk("b200dm_conv_wgrad", C.byref(wd), kname="wgrad_tc", flops=2.0 * B * S * S * dim * K)
+                self.Bk("b200dm_conv_wgrad", C.byref(wd), kname="wgrad_tc", flops=2.0 * B * S * S * dim * K,
+                        side=True, reads=(P, gr))
                 self._keep.append(wd)
-                self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
+                self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1,
+                        side=True, reads=(gr,))
         else:
             self.F("b200dm_init_conv_fwd", self.dt, self.x_in.data_ptr(), a.ptr("init_conv.weight"),
                    a.ptr("init_conv.bias"), r.ptr, r.ld, B, ch, S, S, dim)
@@ -448,7 +462,7 @@ class Plan:
         if tr:
             self.Bk("b200dm_final_conv_bwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
                     self.d_out.data_ptr(), gy.ptr, gy.ld, a.gptr("final_conv.weight"),
-                    a.gptr("final_conv.bias"), B, S * S, dim, ch)
+                    a.gptr("final_conv.bias"), B, S * S, dim, ch, writes=(gy,))
 
     # ---- execution --------------------------------------------------------------------------------------
     def run_forward(self):
@@ -462,6 +476,40 @@ class Plan:
             op(st)
 
     def run_backward_segment(self, i: int):
-        st = L.stream_ptr()
-        for op in self.bwd_segments[i]:
-            op(st)
+        """Launch backward segment i.  Parameter-gradient kernels (op.side) go to the plan's second stream and
+        overlap the data-gradient chain; the two streams are ordered by events only where a scratch buffer is
+        reused (write on the main stream after a read on the side stream), and they join at the segment end, so
+        the gradient bucket of the segment is complete when this returns (in stream order).  Works the same
+        under CUDA-graph capture: the side stream forks from and rejoins the capturing stream."""
+        ops = self.bwd_segments[i]
+        if not self.side_enabled or not any(op.side for op in ops):
+            st = L.stream_ptr()
+            for op in ops:
+                op(st)
+            return
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        main_ptr, side_ptr = main.cuda_stream, side.cuda_stream
+        pending = {}                       # buffer -> event of the last side-stream kernel reading it
+        fork, dirty = None, True
+        for op in ops:
+            if op.side:
+                if dirty:                  # everything issued on the main stream so far (incl. the producer)
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    side.wait_event(fork)
+                    dirty = False
+                op(side_ptr)
+                if op.reads:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    for b in op.reads:
+                        pending[b] = ev
+            else:
+                for b in op.writes:
+                    ev = pending.pop(b, None)
+                    if ev is not None:
+                        main.wait_event(ev)
+                op(main_ptr)
+                dirty = True
+        main.wait_stream(side)
