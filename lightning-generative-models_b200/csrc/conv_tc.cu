@@ -940,6 +940,215 @@ static int launch_wgrad_tc(const CUtensorMap& tmDY, const CUtensorMap& tmX, cons
   return check_launch("wgrad_tc");
 }
 
+// =====================================================================================================
+// 3x3 weight gradient with an on-chip halo.  The generic kernel above runs one GEMM per filter tap, i.e. it
+// streams dY and X through L2 nine times (measured: L2-bandwidth-bound, ~7 TB/s, 230 TFLOP/s on 64->64).
+// Here a CTA walks 8x16-pixel tiles; per tile ONE TMA box brings the 18x16 halo of X (64 input channels) and
+// one box the 8x16 tile of dY (64 output channels), and all nine taps are computed from them:
+//   D[(tap slot, ci)][co] += sum_pixels X[pixel + tap, ci] * dY[pixel, co]
+// A = X^T is MN-major straight from the NHWC halo; its 128 rows are TWO taps x 64 channels — the second
+// 64-row slab is the same buffer shifted by the tap distance (the descriptor's leading-dimension byte
+// offset), so the tensor core's M = 128 is filled even for 64-channel layers.  K = 16 pixels per MMA = two
+// image rows of the tile (8-row groups 2048 B apart in the halo, 1024 B apart in the dY tile).  Six
+// accumulators (taps 01, 2-, 34, 5-, 67, 8-) of 64 fp32 columns live in TMEM for the whole pixel range of
+// the CTA (split-K over tiles across CTAs); the epilogue adds them into dW with coalesced fp32 reductions.
+// =====================================================================================================
+struct TcWgradHaloParams {
+  int H, W, tiles_x, tiles_y, m_tiles;
+  int ci_blocks, co_blocks, splits;
+  float* dw;
+  long long s_tap, s_co, s_ci;
+};
+
+// tap grouping: slot-0 tap / slot-1 tap (9 = none) of each accumulator: {0,1} {2,-} {3,4} {5,-} {6,7} {8,-}.
+// Every pair is one pixel apart (LBO = 128 B).  MEASURED on B200: pairing taps one halo ROW apart (LBO = 2048 B)
+// or across rows (LBO = 1792 B) gives a wrong second slab — a leading-dimension offset of a full swizzle atom
+// or more is not a plain byte offset for MN-major SWIZZLE_128B operands — so only dx-neighbours are paired.
+template <int PAIRING> struct WgPairs;
+template <> struct WgPairs<1> {
+  static constexpr int G = 6;
+  __host__ __device__ static constexpr int t0(int g) { return g == 0 ? 0 : g == 1 ? 2 : g == 2 ? 3 : g == 3 ? 5 : g == 4 ? 6 : 8; }
+  __host__ __device__ static constexpr int t1(int g) { return g == 0 ? 1 : g == 2 ? 4 : g == 4 ? 7 : 9; }
+};
+
+template <int STAGES, int PAIRING>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                     const TcWgradHaloParams p) {
+  constexpr int DY_BYTES = TC_BM * TC_BK * 2;                  // 16 KiB: [128 pixels][64 co]
+  constexpr int STAGE_BYTES = HALO_BYTES + DY_BYTES;           // 52 KiB
+  constexpr int TMEM_COLS = 512;                               // 6 x 64 accumulator columns
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item: (ci block, co block, split of the pixel tiles)
+  const int pair = blockIdx.x / p.splits, split = blockIdx.x - pair * p.splits;
+  const int cib = pair / p.co_blocks, cob = pair - cib * p.co_blocks;
+  const int per = (p.m_tiles + p.splits - 1) / p.splits;
+  const int t0 = split * per, t1 = min(t0 + per, p.m_tiles);
+  const bool has_work = t1 > t0;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDY);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && has_work) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
+        const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        const uint32_t x_dst = base + stage * STAGE_BYTES;
+        tma_load_5d(x_dst, &tmX, full_bar(stage), cib * TC_BK, x0 - 1, y0 - 1, b, 0);
+        tma_load_5d(x_dst + HALO_BYTES, &tmDY, full_bar(stage), cob * TC_BK, x0, y0, b, 0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (has_work) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, 64, 1, 1);
+      // A: MN-major halo view.  SBO = 2048 B (next image row of the tile = next 8-row group);
+      //    LBO = byte distance between the two taps of a pair (second 64-row slab of M).
+      // B: MN-major dY tile, 8-row groups 1024 B apart; N = 64 needs no second slab.
+      const uint64_t b_desc0 = make_smem_desc(base + HALO_BYTES, DY_BYTES, 1024);
+      const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+      const uint64_t a_desc_near = make_smem_desc(base, 128, HALO_W * 128);                    // taps dx, dx+1
+      const uint32_t a_hi = (uint32_t)(a_desc_near >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_desc_near;
+      const bool leader = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t so = (uint32_t)stage * (STAGE_BYTES >> 4);
+#pragma unroll
+          for (int g = 0; g < WgPairs<PAIRING>::G; ++g) {
+            const int tap = WgPairs<PAIRING>::t0(g);
+            const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+            for (int k = 0; k < TC_BM / 16; ++k)
+              umma_bf16_lohi(tmem_base + (uint32_t)(g * 64),
+                             a_lo0 + so + (uint32_t)((((2 * k + dy) * HALO_W + dx) * 128) >> 4), a_hi,
+                             b_lo0 + so + (uint32_t)((k * 2048) >> 4), b_hi, idesc, (k > 0) ? 1u : (t > t0 ? 1u : 0u));
+          }
+          umma_commit(empty_bar(stage));
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit(tmem_full_bar);
+    }
+  } else if (has_work) {
+    // epilogue: TMEM lane = (tap slot, ci), column = (pair, co)
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane, slot = m >> 6, ci = cib * TC_BK + (m & 63);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < WgPairs<PAIRING>::G; ++g) {
+      const int tap = slot ? WgPairs<PAIRING>::t1(g) : WgPairs<PAIRING>::t0(g);
+      float* dcol = p.dw + (long long)tap * p.s_tap + (long long)(cob * 64) * p.s_co + (long long)ci * p.s_ci;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 64 + c), r);
+        tmem_ld_wait();
+        if (tap < 9) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + (long long)(c + j) * p.s_co),
+                         "f"(__uint_as_float(r[j]))
+                         : "memory");
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+static bool wgrad_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200DM_NO_WGRAD_HALO");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int conv_wgrad_halo(const b200dm_wgrad_desc* d, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  TcWgradHaloParams p{};
+  p.H = d->H; p.W = d->W; p.tiles_x = d->W / 8; p.tiles_y = d->H / 16;
+  p.m_tiles = d->B * p.tiles_x * p.tiles_y;
+  p.ci_blocks = d->Cin / 64; p.co_blocks = d->Cout / 64;
+  const int pairs = p.ci_blocks * p.co_blocks;
+  int splits = num_sms() / pairs;
+  if (splits < 1) splits = 1;
+  if (splits > p.m_tiles) splits = p.m_tiles;
+  p.splits = splits;
+  p.dw = d->dw;
+  p.s_tap = d->s_tap; p.s_co = d->s_co; p.s_ci = d->s_ci;
+  if (p.s_tap == 0 && p.s_co == 0 && p.s_ci == 0) { p.s_tap = (long long)d->Cout * d->Cin; p.s_co = d->Cin; p.s_ci = 1; }
+  CUtensorMap tmX, tmDY;
+  const cuuint64_t e = 2;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)d->x_ld * e, (cuuint64_t)d->W * d->x_ld * e,
+                         (cuuint64_t)d->H * d->W * d->x_ld * e, (cuuint64_t)d->B * d->H * d->W * d->x_ld * e};
+    cuuint32_t box[5] = {TC_BK, HALO_W, HALO_H, 1, 1};
+    int rc = encode_map(&tmX, d->x, 5, dims, str, box, "conv_wgrad_halo X");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)d->dy_ld * e, (cuuint64_t)d->W * d->dy_ld * e,
+                         (cuuint64_t)d->H * d->W * d->dy_ld * e, (cuuint64_t)d->B * d->H * d->W * d->dy_ld * e};
+    cuuint32_t box[5] = {TC_BK, 8, 16, 1, 1};
+    int rc = encode_map(&tmDY, d->dy, 5, dims, str, box, "conv_wgrad_halo dY");
+    if (rc) return rc;
+  }
+  constexpr int smem = STAGES * (HALO_BYTES + TC_BM * TC_BK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(wgrad3x3_halo_kernel<STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(err == cudaSuccess, B200DM_ERR_CUDA, "wgrad3x3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = true;
+  }
+  wgrad3x3_halo_kernel<STAGES, 1><<<pairs * splits, WG_THREADS, smem, st>>>(tmX, tmDY, p);
+  count_launch();
+  return check_launch("wgrad3x3_halo");
+}
+
 int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
   B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_wgrad(tc): needs an sm_100 device and a TMA-capable driver");
   B200DM_REQUIRE(d->Cin % 64 == 0 && d->Cout % 64 == 0, B200DM_ERR_SHAPE,
@@ -947,6 +1156,9 @@ int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream) {
   B200DM_REQUIRE(d->x_ld % 8 == 0 && d->dy_ld % 8 == 0, B200DM_ERR_SHAPE, "conv_wgrad(tc): ld must be a multiple of 8");
   B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->dy & 15) == 0, B200DM_ERR_SHAPE,
                  "conv_wgrad(tc): pointers must be 16-byte aligned");
+  if (d->mode == 0 && d->ksize == 3 && d->W >= 16 && d->W % 8 == 0 && d->H % 16 == 0 &&
+      !(d->cin_valid > 0 && d->cin_valid < d->Cin) && wgrad_halo_enabled())
+    return conv_wgrad_halo(d, (cudaStream_t)stream);
   int bh, bn;
   int rc = tile_geometry(d->H, d->W, &bh, &bn, "conv_wgrad(tc)");
   if (rc) return rc;
