@@ -237,6 +237,8 @@ def profile_plan(plan, passes=3, backward=True):
         torch.cuda.synchronize()
         for i in range(len(ops)):
             tot[i] += evs[i].elapsed_time(evs[i + 1]) / passes
+    profile_plan.detail = [{"i": i, "kernel": n, "us": round(ms * 1e3, 2), "gflop": round(fl / 1e9, 3)}
+                           for i, (n, ms, fl) in enumerate(zip(names, tot, flops))]
     fam = {}
     for n, ms, fl in zip(names, tot, flops):
         f = fam.setdefault(n, {"ms": 0.0, "launches": 0, "flops": 0.0})
@@ -409,7 +411,8 @@ def main():
                 "step_mfu": round(step_flops / (ms / K * 1e-3) / 1e12 / peaks["tf_sustained"], 4)}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"kernels": table, "sum_ms": total_ms, "workload": cfg["workload"]}, f, indent=1)
+                json.dump({"kernels": table, "sum_ms": total_ms, "workload": cfg["workload"],
+                           "launches": getattr(profile_plan, "detail", None)}, f, indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

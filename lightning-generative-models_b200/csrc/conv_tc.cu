@@ -124,33 +124,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
-        const long long first = (long long)m_tile * TC_BM;  // first pixel (linear NHW order)
-        const int n_first = (int)(first / ((long long)p.H * p.W));
-        const int y_first = (int)((first / p.W) % p.H);
-        for (int kb = 0; kb < num_k; ++kb) {
-          const int tap = kb / p.kblocks, kc = kb - tap * p.kblocks;
+    // Warp-uniform loop, one elected lane issues.  No divisions inside the K loop: taps and channel blocks are
+    // nested counters (measured: decoding (tap, kc, dy, dx) from a flat index with runtime divisors cost the
+    // single producer thread ~900 cycles per K block and starved the tensor pipe on the small-M layers).
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const int pad = p.ksize >> 1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      const long long first = (long long)m_tile * TC_BM;  // first pixel (linear NHW order)
+      const int n_first = (int)(first / ((long long)p.H * p.W));
+      const int y_first = (int)((first / p.W) % p.H);
+      int dy = -pad, dx = -pad;                           // mode 0 filter offsets of the current tap
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-          const uint32_t a_dst = base + stage * STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-          if (p.mode == 1) {
-            // unshuffle view (c' = p2*ld + c, ox, p1, oy, b)
-            tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld + kc * TC_BK, 0, tap >> 1, y_first,
-                        n_first);
-          } else {
-            const int pad = p.ksize >> 1;
-            const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
-            const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
-            tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+          if (leader) {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            const uint32_t a_dst = base + stage * STAGE_BYTES;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            if (p.mode == 1)   // unshuffle view (c' = p2*ld + c, ox, p1, oy, b)
+              tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld + kc * TC_BK, 0, tap >> 1, y_first,
+                          n_first);
+            else if (p.mode == 0)
+              tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+            else
+              tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, 0, y_first, n_first, 0);
+            tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
           }
-          tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (++dx > pad) { dx = -pad; ++dy; }
       }
     }
   } else if (warp == 1) {
@@ -212,6 +217,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long b = q / p.H;
         opix = (b * (2 * p.H) + 2 * oy + (tap2 >> 1)) * (long long)(2 * p.W) + 2 * ox + (tap2 & 1);
       }
+      // residual / accumulate sources are fetched BEFORE waiting for the accumulator (and for the next
+      // sub-tile while the current one is being stored), so their L2 latency hides behind the MMAs
+      uint4 src_res[4], src_acc[4];
+      auto prefetch_src = [&](int s) {
+        const int c = s * 64 + half * 32;
+        if (valid && p.res) {
+          const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + co0 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) src_res[g] = rr[g];
+        }
+        if (valid && p.y_read) {
+          const uint4* yr = reinterpret_cast<const uint4*>(p.y_read + opix * p.y_ld + co0 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) src_acc[g] = yr[g];
+        }
+      };
+      prefetch_src(0);
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -233,25 +255,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co0 + c + j);
         }
         if (valid && p.res) {
-          const __nv_bfloat16* rr = p.res + opix * p.res_ld + co0 + c;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float t[8];
-            ld8(rr + g * 8, t);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              v[g * 8 + 2 * j] += f.x;
+              v[g * 8 + 2 * j + 1] += f.y;
+            }
           }
         }
         if (valid && p.y_read) {
-          const __nv_bfloat16* yr = p.y_read + opix * p.y_ld + co0 + c;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float t[8];
-            ld8(yr + g * 8, t);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              v[g * 8 + 2 * j] += f.x;
+              v[g * 8 + 2 * j + 1] += f.y;
+            }
           }
         }
+        if (s + 1 < SUBTILES) prefetch_src(s + 1);
         // staging buffer `sbuf` was last used two sub-tiles ago: its TMA store must have read it
         if (store_thread) tma_store_wait_read<1>();
         named_bar_sync(1, 32 * TC_EPI_WARPS);
@@ -473,6 +500,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int b = m_tile / tiles_per_img, rem = m_tile - b * tiles_per_img;
       const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
       const long long opix = ((long long)b * p.H + y0 + ty) * p.W + x0 + tx;
+      // residual / accumulate sources: fetched before the accumulator wait (latency hidden behind the MMAs)
+      uint4 src_res[4], src_acc[4];
+      auto prefetch_src = [&](int s2) {
+        const int c = s2 * 64 + half * 32;
+        if (p.res) {
+          const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + n0 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) src_res[g] = rr[g];
+        }
+        if (p.y_read) {
+          const uint4* yr = reinterpret_cast<const uint4*>(p.y_read + opix * p.y_ld + n0 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) src_acc[g] = yr[g];
+        }
+      };
+      prefetch_src(0);
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -495,25 +538,30 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c + j);
         }
         if (p.res) {
-          const __nv_bfloat16* rr = p.res + opix * p.res_ld + n0 + c;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float t[8];
-            ld8(rr + g * 8, t);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              v[g * 8 + 2 * j] += f.x;
+              v[g * 8 + 2 * j + 1] += f.y;
+            }
           }
         }
         if (p.y_read) {
-          const __nv_bfloat16* yr = p.y_read + opix * p.y_ld + n0 + c;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            float t[8];
-            ld8(yr + g * 8, t);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += t[j];
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(h2[j]);
+              v[g * 8 + 2 * j] += f.x;
+              v[g * 8 + 2 * j + 1] += f.y;
+            }
           }
         }
+        if (s2 + 1 < SUBTILES) prefetch_src(s2 + 1);
         if (store_thread) tma_store_wait_read<1>();
         named_bar_sync(1, 32 * TC_EPI_WARPS);
         uint8_t* srow = out_stage_ptr + sbuf * OUT_STAGE_BYTES + row * 128;
@@ -836,10 +884,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
       const int pad = p.ksize >> 1;
       const int dy = (p.mode == 0) ? tap / p.ksize - pad : 0;
       const int dx = (p.mode == 0) ? tap % p.ksize - pad : 0;
+      // (image, row) of the first pixel of the K tile, advanced incrementally (no divisions in the loop)
+      const int rows_per_tile = TC_BM / p.W;                       // image rows covered by one 128-pixel tile
+      const int step_y = rows_per_tile <= p.H ? rows_per_tile : 0;
+      const int step_n = rows_per_tile <= p.H ? 0 : rows_per_tile / p.H;
+      const long long first0 = (long long)kt0 * TC_BM;
+      int n_first = (int)(first0 / ((long long)p.H * p.W));
+      int y_first = (int)((first0 / p.W) % p.H);
       for (int kt = kt0; kt < kt1; ++kt) {
-        const long long first = (long long)kt * TC_BM;
-        const int n_first = (int)(first / ((long long)p.H * p.W));
-        const int y_first = (int)((first / p.W) % p.H);
         mbar_wait(empty_bar(stage), phase ^ 1u);
         mbar_expect_tx(full_bar(stage), STAGE_BYTES);
         const uint32_t a_dst = base + stage * STAGE_BYTES;
@@ -857,6 +909,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                         n_first, 0);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        y_first += step_y;
+        n_first += step_n;
+        if (y_first >= p.H) { y_first = 0; ++n_first; }
       }
     }
   } else if (warp == 1) {
