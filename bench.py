@@ -35,6 +35,22 @@ TRAIN_B, TRAIN_S = 128, 32
 DDIM_B, DDIM_S, DDIM_STEPS = 256, 64, 50
 
 
+def profiled_traffic(family):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family from the committed
+    `ncu --set full` capture (profiles/r1_roofline_traffic.json, scripts/make_profiles.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if not os.path.isfile(p):
+        return None
+    d = json.load(open(p))
+    names = {"wgrad_tc": ("wgrad3x3_halo_kernel", "wgrad_tc_kernel"),
+             "conv_tc_fwd": ("conv3x3_halo_kernel", "conv_tc_kernel"),
+             "conv_tc_dgrad": ("conv3x3_halo_kernel", "conv_tc_kernel")}.get(family, (family,))
+    n = sum(d[k]["launches"] for k in names if k in d)
+    if n == 0:
+        return None
+    return round(sum(d[k]["dram_MB"] for k in names if k in d) * 1e6 / n)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -404,7 +420,7 @@ def main():
         k, v = top
         achieved = v["flops"] / (v["ms"] * 1e-3) / 1e12
         roof = {"kernel": k, "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tf_burst"],
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_burst"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_burst"], 4), "traffic": profiled_traffic(k),
                 "peak_source": peaks["source"] + " bf16_tflops (burst: kernel timed per launch with CUDA events)",
                 "launches_per_pass": v["launches"], "avg_launch_us": round(v["ms"] * 1e3 / v["launches"], 2),
                 "share_of_step": round(v["ms"] / total_ms, 4),

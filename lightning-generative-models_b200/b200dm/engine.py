@@ -106,7 +106,7 @@ class Plan:
         dim, ch = arena.dim, arena.channels
         self._keep.append(pack)
         import os
-        self.side_enabled = training and os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
+        self.side_enabled = os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
@@ -163,8 +163,8 @@ class Plan:
         # for: it runs on the plan's second stream.  reads (side ops) / writes (main ops) name the buffers
         # whose reuse must be ordered across the two streams (write-after-read on shared scratch).
         op.side = side
-        op.reads = frozenset(v.buf.data_ptr() for v in reads if v is not None)
-        op.writes = frozenset(v.buf.data_ptr() for v in writes if v is not None)
+        op.reads = frozenset(getattr(v, "buf", v).data_ptr() for v in reads if v is not None)
+        op.writes = frozenset(getattr(v, "buf", v).data_ptr() for v in writes if v is not None)
         lst.append(op)
 
     def F(self, name, *args, **kw):
@@ -183,7 +183,7 @@ class Plan:
         return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
 
     def conv_fwd(self, lst_fn, nm, x: View, y: View, *, dgrad=False, res: Optional[View] = None,
-                 accumulate=0, bias=True):
+                 accumulate=0, bias=True, side=False):
         """Forward conv `nm` (x -> y), or with dgrad=True its data gradient (x = dY, y = dX)."""
         ci = self.arena.convs[nm]
         if not dgrad:
@@ -204,7 +204,7 @@ class Plan:
         taps = ci.taps
         flops = 2.0 * self.B * H * H * cout * cin * taps
         fam = ("conv_tc" if d.impl == 1 else "conv_simt") + ("_dgrad" if dgrad else "_fwd")
-        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops, writes=(y,))
+        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops, writes=(y,), side=side)
         self._keep.append(d)
 
     def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None,
@@ -242,20 +242,19 @@ class Plan:
         st1, st2 = self.f32(self.B, GROUPS, 2), self.f32(self.B, GROUPS, 2)
         film_ptr = self.film.data_ptr() + 4 * a.film_off[nm]
         b1, b2 = nm + ".block1", nm + ".block2"
+        rc = None
+        if has_res_conv:      # issued first: runs on the second stream next to the whole conv/norm chain
+            rc = self.buf(H, cout)
+            self.conv_fwd(self.F, nm + ".res_conv", x, rc, side=True)
         self.conv_fwd(self.F, b1 + ".proj", x, c1)
         self.F("b200dm_gn_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
                a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout, GROUPS,
-               GN_EPS)
+               GN_EPS, reads=(self.film,))
         self.conv_fwd(self.F, b2 + ".proj", h1, c2)
-        if has_res_conv:
-            rc = self.buf(H, cout)
-            self.conv_fwd(self.F, nm + ".res_conv", x, rc)
-            res = rc
-        else:
-            res = x
+        res = rc if has_res_conv else x
         self.F("b200dm_gn_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
                a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS,
-               GN_EPS)
+               GN_EPS, reads=(res,))
         if not self.training:
             return
         # dc2 / dc1: separate scratch for the two norm gradients, so block1's norm backward does not have to wait
@@ -350,13 +349,14 @@ class Plan:
             self.sums, self.gmeans = self.f32(int(ws)), self.f32(B, GROUPS, 2)
             self.dctx = self.f32(B, 4, 33, 32)
         self.begin_unit()
-        self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0)
+        # the time-embedding chain only feeds the FiLM scale/shift of the first norm: second stream, next to the stem
+        self.F("b200dm_sinusoidal", self.t_in.data_ptr(), self.emb.data_ptr(), B, dim, 10000.0, side=True)
         self.F("b200dm_linear_fwd", self.emb.data_ptr(), a.ptr("time_mlp.1.weight"), a.ptr("time_mlp.1.bias"),
-               self.h.data_ptr(), self.pre1.data_ptr(), B, td, dim, 1)
+               self.h.data_ptr(), self.pre1.data_ptr(), B, td, dim, 1, side=True)
         self.F("b200dm_linear_fwd", self.h.data_ptr(), a.ptr("time_mlp.3.weight"), a.ptr("time_mlp.3.bias"),
-               self.tact.data_ptr(), self.pre3.data_ptr(), B, td, td, 2)
+               self.tact.data_ptr(), self.pre3.data_ptr(), B, td, td, 2, side=True)
         self.F("b200dm_linear_fwd", self.tact.data_ptr(), a.film_weight_ptr, a.film_bias_ptr,
-               self.film.data_ptr(), None, B, a.film_cols, td, 0)
+               self.film.data_ptr(), None, B, a.film_cols, td, 0, side=True, writes=(self.film,))
         if tr:  # runs LAST in backward (dfilm is complete once every block has run)
             self.Bk("b200dm_linear_bwd", self.tact.data_ptr(), a.film_weight_ptr, None, self.dfilm.data_ptr(),
                     self.dtact.data_ptr(), a.film_weight_gptr, a.film_bias_gptr, B, a.film_cols, td, 0)
@@ -466,9 +466,7 @@ class Plan:
 
     # ---- execution --------------------------------------------------------------------------------------
     def run_forward(self):
-        st = L.stream_ptr()
-        for op in self.fwd:
-            op(st)
+        self._run_ops(self.fwd)
 
     def run_backward(self):
         st = L.stream_ptr()
@@ -476,12 +474,19 @@ class Plan:
             op(st)
 
     def run_backward_segment(self, i: int):
-        """Launch backward segment i.  Parameter-gradient kernels (op.side) go to the plan's second stream and
-        overlap the data-gradient chain; the two streams are ordered by events only where a scratch buffer is
-        reused (write on the main stream after a read on the side stream), and they join at the segment end, so
-        the gradient bucket of the segment is complete when this returns (in stream order).  Works the same
-        under CUDA-graph capture: the side stream forks from and rejoins the capturing stream."""
-        ops = self.bwd_segments[i]
+        """Launch backward segment i (see `_run_ops`); the gradient bucket of the segment is complete, in stream
+        order, when this returns."""
+        self._run_ops(self.bwd_segments[i])
+
+    def _run_ops(self, ops):
+        """Launch a list of ops on two streams.  Ops marked `side` (parameter-gradient kernels in backward, the
+        1x1 residual convs in forward) go to the plan's second stream and overlap the main chain, which is
+        latency-bound at the benchmark batch.  Ordering across the streams is by events, only where needed:
+          * a side op starts after everything issued on the main stream so far (its inputs' producers);
+          * a main op that writes a buffer a side op is still reading, or touches a buffer a side op writes,
+            waits for that side op;
+        and the streams join at the end, so everything is complete (in stream order) when this returns.  Works
+        the same under CUDA-graph capture: the side stream forks from and rejoins the capturing stream."""
         if not self.side_enabled or not any(op.side for op in ops):
             st = L.stream_ptr()
             for op in ops:
@@ -490,26 +495,36 @@ class Plan:
         main = torch.cuda.current_stream()
         side = self.side_stream
         main_ptr, side_ptr = main.cuda_stream, side.cuda_stream
-        pending = {}                       # buffer -> event of the last side-stream kernel reading it
-        fork, dirty = None, True
+        pending_r, pending_w = {}, {}      # buffer -> event of the last side kernel reading / writing it
+        dirty = True
         for op in ops:
             if op.side:
-                if dirty:                  # everything issued on the main stream so far (incl. the producer)
+                if dirty:                  # everything issued on the main stream so far (incl. the producers)
                     fork = torch.cuda.Event()
                     fork.record(main)
                     side.wait_event(fork)
                     dirty = False
                 op(side_ptr)
-                if op.reads:
+                if op.reads or op.writes:
                     ev = torch.cuda.Event()
                     ev.record(side)
                     for b in op.reads:
-                        pending[b] = ev
+                        pending_r[b] = ev
+                    for b in op.writes:
+                        pending_w[b] = ev
             else:
+                waited = set()
                 for b in op.writes:
-                    ev = pending.pop(b, None)
-                    if ev is not None:
+                    for pend in (pending_r, pending_w):
+                        ev = pend.pop(b, None)
+                        if ev is not None and id(ev) not in waited:
+                            main.wait_event(ev)
+                            waited.add(id(ev))
+                for b in op.reads:
+                    ev = pending_w.pop(b, None)
+                    if ev is not None and id(ev) not in waited:
                         main.wait_event(ev)
+                        waited.add(id(ev))
                 op(main_ptr)
                 dirty = True
         main.wait_stream(side)
