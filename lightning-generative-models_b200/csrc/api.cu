@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // C-ABI plumbing: error string, launch counter, capability probe, conv dispatch.
 #include <stdarg.h>
 
@@ -6,6 +7,15 @@
 #include "common.cuh"
 
 namespace b200dm {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200DM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread

@@ -35,6 +35,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 linattn_ctx_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
                    float* __restrict__ ctx, float* __restrict__ kstat, int n) {
+  pdl_prologue();
   const int b = blockIdx.x / HEADS, h = blockIdx.x % HEADS;
   const int tid = threadIdx.x;
   const T* kbase = qkv + (int64_t)b * n * ld + HID + h * DH;
@@ -156,6 +157,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 linattn_out_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ ctx,
                    T* __restrict__ out, int out_ld, int n) {
+  pdl_prologue();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
   const int tid = threadIdx.x;
   __shared__ __align__(16) float C_s[DH][DH];        // ctx[d][e]
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(256)
 linattn_bwd_q_kernel(const T* __restrict__ dout, int dout_ld, const T* __restrict__ qkv, int ld,
                      const float* __restrict__ ctx, float* __restrict__ dctx, T* __restrict__ dqkv,
                      int dld, int n) {
+  pdl_prologue();
   const int bh = blockIdx.x, b = bh / HEADS, h = bh % HEADS;
   const int tid = threadIdx.x;
   __shared__ __align__(16) float CT_s[DH][DH];        // ctx transposed: CT_s[e][d]
@@ -297,6 +300,7 @@ linattn_bwd_kv_kernel(const T* __restrict__ qkv, int ld, const float* __restrict
                       const float* __restrict__ ctx, const float* __restrict__ kstat,
                       const float* __restrict__ dctx, T* __restrict__ dqkv, int dld,
                       float* __restrict__ dmem_kv, int n) {
+  pdl_prologue();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
   const int tid = threadIdx.x;
   __shared__ __align__(16) float D_s[DH][DH];         // dctx[d][e]
@@ -447,6 +451,7 @@ __global__ void __launch_bounds__(256)
 linattn_fwd_cluster_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
                            float* __restrict__ ctx_out, float* __restrict__ kstat, T* __restrict__ out,
                            int out_ld, int n) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
@@ -639,6 +644,7 @@ linattn_bwd_cluster_kernel(const T* __restrict__ dout, int dout_ld, const T* __r
                            const float* __restrict__ mem_kv, const float* __restrict__ ctx,
                            const float* __restrict__ kstat, T* __restrict__ dqkv, int dld,
                            float* __restrict__ dmem_kv, int n) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
@@ -957,6 +963,7 @@ __global__ void __launch_bounds__(256)
 linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
                       float* __restrict__ ctx_out, float* __restrict__ kstat, lbf* __restrict__ out,
                       int out_ld, int n) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
@@ -1130,6 +1137,7 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
                       const float* __restrict__ mem_kv, const float* __restrict__ ctx,
                       const float* __restrict__ kstat, lbf* __restrict__ dqkv, int dld,
                       float* __restrict__ dmem_kv, int n) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int bh = blockIdx.y, b = bh / HEADS, h = bh % HEADS;
@@ -1334,13 +1342,15 @@ static cudaError_t la_launch_cluster(K kernel, dim3 grid, int cl, size_t smem, c
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -1402,6 +1412,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attn_fwd_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
                 T* __restrict__ out, int out_ld, int n) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smraw[];
   FaSmem& s = *reinterpret_cast<FaSmem*>(smraw);
   const int b = blockIdx.x / HEADS, h = blockIdx.x % HEADS, kv = n + NMEM;
@@ -1427,6 +1438,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const T* __restrict__ dout, int dout_ld, const T* __restrict__ qkv, int ld,
                 const float* __restrict__ mem_kv, T* __restrict__ dqkv, int dld,
                 float* __restrict__ dmem_kv, int n) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smraw[];
   FaBwdSmem& s = *reinterpret_cast<FaBwdSmem*>(smraw);
   const int b = blockIdx.x / HEADS, h = blockIdx.x % HEADS, kv = n + NMEM;
@@ -1559,10 +1571,10 @@ extern "C" int b200dm_attn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, c
   size_t smem = sizeof(FaSmem);
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_fwd_kernel<float><<<B * HEADS, 256, smem, st>>>((const float*)qkv, qkv_ld, mem_kv, (float*)out, out_ld, n);
+    launch_k(attn_fwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)qkv, qkv_ld, mem_kv, (float*)out, out_ld, n);
   } else {
     cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_fwd_kernel<bf16><<<B * HEADS, 256, smem, st>>>((const bf16*)qkv, qkv_ld, mem_kv, (bf16*)out, out_ld, n);
+    launch_k(attn_fwd_kernel<bf16>, B * HEADS, 256, smem, st, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)out, out_ld, n);
   }
   count_launch();
   return check_launch("attn_fwd");
@@ -1577,10 +1589,10 @@ extern "C" int b200dm_attn_bwd(int32_t dtype, const void* dout, int32_t dout_ld,
   size_t smem = sizeof(FaBwdSmem);
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_bwd_kernel<float><<<B * HEADS, 256, smem, st>>>((const float*)dout, dout_ld, (const float*)qkv, qkv_ld, mem_kv, (float*)dqkv, dqkv_ld, dmem_kv, n);
+    launch_k(attn_bwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)dout, dout_ld, (const float*)qkv, qkv_ld, mem_kv, (float*)dqkv, dqkv_ld, dmem_kv, n);
   } else {
     cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attn_bwd_kernel<bf16><<<B * HEADS, 256, smem, st>>>((const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)dqkv, dqkv_ld, dmem_kv, n);
+    launch_k(attn_bwd_kernel<bf16>, B * HEADS, 256, smem, st, (const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)dqkv, dqkv_ld, dmem_kv, n);
   }
   count_launch();
   return check_launch("attn_bwd");

@@ -22,6 +22,36 @@ int check_launch(const char* what);  // cudaGetLastError -> B200DM_ERR_CUDA
     }                                    \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------
+// Every kernel is launched with the programmatic-stream-serialization attribute and starts with
+// griddepcontrol.launch_dependents + griddepcontrol.wait: the next kernel of the stream may be scheduled while
+// this one drains, runs its prologue (barrier / TMEM / descriptor setup) and blocks in `pdl_wait()` until this
+// kernel has completed and its writes are visible.  Because EVERY kernel waits, completion is transitive along
+// the stream.  Nothing before `pdl_wait()` may touch global memory.  B200DM_PDL=0 disables the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -37,6 +37,7 @@ template <typename T>
 __global__ void __launch_bounds__(kConvThreads)
 conv_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ w,
                  const float* __restrict__ bias, T* __restrict__ y, const T* __restrict__ res) {
+  pdl_prologue();
   __shared__ float As[BK][BM + PADM];
   __shared__ float Bs[BK][BN + PADM];
   const int tid = threadIdx.x;
@@ -122,6 +123,7 @@ template <typename T>
 __global__ void __launch_bounds__(kConvThreads)
 wgrad_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ dy, int dy_ld,
                   float* __restrict__ dw, int splits, long long s_tap, long long s_co, long long s_ci) {
+  pdl_prologue();
   __shared__ float As[BK][BM + PADM];  // dY chunk: [pixel][co]
   __shared__ float Bs[BK][BN + PADM];  // X chunk:  [pixel][ci]
   const int tid = threadIdx.x;
@@ -183,6 +185,7 @@ wgrad_simt_kernel(ConvP c, const T* __restrict__ x, const T* __restrict__ dy, in
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int ld, int64_t rows, int C,
                               float* __restrict__ out, int64_t rows_per_block) {
+  pdl_prologue();
   __shared__ float red[4][64];
   int c = blockIdx.x * 64 + threadIdx.x;
   int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -204,6 +207,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum8_kernel(const T* __restrict__ x, int ld, int64_t rows, int C8, float* __restrict__ out,
                int64_t rows_per_block, int VL) {
+  pdl_prologue();
   __shared__ float red[256][8];
   const int vl = threadIdx.x % VL, rl = threadIdx.x / VL, RL = 256 / VL;
   const int cv = blockIdx.x * VL + vl;  // 8-channel vector index
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(256)
 init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ bias, T* __restrict__ y, int y_ld, int B, int C, int H,
                  int W) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int K = C * 49;
   float* wsm = sm;                          // [K][64]
@@ -305,6 +310,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int dy_ld,
                        float* __restrict__ dw, int B, int C, int H, int W) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   const int PW = W + 6, PH = IC_ROWS + 6;
   float* gsm = sm;                            // [IC_ROWS][W][64] output gradients of the item
@@ -374,6 +380,7 @@ __global__ void __launch_bounds__(256)
 final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w,
                   const float* __restrict__ bias, float* __restrict__ y, int64_t total, int HW,
                   int Cin, int C) {
+  pdl_prologue();
   extern __shared__ float wsm[];  // [C][Cin]
   for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
@@ -400,6 +407,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
                      int dx_ld, int64_t total, int HW, int Cin, int C) {
+  pdl_prologue();
   extern __shared__ float wsm[];
   for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
@@ -429,6 +437,7 @@ template <typename T>
 __global__ void final_conv_dw_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ dy,
                                      float* __restrict__ dw, float* __restrict__ db, int64_t total,
                                      int HW, int Cin, int C, int64_t per_block) {
+  pdl_prologue();
   extern __shared__ float red[];  // [blockDim.y][5][Cin]
   const int ci = threadIdx.x, ly = threadIdx.y, ny = blockDim.y;
   int64_t p0 = (int64_t)blockIdx.x * per_block;
@@ -464,6 +473,7 @@ __global__ void final_conv_dw_kernel(const T* __restrict__ x, int x_ld, const fl
 template <typename T>
 __global__ void upsample_fwd_kernel(const T* __restrict__ x, int x_ld, T* __restrict__ y, int y_ld,
                                     int64_t total8, int H, int W, int C8) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c8 = (int)(i % C8);
@@ -480,6 +490,7 @@ __global__ void upsample_fwd_kernel(const T* __restrict__ x, int x_ld, T* __rest
 template <typename T>
 __global__ void upsample_bwd_kernel(const T* __restrict__ dy, int dy_ld, T* __restrict__ dx,
                                     int dx_ld, int64_t total8, int H, int W, int C8) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c8 = (int)(i % C8);
@@ -511,7 +522,7 @@ static int launch_conv(const b200dm_conv_desc* d, cudaStream_t st) {
   c.taps = d->mode == 0 ? d->ksize * d->ksize : 4;
   c.N = d->mode == 2 ? 4 * d->Cout : d->Cout;
   dim3 grid((unsigned)((c.M + BM - 1) / BM), (unsigned)((c.N + BN - 1) / BN));
-  conv_simt_kernel<T><<<grid, kConvThreads, 0, st>>>(c, (const T*)d->x, (const T*)d->w, d->bias,
+  launch_k(conv_simt_kernel<T>, grid, kConvThreads, 0, st, c, (const T*)d->x, (const T*)d->w, d->bias,
                                                       (T*)d->y, (const T*)d->res);
   count_launch();
   return check_launch("conv_simt");
@@ -540,7 +551,7 @@ static int launch_wgrad(const b200dm_wgrad_desc* d, cudaStream_t st) {
   dim3 grid(tiles, c.taps, splits);
   long long s_tap = d->s_tap, s_co = d->s_co, s_ci = d->s_ci;
   if (s_tap == 0 && s_co == 0 && s_ci == 0) { s_tap = (long long)c.Cout * c.Cin; s_co = c.Cin; s_ci = 1; }
-  wgrad_simt_kernel<T><<<grid, kConvThreads, 0, st>>>(c, (const T*)d->x, (const T*)d->dy, d->dy_ld,
+  launch_k(wgrad_simt_kernel<T>, grid, kConvThreads, 0, st, c, (const T*)d->x, (const T*)d->dy, d->dy_ld,
                                                        d->dw, splits, s_tap, s_co, s_ci);
   count_launch();
   return check_launch("wgrad_simt");
@@ -575,9 +586,9 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
     int64_t per8 = (rows + rb - 1) / rb;
     dim3 grid8(cb, (unsigned)rb);
     if (dtype == B200DM_F32)
-      colsum8_kernel<float><<<grid8, 256, 0, st>>>((const float*)x, ld, rows, C8, out, per8, VL);
+      launch_k(colsum8_kernel<float>, grid8, 256, 0, st, (const float*)x, ld, rows, C8, out, per8, VL);
     else
-      colsum8_kernel<__nv_bfloat16><<<grid8, 256, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C8, out, per8, VL);
+      launch_k(colsum8_kernel<__nv_bfloat16>, grid8, 256, 0, st, (const __nv_bfloat16*)x, ld, rows, C8, out, per8, VL);
     count_launch();
     return check_launch("colsum8");
   }
@@ -588,9 +599,9 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
   int64_t per = (rows + rblocks - 1) / rblocks;
   dim3 grid(cblocks, (unsigned)rblocks), block(64, 4);
   if (dtype == B200DM_F32)
-    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, rows, C, out, per);
+    launch_k(colsum_kernel<float>, grid, block, 0, st, (const float*)x, ld, rows, C, out, per);
   else
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ld, rows, C, out, per);
+    launch_k(colsum_kernel<__nv_bfloat16>, grid, block, 0, st, (const __nv_bfloat16*)x, ld, rows, C, out, per);
   count_launch();
   return check_launch("colsum");
 }
@@ -603,6 +614,7 @@ namespace b200dm {
 // block = (KP/8 vector lanes, 8 pixels): no per-thread division for the vector index, 32-bit pixel math
 __global__ void im2col7_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, unsigned npix, int C, int H,
                                int W, int KP) {
+  pdl_prologue();
   const int K = C * 49;
   const int v = threadIdx.x;
   int kch[8], kdy[8], kdx[8];
@@ -628,6 +640,7 @@ __global__ void im2col7_kernel(const float* __restrict__ x, __nv_bfloat16* __res
   }
 }
 __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int K, int KP) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Cout * KP) {
     const int co = i / KP, k = i - co * KP;
@@ -644,7 +657,7 @@ extern "C" int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int
   const unsigned npix = (unsigned)((int64_t)B * H * W);
   dim3 block(KP / 8, 8);
   unsigned blocks = (npix + 7) / 8, cap = (unsigned)b200dm::num_sms() * 16;
-  b200dm::im2col7_kernel<<<blocks > cap ? cap : blocks, block, 0, (cudaStream_t)stream>>>(
+  launch_k(b200dm::im2col7_kernel, blocks > cap ? cap : blocks, block, 0, (cudaStream_t)stream, 
       x, (__nv_bfloat16*)P, npix, C, H, W, KP);
   b200dm::count_launch();
   return b200dm::check_launch("im2col7");
@@ -652,7 +665,7 @@ extern "C" int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int
 
 extern "C" int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream) {
   B200DM_REQUIRE(Cout > 0 && K > 0 && K <= KP, B200DM_ERR_SHAPE, "pack_stem_weight: K=%d KP=%d", K, KP);
-  b200dm::pack_stem_kernel<<<(Cout * KP + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, K, KP);
+  launch_k(b200dm::pack_stem_kernel, (Cout * KP + 255) / 256, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, Cout, K, KP);
   b200dm::count_launch();
   return b200dm::check_launch("pack_stem_weight");
 }
@@ -669,10 +682,10 @@ extern "C" int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(init_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    init_conv_kernel<float><<<grid, 256, smem, st>>>(x, w, bias, (float*)y, y_ld, B, C, H, W);
+    launch_k(init_conv_kernel<float>, grid, 256, smem, st, x, w, bias, (float*)y, y_ld, B, C, H, W);
   } else {
     cudaFuncSetAttribute(init_conv_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    init_conv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, w, bias, (__nv_bfloat16*)y, y_ld, B, C, H, W);
+    launch_k(init_conv_kernel<__nv_bfloat16>, grid, 256, smem, st, x, w, bias, (__nv_bfloat16*)y, y_ld, B, C, H, W);
   }
   count_launch();
   return check_launch("init_conv_fwd");
@@ -690,10 +703,10 @@ extern "C" int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void*
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(init_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    init_conv_wgrad_kernel<float><<<grid, 256, smem, st>>>(x, (const float*)dy, dy_ld, dw, B, C, H, W);
+    launch_k(init_conv_wgrad_kernel<float>, grid, 256, smem, st, x, (const float*)dy, dy_ld, dw, B, C, H, W);
   } else {
     cudaFuncSetAttribute(init_conv_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    init_conv_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(x, (const __nv_bfloat16*)dy, dy_ld, dw, B, C, H, W);
+    launch_k(init_conv_wgrad_kernel<__nv_bfloat16>, grid, 256, smem, st, x, (const __nv_bfloat16*)dy, dy_ld, dw, B, C, H, W);
   }
   count_launch();
   return check_launch("init_conv_wgrad");
@@ -708,9 +721,9 @@ extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld,
   unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    final_conv_kernel<float><<<grid, 256, smem, st>>>((const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<float>, grid, 256, smem, st, (const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
   else
-    final_conv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, smem, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
   count_launch();
   return check_launch("final_conv_fwd");
 }
@@ -731,11 +744,11 @@ extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld,
   dim3 block2(Cin, ny);
   size_t smem2 = (size_t)ny * 4 * Cin * sizeof(float);
   if (dtype == B200DM_F32) {
-    final_conv_dx_kernel<float><<<grid, 256, smem, st>>>(w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
-    final_conv_dw_kernel<float><<<(unsigned)nblk, block2, smem2, st>>>((const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    launch_k(final_conv_dx_kernel<float>, grid, 256, smem, st, w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
+    launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, block2, smem2, st, (const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
   } else {
-    final_conv_dx_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
-    final_conv_dw_kernel<__nv_bfloat16><<<(unsigned)nblk, block2, smem2, st>>>((const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, smem, st, w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
+    launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, block2, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
   }
   count_launch(2);
   return check_launch("final_conv_bwd");
@@ -749,9 +762,9 @@ extern "C" int b200dm_upsample2x_fwd(int32_t dtype, const void* x, int32_t x_ld,
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    upsample_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, x_ld, (float*)y, y_ld, total8, H, W, C / 8);
+    launch_k(upsample_fwd_kernel<float>, (unsigned)blocks, 256, 0, st, (const float*)x, x_ld, (float*)y, y_ld, total8, H, W, C / 8);
   else
-    upsample_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, total8, H, W, C / 8);
+    launch_k(upsample_fwd_kernel<__nv_bfloat16>, (unsigned)blocks, 256, 0, st, (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)y, y_ld, total8, H, W, C / 8);
   count_launch();
   return check_launch("upsample2x_fwd");
 }
@@ -765,9 +778,9 @@ extern "C" int b200dm_upsample2x_bwd(int32_t dtype, const void* dy, int32_t dy_l
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    upsample_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, dy_ld, (float*)dx, dx_ld, total8, H, W, C / 8);
+    launch_k(upsample_bwd_kernel<float>, (unsigned)blocks, 256, 0, st, (const float*)dy, dy_ld, (float*)dx, dx_ld, total8, H, W, C / 8);
   else
-    upsample_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)dx, dx_ld, total8, H, W, C / 8);
+    launch_k(upsample_bwd_kernel<__nv_bfloat16>, (unsigned)blocks, 256, 0, st, (const __nv_bfloat16*)dy, dy_ld, (__nv_bfloat16*)dx, dx_ld, total8, H, W, C / 8);
   count_launch();
   return check_launch("upsample2x_bwd");
 }

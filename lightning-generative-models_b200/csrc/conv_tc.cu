@@ -85,6 +85,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
   constexpr int SUBTILES = N_TILE / 64;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B wants 1024-B alignment
   const uint32_t out_stage = base + STAGES * STAGE_BYTES;        // 2 x 16 KiB staging for TMA stores
@@ -121,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -350,6 +352,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int B_BYTES = N_TILE * TC_BK * 2;
   constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
   constexpr int SUBTILES = N_TILE / 64;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -389,6 +392,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -661,7 +665,7 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_tc_kernel<N_TILE, STAGES><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p);
+  launch_k(conv_tc_kernel<N_TILE, STAGES>, grid, TC_THREADS, smem, st, tmA, tmB, tmY, p);
   count_launch();
   return check_launch("conv_tc");
 }
@@ -681,7 +685,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv3x3_halo_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p);
+  launch_k(conv3x3_halo_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT>, grid, TC_THREADS, smem, st, tmA, tmB, tmY, p);
   count_launch();
   return check_launch("conv3x3_halo");
 }
@@ -844,6 +848,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   constexpr int NB = N_TILE / 64;
   constexpr int STAGE_BYTES = (2 + NB) * BOX_BYTES;
   constexpr int TMEM_COLS = N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -876,6 +881,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0 && has_work) {
@@ -990,7 +996,7 @@ static int launch_wgrad_tc(const CUtensorMap& tmDY, const CUtensorMap& tmX, cons
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  wgrad_tc_kernel<N_TILE, STAGES><<<grid, WG_THREADS, smem, st>>>(tmDY, tmX, p);
+  launch_k(wgrad_tc_kernel<N_TILE, STAGES>, grid, WG_THREADS, smem, st, tmDY, tmX, p);
   count_launch();
   return check_launch("wgrad_tc");
 }
@@ -1033,6 +1039,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr int DY_BYTES = TC_BM * TC_BK * 2;                  // 16 KiB: [128 pixels][64 co]
   constexpr int STAGE_BYTES = HALO_BYTES + DY_BYTES;           // 52 KiB
   constexpr int TMEM_COLS = 512;                               // 6 x 64 accumulator columns
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -1066,6 +1073,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0 && has_work) {
@@ -1199,7 +1207,7 @@ static int conv_wgrad_halo(const b200dm_wgrad_desc* d, cudaStream_t st) {
     B200DM_REQUIRE(err == cudaSuccess, B200DM_ERR_CUDA, "wgrad3x3_halo: cudaFuncSetAttribute: %s", cudaGetErrorString(err));
     configured = true;
   }
-  wgrad3x3_halo_kernel<STAGES, 1><<<pairs * splits, WG_THREADS, smem, st>>>(tmX, tmDY, p);
+  launch_k(wgrad3x3_halo_kernel<STAGES, 1>, pairs * splits, WG_THREADS, smem, st, tmX, tmDY, p);
   count_launch();
   return check_launch("wgrad3x3_halo");
 }
@@ -1261,6 +1269,7 @@ namespace b200dm {
 template <int N_TILE>
 __global__ void __launch_bounds__(128, 1)
 umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + 64 * 1024;     // 64 KiB A region, up to 32 KiB B region
@@ -1276,6 +1285,7 @@ umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
   if (warp == 1) {
     const bool leader = elect_one();
     const uint32_t idesc = mode == 2 ? make_idesc_bf16(TC_BM, N_TILE, 1, 1) : make_idesc_bf16(TC_BM, N_TILE, 0, 0);
@@ -1314,7 +1324,7 @@ extern "C" int b200dm_debug_umma_rate(int32_t n_tile, int32_t iters, int32_t mod
 #define LAUNCH_RATE(N)                                                                                       \
   do {                                                                                                       \
     cudaFuncSetAttribute(umma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);            \
-    umma_rate_kernel<N><<<ctas, 128, smem, st>>>(iters, mode, out_cycles);                                   \
+    launch_k(umma_rate_kernel<N>, ctas, 128, smem, st, iters, mode, out_cycles);                                   \
   } while (0)
   if (n_tile == 64) LAUNCH_RATE(64);
   else if (n_tile == 128) LAUNCH_RATE(128);

@@ -37,6 +37,7 @@ q_sample_kernel(const float* __restrict__ img, const int64_t* __restrict__ t,
                 const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
                 int64_t nvec, int64_t chw4, int normalize, uint64_t seed, uint64_t stream_id,
                 uint64_t vec_offset) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     int b = (int)(i / chw4);
@@ -72,6 +73,7 @@ loss_kernel(const float* __restrict__ out, const float* __restrict__ x0, const f
             const float* __restrict__ sqrt_1mac, const float* __restrict__ loss_weight,
             float* __restrict__ loss_acc, float* __restrict__ d_out, int64_t nvec, int64_t chw4,
             int objective, float inv_count) {
+  pdl_prologue();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -129,6 +131,7 @@ ddim_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
                  float* __restrict__ x0_out, StepCoef c, float sqrt_an, float cc, float sigma,
                  int last, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
                  uint64_t vec_offset) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 x = ld4(x_t, i), o = ld4(out, i);
@@ -157,6 +160,7 @@ ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
                  float* __restrict__ x0_out, StepCoef c, float coef1, float coef2, float noise_std,
                  int add_noise, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
                  uint64_t vec_offset) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 x = ld4(x_t, i), o = ld4(out, i);
@@ -184,6 +188,7 @@ ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
 __global__ void __launch_bounds__(kElemThreads)
 randn_kernel(float* __restrict__ out, int64_t nvec, uint64_t seed, uint64_t stream_id,
              uint64_t vec_offset) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x)
     st4(out, i, Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id));
@@ -191,6 +196,7 @@ randn_kernel(float* __restrict__ out, int64_t nvec, uint64_t seed, uint64_t stre
 
 __global__ void __launch_bounds__(kElemThreads)
 unnormalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t nvec) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = ld4(x, i);
@@ -200,6 +206,7 @@ unnormalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n
 }
 
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     p[i] = v;
@@ -225,7 +232,7 @@ extern "C" int b200dm_q_sample(const float* img, const int64_t* t, const float* 
   CHECK_ALIGN16(noise, "q_sample noise"); CHECK_ALIGN16(noise_out, "q_sample noise_out");
   CHECK_ALIGN16(x0_out, "q_sample x0_out");
   int64_t nvec = (int64_t)B * chw / 4;
-  q_sample_kernel<<<elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream>>>(
+  launch_k(q_sample_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, 
       img, t, noise, x_t, noise_out, x0_out, sqrt_ac, sqrt_1mac, nvec, chw / 4, normalize, seed,
       stream_id, elem_offset / 4);
   count_launch();
@@ -243,7 +250,7 @@ extern "C" int b200dm_loss_fwd_bwd(const float* model_out, const float* x0, cons
   CHECK_ALIGN16(d_out, "loss d_out");
   int64_t nvec = (int64_t)B * chw / 4;
   float inv_count = 1.f / ((float)B * (float)chw);
-  loss_kernel<<<elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream>>>(
+  launch_k(loss_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, 
       model_out, x0, noise, t, sqrt_ac, sqrt_1mac, loss_weight, loss_acc, d_out, nvec, chw / 4,
       objective, inv_count);
   count_launch();
@@ -261,7 +268,7 @@ extern "C" int b200dm_ddim_step(const float* x_t, const float* model_out, const 
   CHECK_ALIGN16(x_t, "ddim x_t"); CHECK_ALIGN16(model_out, "ddim out"); CHECK_ALIGN16(x_next, "ddim x_next");
   CHECK_ALIGN16(noise, "ddim noise"); CHECK_ALIGN16(x0_out, "ddim x0_out");
   StepCoef sc{c_sqrt_ac, c_sqrt_1mac, c_sqrt_recip, c_sqrt_recipm1};
-  ddim_step_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(
+  launch_k(ddim_step_kernel, elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream, 
       x_t, model_out, noise, x_next, x0_out, sc, sqrt_alpha_next, c, sigma, last, objective, n / 4,
       seed, stream_id, elem_offset / 4);
   count_launch();
@@ -279,7 +286,7 @@ extern "C" int b200dm_ddpm_step(const float* x_t, const float* model_out, const 
   CHECK_ALIGN16(x_t, "ddpm x_t"); CHECK_ALIGN16(model_out, "ddpm out"); CHECK_ALIGN16(x_prev, "ddpm x_prev");
   CHECK_ALIGN16(noise, "ddpm noise"); CHECK_ALIGN16(x0_out, "ddpm x0_out");
   StepCoef sc{c_sqrt_ac, c_sqrt_1mac, c_sqrt_recip, c_sqrt_recipm1};
-  ddpm_step_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(
+  launch_k(ddpm_step_kernel, elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream, 
       x_t, model_out, noise, x_prev, x0_out, sc, coef1, coef2, noise_std, add_noise, objective, n / 4,
       seed, stream_id, elem_offset / 4);
   count_launch();
@@ -291,7 +298,7 @@ extern "C" int b200dm_randn(float* out, int64_t n, uint64_t seed, uint64_t strea
   CHECK_VEC(n, "randn");
   B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "randn: elem_offset must be a multiple of 4");
   CHECK_ALIGN16(out, "randn out");
-  randn_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(out, n / 4, seed, stream_id,
+  launch_k(randn_kernel, elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream, out, n / 4, seed, stream_id,
                                                                            elem_offset / 4);
   count_launch();
   return check_launch("randn");
@@ -300,14 +307,14 @@ extern "C" int b200dm_randn(float* out, int64_t n, uint64_t seed, uint64_t strea
 extern "C" int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream) {
   CHECK_VEC(n, "unnormalize");
   CHECK_ALIGN16(x, "unnormalize x"); CHECK_ALIGN16(y, "unnormalize y");
-  unnormalize_kernel<<<elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream>>>(x, y, n / 4);
+  launch_k(unnormalize_kernel, elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream, x, y, n / 4);
   count_launch();
   return check_launch("unnormalize");
 }
 
 extern "C" int b200dm_fill_f32(float* p, int64_t n, float value, void* stream) {
   if (n <= 0) return B200DM_OK;
-  fill_kernel<<<elem_grid(n), kElemThreads, 0, (cudaStream_t)stream>>>(p, n, value);
+  launch_k(fill_kernel, elem_grid(n), kElemThreads, 0, (cudaStream_t)stream, p, n, value);
   count_launch();
   return check_launch("fill_f32");
 }

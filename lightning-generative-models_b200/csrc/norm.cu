@@ -14,6 +14,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const T* __restrict__ x, int ld, float* __restrict__ stats, int HW, int C, int G,
                 float eps) {
+  pdl_prologue();
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int gs = C / G, vpp = gs / 8;  // 8-wide vectors per pixel within the group
   const int64_t nvec = (int64_t)HW * vpp;
@@ -71,6 +72,7 @@ gn_apply_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__
                     const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ film, int film_ld, const T* __restrict__ res,
                     int res_ld, T* __restrict__ y, int y_ld, int64_t total8, int HW, int C, int G) {
+  pdl_prologue();
   const int C8 = C / 8, gs = C / G;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -100,6 +102,7 @@ gn_bwd_reduce_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ 
                      const float* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                      float* __restrict__ sums, int HW, int C, int G, int pix_per_block) {
+  pdl_prologue();
   extern __shared__ float sred[];  // [lanes][C][3]
   const int b = blockIdx.y;
   const int C8 = C / 8, gs = C / G;
@@ -161,6 +164,7 @@ gn_bwd_params_kernel(const float* __restrict__ sums, const float* __restrict__ s
                      const float* __restrict__ film, int film_ld, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dfilm, float* __restrict__ dbias,
                      float* __restrict__ gmeans, int B, int HW, int C, int G, int chunks) {
+  pdl_prologue();
   // one CTA per group: thread = (channel of the group, sample lane); every parameter gradient of the
   // group's channels is reduced over the batch inside the CTA -> plain (+=) stores, no global atomics
   extern __shared__ float sh[];            // tot[gs][3] per sample lane, then reductions
@@ -243,6 +247,7 @@ gn_bwd_apply_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x
                     const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                     const float* __restrict__ gmeans, T* __restrict__ dx, int dx_ld, int64_t total8,
                     int HW, int C, int G) {
+  pdl_prologue();
   const int C8 = C / 8, gs = C / G;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -282,6 +287,19 @@ constexpr int GNC_THREADS = 256;
 constexpr int GNC_MAXC = 512;          // channels handled by the cluster kernels (C8 <= 64 -> >= 4 pixel lanes)
 
 __device__ __forceinline__ float fast_sigmoid(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+// bf16 path: sigmoid(z) = 0.5*tanh(0.5 z) + 0.5 with the single-instruction tanh.approx (abs. error ~5e-4, below
+// bf16 resolution) — ONE SFU op per element instead of two (ex2 + rcp); the SFU (16 ops/clk/SM) was a co-limiter
+// of the GroupNorm kernels, which evaluate SiLU (forward) / SiLU' (twice, backward) for every element.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> __device__ __forceinline__ float sigmoid_t(float z);
+template <> __device__ __forceinline__ float sigmoid_t<float>(float z) { return fast_sigmoid(z); }
+template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float z) {
+  return fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+}
 
 // raw 8-element vectors: issue the loads of several pixels first, convert afterwards (memory-level parallelism)
 template <typename T> struct Raw8;
@@ -318,6 +336,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
                       T* __restrict__ y, int y_ld, int HW, int C, int G, float eps, int write_stats) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -423,7 +442,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], v[j], Bc[j]);
-          const float o = z * fast_sigmoid(z);
+          const float o = z * sigmoid_t<T>(z);
           v[j] = rp ? o + r[j] : o;
         }
         st8(yp + (int64_t)(p + u * lanes) * y_ld, v);
@@ -440,6 +459,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                       T* __restrict__ dx, int dx_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dfilm, float* __restrict__ dbias, int HW, int C, int G) {
+  pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -491,7 +511,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], xv[j], Bc[j]);
-          const float sg = fast_sigmoid(z);
+          const float sg = sigmoid_t<T>(z);
           const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
           const float xn = (xv[j] - mean) * rstd;
           s1[j] += dz;
@@ -577,7 +597,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], xv[j], Bc[j]);
-          const float sg = fast_sigmoid(z);
+          const float sg = sigmoid_t<T>(z);
           const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
           xv[j] = fmaf(P[j], dz, fmaf(R, xv[j], Q));
         }
@@ -610,13 +630,15 @@ static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, size_t smem, cuda
   cfg.blockDim = dim3(GNC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -633,6 +655,7 @@ __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ g,
                    const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int64_t rows,
                    int C, int L) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, sl = lane % L, rpw = 32 / L;      // row slot inside the warp, lane in the row
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -677,6 +700,7 @@ __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                    const float* __restrict__ g, const T* __restrict__ res, int res_ld,
                    T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int64_t rows, int C, int L) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, sl = lane % L, rpw = 32 / L;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -767,9 +791,9 @@ extern "C" int b200dm_gn_stats(int32_t dtype, const void* x, int32_t x_ld, float
   B200DM_REQUIRE(x_ld % 8 == 0, B200DM_ERR_SHAPE, "gn_stats: ld must be a multiple of 8");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    gn_stats_kernel<float><<<B * G, 256, 0, st>>>((const float*)x, x_ld, stats, HW, C, G, eps);
+    launch_k(gn_stats_kernel<float>, B * G, 256, 0, st, (const float*)x, x_ld, stats, HW, C, G, eps);
   else
-    gn_stats_kernel<bf16><<<B * G, 256, 0, st>>>((const bf16*)x, x_ld, stats, HW, C, G, eps);
+    launch_k(gn_stats_kernel<bf16>, B * G, 256, 0, st, (const bf16*)x, x_ld, stats, HW, C, G, eps);
   count_launch();
   return check_launch("gn_stats");
 }
@@ -785,11 +809,11 @@ extern "C" int b200dm_gn_apply_fwd(int32_t dtype, const void* x, int32_t x_ld, c
   int64_t total8 = (int64_t)B * HW * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    gn_apply_fwd_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
+    launch_k(gn_apply_fwd_kernel<float>, ew_grid(total8), 256, 0, st, 
         (const float*)x, x_ld, stats, gamma, beta, film, film_ld, (const float*)res, res_ld, (float*)y,
         y_ld, total8, HW, C, G);
   else
-    gn_apply_fwd_kernel<bf16><<<ew_grid(total8), 256, 0, st>>>(
+    launch_k(gn_apply_fwd_kernel<bf16>, ew_grid(total8), 256, 0, st, 
         (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, (const bf16*)res, res_ld, (bf16*)y,
         y_ld, total8, HW, C, G);
   count_launch();
@@ -891,12 +915,12 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   if (dtype == B200DM_F32) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(gn_bwd_reduce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gn_bwd_reduce_kernel<float><<<grid, threads, smem, st>>>(
+    launch_k(gn_bwd_reduce_kernel<float>, grid, threads, smem, st, 
         (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
   } else {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(gn_bwd_reduce_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gn_bwd_reduce_kernel<bf16><<<grid, threads, smem, st>>>(
+    launch_k(gn_bwd_reduce_kernel<bf16>, grid, threads, smem, st, 
         (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, sums, HW, C, G, ppb);
   }
   {
@@ -904,15 +928,15 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     B200DM_REQUIRE(gs <= 256 && 256 % gs == 0, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: group size %d", gs);
     const int BL = 256 / gs;
     dim3 pgrid(G, (B + 4 * BL - 1) / (4 * BL));
-    gn_bwd_params_kernel<<<pgrid, 256, (size_t)(BL * gs * 3 + BL * 2) * sizeof(float), st>>>(
+    launch_k(gn_bwd_params_kernel, pgrid, 256, (size_t)(BL * gs * 3 + BL * 2) * sizeof(float), st, 
         sums, stats, gamma, beta, film, film_ld, dgamma, dbeta, dfilm, dbias, gmeans, B, HW, C, G, chunks);
   }
   if (dtype == B200DM_F32)
-    gn_bwd_apply_kernel<float><<<ew_grid(total8), 256, 0, st>>>(
+    launch_k(gn_bwd_apply_kernel<float>, ew_grid(total8), 256, 0, st, 
         (const float*)dy, dy_ld, (const float*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,
         (float*)dx, dx_ld, total8, HW, C, G);
   else
-    gn_bwd_apply_kernel<bf16><<<ew_grid(total8), 256, 0, st>>>(
+    launch_k(gn_bwd_apply_kernel<bf16>, ew_grid(total8), 256, 0, st, 
         (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, stats, gamma, beta, film, film_ld, gmeans,
         (bf16*)dx, dx_ld, total8, HW, C, G);
   count_launch(3);
@@ -929,9 +953,9 @@ extern "C" int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, co
   while (L < C / 8 && L < 32) L <<= 1;
   unsigned grid = ew_grid(rows * L);
   if (dtype == B200DM_F32)
-    rmsnorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
+    launch_k(rmsnorm_fwd_kernel<float>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
   else
-    rmsnorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
+    launch_k(rmsnorm_fwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
   count_launch();
   return check_launch("rmsnorm_fwd");
 }
@@ -948,9 +972,9 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   if (dtype == B200DM_F32)
-    rmsnorm_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C, L);
+    launch_k(rmsnorm_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C, L);
   else
-    rmsnorm_bwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C, L);
+    launch_k(rmsnorm_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C, L);
   count_launch();
   return check_launch("rmsnorm_bwd");
 }

@@ -10,6 +10,7 @@ template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wt,
                                    int taps, int Cout, int Cin, int flip, long long s_tap,
                                    long long s_co, long long s_ci) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -35,6 +36,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 // (tensor, tap, 32x32 tile) by binary search over the tile prefix sums.
 template <typename T>
 __global__ void pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   int lo = 0, hi = n - 1;
   const int bid = blockIdx.x;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
             float weight_decay, float bc2_sqrt, float grad_scale) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
@@ -89,6 +92,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void __launch_bounds__(256)
 ema_kernel(float* __restrict__ ema, const float* __restrict__ online, int64_t n, float w) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float e = ema[i];
@@ -108,9 +112,9 @@ extern "C" int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, 
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps), block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    pack_weight_kernel<float><<<grid, block, 0, st>>>(w, (float*)wf, (float*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
+    launch_k(pack_weight_kernel<float>, grid, block, 0, st, w, (float*)wf, (float*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
   else
-    pack_weight_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
+    launch_k(pack_weight_kernel<__nv_bfloat16>, grid, block, 0, st, w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wt, taps, Cout, Cin, flip, s_tap, s_co, s_ci);
   count_launch();
   return check_launch("pack_conv_weight");
 }
@@ -121,9 +125,9 @@ extern "C" int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack
   dim3 block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    pack_weights_batched_kernel<float><<<total_tiles, block, 0, st>>>(table, n_entries);
+    launch_k(pack_weights_batched_kernel<float>, total_tiles, block, 0, st, table, n_entries);
   else
-    pack_weights_batched_kernel<__nv_bfloat16><<<total_tiles, block, 0, st>>>(table, n_entries);
+    launch_k(pack_weights_batched_kernel<__nv_bfloat16>, total_tiles, block, 0, st, table, n_entries);
   count_launch();
   return check_launch("pack_conv_weights_batched");
 }
@@ -137,7 +141,7 @@ extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, in
   float step_size = (float)((double)lr / bc1);
   float bc2_sqrt = (float)sqrt(bc2);
   int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
-  adam_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(adam_kernel, (unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream, 
       p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
   count_launch();
   return check_launch("adam_step");
@@ -146,7 +150,7 @@ extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, in
 extern "C" int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream) {
   B200DM_REQUIRE(n > 0, B200DM_ERR_SHAPE, "ema_update: empty");
   int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
-  ema_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream>>>(ema, online, n, 1.f - decay);
+  launch_k(ema_kernel, (unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream, ema, online, n, 1.f - decay);
   count_launch();
   return check_launch("ema_update");
 }

@@ -7,6 +7,7 @@ namespace b200dm {
 
 __global__ void sinusoidal_kernel(const int64_t* __restrict__ t, float* __restrict__ emb, int B,
                                   int dim, float neg_log_theta_over) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int half = dim / 2;
   if (i >= B * half) return;
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
              float* __restrict__ C, int ldc, const float* __restrict__ bias, float* __restrict__ pre,
              int M, int N, int K, int act, int beta, int splits) {
+  pdl_prologue();
   __shared__ float As[GK][GM + GPAD];
   __shared__ float Bs[GK][GN + GPAD];
   const int tid = threadIdx.x;
@@ -124,6 +126,7 @@ sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
 
 __global__ void act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ pre, int64_t n,
                                int act) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     dy[i] *= act_grad(act, pre[i]);
@@ -141,7 +144,7 @@ extern "C" int b200dm_sinusoidal(const int64_t* t, float* emb, int32_t B, int32_
   // negated double, producing fp32: emulate by rounding the scalar to fp32 first.
   float neg = (float)(-(log((double)theta) / (double)(half - 1)));
   int n = B * half;
-  sinusoidal_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, emb, B, dim, neg);
+  launch_k(sinusoidal_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, t, emb, B, dim, neg);
   count_launch();
   return check_launch("sinusoidal");
 }
@@ -150,7 +153,7 @@ extern "C" int b200dm_linear_fwd(const float* X, const float* W, const float* b,
                                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream) {
   B200DM_REQUIRE(M > 0 && N > 0 && K > 0 && act >= 0 && act <= 2, B200DM_ERR_SHAPE, "linear_fwd: bad shape");
   dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN, 1);
-  sgemm_kernel<false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(X, K, W, K, Y, N, b, pre, M, N, K,
+  launch_k(sgemm_kernel<false, true>, grid, 256, 0, (cudaStream_t)stream, X, K, W, K, Y, N, b, pre, M, N, K,
                                                                      act, 0, 1);
   count_launch();
   return check_launch("linear_fwd");
@@ -167,7 +170,7 @@ extern "C" int b200dm_linear_bwd(const float* X, const float* W, const float* pr
     int64_t n = (int64_t)M * N;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)num_sms() * 8) blocks = (int64_t)num_sms() * 8;
-    act_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dY, pre, n, act);
+    launch_k(act_bwd_kernel, (unsigned)blocks, 256, 0, st, dY, pre, n, act);
     ++launches;
   }
   if (dX) {  // dX[M,K] = dY[M,N] * W[N,K]; split the N reduction when the output grid is tiny
@@ -184,12 +187,12 @@ extern "C" int b200dm_linear_bwd(const float* X, const float* W, const float* pr
       if (rc) return rc;
     }
     dim3 grid((M + GM - 1) / GM, (K + GN - 1) / GN, splits);
-    sgemm_kernel<false, false><<<grid, 256, 0, st>>>(dY, N, W, K, dX, K, nullptr, nullptr, M, K, N, 0, 0, splits);
+    launch_k(sgemm_kernel<false, false>, grid, 256, 0, st, dY, N, W, K, dX, K, nullptr, nullptr, M, K, N, 0, 0, splits);
     ++launches;
   }
   if (dW) {  // dW[N,K] += dY^T[N,M] * X[M,K]
     dim3 grid((N + GM - 1) / GM, (K + GN - 1) / GN, 1);
-    sgemm_kernel<true, false><<<grid, 256, 0, st>>>(dY, N, X, K, dW, K, nullptr, nullptr, N, K, M, 0, 1, 1);
+    launch_k(sgemm_kernel<true, false>, grid, 256, 0, st, dY, N, X, K, dW, K, nullptr, nullptr, N, K, M, 0, 1, 1);
     ++launches;
   }
   count_launch(launches);
