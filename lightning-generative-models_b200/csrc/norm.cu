@@ -643,14 +643,13 @@ static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, size_t smem, cuda
 }
 
 // ---- RMSNorm: a row (pixel) is handled by L = min(32, C/8) lanes, 32/L rows per warp; C <= 512 ----------
-constexpr int RMS_MAXV = 2;  // 8-wide vectors per lane (C <= 512)
 
 __device__ __forceinline__ float seg_sum(float v, int L) {   // sum over aligned groups of L lanes
   for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-template <typename T>
+template <typename T, int MAXV>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ g,
                    const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int64_t rows,
@@ -662,40 +661,66 @@ rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ 
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
-  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
-    const int64_t r = r0 + sub;
-    const bool ok = r < rows;
-    float v[RMS_MAXV][8];
-    float ss = 0.f;
+  // this thread's gains (its channel vectors are the same for every row it visits)
+  float gs[MAXV][8];
 #pragma unroll
-    for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = sl + L * k;
-      if (ok && cv < C8) {
-        ld8(x + r * x_ld + cv * 8, v[k]);
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = sl + L * k;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(v[k][j], v[k][j], ss);
+    for (int j = 0; j < 8; ++j) gs[k][j] = cv < C8 ? g[cv * 8 + j] * sqrtC : 0.f;
+  }
+  constexpr int U = 2;                                         // rows in flight per thread
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw * U) {
+    Raw8<T> rx[U][MAXV], rr[U][MAXV];
+    // all loads of the U rows (input and residual) are issued before any arithmetic
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * nwarps * rpw + sub;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int cv = sl + L * k;
+        if (r < rows && cv < C8) {
+          rx[u][k].load(x + r * x_ld + cv * 8);
+          if (res) rr[u][k].load(res + r * res_ld + cv * 8);
+        }
       }
     }
-    ss = seg_sum(ss, L);
-    float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-    for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = sl + L * k;
-      if (ok && cv < C8) {
-        float o[8], rr[8];
-        if (res) ld8(res + r * res_ld + cv * 8, rr);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * nwarps * rpw + sub;
+      const bool ok = r < rows;
+      float v[MAXV][8];
+      float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = v[k][j] * rn * g[cv * 8 + j] * sqrtC;
-          if (res) o[j] += rr[j];
+      for (int k = 0; k < MAXV; ++k) {
+        const int cv = sl + L * k;
+        if (ok && cv < C8) {
+          rx[u][k].unpack(v[k]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss = fmaf(v[k][j], v[k][j], ss);
         }
-        st8(y + r * y_ld + cv * 8, o);
+      }
+      ss = seg_sum(ss, L);
+      const float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        const int cv = sl + L * k;
+        if (ok && cv < C8) {
+          float o[8], rv[8];
+          if (res) rr[u][k].unpack(rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = v[k][j] * rn * gs[k][j];
+            if (res) o[j] += rv[j];
+          }
+          st8(y + r * y_ld + cv * 8, o);
+        }
       }
     }
   }
 }
 
-template <typename T>
+template <typename T, int MAXV>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                    const float* __restrict__ g, const T* __restrict__ res, int res_ld,
@@ -707,49 +732,69 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
-  float dgacc[RMS_MAXV][8] = {};
+  float gs[MAXV][8], dgacc[MAXV][8];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = sl + L * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gs[k][j] = cv < C8 ? g[cv * 8 + j] : 0.f;
+      dgacc[k][j] = 0.f;
+    }
+  }
   for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
     const int64_t r = r0 + sub;
     const bool ok = r < rows;
-    float u[RMS_MAXV][8], gd[RMS_MAXV][8];
+    Raw8<T> rx[MAXV], rg[MAXV], rr[MAXV];
+    // input, upstream gradient and skip gradient are all requested before the first reduction
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int cv = sl + L * k;
+      if (ok && cv < C8) {
+        rx[k].load(x + r * x_ld + cv * 8);
+        rg[k].load(dy + r * dy_ld + cv * 8);
+        if (res) rr[k].load(res + r * res_ld + cv * 8);
+      }
+    }
+    float u[MAXV][8], gd[MAXV][8];
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = sl + L * k;
+    for (int k = 0; k < MAXV; ++k) {
+      const int cv = sl + L * k;
       if (ok && cv < C8) {
-        ld8(x + r * x_ld + cv * 8, u[k]);
-        ld8(dy + r * dy_ld + cv * 8, gd[k]);
+        rx[k].unpack(u[k]);
+        rg[k].unpack(gd[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
       }
     }
     ss = seg_sum(ss, L);
-    float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    const float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     float dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = sl + L * k;
+    for (int k = 0; k < MAXV; ++k) {
+      const int cv = sl + L * k;
       if (ok && cv < C8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           u[k][j] *= rn;                                       // unit vector
           dgacc[k][j] = fmaf(gd[k][j], u[k][j], dgacc[k][j]);  // dg_c += dy_c*u_c (x sqrtC at the end)
-          gd[k][j] *= g[cv * 8 + j];                           // g .* dy
+          gd[k][j] *= gs[k][j];                                // g .* dy
           dot = fmaf(gd[k][j], u[k][j], dot);
         }
       }
     }
     dot = seg_sum(dot, L);
 #pragma unroll
-    for (int k = 0; k < RMS_MAXV; ++k) {
-      int cv = sl + L * k;
+    for (int k = 0; k < MAXV; ++k) {
+      const int cv = sl + L * k;
       if (ok && cv < C8) {
-        float o[8], rr[8];
-        if (res) ld8(res + r * res_ld + cv * 8, rr);
+        float o[8], rv[8];
+        if (res) rr[k].unpack(rv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           o[j] = rn * sqrtC * (gd[k][j] - u[k][j] * dot);
-          if (res) o[j] += rr[j];
+          if (res) o[j] += rv[j];
         }
         st8(dx + r * dx_ld + cv * 8, o);
       }
@@ -760,8 +805,8 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
   for (int c = threadIdx.x; c < C; c += blockDim.x) dgs[c] = 0.f;
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < RMS_MAXV; ++k) {
-    int cv = sl + L * k;
+  for (int k = 0; k < MAXV; ++k) {
+    const int cv = sl + L * k;
     if (cv < C8) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) atomicAdd(&dgs[cv * 8 + j], dgacc[k][j]);
@@ -952,10 +997,14 @@ extern "C" int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, co
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
   unsigned grid = ew_grid(rows * L);
-  if (dtype == B200DM_F32)
-    launch_k(rmsnorm_fwd_kernel<float>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
-  else
-    launch_k(rmsnorm_fwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
+  const bool two = C / 8 > 32;      // 512 channels: two 8-wide vectors per lane
+  if (dtype == B200DM_F32) {
+    if (two) launch_k(rmsnorm_fwd_kernel<float, 2>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
+    else launch_k(rmsnorm_fwd_kernel<float, 1>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
+  } else {
+    if (two) launch_k(rmsnorm_fwd_kernel<bf16, 2>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
+    else launch_k(rmsnorm_fwd_kernel<bf16, 1>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
+  }
   count_launch();
   return check_launch("rmsnorm_fwd");
 }
@@ -971,10 +1020,16 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   while (L < C / 8 && L < 32) L <<= 1;
   int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
-  if (dtype == B200DM_F32)
-    launch_k(rmsnorm_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, dy_ld, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)dx, dx_ld, dg, rows, C, L);
-  else
-    launch_k(rmsnorm_bwd_kernel<bf16>, grid, 256, 0, st, (const bf16*)dy, dy_ld, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)dx, dx_ld, dg, rows, C, L);
+  const bool two = C / 8 > 32;
+#define RMS_BWD(TT, MV)                                                                                      \
+  launch_k(rmsnorm_bwd_kernel<TT, MV>, grid, 256, 0, st, (const TT*)dy, dy_ld, (const TT*)x, x_ld, g,       \
+           (const TT*)res, res_ld, (TT*)dx, dx_ld, dg, rows, C, L)
+  if (dtype == B200DM_F32) {
+    if (two) RMS_BWD(float, 2); else RMS_BWD(float, 1);
+  } else {
+    if (two) RMS_BWD(bf16, 2); else RMS_BWD(bf16, 1);
+  }
+#undef RMS_BWD
   count_launch();
   return check_launch("rmsnorm_bwd");
 }
