@@ -98,6 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* out_stage_ptr = smem_raw + (out_stage - smem_u32(smem_raw));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [Ncols]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.taps * p.kblocks;
@@ -113,7 +114,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), TC_EPI_WARPS);
+      mbar_init(tmem_empty_bar(a), SUBTILES == 1 ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -195,17 +196,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // Every warp is self-contained: it owns 32 pixel rows (its TMEM lane quarter) x the 64 channels of a
+    // sub-tile, stages them as one 4 KiB swizzled block in its PRIVATE buffer and issues its own TMA store
+    // (box = 32 pixels x 64 channels) - no CTA-wide barriers in the loop.  The two warps of a quarter
+    // alternate: sub-tiles (N_TILE >= 128) or whole tiles (N_TILE = 64, accumulator = warp set).
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // which 32 of the 64 sub-tile columns
+    const int wset = (warp - 2) >> 2;        // 0 / 1
     const int row = quarter * 32 + lane;
-    const bool store_thread = (threadIdx.x == 64);
-    int acc = 0, sbuf = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t my_stage = out_stage + (uint32_t)(warp - 2) * 4096u;
+    uint8_t* my_row = out_stage_ptr + (warp - 2) * 4096 + lane * 128;
+    // bias of all N columns, once per CTA
+    for (int i = threadIdx.x - 64; i < p.Ncols; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    named_bar_sync(1, 32 * TC_EPI_WARPS);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (SUBTILES == 1 && (it & 1) != wset) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
       const long long first = (long long)m_tile * TC_BM;
-      const int n_first = (int)(first / ((long long)p.H * p.W));
-      const int y_first = (int)((first / p.W) % p.H);
       const long long pix = first + row;
       const bool valid = pix < p.M;
       long long opix = pix;
@@ -219,11 +228,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const long long b = q / p.H;
         opix = (b * (2 * p.H) + 2 * oy + (tap2 >> 1)) * (long long)(2 * p.W) + 2 * ox + (tap2 & 1);
       }
-      // residual / accumulate sources are fetched BEFORE waiting for the accumulator (and for the next
-      // sub-tile while the current one is being stored), so their L2 latency hides behind the MMAs
+      // store coordinates of this warp's 32-pixel slice
+      const unsigned slice = (unsigned)first + 32u * (unsigned)quarter;
+      const unsigned hw = (unsigned)(p.H * p.W);
+      const int sn = (int)(slice / hw);
+      const unsigned srem = slice - (unsigned)sn * hw;
+      const int sy = (int)(srem / (unsigned)p.W), sx = (int)(srem - (unsigned)sy * (unsigned)p.W);
+      // residual / accumulate sources are fetched BEFORE waiting for the accumulator, so their L2 latency
+      // hides behind the MMAs
       uint4 src_res[4], src_acc[4];
-      auto prefetch_src = [&](int s) {
-        const int c = s * 64 + half * 32;
+      auto prefetch_src = [&](int c) {
         if (valid && p.res) {
           const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + co0 + c);
 #pragma unroll
@@ -235,81 +249,87 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int g = 0; g < 4; ++g) src_acc[g] = yr[g];
         }
       };
-      prefetch_src(0);
+      const int s_first = SUBTILES == 1 ? 0 : wset;
+      prefetch_src(s_first * 64);
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int s = 0; s < SUBTILES; ++s) {
-        uint32_t r[32];
-        const int c = s * 64 + half * 32;     // column offset inside the N tile
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
-        tmem_ld_wait();
-        if (s == SUBTILES - 1) {              // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-        }
-        float v[32];
+      for (int s = s_first; s < SUBTILES; s += 2) {
+        // the private staging block was handed to the TMA engine one sub-tile ago
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = s * 64 + hh * 32;     // column offset inside the N tile
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
+          tmem_ld_wait();
+          if (hh == 1 && s + 2 >= SUBTILES) {   // last read of this accumulator by this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          }
+          float v[32];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + co0 + c + j);
-        }
-        if (valid && p.res) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h2[j]);
-              v[g * 8 + 2 * j] += f.x;
-              v[g * 8 + 2 * j + 1] += f.y;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
             }
           }
-        }
-        if (valid && p.y_read) {
+          if (valid && p.res) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h2[j]);
-              v[g * 8 + 2 * j] += f.x;
-              v[g * 8 + 2 * j + 1] += f.y;
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
             }
           }
-        }
-        if (s + 1 < SUBTILES) prefetch_src(s + 1);
-        // staging buffer `sbuf` was last used two sub-tiles ago: its TMA store must have read it
-        if (store_thread) tma_store_wait_read<1>();
-        named_bar_sync(1, 32 * TC_EPI_WARPS);
-        uint8_t* srow = out_stage_ptr + sbuf * OUT_STAGE_BYTES + row * 128;
+          if (valid && p.y_read) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-          const int chunk = (half * 4 + g) ^ (row & 7);   // 128-B swizzle: 16-B chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(srow + chunk * 16) = u;
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          // next 32 columns this warp will need: second half of this sub-tile, or its next sub-tile
+          if (hh == 0) prefetch_src(c + 32);
+          else if (s + 2 < SUBTILES) prefetch_src((s + 2) * 64);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            const int chunk = (hh * 4 + g) ^ (lane & 7);   // 128-B swizzle: 16-B chunk index XOR (row mod 8)
+            *reinterpret_cast<uint4*>(my_row + chunk * 16) = u;
+          }
         }
         fence_proxy_async();                  // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(2, 32 * TC_EPI_WARPS);
-        if (store_thread) {
-          const uint32_t src = out_stage + sbuf * OUT_STAGE_BYTES;
+        __syncwarp();
+        if (lane == 0) {
           if (p.mode == 2)
-            tma_store_5d(&tmY, src, (tap2 & 1) * p.y_ld + co0 + s * 64, 0, tap2 >> 1, y_first, n_first);
+            tma_store_5d(&tmY, my_stage, (tap2 & 1) * p.y_ld + co0 + s * 64, sx, tap2 >> 1, sy, sn);
           else
-            tma_store_5d(&tmY, src, co0 + s * 64, 0, y_first, n_first, 0);
+            tma_store_5d(&tmY, my_stage, co0 + s * 64, sx, sy, sn, 0);
           tma_store_commit();
         }
-        sbuf ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -371,6 +391,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* out_stage_ptr = smem_raw + (out_stage - smem_u32(smem_raw));
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [Cout]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.dbg & 8) return;
@@ -383,7 +404,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmY);
     for (int a = 0; a < A_BUFS; ++a) { mbar_init(afull(a), 1); mbar_init(aempty(a), 1); }
     for (int s2 = 0; s2 < B_STAGES; ++s2) { mbar_init(bfull(s2), 1); mbar_init(bempty(s2), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), TC_EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), SUBTILES == 1 ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
+    }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -492,22 +516,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
+    // self-contained warps (see conv_tc_kernel): 32 rows = 4 image rows x 8 pixels of the tile, private 4 KiB
+    // staging block, own TMA store (box 64 ch x 8 x 4); the two warps of a quarter alternate sub-tiles / tiles
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int wset = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int tx = row & 7, ty = row >> 3;
-    const bool store_thread = (threadIdx.x == 64);
-    int acc = 0, sbuf = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t my_stage = out_stage + (uint32_t)(warp - 2) * 4096u;
+    uint8_t* my_row = out_stage_ptr + (warp - 2) * 4096 + lane * 128;
+    for (int i = threadIdx.x - 64; i < p.Cout; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    named_bar_sync(1, 32 * TC_EPI_WARPS);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (SUBTILES == 1 && (it & 1) != wset) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
       const int b = m_tile / tiles_per_img, rem = m_tile - b * tiles_per_img;
       const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
       const long long opix = ((long long)b * p.H + y0 + ty) * p.W + x0 + tx;
       // residual / accumulate sources: fetched before the accumulator wait (latency hidden behind the MMAs)
       uint4 src_res[4], src_acc[4];
-      auto prefetch_src = [&](int s2) {
-        const int c = s2 * 64 + half * 32;
+      auto prefetch_src = [&](int c) {
         if (p.res) {
           const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + n0 + c);
 #pragma unroll
@@ -519,77 +549,84 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int g = 0; g < 4; ++g) src_acc[g] = yr[g];
         }
       };
-      prefetch_src(0);
+      const int s_first = SUBTILES == 1 ? 0 : wset;
+      prefetch_src(s_first * 64);
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int s2 = 0; s2 < SUBTILES; ++s2) {
-        uint32_t r[32];
-        const int c = s2 * 64 + half * 32;
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
-        tmem_ld_wait();
-        if (s2 == SUBTILES - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      for (int s2 = s_first; s2 < SUBTILES; s2 += 2) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = s2 * 64 + hh * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + c), r);
+          tmem_ld_wait();
+          if (hh == 1 && s2 + 2 >= SUBTILES) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          }
+          if (p.dbg & 1) continue;
+          float v[32];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
+          }
+          if (p.res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (p.y_read) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (hh == 0) prefetch_src(c + 32);
+          else if (s2 + 2 < SUBTILES) prefetch_src((s2 + 2) * 64);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            const int chunk = (hh * 4 + g) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(my_row + chunk * 16) = u;
+          }
         }
         if (p.dbg & 1) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + c + j);
-        }
-        if (p.res) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h2[j]);
-              v[g * 8 + 2 * j] += f.x;
-              v[g * 8 + 2 * j + 1] += f.y;
-            }
-          }
-        }
-        if (p.y_read) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_acc[g]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(h2[j]);
-              v[g * 8 + 2 * j] += f.x;
-              v[g * 8 + 2 * j + 1] += f.y;
-            }
-          }
-        }
-        if (s2 + 1 < SUBTILES) prefetch_src(s2 + 1);
-        if (store_thread) tma_store_wait_read<1>();
-        named_bar_sync(1, 32 * TC_EPI_WARPS);
-        uint8_t* srow = out_stage_ptr + sbuf * OUT_STAGE_BYTES + row * 128;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
-          const int chunk = (half * 4 + g) ^ (row & 7);
-          *reinterpret_cast<uint4*>(srow + chunk * 16) = u;
-        }
         fence_proxy_async();
-        named_bar_sync(2, 32 * TC_EPI_WARPS);
-        if (store_thread) {
-          tma_store_5d(&tmY, out_stage + sbuf * OUT_STAGE_BYTES, n0 + s2 * 64, x0, y0, b, 0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_5d(&tmY, my_stage, n0 + s2 * 64, x0, y0 + 4 * quarter, b, 0);
           tma_store_commit();
         }
-        sbuf ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -636,6 +673,30 @@ int make_act_map(CUtensorMap* m, int mode, const void* x, int x_ld, int C, int B
   return encode_map(m, x, 5, dims, str, box, what);
 }
 
+// Output map of the per-warp epilogue: box = 32 consecutive pixels (NHW order) x 64 channels.
+//   W >= 32: 32 pixels of one image row; otherwise 32/W rows (of one image) or 32/(W*H) whole images.
+static int make_out_map32(CUtensorMap* m, int mode, const void* y, int y_ld, int C, int B, int H, int W,
+                          const char* what) {
+  const cuuint64_t e = 2;
+  const int bw = W >= 32 ? 32 : W;
+  const int rows = 32 / bw;
+  int bh, bn;
+  if (rows <= H) { bh = rows; bn = 1; } else { bh = H; bn = rows / H; }
+  B200DM_REQUIRE(W % bw == 0 && H % bh == 0 && bh * bn * bw == 32, B200DM_ERR_UNSUPPORTED,
+                 "%s: cannot cut %dx%d images into 32-pixel store boxes", what, H, W);
+  if (mode == 1) {   // [B, 2H, 2W, ld] viewed as (c' = p2*ld + c, ox, p1, oy, b)
+    cuuint64_t dims[5] = {(cuuint64_t)y_ld + C, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[4] = {2ull * y_ld * e, 2ull * W * y_ld * e, 4ull * W * y_ld * e, 4ull * H * W * y_ld * e};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+    return encode_map(m, y, 5, dims, str, box, what);
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 1};
+  cuuint64_t str[4] = {(cuuint64_t)y_ld * e, (cuuint64_t)W * y_ld * e, (cuuint64_t)H * W * y_ld * e,
+                       (cuuint64_t)B * H * W * y_ld * e};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  return encode_map(m, y, 5, dims, str, box, what);
+}
+
 int tile_geometry(int H, int W, int* bh, int* bn, const char* what) {
   B200DM_REQUIRE(W >= 4 && W <= 128 && (W & (W - 1)) == 0, B200DM_ERR_UNSUPPORTED,
                  "%s: W=%d must be a power of two in [4,128]", what, W);
@@ -655,13 +716,14 @@ int tile_geometry(int H, int W, int* bh, int* bn, const char* what) {
 template <int N_TILE, int STAGES>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                      const TcParams& p, cudaStream_t st) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
+  const int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 256 + p.Ncols * 4;
+  B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv_tc: %d B of shared memory", smem);
+  static int configured = 0;
+  if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<N_TILE, STAGES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
+    configured = smem;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -674,7 +736,7 @@ template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
                        const TcHaloParams& p, cudaStream_t st) {
   const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
-  const int smem = A_BUFS * HALO_BYTES + b_slots * (N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 512;
+  const int smem = A_BUFS * HALO_BYTES + b_slots * (N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 512 + p.Cout * 4;
   B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv3x3_halo: %d B of shared memory", smem);
   static int configured = 0;
   if (configured < smem) {
@@ -740,7 +802,7 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
     cuuint64_t dims[5] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
     cuuint64_t str[4] = {(cuuint64_t)d->y_ld * e, (cuuint64_t)d->W * d->y_ld * e,
                          (cuuint64_t)d->H * d->W * d->y_ld * e, (cuuint64_t)d->B * d->H * d->W * d->y_ld * e};
-    cuuint32_t box[5] = {64, 8, 16, 1, 1};
+    cuuint32_t box[5] = {64, 8, 4, 1, 1};      // one epilogue warp: 4 image rows x 8 pixels x 64 channels
     int rc = encode_map(&tmY, d->y, 5, dims, str, box, "conv3x3_halo Y");
     if (rc) return rc;
   }
@@ -804,7 +866,7 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   rc = make_act_map(&tmA, d->mode == 1 ? 1 : 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) A");
   if (rc) return rc;
   // output: NHWC tensor (modes 0/1) or the unshuffle view of the [2H,2W] tensor (mode 2)
-  rc = make_act_map(&tmY, d->mode == 2 ? 1 : 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) Y");
+  rc = make_out_map32(&tmY, d->mode == 2 ? 1 : 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, "conv_fwd(tc) Y");
   if (rc) return rc;
   {
     const int wt = d->mode == 2 ? 1 : p.taps;
