@@ -453,7 +453,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 }
 
 template <typename T>
-__global__ void __launch_bounds__(GNC_THREADS, 3)
+__global__ void __launch_bounds__(GNC_THREADS, 4)
 gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                       const float* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
@@ -929,7 +929,7 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (gn_cluster_ok(C, G)) {
-    const int cl = gn_cluster_size(B, HW, C, 3);
+    const int cl = gn_cluster_size(B, HW, C, 4);
     dim3 grid(cl, B);
     cudaError_t e;
     if (dtype == B200DM_F32)
