@@ -52,7 +52,8 @@ bool tc_supported() {
 constexpr int TC_BM = 128;      // pixels per CTA tile  (UMMA M)
 constexpr int TC_BK = 64;       // channels per K-block (128 B of bf16 = one swizzle row)
 constexpr int TC_EPI_WARPS = 8; // two warps per TMEM lane quarter (each takes half of the columns)
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_THREADS = 96 + 32 * TC_EPI_WARPS;   // warp 0 TMA (A), warp 1 MMA, warps 2..9 epilogue, warp 10 TMA (B)
+constexpr int TC_BWARP = 2 + TC_EPI_WARPS;            // the weight-tile producer warp
 constexpr int WG_THREADS = 192;                      // wgrad kernel: 4 epilogue warps
 constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 2;     // 16 KiB
 constexpr int OUT_STAGE_BYTES = TC_BM * 64 * 2;      // 16 KiB: [128 rows][64 bf16], 128-B swizzled
@@ -144,9 +145,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (leader) {
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);     // activation box (here) + weight box (warp 10)
             const uint32_t a_dst = base + stage * STAGE_BYTES;
-            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
             if (p.mode == 1)   // unshuffle view (c' = p2*ld + c, ox, p1, oy, b)
               tma_load_5d(a_dst, &tmA, full_bar(stage), (tap & 1) * p.x_ld + kc * TC_BK, 0, tap >> 1, y_first,
                           n_first);
@@ -154,11 +154,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
             else
               tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, 0, y_first, n_first, 0);
-            tma_load_3d(b_dst, &tmB, full_bar(stage), kc * TC_BK, n0, (p.mode == 2) ? 0 : tap);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++dx > pad) { dx = -pad; ++dy; }
+      }
+    }
+  } else if (warp == TC_BWARP) {
+    // ===================== TMA producer, weight tiles =====================
+    // A second issuing thread: one thread setting up both boxes of a K block (~45 dependent uniform-datapath
+    // instructions) took longer than the 4 MMAs of an N=64 block (192 cycles) and starved the tensor pipe.
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader)
+            tma_load_3d(base + stage * STAGE_BYTES + A_STAGE_BYTES, &tmB, full_bar(stage), kc * TC_BK, n0,
+                        (p.mode == 2) ? 0 : tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -427,10 +445,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int kc = 0; kc < p.kblocks; ++kc)
             tma_load_3d(b_base + (tap * p.kblocks + kc) * B_BYTES, &tmB, bres_bar, kc * TC_BK, 0, tap);
       }
-      int ab = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int ab = 0;
+      uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+        const int m_tile = tile / p.n_tiles;
         const int b = m_tile / tiles_per_img, rem = m_tile - b * tiles_per_img;
         const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
         for (int kc = 0; kc < p.kblocks; ++kc) {
@@ -442,13 +460,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
           }
           if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
-          if (!B_RESIDENT) {
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(bempty(bs), bph ^ 1u);
-              mbar_expect_tx(bfull(bs), B_BYTES);
-              tma_load_3d(b_base + bs * B_BYTES, &tmB, bfull(bs), kc * TC_BK, n0, tap);
-              if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
-            }
+        }
+      }
+    }
+  } else if (warp == TC_BWARP) {
+    // ===================== TMA producer, weight tiles (streamed variant) =====================
+    if (lane == 0 && !B_RESIDENT) {
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bempty(bs), bph ^ 1u);
+            mbar_expect_tx(bfull(bs), B_BYTES);
+            tma_load_3d(b_base + bs * B_BYTES, &tmB, bfull(bs), kc * TC_BK, n0, tap);
+            if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
           }
         }
       }
