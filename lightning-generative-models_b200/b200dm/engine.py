@@ -204,11 +204,12 @@ class Plan:
         taps = ci.taps
         flops = 2.0 * self.B * H * H * cout * cin * taps
         fam = ("conv_tc" if d.impl == 1 else "conv_simt") + ("_dgrad" if dgrad else "_fwd")
-        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops, writes=(y,), side=side)
+        lst_fn("b200dm_conv_fwd", C.byref(d), kname=fam, flops=flops, writes=(y,), side=side,
+               reads=(x, res) if side else ())
         self._keep.append(d)
 
     def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None,
-                 bias_grad=True):
+                 bias_grad=True, dgrad_side=False):
         """wgrad + bias grad + (optional) dgrad of conv `nm` whose forward was x -> y, given dy."""
         if not self.training:
             return
@@ -229,7 +230,7 @@ class Plan:
             self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
                     self.arena.gptr(nm + ".bias"), 1, side=True, reads=(dy,))
         if dx is not None:
-            self.conv_fwd(self.Bk, nm, dy, dx, dgrad=True, res=dx_res, accumulate=dx_acc)
+            self.conv_fwd(self.Bk, nm, dy, dx, dgrad=True, res=dx_res, accumulate=dx_acc, side=dgrad_side)
 
     # ---- composite units -----------------------------------------------------------------------------
     def resblock(self, nm, x: View, out: View, gx: Optional[View], gout: Optional[View], gx_prior: bool):
@@ -261,6 +262,10 @@ class Plan:
         # for block2's weight gradient (second stream) to finish reading its operand
         dc2, dc, gh1 = self.scratch("dc2", H, cout), self.scratch("dc", H, cout), self.scratch("gh1", H, cout)
         dfilm_ptr = self.dfilm.data_ptr() + 4 * a.film_off[nm]
+        if has_res_conv:
+            # the 1x1 skip conv's backward only needs gout: issued first, on the second stream, next to the whole
+            # norm/conv chain of the block; conv1's data gradient then accumulates into gx
+            self.conv_bwd(nm + ".res_conv", x, gout, gx, dx_acc=1 if gx_prior else 0, dgrad_side=True)
         # block2: GN/SiLU backward -> dc2 ; conv2 backward -> gh1
         self.Bk("b200dm_gn_apply_bwd", self.dt, gout.ptr, gout.ld, c2.ptr, c2.ld, st2.data_ptr(),
                 a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, dc2.ptr, dc2.ld,
@@ -272,10 +277,8 @@ class Plan:
                 a.ptr(b1 + ".norm.weight"), a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, dc.ptr, dc.ld,
                 a.gptr(b1 + ".norm.weight"), a.gptr(b1 + ".norm.bias"), dfilm_ptr, a.gptr(b1 + ".proj.bias"),
                 self.sums.data_ptr(), self.gmeans.data_ptr(), self.B, HW, cout, GROUPS, writes=(dc,))
-        self.conv_bwd(b1 + ".proj", x, dc, gx, dx_acc=1 if gx_prior else 0,
+        self.conv_bwd(b1 + ".proj", x, dc, gx, dx_acc=1 if (gx_prior or has_res_conv) else 0,
                       dx_res=None if has_res_conv else gout, bias_grad=False)
-        if has_res_conv:
-            self.conv_bwd(nm + ".res_conv", x, gout, gx, dx_acc=1)
 
     def attention(self, nm, x: View, out: View, gx: Optional[View], gout: Optional[View], full: bool):
         a = self.arena
