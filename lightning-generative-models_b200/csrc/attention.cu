@@ -951,8 +951,8 @@ __device__ __forceinline__ void la_col_reduce(float (&v)[8], float (*scratch)[DH
 }
 
 struct LaFwdTc {
-  lbf Kb[LA_CHUNK][LP];        // exp(k - m_loc) / scale*softmax(q) in the output phase
-  lbf Vb[LA_CHUNK][LP];        // v / output staging in the output phase
+  lbf Kb[2][LA_CHUNK][LP];     // double-buffered: exp(k - m_loc) / scale*softmax(q) in the output phase
+  lbf Vb[2][LA_CHUNK][LP];     // double-buffered: v / output staging in the output phase
   lbf Cb[DH][LP];              // merged context, bf16, [d][e]
   float mred[8][DH];           // reduction scratch (max, exp sums)
   float ctx_loc[DH][DH];       // partial context (read by the cluster peers)
@@ -1024,7 +1024,9 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
       }
     };
     if (total > 0) fetch(0);
-    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+    // one barrier per chunk: the operand tiles are double-buffered, so staging chunk c+1 may overlap the MMAs
+    // of chunk c (buffer c&1 was last read two barriers ago)
+    for (int c0 = 0, cb = 0; c0 < total; c0 += LA_CHUNK, cb ^= 1) {
       float kv[8];
       unpack8(rk, kv);
       uint4 vraw = rv;
@@ -1047,12 +1049,12 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
       unpack8(praw, pv);                               // sum what the tensor core will see
 #pragma unroll
       for (int i = 0; i < 8; ++i) psum[i] += pv[i];
-      *reinterpret_cast<uint4*>(&s.Kb[pix][part * 8]) = praw;
-      *reinterpret_cast<uint4*>(&s.Vb[pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(&s.Kb[cb][pix][part * 8]) = praw;
+      *reinterpret_cast<uint4*>(&s.Vb[cb][pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
       __syncthreads();
-      mma_atb(&s.Kb[0][0], &s.Vb[0][0], acc, warp, lane);
-      __syncthreads();
+      mma_atb(&s.Kb[cb][0][0], &s.Vb[cb][0][0], acc, warp, lane);
     }
+    __syncthreads();
     {
       const int mt = warp >> 2, nt = warp & 3, row = lane >> 2, col = 2 * (lane & 3);
       s.ctx_loc[mt * 16 + row][nt * 8 + col] = acc[0];
@@ -1092,47 +1094,55 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
       else rq = make_uint4(0, 0, 0, 0);
     };
     if (p0 < p1) fetchq(p0);
-    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+    // software pipeline with one barrier per chunk: stage q(c) | barrier | write out(c-1) | MMA(c) -> staging(c)
+    int cb = 0;
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK, cb ^= 1) {
       float v[8];
       unpack8(rq, v);
       if (j0 + LA_CHUNK < p1) fetchq(j0 + LA_CHUNK);
       softmax32_quad(v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= kScale;
-      *reinterpret_cast<uint4*>(&s.Kb[pix][part * 8]) = pack8(v);
+      *reinterpret_cast<uint4*>(&s.Kb[cb][pix][part * 8]) = pack8(v);
       __syncthreads();
+      if (j0 > p0 && j0 - LA_CHUNK + pix < p1)
+        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + j0 - LA_CHUNK + pix) * out_ld + h * DH + part * 8) =
+            *reinterpret_cast<const uint4*>(&s.Vb[cb ^ 1][pix][part * 8]);
       float acc[2][4] = {};
-      mma_xw<true>(&s.Kb[0][0], &s.Cb[0][0], acc, warp, lane);
+      mma_xw<true>(&s.Kb[cb][0][0], &s.Cb[0][0], acc, warp, lane);
       {
         const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[mt * 16 + row][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][0], acc[t][1]);
-          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[mt * 16 + row + 8][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][2], acc[t][3]);
+          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[cb][mt * 16 + row][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][0], acc[t][1]);
+          *reinterpret_cast<__nv_bfloat162*>(&s.Vb[cb][mt * 16 + row + 8][(nt0 + t) * 8 + col]) = __floats2bfloat162_rn(acc[t][2], acc[t][3]);
         }
       }
-      __syncthreads();
-      if (j0 + pix < p1)
-        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + j0 + pix) * out_ld + h * DH + part * 8) =
-            *reinterpret_cast<const uint4*>(&s.Vb[pix][part * 8]);
+    }
+    __syncthreads();
+    if (p0 < p1) {
+      const int jl = p0 + ((p1 - p0 - 1) / LA_CHUNK) * LA_CHUNK;      // first pixel of the last chunk
+      if (jl + pix < p1)
+        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + jl + pix) * out_ld + h * DH + part * 8) =
+            *reinterpret_cast<const uint4*>(&s.Vb[cb ^ 1][pix][part * 8]);
     }
   }
   cluster.sync();
 }
 
-struct LaBwdTc {
-  lbf Ab[LA_CHUNK][LP];        // softmax(q) (phase 1) / softmax_n(k) (phase 2)
-  lbf Bb[LA_CHUNK][LP];        // dout (phase 1) / v (phase 2)
+struct LaBwdTc {                // operand / staging tiles are double-buffered: one barrier per chunk
+  lbf Ab[2][LA_CHUNK][LP];     // softmax(q) (phase 1) / softmax_n(k) (phase 2)
+  lbf Bb[2][LA_CHUNK][LP];     // dout (phase 1) / v (phase 2)
   lbf Cb[DH][LP];              // ctx, bf16, [d][e]
   lbf Db[DH][LP];              // merged dctx, bf16, [d][e]
-  lbf Ob[LA_CHUNK][LP];        // dv staging
-  float F[LA_CHUNK][DH + 1];   // fp32 product staging (dqs / dks)
+  lbf Ob[2][LA_CHUNK][LP];     // dv staging
+  float F[2][LA_CHUNK][DH + 1];  // fp32 product staging (dqs / dks)
   float dctx_loc[DH][DH];      // partial dctx (read by the cluster peers)
   float D[DH][DH];             // merged dctx * ctx scratch
   float Dd[DH], kmx[DH], kinv[DH];
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __restrict__ qkv, int ld,
                       const float* __restrict__ mem_kv, const float* __restrict__ ctx,
                       const float* __restrict__ kstat, lbf* __restrict__ dqkv, int dld,
@@ -1173,7 +1183,25 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
     };
     if (p0 < p1) fetch(p0);
     __syncthreads();
-    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK) {
+    // software pipeline, one barrier per chunk:  stage(c) | barrier | finish dq(c-1) from F[(c-1)&1] | MMA(c)
+    float pvp[8];                      // softmax(q) of the previous chunk (this thread's 8 channels)
+    bool okp = false;
+    int j0p = 0;
+    auto finish_dq = [&](int cbp) {
+      float t = 0.f, dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dv[i] = s.F[cbp][pix][part * 8 + i];
+        t = fmaf(pvp[i], dv[i], t);
+      }
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dv[i] = kScale * pvp[i] * (dv[i] - t);
+      if (okp) *reinterpret_cast<uint4*>(dqbase + (int64_t)(j0p + pix) * dld + part * 8) = pack8(dv);
+    };
+    int cb = 0;
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK, cb ^= 1) {
       float pv[8];
       unpack8(rq, pv);
       const uint4 graw = rg;
@@ -1184,39 +1212,31 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
 #pragma unroll
         for (int i = 0; i < 8; ++i) pv[i] = 0.f;
       }
-      *reinterpret_cast<uint4*>(&s.Ab[pix][part * 8]) = pack8(pv);
-      *reinterpret_cast<uint4*>(&s.Bb[pix][part * 8]) = graw;
+      *reinterpret_cast<uint4*>(&s.Ab[cb][pix][part * 8]) = pack8(pv);
+      *reinterpret_cast<uint4*>(&s.Bb[cb][pix][part * 8]) = graw;
       __syncthreads();
+      if (j0 > p0) finish_dq(cb ^ 1);
       // dqs[j][d] = sum_e dout[j][e] * ctx[d][e]   (W stored [n = d][k = e])
       float dqs[2][4] = {};
-      mma_xw<false>(&s.Bb[0][0], &s.Cb[0][0], dqs, warp, lane);
+      mma_xw<false>(&s.Bb[cb][0][0], &s.Cb[0][0], dqs, warp, lane);
       {
         const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          s.F[mt * 16 + row][(nt0 + t) * 8 + col] = dqs[t][0];
-          s.F[mt * 16 + row][(nt0 + t) * 8 + col + 1] = dqs[t][1];
-          s.F[mt * 16 + row + 8][(nt0 + t) * 8 + col] = dqs[t][2];
-          s.F[mt * 16 + row + 8][(nt0 + t) * 8 + col + 1] = dqs[t][3];
+          s.F[cb][mt * 16 + row][(nt0 + t) * 8 + col] = dqs[t][0];
+          s.F[cb][mt * 16 + row][(nt0 + t) * 8 + col + 1] = dqs[t][1];
+          s.F[cb][mt * 16 + row + 8][(nt0 + t) * 8 + col] = dqs[t][2];
+          s.F[cb][mt * 16 + row + 8][(nt0 + t) * 8 + col + 1] = dqs[t][3];
         }
       }
-      mma_atb(&s.Ab[0][0], &s.Bb[0][0], acc, warp, lane);     // dctx += P^T dout
-      __syncthreads();
-      {
-        float t = 0.f, dv[8];
+      mma_atb(&s.Ab[cb][0][0], &s.Bb[cb][0][0], acc, warp, lane);     // dctx += P^T dout
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          dv[i] = s.F[pix][part * 8 + i];
-          t = fmaf(pv[i], dv[i], t);
-        }
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dv[i] = kScale * pv[i] * (dv[i] - t);
-        if (ok) *reinterpret_cast<uint4*>(dqbase + (int64_t)(j0 + pix) * dld + part * 8) = pack8(dv);
-      }
-      __syncthreads();
+      for (int i = 0; i < 8; ++i) pvp[i] = pv[i];
+      okp = ok;
+      j0p = j0;
     }
+    __syncthreads();
+    if (p0 < p1) finish_dq(cb ^ 1);
     {
       const int mt = warp >> 2, nt = warp & 3, row = lane >> 2, col = 2 * (lane & 3);
       s.dctx_loc[mt * 16 + row][nt * 8 + col] = acc[0] * kScale;
@@ -1263,7 +1283,31 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
       }
     };
     if (total > 0) fetch(0);
-    for (int c0 = 0; c0 < total; c0 += LA_CHUNK) {
+    // software pipeline, one barrier per chunk:  stage(c) | barrier | finish dk/dv(c-1) | MMA(c)
+    float ksp[8];
+    int jlp = 0;
+    bool okp = false;
+    auto finish_kv = [&](int cbp) {
+      if (!okp) return;
+      float dk[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dk[i] = ksp[i] * (s.F[cbp][pix][part * 8 + i] - Dd[i]);
+      if (jlp < lead) {
+        float dvf[8];
+        unpack8(*reinterpret_cast<const uint4*>(&s.Ob[cbp][pix][part * 8]), dvf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(dmem_kv + ((0 * HEADS + h) * DH + part * 8 + i) * NMEM + jlp, dk[i]);
+          atomicAdd(dmem_kv + ((1 * HEADS + h) * DH + part * 8 + i) * NMEM + jlp, dvf[i]);
+        }
+      } else {
+        lbf* o = dqbase + (int64_t)(p0 + jlp - lead) * dld + part * 8;
+        *reinterpret_cast<uint4*>(o + HID) = pack8(dk);
+        *reinterpret_cast<uint4*>(o + 2 * HID) = *reinterpret_cast<const uint4*>(&s.Ob[cbp][pix][part * 8]);
+      }
+    };
+    int cb = 0;
+    for (int c0 = 0; c0 < total; c0 += LA_CHUNK, cb ^= 1) {
       float ks[8];
       unpack8(rk, ks);
       uint4 vraw = rv;
@@ -1281,46 +1325,33 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
       const bool ok = jl < total;
 #pragma unroll
       for (int i = 0; i < 8; ++i) ks[i] = ok ? __expf(ks[i] - kmx[i]) * kinv[i] : 0.f;
-      *reinterpret_cast<uint4*>(&s.Ab[pix][part * 8]) = pack8(ks);
-      *reinterpret_cast<uint4*>(&s.Bb[pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(&s.Ab[cb][pix][part * 8]) = pack8(ks);
+      *reinterpret_cast<uint4*>(&s.Bb[cb][pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
       __syncthreads();
+      if (c0 > 0) finish_kv(cb ^ 1);
       float dvv[2][4] = {}, dks[2][4] = {};
-      mma_xw<true>(&s.Ab[0][0], &s.Db[0][0], dvv, warp, lane);    // dv[j][e] = sum_d ks[j][d] dctx[d][e]
-      mma_xw<false>(&s.Bb[0][0], &s.Db[0][0], dks, warp, lane);   // dks[j][d] = sum_e v[j][e] dctx[d][e]
+      mma_xw<true>(&s.Ab[cb][0][0], &s.Db[0][0], dvv, warp, lane);    // dv[j][e] = sum_d ks[j][d] dctx[d][e]
+      mma_xw<false>(&s.Bb[cb][0][0], &s.Db[0][0], dks, warp, lane);   // dks[j][d] = sum_e v[j][e] dctx[d][e]
       {
         const int mt = warp >> 1, nt0 = (warp & 1) * 2, row = lane >> 2, col = 2 * (lane & 3);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int c = (nt0 + t) * 8 + col;
-          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[mt * 16 + row][c]) = __floats2bfloat162_rn(dvv[t][0], dvv[t][1]);
-          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[mt * 16 + row + 8][c]) = __floats2bfloat162_rn(dvv[t][2], dvv[t][3]);
-          s.F[mt * 16 + row][c] = dks[t][0];
-          s.F[mt * 16 + row][c + 1] = dks[t][1];
-          s.F[mt * 16 + row + 8][c] = dks[t][2];
-          s.F[mt * 16 + row + 8][c + 1] = dks[t][3];
+          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[cb][mt * 16 + row][c]) = __floats2bfloat162_rn(dvv[t][0], dvv[t][1]);
+          *reinterpret_cast<__nv_bfloat162*>(&s.Ob[cb][mt * 16 + row + 8][c]) = __floats2bfloat162_rn(dvv[t][2], dvv[t][3]);
+          s.F[cb][mt * 16 + row][c] = dks[t][0];
+          s.F[cb][mt * 16 + row][c + 1] = dks[t][1];
+          s.F[cb][mt * 16 + row + 8][c] = dks[t][2];
+          s.F[cb][mt * 16 + row + 8][c + 1] = dks[t][3];
         }
       }
-      __syncthreads();
-      if (ok) {
-        float dk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dk[i] = ks[i] * (s.F[pix][part * 8 + i] - Dd[i]);
-        if (jl < lead) {
-          float dvf[8];
-          unpack8(*reinterpret_cast<const uint4*>(&s.Ob[pix][part * 8]), dvf);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            atomicAdd(dmem_kv + ((0 * HEADS + h) * DH + part * 8 + i) * NMEM + jl, dk[i]);
-            atomicAdd(dmem_kv + ((1 * HEADS + h) * DH + part * 8 + i) * NMEM + jl, dvf[i]);
-          }
-        } else {
-          lbf* o = dqbase + (int64_t)(p0 + jl - lead) * dld + part * 8;
-          *reinterpret_cast<uint4*>(o + HID) = pack8(dk);
-          *reinterpret_cast<uint4*>(o + 2 * HID) = *reinterpret_cast<const uint4*>(&s.Ob[pix][part * 8]);
-        }
-      }
-      __syncthreads();
+      for (int i = 0; i < 8; ++i) ksp[i] = ks[i];
+      jlp = jl;
+      okp = ok;
     }
+    __syncthreads();
+    if (total > 0) finish_kv(cb ^ 1);
   }
   cluster.sync();
 }
