@@ -2,6 +2,7 @@
 // Reference: Block.forward ddpm.py:164-173, ResnetBlock.forward :189-200, RMSNorm :107-113.
 // All statistics and arithmetic in fp32; tensors in the activation dtype.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -452,14 +453,21 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   cluster.sync();        // peers may still be reading this CTA's gpart
 }
 
+#ifndef GN_BWD_MINB
+#define GN_BWD_MINB 3
+#endif
+__device__ int g_gn_dbg = 0;   // experiment knob: early-exit stage of gn_bwd_cluster_kernel
+
 template <typename T>
-__global__ void __launch_bounds__(GNC_THREADS, 4)
+__global__ void __launch_bounds__(GNC_THREADS, GN_BWD_MINB)
 gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                       const float* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
                       T* __restrict__ dx, int dx_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dfilm, float* __restrict__ dbias, int HW, int C, int G) {
   pdl_prologue();
+  const int dbg = g_gn_dbg;
+  if (dbg == 1) return;
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -473,28 +481,12 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   __shared__ float cpart[GNC_MAXC * 3];                // this CTA's per-channel (S1, S2, S0): read by the peers
   __shared__ float ctot[GNC_MAXC * 3];                 // cluster totals
   __shared__ float gm[64][2];                          // (M1, M2) per group
-  const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
-  float A[8], Bc[8], sc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float ga = gamma[c0 + j] * rstd;
-    float be = beta[c0 + j] - mean * ga;
-    sc[j] = 1.f;
-    if (film) {
-      sc[j] = film[(int64_t)b * film_ld + c0 + j] + 1.f;
-      const float sh = film[(int64_t)b * film_ld + C + c0 + j];
-      ga *= sc[j];
-      be = be * sc[j] + sh;
-    }
-    A[j] = ga;
-    Bc[j] = be;
-  }
+  __shared__ float coef_s[GNC_MAXC * 3];               // per channel: gamma, beta, FiLM scale + 1
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
   const T* gp = dy + (int64_t)b * HW * dy_ld + c0;
-  // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk)
-  float s1[8] = {}, s2[8] = {}, s0[8] = {};
-  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    Raw8<T> rx[2], rg[2];
+  // the first pixels of the chunk are requested before anything else: their latency overlaps the coefficient setup
+  Raw8<T> rx[2], rg[2];
+  auto fetch = [&](int p) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
@@ -502,12 +494,60 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
         rg[u].load(gp + (int64_t)(p + u * lanes) * dy_ld);
       }
     }
+  };
+  fetch(p0 + lane);
+  const float mean = __ldg(stats + (b * G + g) * 2), rstd = __ldg(stats + (b * G + g) * 2 + 1);
+  float A[8], Bc[8], sc[8];
+  {
+    float gv[8], bv[8], sv[8], hv[8];
+    ld8(gamma + c0, gv);
+    ld8(beta + c0, bv);
+    if (film) {      // FiLM rows may start at any float offset (the C ABI only asks for fp32 alignment)
+      const float* fs = film + (int64_t)b * film_ld + c0;
+      if ((((uintptr_t)fs | (uintptr_t)(fs + C)) & 15) == 0) {
+        ld8(fs, sv);
+        ld8(fs + C, hv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sv[j] = fs[j];
+          hv[j] = fs[C + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ga = gv[j] * rstd;
+      float be = bv[j] - mean * ga;
+      sc[j] = 1.f;
+      if (film) {
+        sc[j] = sv[j] + 1.f;
+        ga *= sc[j];
+        be = be * sc[j] + hv[j];
+      }
+      A[j] = ga;
+      Bc[j] = be;
+      if (lane == 0) {      // one copy of the per-channel coefficients for the (few-thread) reductions below
+        coef_s[(c0 + j) * 3] = gv[j];
+        coef_s[(c0 + j) * 3 + 1] = bv[j];
+        coef_s[(c0 + j) * 3 + 2] = sc[j];
+      }
+    }
+  }
+  if (threadIdx.x < 2 * G) (&gm[0][0])[threadIdx.x] = 0.f;
+  if (dbg == 2) { if (A[0] + Bc[3] == 123.456f) dx[0] = (T)0; return; }
+  // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk); the loads of the
+  //      next two pixels are in flight while the current two are processed
+  float s1[8] = {}, s2[8] = {}, s0[8] = {};
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
+    Raw8<T> cx[2] = {rx[0], rx[1]}, cg2[2] = {rg[0], rg[1]};
+    if (p + 2 * lanes < p1) fetch(p + 2 * lanes);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
         float xv[8], gv[8];
-        rx[u].unpack(xv);
-        rg[u].unpack(gv);
+        cx[u].unpack(xv);
+        cg2[u].unpack(gv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], xv[j], Bc[j]);
@@ -521,6 +561,8 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
       }
     }
   }
+  // phase 2 starts from the first pixels again: request them now, the reductions below hide the latency
+  fetch(p0 + lane);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float* r = red + ((lane * C + c0 + j) * 3);
@@ -534,31 +576,39 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
     for (int l = 0; l < lanes; ++l) a += red[l * C * 3 + i];
     cpart[i] = a;
   }
+  if (dbg == 3) return;
   cluster.sync();
+  if (dbg == 4) { cluster.sync(); return; }
   for (int i = threadIdx.x; i < C * 3; i += GNC_THREADS) {
     float a = 0.f;
     for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(&cpart[0], r)[i];
     ctot[i] = a;
   }
   __syncthreads();
-  // group means of a*S1 and a*S2 (a = scale * gamma)
-  if (threadIdx.x < 2 * G) {
-    const int gg = threadIdx.x >> 1, k = threadIdx.x & 1;
-    float a = 0.f;
-    for (int c = gg * gs; c < (gg + 1) * gs; ++c) {
-      const float scl = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
-      a += scl * gamma[c] * ctot[c * 3 + k];
+  // group means of a*S1 and a*S2 (a = scale * gamma): every thread takes channels, shared-memory atomics per group
+  {
+    const float inv = 1.f / ((float)gs * (float)HW);
+    const int seg = gs < 32 ? gs : 32;                 // lanes of a warp that belong to the same group
+    for (int c = threadIdx.x; c < C; c += GNC_THREADS) {   // C is a multiple of 32: whole warps iterate together
+      const float a = coef_s[c * 3 + 2] * coef_s[c * 3] * inv;
+      float v1 = a * ctot[c * 3], v2 = a * ctot[c * 3 + 1];
+      for (int o = 1; o < seg; o <<= 1) {
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      }
+      if ((c & (seg - 1)) == 0) {                      // at most gs/32 adders per group
+        atomicAdd(&gm[c / gs][0], v1);
+        atomicAdd(&gm[c / gs][1], v2);
+      }
     }
-    gm[gg][k] = a / ((float)gs * (float)HW);
   }
   __syncthreads();
-  // parameter gradients (one CTA of the cluster): batch reduction through fp32 atomics
-  if (rank == 0) {
+  // parameter gradients (one CTA of the cluster): batch reduction through fp32 reductions in L2
+  if (rank == 0 && dgamma != nullptr) {
     for (int c = threadIdx.x; c < C; c += GNC_THREADS) {
       const int gg = c / gs;
       const float S1 = ctot[c * 3], S2 = ctot[c * 3 + 1], S0 = ctot[c * 3 + 2];
-      const float ga = gamma[c], be = beta[c];
-      const float scl = film ? film[(int64_t)b * film_ld + c] + 1.f : 1.f;
+      const float ga = coef_s[c * 3], be = coef_s[c * 3 + 1], scl = coef_s[c * 3 + 2];
       if (dfilm) {
         dfilm[(int64_t)b * film_ld + c] = ga * S2 + be * S1;
         dfilm[(int64_t)b * film_ld + C + c] = S1;
@@ -572,6 +622,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
       }
     }
   }
+  if (dbg == 5) { cluster.sync(); return; }
   // ---- phase 2: dx = P*dz + Q + R*x,  P = rstd*scale*gamma, R = -rstd^2*M2, Q = -rstd*M1 - R*mean
   const float M1 = gm[g][0], M2 = gm[g][1];
   const float R = -rstd * rstd * M2, Q = -rstd * M1 - R * mean;
@@ -580,20 +631,14 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   for (int j = 0; j < 8; ++j) P[j] = rstd * sc[j] * gamma[c0 + j];
   T* dp = dx + (int64_t)b * HW * dx_ld + c0;
   for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    Raw8<T> rx[2], rg[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (p + u * lanes < p1) {
-        rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
-        rg[u].load(gp + (int64_t)(p + u * lanes) * dy_ld);
-      }
-    }
+    Raw8<T> cx[2] = {rx[0], rx[1]}, cg2[2] = {rg[0], rg[1]};
+    if (p + 2 * lanes < p1) fetch(p + 2 * lanes);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
         float xv[8], gv[8];
-        rx[u].unpack(xv);
-        rg[u].unpack(gv);
+        cx[u].unpack(xv);
+        cg2[u].unpack(gv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], xv[j], Bc[j]);
@@ -611,6 +656,10 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 // cluster size: as many CTAs per sample as still fit on the machine in ONE wave (a second, partial wave costs
 // more than the smaller chunks save), each chunk at least two passes of the pixel lanes; any size 1..8.
 static int gn_cluster_size(int B, int HW, int C, int ctas_per_sm) {
+  {
+    const char* e = getenv("B200DM_GN_CL");      // experiment knob
+    if (e && e[0] >= '1' && e[0] <= '8') return e[0] - '0';
+  }
   const int lanes = GNC_THREADS / (C / 8);
   const long long slots = (long long)num_sms() * ctas_per_sm;
   int cl = (int)(slots / B);
@@ -929,7 +978,15 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (gn_cluster_ok(C, G)) {
-    const int cl = gn_cluster_size(B, HW, C, 4);
+    {
+      static int dbg_set = 0;
+      if (!dbg_set) {
+        dbg_set = 1;
+        const char* e = getenv("B200DM_GN_DBG");
+        if (e) { int v = atoi(e); cudaMemcpyToSymbol(g_gn_dbg, &v, sizeof(int)); }
+      }
+    }
+    const int cl = gn_cluster_size(B, HW, C, GN_BWD_MINB);
     dim3 grid(cl, B);
     cudaError_t e;
     if (dtype == B200DM_F32)
