@@ -85,7 +85,7 @@ class EMA(nn.Module):
         src, _ = self.online_model.model.flat_parameters()
         dst, _ = self.ema_model.model.flat_parameters()
         L.call("b200dm_ema_update", dst.data_ptr(), src.data_ptr(), dst.numel(), self.get_current_decay())
-        dst.add_(0)          # version bump -> EMA weight pack refresh
+        self.ema_model.model.arena.touch()      # EMA weight pack refresh
 
     def forward(self, *a, **k):
         return self.ema_model(*a, **k)

@@ -111,4 +111,4 @@ def broadcast_parameters(arena, src: int = 0, group=None):
     """DDP construction semantics: every rank starts from rank `src`'s weights."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(arena.flat, src, group=group)
-        arena.flat.add_(0)      # bump the version so weight packs refresh
+        arena.touch()           # weight packs refresh

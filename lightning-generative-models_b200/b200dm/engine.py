@@ -46,7 +46,7 @@ class WeightPack:
             if with_dgrad:
                 self.tr[nm] = self.tbuf[off:off + n]
             off += n
-        self.version = -1
+        self.version = None
         # stem (7x7, C -> dim) as a GEMM over im2col patches: zero-padded bf16 weight rows [dim][KP]
         self.stem_k = arena.channels * 49
         self.stem_kp = (self.stem_k + 63) // 64 * 64
@@ -73,7 +73,7 @@ class WeightPack:
 
     def refresh(self, force: bool = False):
         """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
-        v = self.arena.flat._version
+        v = self.arena.version
         if not force and v == self.version:
             return
         L.call("b200dm_pack_conv_weights_batched", self.dt, self.table.data_ptr(), self.n_entries,

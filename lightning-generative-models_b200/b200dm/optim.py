@@ -34,7 +34,7 @@ class FusedAdam(torch.optim.Optimizer):
         L.call("b200dm_adam_step", flat.data_ptr(), gflat.data_ptr(), self.exp_avg.data_ptr(),
                self.exp_avg_sq.data_ptr(), flat.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
                g["weight_decay"], self.step_count, self.grad_scale)
-        flat.add_(0)                   # bump the version counter: the weight pack re-syncs lazily
+        self.unet.arena.touch()        # the weight pack re-syncs lazily (no kernel needed for the bump)
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

@@ -142,6 +142,7 @@ class ParamArena:
                 n *= s
             off += (n + 3) // 4 * 4            # keep every tensor 16-byte aligned
         self.numel = off
+        self.epoch = 0            # bumped by kernels that update `flat` through raw pointers (Adam, EMA)
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.gflat = torch.zeros(off, dtype=torch.float32, device=device) if with_grad else None
         self.views = {nm: self._logical(self.flat, nm) for nm, _ in self.spec}
@@ -168,6 +169,15 @@ class ParamArena:
             co, cin, kh, kw = self.shapes[nm]
             return raw.view(kh, kw, co, cin).permute(2, 3, 0, 1)      # logical OIHW over tap-major memory
         return raw.view(self.shapes[nm])
+
+    def touch(self):
+        """Mark the parameters as modified by a raw-pointer kernel (the GEMM weight packs re-sync lazily).  In-place
+        torch ops on `flat` or on the parameter views are detected through the tensor version counter instead."""
+        self.epoch += 1
+
+    @property
+    def version(self):
+        return (self.flat._version, self.epoch)
 
     def ptr(self, nm: str) -> int:
         return self.flat.data_ptr() + 4 * self.offset[nm]

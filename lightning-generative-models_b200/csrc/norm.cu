@@ -454,9 +454,8 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 }
 
 #ifndef GN_BWD_MINB
-#define GN_BWD_MINB 3
+#define GN_BWD_MINB 3      // resident CTAs per SM the backward kernel is compiled for (80 registers)
 #endif
-__device__ int g_gn_dbg = 0;   // experiment knob: early-exit stage of gn_bwd_cluster_kernel
 
 template <typename T>
 __global__ void __launch_bounds__(GNC_THREADS, GN_BWD_MINB)
@@ -466,8 +465,6 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
                       T* __restrict__ dx, int dx_ld, float* __restrict__ dgamma, float* __restrict__ dbeta,
                       float* __restrict__ dfilm, float* __restrict__ dbias, int HW, int C, int G) {
   pdl_prologue();
-  const int dbg = g_gn_dbg;
-  if (dbg == 1) return;
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -535,7 +532,6 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
     }
   }
   if (threadIdx.x < 2 * G) (&gm[0][0])[threadIdx.x] = 0.f;
-  if (dbg == 2) { if (A[0] + Bc[3] == 123.456f) dx[0] = (T)0; return; }
   // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk); the loads of the
   //      next two pixels are in flight while the current two are processed
   float s1[8] = {}, s2[8] = {}, s0[8] = {};
@@ -576,9 +572,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
     for (int l = 0; l < lanes; ++l) a += red[l * C * 3 + i];
     cpart[i] = a;
   }
-  if (dbg == 3) return;
   cluster.sync();
-  if (dbg == 4) { cluster.sync(); return; }
   for (int i = threadIdx.x; i < C * 3; i += GNC_THREADS) {
     float a = 0.f;
     for (int r = 0; r < CL; ++r) a += cluster.map_shared_rank(&cpart[0], r)[i];
@@ -622,7 +616,6 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
       }
     }
   }
-  if (dbg == 5) { cluster.sync(); return; }
   // ---- phase 2: dx = P*dz + Q + R*x,  P = rstd*scale*gamma, R = -rstd^2*M2, Q = -rstd*M1 - R*mean
   const float M1 = gm[g][0], M2 = gm[g][1];
   const float R = -rstd * rstd * M2, Q = -rstd * M1 - R * mean;
@@ -978,14 +971,6 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (gn_cluster_ok(C, G)) {
-    {
-      static int dbg_set = 0;
-      if (!dbg_set) {
-        dbg_set = 1;
-        const char* e = getenv("B200DM_GN_DBG");
-        if (e) { int v = atoi(e); cudaMemcpyToSymbol(g_gn_dbg, &v, sizeof(int)); }
-      }
-    }
     const int cl = gn_cluster_size(B, HW, C, GN_BWD_MINB);
     dim3 grid(cl, B);
     cudaError_t e;
