@@ -122,6 +122,12 @@ typedef struct {
   const void* res;
   int32_t res_ld;
   int32_t accumulate;
+  /* tcgen05 path, mode 0: GroupNorm partial statistics of y fused into the epilogue (deterministic, no atomics).
+   * gn_part: fp32 [B*H*W/seg][Cout/8][2] = (sum, sum of squares) per pixel slot of seg = min(32, H*W) pixels
+   * and 8-channel chunk; b200dm_gn_fwd_pre adds the H*W/seg slots of a sample and the chunks of a group.
+   * gn_groups > 0 with Cout/gn_groups a multiple of 8.  NULL = off. */
+  float* gn_part;
+  int32_t gn_groups;
 } b200dm_conv_desc;
 
 int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream);
@@ -200,6 +206,13 @@ int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* stats, cons
                   const float* beta, const float* film, int32_t film_ld, const void* res, int32_t res_ld,
                   void* y, int32_t y_ld, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
                   void* stream);
+/* apply only: the statistics come from the conv epilogue (b200dm_conv_desc.gn_part): part = fp32
+ * [B][slots][C/8][2] (sum, sum of squares per 8-channel chunk) with slots = H*W / min(32, H*W) per sample.  One pass, no cluster;
+ * also writes stats [B][G][2] = (mean, rstd) for the backward pass. */
+int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, const float* part, int32_t slots, float* stats,
+                      const float* gamma, const float* beta, const float* film, int32_t film_ld, const void* res,
+                      int32_t res_ld, void* y, int32_t y_ld, int32_t B, int32_t HW, int32_t C, int32_t G, float eps,
+                      void* stream);
 /* backward.  C <= 512: one cluster launch per call (per-channel sums exchanged through distributed shared
  * memory; dgamma/dbeta/dbias reduced over the batch with fp32 atomics; sums/gmeans unused).  Otherwise
  * three launches inside:  (1) per-(b,c) sums of dz, dz*xnorm and x  (2) parameter / FiLM

@@ -31,6 +31,7 @@ class ConvDesc(C.Structure):
         ("y", C.c_void_p), ("y_ld", C.c_int32),
         ("res", C.c_void_p), ("res_ld", C.c_int32),
         ("accumulate", C.c_int32),
+        ("gn_part", C.c_void_p), ("gn_groups", C.c_int32),
     ]
 
 
@@ -79,6 +80,7 @@ PROTOTYPES = {
     "b200dm_upsample2x_bwd": [_I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_gn_stats": [_I, _P, _I, _P, _I, _I, _I, _I, _F, _P],
     "b200dm_gn_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
+    "b200dm_gn_fwd_pre": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P],
     "b200dm_gn_apply_fwd": [_I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_gn_apply_bwd": [_I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P,
                             _I, _I, _I, _I, _P],

@@ -107,6 +107,7 @@ class Plan:
         self._keep.append(pack)
         import os
         self.side_enabled = os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
+        self.fuse_gn_stats = os.environ.get("B200DM_FUSE_GN_STATS", "1") != "0"
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
@@ -183,7 +184,7 @@ class Plan:
         return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
 
     def conv_fwd(self, lst_fn, nm, x: View, y: View, *, dgrad=False, res: Optional[View] = None,
-                 accumulate=0, bias=True, side=False):
+                 accumulate=0, bias=True, side=False, gn_part: Optional[torch.Tensor] = None):
         """Forward conv `nm` (x -> y), or with dgrad=True its data gradient (x = dY, y = dX)."""
         ci = self.arena.convs[nm]
         if not dgrad:
@@ -200,7 +201,8 @@ class Plan:
                        impl=self._impl(cin, cout), B=self.B, H=H, W=H, Cin=cin, Cout=cout,
                        x=x.ptr, x_ld=x.ld, w=w, bias=b, y=y.ptr, y_ld=y.ld,
                        res=None if res is None else res.ptr, res_ld=0 if res is None else res.ld,
-                       accumulate=accumulate)
+                       accumulate=accumulate, gn_part=None if gn_part is None else gn_part.data_ptr(),
+                       gn_groups=GROUPS if gn_part is not None else 0)
         taps = ci.taps
         flops = 2.0 * self.B * H * H * cout * cin * taps
         fam = ("conv_tc" if d.impl == 1 else "conv_simt") + ("_dgrad" if dgrad else "_fwd")
@@ -247,15 +249,31 @@ class Plan:
         if has_res_conv:      # issued first: runs on the second stream next to the whole conv/norm chain
             rc = self.buf(H, cout)
             self.conv_fwd(self.F, nm + ".res_conv", x, rc, side=True)
-        self.conv_fwd(self.F, b1 + ".proj", x, c1)
-        self.F("b200dm_gn_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
-               a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout, GROUPS,
-               GN_EPS, reads=(self.film,))
-        self.conv_fwd(self.F, b2 + ".proj", h1, c2)
         res = rc if has_res_conv else x
-        self.F("b200dm_gn_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
-               a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS,
-               GN_EPS, reads=(res,))
+        gs = cout // GROUPS
+        fused = (self.fuse_gn_stats and self._impl(cin, cout) == 1 and self._impl(cout, cout) == 1
+                 and gs % 8 == 0)
+        if fused:
+            # GroupNorm statistics come out of the conv epilogues as per-slot partial sums; the norm is one pass
+            slots = HW // min(32, HW)
+            pt1, pt2 = self.f32(self.B, slots, cout // 8, 2), self.f32(self.B, slots, cout // 8, 2)
+            self.conv_fwd(self.F, b1 + ".proj", x, c1, gn_part=pt1)
+            self.F("b200dm_gn_fwd_pre", self.dt, c1.ptr, c1.ld, pt1.data_ptr(), slots, st1.data_ptr(),
+                   a.ptr(b1 + ".norm.weight"), a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr,
+                   h1.ld, self.B, HW, cout, GROUPS, GN_EPS, reads=(self.film,), kname="gn_fwd")
+            self.conv_fwd(self.F, b2 + ".proj", h1, c2, gn_part=pt2)
+            self.F("b200dm_gn_fwd_pre", self.dt, c2.ptr, c2.ld, pt2.data_ptr(), slots, st2.data_ptr(),
+                   a.ptr(b2 + ".norm.weight"), a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld,
+                   self.B, HW, cout, GROUPS, GN_EPS, reads=(res,), kname="gn_fwd")
+        else:
+            self.conv_fwd(self.F, b1 + ".proj", x, c1)
+            self.F("b200dm_gn_fwd", self.dt, c1.ptr, c1.ld, st1.data_ptr(), a.ptr(b1 + ".norm.weight"),
+                   a.ptr(b1 + ".norm.bias"), film_ptr, a.film_cols, None, 0, h1.ptr, h1.ld, self.B, HW, cout,
+                   GROUPS, GN_EPS, reads=(self.film,))
+            self.conv_fwd(self.F, b2 + ".proj", h1, c2)
+            self.F("b200dm_gn_fwd", self.dt, c2.ptr, c2.ld, st2.data_ptr(), a.ptr(b2 + ".norm.weight"),
+                   a.ptr(b2 + ".norm.bias"), None, 0, res.ptr, res.ld, out.ptr, out.ld, self.B, HW, cout, GROUPS,
+                   GN_EPS, reads=(res,))
         if not self.training:
             return
         # dc2 / dc1: separate scratch for the two norm gradients, so block1's norm backward does not have to wait

@@ -72,6 +72,8 @@ extern "C" int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream) {
     return conv_fwd_tc(d, stream);
   }
   B200DM_REQUIRE(d->impl == 0, B200DM_ERR_UNSUPPORTED, "conv_fwd: impl %d", d->impl);
+  B200DM_REQUIRE(d->gn_part == nullptr, B200DM_ERR_UNSUPPORTED,
+                 "conv_fwd: fused GroupNorm statistics are built for the tcgen05 path (impl 1) only");
   return conv_fwd_simt(d, stream);
 }
 

@@ -69,7 +69,40 @@ struct TcParams {
   const __nv_bfloat16* res;
   int res_ld;
   const float* bias;
+  float* gn_part;                  // GroupNorm partial sums [pixel slot][G][2] of the output, or nullptr
+  int gn_groups, gn_seg;           // groups; pixels per slot (= lanes of a warp that belong to one image)
 };
+
+// GroupNorm statistics of a conv output, fused into the epilogue (deterministic: no atomics).
+// A warp owns 32 pixels x 64 channels of a sub-tile.  S/Q hold this thread's (= pixel's) sum and sum of squares of
+// the eight 8-channel chunks.  The 16 values are reduced over the `seg` lanes (32, or 16 when two 4x4 images share
+// a warp) that belong to the same image by recursive halving - 16 shuffles instead of 16 x log2(seg) - after
+// which every lane of a segment holds the total of ONE value and writes it:
+//   part[(slot * C/8 + chunk) * 2 + {0: sum, 1: sum of squares}],  slot = pixel index / seg.
+// The norm kernel adds the H*W/seg slots of an image and the chunks of a group.
+__device__ __forceinline__ void gn_part_store(const float (&S)[8], const float (&Q)[8], int seg, int lane, bool ok,
+                                              float* part, long long slot, int chunks_total, int chunk0) {
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = S[k]; v[8 + k] = Q[k]; }
+  int idx = 0;
+  // halving steps: the lane keeps the half of its values selected by one of its index bits, sends the other half
+#pragma unroll
+  for (int n = 8, step = 0; n >= 1; n >>= 1, ++step) {
+    const int m = (seg >> 1) >> step;                    // partner distance: 16, 8, 4, 2 (seg 32) / 8, 4, 2, 1 (seg 16)
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float keep = up ? v[i + n] : v[i];
+      const float send = up ? v[i] : v[i + n];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+    idx = idx * 2 + (up ? 1 : 0);
+  }
+  if (seg == 32) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);   // the last pair of lanes holds the same value index
+  const bool writer = seg == 32 ? (lane & 1) == 0 : true;
+  if (ok && writer) part[(slot * chunks_total + chunk0 + (idx & 7)) * 2 + (idx >> 3)] = v[0];
+}
 
 // Persistent, warp-specialised implicit-GEMM convolution.  Each CTA walks tiles
 // (tile = blockIdx.x + i*gridDim.x, N fastest so CTAs running together share the activation tile in L2):
@@ -276,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the private staging block was handed to the TMA engine one sub-tile ago
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        float gS[8], gQ[8];
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int c = s * 64 + hh * 32;     // column offset inside the N tile
@@ -297,6 +331,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
               v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
               v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
+          }
+          if (p.gn_part) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float a = 0.f, q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float t = valid ? v[8 * k + j] : 0.f;
+                a += t;
+                q = fmaf(t, t, q);
+              }
+              if (hh == 0) { gS[k] = a; gQ[k] = q; } else { gS[4 + k] = a; gQ[4 + k] = q; }   // static register indices
             }
           }
           if (valid && p.res) {
@@ -336,6 +383,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<uint4*>(my_row + chunk * 16) = u;
           }
         }
+        if (p.gn_part)
+          gn_part_store(gS, gQ, p.gn_seg, lane, valid, p.gn_part, (long long)((unsigned)first + 32u * (unsigned)quarter + (unsigned)lane) / p.gn_seg,
+                        p.Cout / 8, (co0 + s * 64) / 8);
         fence_proxy_async();                  // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
@@ -380,6 +430,8 @@ struct TcHaloParams {
   const __nv_bfloat16* res;
   int res_ld;
   const float* bias;
+  float* gn_part;              // GroupNorm partial sums [pixel slot][G][2] of the output, or nullptr
+  int gn_groups;
   int dbg;                     // B200DM_HALO_DEBUG bit 0: skip epilogue stores, 1: skip A loads, 2: skip MMAs
 };
 
@@ -584,6 +636,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int s2 = s_first; s2 < SUBTILES; s2 += 2) {
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        float gS[8], gQ[8];
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int c = s2 * 64 + hh * 32;
@@ -606,6 +659,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
               v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
               v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
+          }
+          if (p.gn_part) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float a = 0.f, q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                a += v[8 * k + j];
+                q = fmaf(v[8 * k + j], v[8 * k + j], q);
+              }
+              if (hh == 0) { gS[k] = a; gQ[k] = q; } else { gS[4 + k] = a; gQ[4 + k] = q; }   // static register indices
             }
           }
           if (p.res) {
@@ -645,6 +710,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (p.dbg & 1) continue;
+        if (p.gn_part)
+          gn_part_store(gS, gQ, 32, lane, true, p.gn_part, (long long)m_tile * 4 + quarter, p.Cout / 8, (n0 + s2 * 64) / 8);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -798,6 +865,7 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
   p.y_read = d->accumulate ? (const __nv_bfloat16*)d->y : nullptr;
   p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
   p.bias = d->bias;
+  p.gn_part = d->gn_part; p.gn_groups = d->gn_groups;
   {
     // MEASURED on B200 (scripts/halo_debug.py): the tensor core derives the 128-B swizzle phase from the
     // absolute shared-memory address bits [7,10), exactly like the TMA unit that wrote the tile, so a
@@ -854,6 +922,13 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->y & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
                      ((uintptr_t)d->res & 15) == 0,
                  B200DM_ERR_SHAPE, "conv_fwd(tc): pointers must be 16-byte aligned");
+  if (d->gn_part) {
+    const int gs = d->gn_groups > 0 ? d->Cout / d->gn_groups : 0;
+    B200DM_REQUIRE(d->mode == 0 && d->gn_groups > 0 && d->Cout % d->gn_groups == 0 &&
+                       gs % 8 == 0 && !d->res && !d->accumulate,
+                   B200DM_ERR_UNSUPPORTED, "conv_fwd(tc): fused GroupNorm statistics need mode 0, no residual and "
+                   "a multiple of 8 channels per group (Cout=%d groups=%d)", d->Cout, d->gn_groups);
+  }
   const int ksize = d->mode == 0 ? d->ksize : 1;
   if (d->mode == 0 && ksize == 3 && d->W >= 16 && d->W % 8 == 0 && d->H % 16 == 0 && halo_enabled())
     return conv3x3_halo(d, (cudaStream_t)stream);
@@ -872,6 +947,8 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   p.y_read = d->accumulate ? (const __nv_bfloat16*)d->y : nullptr;
   p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
   p.bias = d->bias;
+  p.gn_part = d->gn_part; p.gn_groups = d->gn_groups;
+  p.gn_seg = d->H * d->W >= 32 ? 32 : d->H * d->W;
   p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
 
   // N tile: maximise (MMA efficiency of the tile shape) x (fill of the last wave of the persistent grid)

@@ -336,10 +336,14 @@ __global__ void __launch_bounds__(GNC_THREADS)
 gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
-                      T* __restrict__ y, int y_ld, int HW, int C, int G, float eps, int write_stats) {
+                      T* __restrict__ y, int y_ld, int HW, int C, int G, float eps, int write_stats,
+                      const float* __restrict__ part, int slots) {
   pdl_prologue();
   cg::cluster_group cluster = cg::this_cluster();
-  const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  // part != nullptr: (sum, sumsq) partials [slots per sample][G][2] were produced by the conv epilogue; the kernel
+  // is then a plain grid of pixel chunks (launched without a cluster): one pass, no barriers between CTAs
+  const int CL = part ? (int)gridDim.x : (int)cluster.num_blocks();
+  const int rank = part ? (int)blockIdx.x : (int)cluster.block_rank();
   const int b = blockIdx.y;
   const int C8 = C >> 3, gs8 = C8 / G;                 // 8-wide vectors per group
   const int lanes = GNC_THREADS / C8;
@@ -347,7 +351,8 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   const int c0 = cv * 8, g = cv / gs8;
   const int ppb = (HW + CL - 1) / CL;
   const int p0 = rank * ppb, p1 = min(p0 + ppb, HW);
-  __shared__ float part[GNC_THREADS][2];
+  __shared__ float tpart[GNC_THREADS][2];
+  float* part_s = &tpart[0][0];                        // reused as [slot lanes][2G] in the pre-statistics mode
   __shared__ float gpart[64][2];                       // this CTA's per-group (sum, sumsq): read by the peers
   __shared__ float gstat[64][2];                       // (mean, rstd) per group
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
@@ -355,6 +360,36 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   Raw8<T>* stage = reinterpret_cast<Raw8<T>*>(gn_stage_raw);     // [pixel of the chunk][C8]
   // ---- phase 1: per-group sum / sum of squares of the chunk
   float s = 0.f, ss = 0.f;
+  if (part) {
+    // partials: [sample][slot][C/8 chunks][2].  thread = (slot lane, (group, which)): add the sample's slots and the
+    // chunks of the group, then the slot lanes through shared memory
+    const int gk = threadIdx.x % (2 * G), sl = threadIdx.x / (2 * G), SL = GNC_THREADS / (2 * G);
+    const int gq = gk >> 1, which = gk & 1, cpg = C8 / G;   // chunks per group
+    float a = 0.f;
+    const float* pp = part + (int64_t)b * slots * 2 * C8 + (gq * cpg) * 2 + which;
+    for (int i = sl; i < slots; i += SL)
+      for (int c = 0; c < cpg; ++c) a += pp[((int64_t)i * C8 + c) * 2];
+    part_s[sl * 2 * G + gk] = a;
+    __syncthreads();
+    if (threadIdx.x < G) {
+      float sum = 0.f, sq = 0.f;
+      for (int i = 0; i < SL; ++i) {
+        sum += part_s[i * 2 * G + 2 * threadIdx.x];
+        sq += part_s[i * 2 * G + 2 * threadIdx.x + 1];
+      }
+      const float inv = 1.f / ((float)HW * (float)(C / G));
+      const float mean = sum * inv;
+      const float var = fmaxf(sq * inv - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      gstat[threadIdx.x][0] = mean;
+      gstat[threadIdx.x][1] = rstd;
+      if (rank == 0 && write_stats) {
+        stats[(b * G + threadIdx.x) * 2] = mean;
+        stats[(b * G + threadIdx.x) * 2 + 1] = rstd;
+      }
+    }
+    __syncthreads();
+  } else {
   for (int p = p0 + lane; p < p1; p += 4 * lanes) {
     Raw8<T> raw[4];
 #pragma unroll
@@ -374,14 +409,14 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
       }
     }
   }
-  part[threadIdx.x][0] = s;
-  part[threadIdx.x][1] = ss;
+  tpart[threadIdx.x][0] = s;
+  tpart[threadIdx.x][1] = ss;
   __syncthreads();
   if (threadIdx.x < 2 * G) {
     const int gg = threadIdx.x >> 1, k = threadIdx.x & 1;
     float a = 0.f;
     for (int l = 0; l < lanes; ++l)
-      for (int v = 0; v < gs8; ++v) a += part[l * C8 + gg * gs8 + v][k];
+      for (int v = 0; v < gs8; ++v) a += tpart[l * C8 + gg * gs8 + v][k];
     gpart[gg][k] = a;
   }
   cluster.sync();
@@ -404,6 +439,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
     }
   }
   __syncthreads();
+  }   // statistics from this kernel's own reduction pass
   // ---- phase 2: y = silu(A*x + Bc) (+ res)
   float A[8], Bc[8];
   {
@@ -450,7 +486,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
       }
     }
   }
-  cluster.sync();        // peers may still be reading this CTA's gpart
+  if (!part) cluster.sync();        // peers may still be reading this CTA's gpart
 }
 
 #ifndef GN_BWD_MINB
@@ -930,7 +966,8 @@ extern "C" int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* 
   cudaError_t e;
 #define GN_FWD_LAUNCH(TT, ST)                                                                                 \
   launch_cluster(gn_fwd_cluster_kernel<TT, ST>, grid, cl, smem, st, (const TT*)x, (int)x_ld, stats, gamma, beta, \
-                 film, (int)film_ld, (const TT*)res, (int)res_ld, (TT*)y, (int)y_ld, (int)HW, (int)C, (int)G, eps, 1)
+                 film, (int)film_ld, (const TT*)res, (int)res_ld, (TT*)y, (int)y_ld, (int)HW, (int)C, (int)G, eps, 1,   \
+                 (const float*)nullptr, 0)
   if (dtype == B200DM_F32)
     e = stage ? GN_FWD_LAUNCH(float, true) : GN_FWD_LAUNCH(float, false);
   else
@@ -939,6 +976,36 @@ extern "C" int b200dm_gn_fwd(int32_t dtype, const void* x, int32_t x_ld, float* 
   B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_fwd: launch failed: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("gn_fwd");
+}
+
+extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, const float* part, int32_t slots,
+                                 float* stats, const float* gamma, const float* beta, const float* film,
+                                 int32_t film_ld, const void* res, int32_t res_ld, void* y, int32_t y_ld, int32_t B,
+                                 int32_t HW, int32_t C, int32_t G, float eps, void* stream) {
+  GN_CHECKS("gn_fwd_pre");
+  B200DM_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && (!res || res_ld % 8 == 0), B200DM_ERR_SHAPE,
+                 "gn_fwd_pre: ld must be a multiple of 8");
+  B200DM_REQUIRE(part != nullptr && slots > 0 && stats != nullptr, B200DM_ERR_SHAPE, "gn_fwd_pre: partials and stats required");
+  B200DM_REQUIRE(gn_cluster_ok(C, G) && GNC_THREADS % (2 * G) == 0, B200DM_ERR_UNSUPPORTED,
+                 "gn_fwd_pre: C=%d G=%d not supported", C, G);
+  cudaStream_t st = (cudaStream_t)stream;
+  // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
+  const int lanes = GNC_THREADS / (C / 8);
+  int chunks = (int)(((long long)num_sms() * 4) / B);
+  if (chunks > 16) chunks = 16;
+  while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, B);
+  if (dtype == B200DM_F32)
+    launch_k(gn_fwd_cluster_kernel<float, false>, grid, GNC_THREADS, 0, st, (const float*)x, (int)x_ld, stats, gamma,
+             beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld, (int)HW, (int)C, (int)G,
+             eps, 1, part, (int)slots);
+  else
+    launch_k(gn_fwd_cluster_kernel<bf16, false>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
+             beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW, (int)C, (int)G,
+             eps, 1, part, (int)slots);
+  count_launch();
+  return check_launch("gn_fwd_pre");
 }
 
 static int gn_bwd_chunks(int B, int HW, int C) {

@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_c():
     # 9 int32, then pointer-aligned fields: offsets follow the C ABI on LP64
-    assert ctypes.sizeof(L.ConvDesc) == 104 and L.ConvDesc.x.offset == 40 and L.ConvDesc.accumulate.offset == 100
+    assert ctypes.sizeof(L.ConvDesc) == 120 and L.ConvDesc.x.offset == 40 and L.ConvDesc.accumulate.offset == 100
+    assert L.ConvDesc.gn_part.offset == 104 and L.ConvDesc.gn_groups.offset == 112
     assert ctypes.sizeof(L.PackEntry) == 80
     assert ctypes.sizeof(L.WgradDesc) == 112 and L.WgradDesc.dw.offset == 72 and L.WgradDesc.s_tap.offset == 88
 

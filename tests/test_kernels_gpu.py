@@ -490,6 +490,51 @@ def test_groupnorm_film_silu_fwd_bwd(dtype, B, S, Cc, film, res):
         assert rel(dfilm, fm.grad) < 1e-4
 
 
+@pytest.mark.parametrize("B,S,Cin,Cout,film", [(3, 32, 64, 64, True), (2, 16, 128, 128, False), (5, 8, 128, 256, True),
+                                               (9, 4, 256, 512, False), (1, 64, 64, 64, False)])
+def test_conv_epilogue_groupnorm_statistics_and_one_pass_norm(B, S, Cin, Cout, film):
+    """3x3 conv (tcgen05) emitting per-slot GroupNorm partial sums + the one-pass norm that consumes them,
+    against conv2d -> group_norm -> FiLM -> SiLU of the reference Block (ddpm.py:164-173)."""
+    if not L.load().b200dm_tc_available():
+        pytest.skip("needs the tcgen05 path")
+    G = 8
+    x = q(rnd(B, Cin, S, S, seed=91), L.BF16)
+    w = q(rnd(Cout, Cin, 3, 3, seed=92, scale=1 / math.sqrt(Cin * 9)), L.BF16)
+    bias = rnd(Cout, seed=93, scale=0.3)
+    gamma, beta = 1 + 0.1 * rnd(Cout, seed=94), 0.1 * rnd(Cout, seed=95)
+    fm = rnd(B, 2 * Cout, seed=96, scale=0.3) if film else None
+    conv = F.conv2d(x, w, bias, padding=1)
+    h = F.group_norm(conv, G, gamma, beta, eps=1e-5)
+    if film:
+        h = h * (fm[:, :Cout, None, None] + 1) + fm[:, Cout:, None, None]
+    ref = F.silu(h)
+    xv = nhwc(x, L.BF16)
+    cv = View.zeros(B, S, S, Cout, torch.bfloat16, DEV)
+    yv = View.zeros(B, S, S, Cout, torch.bfloat16, DEV)
+    slots = S * S // min(32, S * S)
+    part = torch.full((B, slots, Cout // 8, 2), float("nan"), device=DEV)   # per pixel slot and 8-channel chunk
+    wp = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous().to(torch.bfloat16)
+    d = L.ConvDesc(dtype=L.BF16, mode=0, ksize=3, impl=1, B=B, H=S, W=S, Cin=Cin, Cout=Cout, x=xv.ptr, x_ld=xv.ld,
+                   w=wp.data_ptr(), bias=bias.data_ptr(), y=cv.ptr, y_ld=cv.ld, res=None, res_ld=0, accumulate=0,
+                   gn_part=part.data_ptr(), gn_groups=G)
+    L.call("b200dm_conv_fwd", d)
+    assert torch.isfinite(part).all()
+    sums = part.sum(1).reshape(B, G, Cout // 8 // G, 2).sum(2)               # [B, G, 2]
+    cg = conv.reshape(B, G, -1)
+    assert rel(sums[..., 0], cg.sum(-1)) < 2e-3 and rel(sums[..., 1], (cg * cg).sum(-1)) < 2e-3
+    stats = torch.empty(B, G, 2, device=DEV)
+    L.call("b200dm_gn_fwd_pre", L.BF16, cv.ptr, cv.ld, part.data_ptr(), slots, stats.data_ptr(), gamma.data_ptr(),
+           beta.data_ptr(), None if fm is None else fm.data_ptr(), 2 * Cout, None, 0, yv.ptr, yv.ld, B, S * S, Cout,
+           G, 1e-5)
+    assert rel(stats[..., 0], cg.mean(-1)) < 2e-3
+    assert rel(stats[..., 1], (cg.var(-1, unbiased=False) + 1e-5).rsqrt()) < 2e-3
+    assert rel(yv.to_nchw(), ref) < 8e-3                 # conv output rounded to bf16 before the norm
+    part2 = torch.full_like(part, float("nan"))          # deterministic: bit-identical on a second run
+    d.gn_part = part2.data_ptr()
+    L.call("b200dm_conv_fwd", d)
+    assert torch.equal(part, part2)
+
+
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("Cc,res", [(64, False), (128, True), (256, True), (512, False)])
 def test_rmsnorm_fwd_bwd(dtype, Cc, res):
