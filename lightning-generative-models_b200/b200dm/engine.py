@@ -64,7 +64,7 @@ class WeightPack:
             e.wt = self.tr[nm].data_ptr() if with_dgrad else None
             e.taps, e.Cout, e.Cin, e.flip = ci.taps, ci.cout, ci.cin, 1 if ci.mode == 0 else 0
             e.s_tap, e.s_co, e.s_ci = s_tap, s_co, s_ci
-            e.tiles_ci, e.tiles_co = (ci.cin + 31) // 32, (ci.cout + 31) // 32
+            e.tiles_ci, e.tiles_co = (ci.cin + 63) // 64, (ci.cout + 63) // 64     # 64x64 tiles (optim.cu PK)
             e.tile_begin = tile
             tile += ci.taps * e.tiles_ci * e.tiles_co
         self.n_entries, self.total_tiles = len(arena.convs), tile

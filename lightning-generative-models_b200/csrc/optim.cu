@@ -33,11 +33,29 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 // All conv weights of the network in ONE launch: `table` lists the tensors, each CTA finds its
-// (tensor, tap, 32x32 tile) by binary search over the tile prefix sums.
+// (tensor, tap, 64x64 tile) by binary search over the tile prefix sums.  256 threads; float4 loads along Cin,
+// 8-byte (4 x bf16) / 16-byte (4 x fp32) stores for both the forward copy and the transposed data-gradient copy.
+constexpr int PK = 64;
 template <typename T>
-__global__ void pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) {
+__device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+  uint2 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h[0] = __floats2bfloat162_rn(a, b);
+  h[1] = __floats2bfloat162_rn(c, d);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) {
   pdl_prologue();
-  __shared__ float tile[32][33];
+  __shared__ float tile[PK][PK + 1];
   int lo = 0, hi = n - 1;
   const int bid = blockIdx.x;
   while (lo < hi) {
@@ -49,23 +67,53 @@ __global__ void pack_weights_batched_kernel(const b200dm_pack_entry* __restrict_
   const int per_tap = e.tiles_ci * e.tiles_co;
   const int t = local / per_tap;
   local -= t * per_tap;
-  const int ci0 = (local % e.tiles_ci) * 32, co0 = (local / e.tiles_ci) * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int ci0 = (local % e.tiles_ci) * PK, co0 = (local / e.tiles_ci) * PK;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int c4 = (tid & 15) * 4, r0 = tid >> 4;          // 4 consecutive columns, rows r0 + 16 i
   const float* wsrc = e.w + (int64_t)t * e.s_tap;
   T* wf = (T*)e.wf;
   T* wt = (T*)e.wt;
-  for (int r = ty; r < 32; r += 8) {
-    int co = co0 + r, ci = ci0 + tx;
-    float v = (co < e.Cout && ci < e.Cin) ? wsrc[(int64_t)co * e.s_co + (int64_t)ci * e.s_ci] : 0.f;
-    tile[r][tx] = v;
-    if (wf && co < e.Cout && ci < e.Cin) Elem<T>::st(wf + ((int64_t)t * e.Cout + co) * e.Cin + ci, v);
+  const bool full = co0 + PK <= e.Cout && ci0 + PK <= e.Cin;
+  const bool vec = full && e.s_ci == 1 && (e.s_co & 3) == 0 && (e.s_tap & 3) == 0 && (e.Cin & 3) == 0 && (e.Cout & 3) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 16 * i, co = co0 + r, ci = ci0 + c4;
+    float v[4];
+    if (vec) {
+      const float4 f = *reinterpret_cast<const float4*>(wsrc + (int64_t)co * e.s_co + ci);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v[j] = (co < e.Cout && ci + j < e.Cin) ? wsrc[(int64_t)co * e.s_co + (int64_t)(ci + j) * e.s_ci] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tile[r][c4 + j] = v[j];
+    if (wf) {
+      T* dst = wf + ((int64_t)t * e.Cout + co) * e.Cin + ci;
+      if (vec) {
+        store4<T>(dst, v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (co < e.Cout && ci + j < e.Cin) Elem<T>::st(dst + j, v[j]);
+      }
+    }
   }
   __syncthreads();
   if (wt) {
     const int tt = e.flip ? e.taps - 1 - t : t;
-    for (int r = ty; r < 32; r += 8) {
-      int ci = ci0 + r, co = co0 + tx;
-      if (co < e.Cout && ci < e.Cin) Elem<T>::st(wt + ((int64_t)tt * e.Cin + ci) * e.Cout + co, tile[tx][r]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 16 * i, ci = ci0 + r, co = co0 + c4;     // row of the transposed tile = input channel
+      T* dst = wt + ((int64_t)tt * e.Cin + ci) * e.Cout + co;
+      if (vec) {
+        store4<T>(dst, tile[c4][r], tile[c4 + 1][r], tile[c4 + 2][r], tile[c4 + 3][r]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ci < e.Cin && co + j < e.Cout) Elem<T>::st(dst + j, tile[c4 + j][r]);
+      }
     }
   }
 }
