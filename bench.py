@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """Benchmark of the B200 diffusion hot path (contract: see the task statement / DESIGN.md §6).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|ddim] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|ddim|ddpm|train64] [--impl reference]
 
 Workload at N=1 (BASELINE.json configs[1], the configuration the metric is quoted on):
   DDPM training step, UNet(dim=64) on 3x32x32, batch 128 per GPU, bf16 activations / fp32 accumulate:
   normalize+q_sample (Philox) -> UNet forward -> loss -> full backward -> fused Adam -> EMA bookkeeping.
 N > 1 (torchrun): the same per-GPU work on every rank (weak scaling) with an NCCL all-reduce of the
 flat gradient arena every step.  `--workload ddim` times DDIM-50 sampling at 3x64x64 (configs[2]),
-batch-sharded with no communication.
+batch-sharded with no communication; `--workload ddpm` times the 1000-step ancestral sampler at 3x32x32,
+global batch 1024 (configs[3]; one "step" is a whole 1000-evaluation chain, so K is capped at 3);
+`--workload train64` is the training step at 3x64x64 with 64 images per GPU (configs[4]: global batch 512 on 8 GPUs).
 
 One JSON line is printed by rank 0.  `value` = device-resident throughput, `e2e` = the same step driven
 through the public API from pinned host memory (H2D of the batch and D2H of the loss inside the timed
@@ -33,6 +35,9 @@ F_FWD_32 = 3.651e9       # algorithmic FLOPs of one UNet forward per image @3x32
 F_FWD_64 = 14.594e9      # @3x64x64
 TRAIN_B, TRAIN_S = 128, 32
 DDIM_B, DDIM_S, DDIM_STEPS = 256, 64, 50
+F_FWD = {32: F_FWD_32, 64: F_FWD_64}
+TRAIN_CFG = {"train": (128, 32), "train64": (64, 64)}                  # per-GPU batch, image size
+SAMPLE_CFG = {"ddim": (256, 64, 50), "ddpm": (1024, 32, 1000)}         # global batch, image size, UNet evaluations
 
 
 def profiled_traffic(family):
@@ -119,7 +124,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (reference algorithm) on the host cores
 # --------------------------------------------------------------------------------------------------------
-def cpu_train_step_fn(batch):
+def cpu_train_step_fn(batch, TRAIN_S=TRAIN_S):
     from oracle import ddpm_oracle as O
     torch.set_num_threads(os.cpu_count())
     sd = {k: v.requires_grad_(True) for k, v in O.synth_state_dict(64, 3, seed=10).items()}
@@ -139,7 +144,7 @@ def cpu_train_step_fn(batch):
     return step
 
 
-def cpu_ddim_eval_fn(batch):
+def cpu_ddim_eval_fn(batch, DDIM_S=DDIM_S):
     from oracle import ddpm_oracle as O
     torch.set_num_threads(os.cpu_count())
     sd = O.synth_state_dict(64, 3, seed=10)
@@ -155,9 +160,10 @@ def cpu_ddim_eval_fn(batch):
 
 def cpu_baseline(workload, budget_s=20.0):
     """Bounded sample of the same workload on the host cores (oracle = port of the reference)."""
-    if workload == "train":
-        b = 16
-        step = cpu_train_step_fn(b)
+    if workload in TRAIN_CFG:
+        S = TRAIN_CFG[workload][1]
+        b = 16 if S == 32 else 4
+        step = cpu_train_step_fn(b, S)
         step()
         t0, n = time.perf_counter(), 0
         while True:
@@ -167,9 +173,10 @@ def cpu_baseline(workload, budget_s=20.0):
                 break
         dt = time.perf_counter() - t0
         return {"value": b * n / dt, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
-                "sample": f"{n} fp32 training steps (fwd+bwd+Adam) at batch {b}, 3x32x32, torch CPU {os.cpu_count()} threads"}
-    b = 2
-    step = cpu_ddim_eval_fn(b)
+                "sample": f"{n} fp32 training steps (fwd+bwd+Adam) at batch {b}, 3x{S}x{S}, torch CPU {os.cpu_count()} threads"}
+    _, S, evals = SAMPLE_CFG[workload]
+    b = 2 if S == 64 else 8
+    step = cpu_ddim_eval_fn(b, S)
     step()
     t0, n = time.perf_counter(), 0
     while True:
@@ -178,8 +185,8 @@ def cpu_baseline(workload, budget_s=20.0):
         if time.perf_counter() - t0 > budget_s or n >= 6:
             break
     dt = time.perf_counter() - t0
-    return {"value": b * n / dt / DDIM_STEPS, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n} fp32 UNet evaluations at batch {b}, 3x64x64, extrapolated x{DDIM_STEPS} steps per image"}
+    return {"value": b * n / dt / evals, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} fp32 UNet evaluations at batch {b}, 3x{S}x{S}, extrapolated x{evals} steps per image"}
 
 
 def run_reference(args):
@@ -188,14 +195,15 @@ def run_reference(args):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    if args.workload == "train":
-        probe = cpu_train_step_fn(4)
+    if args.workload in TRAIN_CFG:
+        TRAIN_B, TRAIN_S = TRAIN_CFG[args.workload]
+        probe = cpu_train_step_fn(4, TRAIN_S)
         probe()
         t0 = time.perf_counter()
         probe()
         per_img = (time.perf_counter() - t0) / 4
         b = int(max(1, min(TRAIN_B, 150.0 / max(1, K + W) / per_img)))
-        step = cpu_train_step_fn(b)
+        step = cpu_train_step_fn(b, TRAIN_S)
         for _ in range(W):
             step()
         t0 = time.perf_counter()
@@ -206,8 +214,9 @@ def run_reference(args):
         sample = f"each step = one fp32 training step (fwd+bwd+Adam) on {b} of the {TRAIN_B} images of the batch"
         cfg = {"workload": f"DDPM train step UNet(dim=64) 3x{TRAIN_S}x{TRAIN_S} batch {TRAIN_B}/GPU (CPU sample batch {b})"}
     else:
+        DDIM_B, DDIM_S, DDIM_STEPS = SAMPLE_CFG[args.workload]
         b = 1
-        step = cpu_ddim_eval_fn(b)
+        step = cpu_ddim_eval_fn(b, DDIM_S)
         for _ in range(min(W, 1)):
             step()
         n = max(1, min(K, 8))
@@ -217,8 +226,9 @@ def run_reference(args):
         dt = time.perf_counter() - t0
         value = b * n / dt / DDIM_STEPS
         K = n
-        sample = f"each step = one fp32 UNet evaluation of 1 image 3x64x64; img/s = evals/s / {DDIM_STEPS}"
-        cfg = {"workload": f"DDIM-{DDIM_STEPS} sampling 3x{DDIM_S}x{DDIM_S} batch {DDIM_B} (CPU sample: single evaluations)"}
+        sample = f"each step = one fp32 UNet evaluation of 1 image 3x{DDIM_S}x{DDIM_S}; img/s = evals/s / {DDIM_STEPS}"
+        kind = "DDIM" if args.workload == "ddim" else "DDPM"
+        cfg = {"workload": f"{kind}-{DDIM_STEPS} sampling 3x{DDIM_S}x{DDIM_S} batch {DDIM_B} (CPU sample: single evaluations)"}
     line = {"impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "img/s",
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -228,7 +238,9 @@ def run_reference(args):
 
 
 def metric_name(workload):
-    return "DDPM train img/s" if workload == "train" else f"DDIM-{DDIM_STEPS} sample img/s"
+    if workload in TRAIN_CFG:
+        return "DDPM train img/s"
+    return f"DDIM-{DDIM_STEPS} sample img/s" if workload == "ddim" else "DDPM-1000 sample img/s"
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -270,7 +282,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=["train", "ddim"], default="train")
+    ap.add_argument("--workload", choices=["train", "ddim", "ddpm", "train64"], default="train")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel time table (JSON) here")
@@ -312,8 +324,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    if args.workload == "train":
-        B, S = TRAIN_B, TRAIN_S
+    is_train = args.workload in TRAIN_CFG
+    if is_train:
+        B, S = TRAIN_CFG[args.workload]
         model = DDPM(img_channels=3, img_size=S, dim=64, diffusion_timesteps=1000, sampling_timesteps=None,
                      lr=2e-5, betas=(0.9, 0.99), ema_update_every=10, ema_decay=0.995, precision="bf16",
                      device=dev)
@@ -365,7 +378,7 @@ def main():
         value, e2e_value = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
         h2d, d2h = B * 3 * S * S * 4, 4
         plan = unet._plan(B, S, training=True)
-        flop_per_img = 3 * F_FWD_32
+        flop_per_img = 3 * F_FWD[S]
         cfg = {"workload": f"DDPM train step UNet(dim=64) 3x{S}x{S} batch {B}/GPU, objective pred_v, sigmoid schedule "
                            "(reference defaults), fwd+loss+bwd+fused Adam+EMA",
                "global_batch": B * world, "parallelism": f"dp{world}",
@@ -374,9 +387,13 @@ def main():
         step_flops = flop_per_img * B
     else:
         from b200dm import GaussianDiffusion, Unet
+        DDIM_B, DDIM_S, DDIM_STEPS = SAMPLE_CFG[args.workload]
+        if args.workload == "ddpm":
+            K = min(K, 3)                 # one step = a whole 1000-evaluation ancestral chain
         B, S = DDIM_B // world, DDIM_S
         unet = Unet(dim=64, channels=3, precision="bf16", device=dev)
-        gd = GaussianDiffusion(unet, img_size=S, timesteps=1000, sampling_timesteps=DDIM_STEPS)
+        gd = GaussianDiffusion(unet, img_size=S, timesteps=1000,
+                               sampling_timesteps=DDIM_STEPS if args.workload == "ddim" else None)
         out_host = torch.zeros(B, 3, S, S).pin_memory()
 
         def step_device(i):
@@ -392,7 +409,8 @@ def main():
         launches_per_step = int(L.load().b200dm_launch_count())
         clocks = ClockSampler(local)
         clocks.start()
-        for i in range(max(1, min(W, 2))):
+        W = max(1, min(W, 2)) if args.workload == "ddim" else 1     # a chain is 50 / 1000 warm evaluations
+        for i in range(W):
             step_device(i)
         clocks.mark()
         ms = timed(step_device, K)
@@ -402,17 +420,18 @@ def main():
         value, e2e_value = imgs / (ms / 1e3), imgs / (ms_e2e / 1e3)
         h2d, d2h = 0, B * 3 * S * S * 4
         plan = unet._plan(B, S, training=False)
-        cfg = {"workload": f"DDIM-{DDIM_STEPS} sampling UNet(dim=64) 3x{S}x{S} global batch {DDIM_B}, eta=0, "
+        kind = "DDIM-%d sampling (eta=0)" % DDIM_STEPS if args.workload == "ddim" else "DDPM-1000 ancestral sampling"
+        cfg = {"workload": f"{kind} UNet(dim=64) 3x{S}x{S} global batch {DDIM_B}, "
                            f"batch-sharded over {world} GPU(s) with no communication",
                "global_batch": DDIM_B, "parallelism": f"shard{world}",
                "l2": f"per-evaluation working set {plan.nbytes / 1e9:.2f} GB > 126 MB L2 (no flush needed)",
                "cuda_graph": bool(unet._cuda_graph)}
-        step_flops = F_FWD_64 * B * DDIM_STEPS
+        step_flops = F_FWD[S] * B * DDIM_STEPS
 
     # per-kernel table and roofline of the dominant kernel (rank 0)
     roof, table = None, None
     if rank == 0:
-        fam, total_ms = profile_plan(plan, passes=3, backward=(args.workload == "train"))
+        fam, total_ms = profile_plan(plan, passes=3, backward=is_train)
         table = {k: {"ms": round(v["ms"], 4), "launches": v["launches"], "share": round(v["ms"] / total_ms, 4),
                      "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] and v["ms"] > 0 else None}
                  for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
@@ -437,7 +456,7 @@ def main():
     if rank == 0:
         line = {"metric": metric_name(args.workload), "value": value, "unit": "img/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak"
-                if args.workload == "train" else "strong", "vs_baseline": None, "dtype": "bf16",
+                if is_train else "strong", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": cfg, "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,

@@ -17,6 +17,18 @@ constexpr float kScale = 0.17677669529663687f;  // 32^-0.5
 // All four kernels work on 64-pixel chunks staged in shared memory and compute the 32x32 products as
 // register micro-tiles (4x4 or 2x4 per thread) instead of one-value-per-lane shuffles.
 constexpr int LA_CHUNK = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+// single-instruction exp2 / reciprocal (MUFU) without the denormal-range fix-up code of expf / division
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int LA_CPB = 4;   // chunks per CTA in the per-pixel kernels (amortises the 32x32 operand loads)
 
 // vectorised tile load: 256 threads, thread = (pixel = tid/4, 8 channels = (tid%4)*8)
@@ -148,6 +160,25 @@ __device__ __forceinline__ void softmax32_quad(float (&v)[8]) {
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   const float inv = 1.f / s;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= inv;
+}
+
+// the same with exp as one FFMA + ex2.approx and a single approximate reciprocal; probabilities times `scale`
+__device__ __forceinline__ void softmax32_quad_fast(float (&v)[8], float scale) {
+  float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  const float nm = -m * kLog2e;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = ex2_ftz(fmaf(v[i], kLog2e, nm));
+    s += v[i];
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  const float inv = rcp_ftz(s) * scale;                  // s >= 1: the maximum contributes exp(0)
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] *= inv;
 }
@@ -1004,53 +1035,64 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
     }
     la_col_reduce<true>(m, s.mred, s.m_loc, tid);
   }
-  // ---- phase 1b: partial context on tensor cores
+  // ---- phase 1b: partial context on tensor cores.  The loop is issue-bound (ncu: 55 % issue slots at 43 %
+  //      occupancy), so it is written for instruction count: exp as one FFMA + ex2.approx (the max is folded into
+  //      the addend), walking pointers, pixels past the end loaded as k = -inf / v = 0 instead of being selected
+  //      away, and the memory key/values of rank 0 as a chunk of their own in front of the loop.
   {
     float acc[4] = {0.f, 0.f, 0.f, 0.f}, psum[8] = {};
-    const int lead = rank == 0 ? NMEM : 0;
-    const int total = (p1 - p0) + lead;
-    float mloc[8];
+    float nm2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) mloc[i] = s.m_loc[part * 8 + i];
-    uint4 rk = make_uint4(0, 0, 0, 0), rv = rk;
-    auto fetch = [&](int c0) {
-      const int j = c0 + pix - lead;
-      if (j >= 0 && j < p1 - p0) {
-        rk = *reinterpret_cast<const uint4*>(kbase + (int64_t)(p0 + j) * ld + part * 8);
-        rv = *reinterpret_cast<const uint4*>(vbase + (int64_t)(p0 + j) * ld + part * 8);
-      } else {
-        rk = make_uint4(0, 0, 0, 0);
-        rv = rk;
+    for (int i = 0; i < 8; ++i) nm2[i] = -s.m_loc[part * 8 + i] * kLog2e;
+    lbf* const kst = &s.Kb[0][pix][part * 8];
+    lbf* const vst = &s.Vb[0][pix][part * 8];
+    constexpr int BUF = LA_CHUNK * LP;                 // elements between the two buffers of a tile
+    int cb = 0;
+    if (rank == 0) {
+      float pv[8], vv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = pix < NMEM;
+        pv[i] = ok ? ex2_ftz(fmaf(mk[(part * 8 + i) * NMEM + (ok ? pix : 0)], kLog2e, nm2[i])) : 0.f;
+        vv[i] = ok ? mv[(part * 8 + i) * NMEM + pix] : 0.f;
+        psum[i] += pv[i];
       }
-    };
-    if (total > 0) fetch(0);
+      *reinterpret_cast<uint4*>(kst) = pack8(pv);
+      *reinterpret_cast<uint4*>(vst) = pack8(vv);
+      __syncthreads();
+      mma_atb(&s.Kb[0][0][0], &s.Vb[0][0][0], acc, warp, lane);
+      cb = 1;
+    }
+    const uint4 kNegInf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf x 8
+    const lbf* kp = kbase + (int64_t)(p0 + pix) * ld + part * 8;
+    const int64_t step = (int64_t)LA_CHUNK * ld;
+    uint4 rk = kNegInf, rv = make_uint4(0, 0, 0, 0);
+    if (p0 + pix < p1) {
+      rk = *reinterpret_cast<const uint4*>(kp);
+      rv = *reinterpret_cast<const uint4*>(kp + HID);
+    }
     // one barrier per chunk: the operand tiles are double-buffered, so staging chunk c+1 may overlap the MMAs
     // of chunk c (buffer c&1 was last read two barriers ago)
-    for (int c0 = 0, cb = 0; c0 < total; c0 += LA_CHUNK, cb ^= 1) {
+    for (int j0 = p0; j0 < p1; j0 += LA_CHUNK, cb ^= 1) {
       float kv[8];
       unpack8(rk, kv);
-      uint4 vraw = rv;
-      const int jl = c0 + pix;
-      if (jl < lead) {
-        float vv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          kv[i] = mk[(part * 8 + i) * NMEM + jl];
-          vv[i] = mv[(part * 8 + i) * NMEM + jl];
-        }
-        vraw = pack8(vv);
+      const uint4 vraw = rv;
+      kp += step;
+      if (j0 + LA_CHUNK + pix < p1) {
+        rk = *reinterpret_cast<const uint4*>(kp);
+        rv = *reinterpret_cast<const uint4*>(kp + HID);
+      } else {
+        rk = kNegInf;
+        rv = make_uint4(0, 0, 0, 0);
       }
-      if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);
-      const bool ok = jl < total;
       float pv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = ok ? __expf(kv[i] - mloc[i]) : 0.f;
-      const uint4 praw = pack8(pv);
-      unpack8(praw, pv);                               // sum what the tensor core will see
-#pragma unroll
-      for (int i = 0; i < 8; ++i) psum[i] += pv[i];
-      *reinterpret_cast<uint4*>(&s.Kb[cb][pix][part * 8]) = praw;
-      *reinterpret_cast<uint4*>(&s.Vb[cb][pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      for (int i = 0; i < 8; ++i) {
+        pv[i] = ex2_ftz(fmaf(kv[i], kLog2e, nm2[i]));   // exp(k - m); 0 for the -inf padding
+        psum[i] += pv[i];
+      }
+      *reinterpret_cast<uint4*>(kst + cb * BUF) = pack8(pv);
+      *reinterpret_cast<uint4*>(vst + cb * BUF) = vraw;
       __syncthreads();
       mma_atb(&s.Kb[cb][0][0], &s.Vb[cb][0][0], acc, warp, lane);
     }
@@ -1088,26 +1130,29 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
   __syncthreads();
   // ---- phase 2: out = (scale * softmax_d(q)) @ ctx for the own pixels
   {
+    const lbf* qp = qbase + (int64_t)(p0 + pix) * ld + part * 8;
+    const int64_t step = (int64_t)LA_CHUNK * ld;
+    lbf* op = out + ((int64_t)b * n + p0 + pix) * out_ld + h * DH + part * 8;     // where chunk c-1 is written
+    const int64_t ostep = (int64_t)LA_CHUNK * out_ld;
+    lbf* const qst = &s.Kb[0][pix][part * 8];
+    const lbf* const ost = &s.Vb[0][pix][part * 8];
+    constexpr int BUF = LA_CHUNK * LP;
     uint4 rq = make_uint4(0, 0, 0, 0);
-    auto fetchq = [&](int j0) {
-      if (j0 + pix < p1) rq = *reinterpret_cast<const uint4*>(qbase + (int64_t)(j0 + pix) * ld + part * 8);
-      else rq = make_uint4(0, 0, 0, 0);
-    };
-    if (p0 < p1) fetchq(p0);
+    if (p0 + pix < p1) rq = *reinterpret_cast<const uint4*>(qp);
     // software pipeline with one barrier per chunk: stage q(c) | barrier | write out(c-1) | MMA(c) -> staging(c)
     int cb = 0;
     for (int j0 = p0; j0 < p1; j0 += LA_CHUNK, cb ^= 1) {
       float v[8];
       unpack8(rq, v);
-      if (j0 + LA_CHUNK < p1) fetchq(j0 + LA_CHUNK);
-      softmax32_quad(v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= kScale;
-      *reinterpret_cast<uint4*>(&s.Kb[cb][pix][part * 8]) = pack8(v);
+      qp += step;
+      if (j0 + LA_CHUNK + pix < p1) rq = *reinterpret_cast<const uint4*>(qp);
+      softmax32_quad_fast(v, kScale);
+      *reinterpret_cast<uint4*>(qst + cb * BUF) = pack8(v);
       __syncthreads();
-      if (j0 > p0 && j0 - LA_CHUNK + pix < p1)
-        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + j0 - LA_CHUNK + pix) * out_ld + h * DH + part * 8) =
-            *reinterpret_cast<const uint4*>(&s.Vb[cb ^ 1][pix][part * 8]);
+      if (j0 > p0) {                                     // every pixel of a non-final chunk is in range
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(ost + (cb ^ 1) * BUF);
+        op += ostep;
+      }
       float acc[2][4] = {};
       mma_xw<true>(&s.Kb[cb][0][0], &s.Cb[0][0], acc, warp, lane);
       {
@@ -1123,8 +1168,7 @@ linattn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restri
     if (p0 < p1) {
       const int jl = p0 + ((p1 - p0 - 1) / LA_CHUNK) * LA_CHUNK;      // first pixel of the last chunk
       if (jl + pix < p1)
-        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + jl + pix) * out_ld + h * DH + part * 8) =
-            *reinterpret_cast<const uint4*>(&s.Vb[cb ^ 1][pix][part * 8]);
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(ost + (cb ^ 1) * BUF);
     }
   }
   cluster.sync();
@@ -1171,11 +1215,16 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
   // ---- phase 1: dq for the own pixels; partial dctx = P^T dout
   {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // (issue-bound loop: walking pointers, exp as FFMA + ex2.approx, see the forward kernel)
     uint4 rq = make_uint4(0, 0, 0, 0), rg = rq;
+    const lbf* qp = qbase + (int64_t)(p0 + pix) * ld + part * 8;
+    const lbf* gp = gbase + (int64_t)(p0 + pix) * dout_ld + part * 8;
+    lbf* dqp = dqbase + (int64_t)(p0 + pix) * dld + part * 8;        // where chunk c-1's dq goes
+    const int64_t qstep = (int64_t)LA_CHUNK * ld, gstep = (int64_t)LA_CHUNK * dout_ld, dstep = (int64_t)LA_CHUNK * dld;
     auto fetch = [&](int j0) {
       if (j0 + pix < p1) {
-        rq = *reinterpret_cast<const uint4*>(qbase + (int64_t)(j0 + pix) * ld + part * 8);
-        rg = *reinterpret_cast<const uint4*>(gbase + (int64_t)(j0 + pix) * dout_ld + part * 8);
+        rq = *reinterpret_cast<const uint4*>(qp);
+        rg = *reinterpret_cast<const uint4*>(gp);
       } else {
         rq = make_uint4(0, 0, 0, 0);
         rg = rq;
@@ -1186,7 +1235,6 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
     // software pipeline, one barrier per chunk:  stage(c) | barrier | finish dq(c-1) from F[(c-1)&1] | MMA(c)
     float pvp[8];                      // softmax(q) of the previous chunk (this thread's 8 channels)
     bool okp = false;
-    int j0p = 0;
     auto finish_dq = [&](int cbp) {
       float t = 0.f, dv[8];
 #pragma unroll
@@ -1198,7 +1246,8 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
       t += __shfl_xor_sync(0xffffffffu, t, 2);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dv[i] = kScale * pvp[i] * (dv[i] - t);
-      if (okp) *reinterpret_cast<uint4*>(dqbase + (int64_t)(j0p + pix) * dld + part * 8) = pack8(dv);
+      if (okp) *reinterpret_cast<uint4*>(dqp) = pack8(dv);
+      dqp += dstep;
     };
     int cb = 0;
     for (int j0 = p0; j0 < p1; j0 += LA_CHUNK, cb ^= 1) {
@@ -1206,12 +1255,10 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
       unpack8(rq, pv);
       const uint4 graw = rg;
       const bool ok = j0 + pix < p1;
+      qp += qstep;
+      gp += gstep;
       if (j0 + LA_CHUNK < p1) fetch(j0 + LA_CHUNK);
-      softmax32_quad(pv);
-      if (!ok) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pv[i] = 0.f;
-      }
+      softmax32_quad_fast(pv, ok ? 1.f : 0.f);           // rows past the end become zeros
       *reinterpret_cast<uint4*>(&s.Ab[cb][pix][part * 8]) = pack8(pv);
       *reinterpret_cast<uint4*>(&s.Bb[cb][pix][part * 8]) = graw;
       __syncthreads();
@@ -1233,7 +1280,6 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
 #pragma unroll
       for (int i = 0; i < 8; ++i) pvp[i] = pv[i];
       okp = ok;
-      j0p = j0;
     }
     __syncthreads();
     if (p0 < p1) finish_dq(cb ^ 1);
@@ -1264,22 +1310,26 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
   {
     const int lead = rank == 0 ? NMEM : 0;
     const int total = (p1 - p0) + lead;
-    float kmx[8], kinv[8], Dd[8];
+    float nkm2[8], kinv[8], Dd[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      kmx[i] = s.kmx[part * 8 + i];
+      nkm2[i] = -s.kmx[part * 8 + i] * kLog2e;
       kinv[i] = s.kinv[part * 8 + i];
       Dd[i] = s.Dd[part * 8 + i];
     }
-    uint4 rk = make_uint4(0, 0, 0, 0), rv = rk;
+    const uint4 kNegInf = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf x 8
+    uint4 rk = kNegInf, rv = make_uint4(0, 0, 0, 0);
+    // row c0 + pix of the (memory rows, own pixels) sequence; never dereferenced outside [p0, p1)
+    const lbf* kp = kbase + ((int64_t)p0 + pix - lead) * ld + part * 8;
+    const int64_t kstep = (int64_t)LA_CHUNK * ld;
     auto fetch = [&](int c0) {
       const int j = c0 + pix - lead;
       if (j >= 0 && j < p1 - p0) {
-        rk = *reinterpret_cast<const uint4*>(kbase + (int64_t)(p0 + j) * ld + part * 8);
-        rv = *reinterpret_cast<const uint4*>(vbase + (int64_t)(p0 + j) * ld + part * 8);
+        rk = *reinterpret_cast<const uint4*>(kp);
+        rv = *reinterpret_cast<const uint4*>(kp + HID);
       } else {
-        rk = make_uint4(0, 0, 0, 0);
-        rv = rk;
+        rk = kNegInf;                                   // exp(-inf - m) = 0: padding rows need no select
+        rv = make_uint4(0, 0, 0, 0);
       }
     };
     if (total > 0) fetch(0);
@@ -1321,12 +1371,13 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
         }
         vraw = pack8(vv);
       }
+      kp += kstep;
       if (c0 + LA_CHUNK < total) fetch(c0 + LA_CHUNK);
       const bool ok = jl < total;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ks[i] = ok ? __expf(ks[i] - kmx[i]) * kinv[i] : 0.f;
+      for (int i = 0; i < 8; ++i) ks[i] = ex2_ftz(fmaf(ks[i], kLog2e, nkm2[i])) * kinv[i];
       *reinterpret_cast<uint4*>(&s.Ab[cb][pix][part * 8]) = pack8(ks);
-      *reinterpret_cast<uint4*>(&s.Bb[cb][pix][part * 8]) = ok ? vraw : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(&s.Bb[cb][pix][part * 8]) = vraw;
       __syncthreads();
       if (c0 > 0) finish_kv(cb ^ 1);
       float dvv[2][4] = {}, dks[2][4] = {};
@@ -1360,6 +1411,10 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
 // reductions and two cluster barriers, so more, smaller CTAs lose), at most 8, at least one chunk each
 static int la_cluster_size(int BH, int n) {
   const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
+  {
+    const char* e = getenv("B200DM_LA_CL");      // experiment knob
+    if (e && e[0] >= '1' && e[0] <= '8') return e[0] - '0' > chunks ? chunks : e[0] - '0';
+  }
   int cl = (int)((2LL * num_sms() * 4 + BH / 2) / BH);
   if (cl > 8) cl = 8;
   if (cl > chunks) cl = chunks;

@@ -611,32 +611,46 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
 // columns [C*49, KP) are zero.  The 7x7 conv (ddpm.py:304) then IS a 1x1 conv with Cin = KP over P, and its
 // weight gradient a plain wgrad over P — both run on the tcgen05 kernels.
 namespace b200dm {
-// block = (KP/8 vector lanes, 8 pixels): no per-thread division for the vector index, 32-bit pixel math
-__global__ void im2col7_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, unsigned npix, int C, int H,
-                               int W, int KP) {
+// One CTA = four output rows of one image.  The 10 input rows those need are staged once in shared memory
+// (zero padding included), then thread (vector lane v, pixel slot) gathers its eight taps from the staged tile and
+// writes one 16-byte vector; the CTA's output is one contiguous span of P.
+constexpr int I2C_ROWS = 4;
+__global__ void im2col7_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ P, int C, int H, int W, int KP) {
   pdl_prologue();
-  const int K = C * 49;
+  extern __shared__ float i2c_tile[];                  // [C][I2C_ROWS + 6][W + 6]
+  const int pitch = W + 6, rows = I2C_ROWS + 6, K = C * 49;
+  const int tiles_per_img = (H + I2C_ROWS - 1) / I2C_ROWS;
+  const int b = blockIdx.x / tiles_per_img, oy0 = (blockIdx.x - b * tiles_per_img) * I2C_ROWS;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const float* xb = x + (size_t)b * C * H * W;
+  for (int i = tid; i < C * rows * pitch; i += nthr) {
+    const int cx = i % pitch, t = i / pitch, r = t % rows, ch = t / rows;
+    const int iy = oy0 + r - 3, ix = cx - 3;
+    i2c_tile[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (ch * H + iy) * W + ix) : 0.f;
+  }
   const int v = threadIdx.x;
-  int kch[8], kdy[8], kdx[8];
+  int off[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = v * 8 + j;
-    const int ch = k / 49, r = k - ch * 49, ky = r / 7;
-    kch[j] = k < K ? ch : -1;
-    kdy[j] = ky - 3;
-    kdx[j] = r - ky * 7 - 3;
+    const int ch = k / 49, r = k - ch * 49, ky = r / 7, kx = r - ky * 7;
+    off[j] = k < K ? (ch * rows + ky) * pitch + kx : -1;
   }
-  for (unsigned pix = blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += gridDim.x * blockDim.y) {
-    const unsigned ox = pix % (unsigned)W, t = pix / (unsigned)W;
-    const unsigned oy = t % (unsigned)H, b = t / (unsigned)H;
-    const float* xb = x + (size_t)b * C * H * W;
+  __syncthreads();
+  const int npx = min(I2C_ROWS, H - oy0) * W;
+  __nv_bfloat16* Pb = P + ((size_t)(b * H + oy0) * W) * KP + v * 8;
+  int cx = threadIdx.y, r = 0;                          // blockDim.y (8) divides W: a slot never straddles rows
+  for (int p = threadIdx.y; p < npx; p += blockDim.y) {
+    const int base = r * pitch + cx;
     float val[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int iy = (int)oy + kdy[j], ix = (int)ox + kdx[j];
-      val[j] = (kch[j] >= 0 && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + (kch[j] * H + iy) * W + ix) : 0.f;
+    for (int j = 0; j < 8; ++j) val[j] = off[j] >= 0 ? i2c_tile[off[j] + base] : 0.f;
+    st8(Pb + (size_t)p * KP, val);
+    cx += blockDim.y;
+    if (cx >= W) {
+      cx -= W;
+      ++r;
     }
-    st8(P + (size_t)pix * KP + v * 8, val);
   }
 }
 __global__ void pack_stem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int K, int KP) {
@@ -654,11 +668,13 @@ extern "C" int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int
   B200DM_REQUIRE(B > 0 && C >= 1 && C * 49 <= KP && KP % 64 == 0 && ((uintptr_t)P & 15) == 0, B200DM_ERR_SHAPE,
                  "im2col7: need C*49 <= KP, KP %% 64 == 0 (C=%d KP=%d)", C, KP);
   B200DM_REQUIRE((int64_t)B * H * W < (1LL << 31) && KP / 8 <= 128, B200DM_ERR_UNSUPPORTED, "im2col7: tensor too large");
-  const unsigned npix = (unsigned)((int64_t)B * H * W);
+  B200DM_REQUIRE(W % 8 == 0 && W <= 1024, B200DM_ERR_SHAPE, "im2col7: W=%d must be a multiple of 8 (<= 1024)", W);
   dim3 block(KP / 8, 8);
-  unsigned blocks = (npix + 7) / 8, cap = (unsigned)b200dm::num_sms() * 16;
-  launch_k(b200dm::im2col7_kernel, blocks > cap ? cap : blocks, block, 0, (cudaStream_t)stream, 
-      x, (__nv_bfloat16*)P, npix, C, H, W, KP);
+  const size_t smem = (size_t)C * (b200dm::I2C_ROWS + 6) * (W + 6) * sizeof(float);
+  const int tiles = B * ((H + b200dm::I2C_ROWS - 1) / b200dm::I2C_ROWS);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(b200dm::im2col7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  launch_k(b200dm::im2col7_kernel, tiles, block, smem, (cudaStream_t)stream, x, (__nv_bfloat16*)P, C, H, W, KP);
   b200dm::count_launch();
   return b200dm::check_launch("im2col7");
 }

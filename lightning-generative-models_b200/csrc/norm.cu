@@ -332,7 +332,7 @@ template <> struct Raw8<__nv_bfloat16> {
 // from there instead of going back to L2 (chunk bytes = ceil(HW/CL) * C * sizeof(T), <= GNC_STAGE_MAX).
 constexpr int GNC_STAGE_MAX = 40 * 1024;
 template <typename T, bool STAGE>
-__global__ void __launch_bounds__(GNC_THREADS)
+__global__ void __launch_bounds__(GNC_THREADS, sizeof(T) == 2 ? 3 : 2)
 gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
@@ -358,6 +358,22 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
   extern __shared__ __align__(16) unsigned char gn_stage_raw[];
   Raw8<T>* stage = reinterpret_cast<Raw8<T>*>(gn_stage_raw);     // [pixel of the chunk][C8]
+  const T* rp = res ? res + (int64_t)b * HW * res_ld + c0 : nullptr;
+  T* yp = y + (int64_t)b * HW * y_ld + c0;
+  const int64_t ys = (int64_t)lanes * y_ld;
+  // phase-2 operands of two pixels (p, p + lanes): input (from the staging buffer when STAGE) and residual
+  Raw8<T> nx[2], nr[2];
+  auto fetch2 = [&](int p) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        if (STAGE) nx[u] = stage[(p + u * lanes - p0) * C8 + cv];
+        else nx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        if (rp) nr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
+      }
+    }
+  };
+  if (part) fetch2(p0 + lane);
   // ---- phase 1: per-group sum / sum of squares of the chunk
   float s = 0.f, ss = 0.f;
   if (part) {
@@ -454,35 +470,33 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
         ga *= sc;
         be = be * sc + sh;
       }
-      A[j] = ga;
-      Bc[j] = be;
+      // bf16 mode: silu(z) = h + h * tanh(h) with h = z / 2, so the halves are folded into the coefficients
+      A[j] = sizeof(T) == 2 ? 0.5f * ga : ga;
+      Bc[j] = sizeof(T) == 2 ? 0.5f * be : be;
     }
   }
-  const T* rp = res ? res + (int64_t)b * HW * res_ld + c0 : nullptr;
-  T* yp = y + (int64_t)b * HW * y_ld + c0;
+  // software pipeline: the loads of the next two pixels are in flight while the current two are processed; in the
+  // pre-statistics mode the first two were requested before the statistics were reduced (top of the kernel)
+  if (!part) fetch2(p0 + lane);
   for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    Raw8<T> rx[2], rr[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (p + u * lanes < p1) {
-        if (STAGE) rx[u] = stage[(p + u * lanes - p0) * C8 + cv];
-        else rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
-        if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
-      }
-    }
+    const Raw8<T> cx[2] = {nx[0], nx[1]}, cr[2] = {nr[0], nr[1]};
+    T* const yq = yp + (int64_t)p * y_ld;
+    if (p + 2 * lanes < p1) fetch2(p + 2 * lanes);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
         float v[8], r[8];
-        rx[u].unpack(v);
-        if (rp) rr[u].unpack(r);
+        cx[u].unpack(v);
+        if (rp) cr[u].unpack(r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], v[j], Bc[j]);
-          const float o = z * sigmoid_t<T>(z);
+          float o;
+          if (sizeof(T) == 2) o = fmaf(z, tanh_approx(z), z);
+          else o = z * sigmoid_t<T>(z);
           v[j] = rp ? o + r[j] : o;
         }
-        st8(yp + (int64_t)(p + u * lanes) * y_ld, v);
+        st8(yq + (int64_t)u * ys, v);
       }
     }
   }
@@ -721,22 +735,38 @@ static cudaError_t launch_cluster(K kernel, dim3 grid, int cl, size_t smem, cuda
 }
 
 // ---- RMSNorm: a row (pixel) is handled by L = min(32, C/8) lanes, 32/L rows per warp; C <= 512 ----------
+// These kernels are issue-bound on B200 (ncu: 69 % issue slots at 45 % occupancy, 78 instructions per 16-byte
+// vector before this version), so they are written for instruction count: L is a template constant (LT; 0 = the
+// run-time value, for channel counts the UNet does not use), rows are 32-bit, the row pointers walk, and
+// 1 / max(||x||, 1e-12) is one rsqrt.approx of max(ss, 1e-24).
 
+template <int LT>
 __device__ __forceinline__ float seg_sum(float v, int L) {   // sum over aligned groups of L lanes
-  for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (LT) {
+#pragma unroll
+    for (int o = LT >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  } else {
+    for (int o = L >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
   return v;
 }
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <typename T, int MAXV>
+template <typename T, int MAXV, int LT>
 __global__ void __launch_bounds__(256)
 rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ g,
-                   const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int64_t rows,
-                   int C, int L) {
+                   const T* __restrict__ res, int res_ld, T* __restrict__ y, int y_ld, int rows,
+                   int C, int Lrt) {
   pdl_prologue();
+  const int L = LT ? LT : Lrt;
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, sl = lane % L, rpw = 32 / L;      // row slot inside the warp, lane in the row
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
   // this thread's gains (its channel vectors are the same for every row it visits)
@@ -748,66 +778,68 @@ rmsnorm_fwd_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ 
     for (int j = 0; j < 8; ++j) gs[k][j] = cv < C8 ? g[cv * 8 + j] * sqrtC : 0.f;
   }
   constexpr int U = 2;                                         // rows in flight per thread
-  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw * U) {
+  const int stride = nwarps * rpw;                             // rows between two visits of a row slot
+  const T* xp = x + (int64_t)(warp * rpw + sub) * x_ld + sl * 8;
+  const T* rp = res ? res + (int64_t)(warp * rpw + sub) * res_ld + sl * 8 : nullptr;
+  T* yp = y + (int64_t)(warp * rpw + sub) * y_ld + sl * 8;
+  const int64_t xs = (int64_t)stride * x_ld, rs = (int64_t)stride * res_ld, ys = (int64_t)stride * y_ld;
+  for (int r0 = warp * rpw; r0 < rows; r0 += stride * U, xp += U * xs, rp += U * rs, yp += U * ys) {
     Raw8<T> rx[U][MAXV], rr[U][MAXV];
     // all loads of the U rows (input and residual) are issued before any arithmetic
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * nwarps * rpw + sub;
+      const bool ok = r0 + u * stride + sub < rows;
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int cv = sl + L * k;
-        if (r < rows && cv < C8) {
-          rx[u][k].load(x + r * x_ld + cv * 8);
-          if (res) rr[u][k].load(res + r * res_ld + cv * 8);
+        if (ok && sl + L * k < C8) {
+          rx[u][k].load(xp + u * xs + k * L * 8);
+          if (res) rr[u][k].load(rp + u * rs + k * L * 8);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * nwarps * rpw + sub;
-      const bool ok = r < rows;
+      const bool ok = r0 + u * stride + sub < rows;
       float v[MAXV][8];
       float ss = 0.f;
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int cv = sl + L * k;
-        if (ok && cv < C8) {
+        if (ok && sl + L * k < C8) {
           rx[u][k].unpack(v[k]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) ss = fmaf(v[k][j], v[k][j], ss);
         }
       }
-      ss = seg_sum(ss, L);
-      const float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      ss = seg_sum<LT>(ss, L);
+      const float rn = rsqrt_ftz(fmaxf(ss, 1e-24f));            // 1 / max(||x||, 1e-12)
 #pragma unroll
       for (int k = 0; k < MAXV; ++k) {
-        const int cv = sl + L * k;
-        if (ok && cv < C8) {
+        if (ok && sl + L * k < C8) {
           float o[8], rv[8];
           if (res) rr[u][k].unpack(rv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            o[j] = v[k][j] * rn * gs[k][j];
-            if (res) o[j] += rv[j];
+            const float t = v[k][j] * rn;
+            o[j] = res ? fmaf(t, gs[k][j], rv[j]) : t * gs[k][j];
           }
-          st8(y + r * y_ld + cv * 8, o);
+          st8(yp + u * ys + k * L * 8, o);
         }
       }
     }
   }
 }
 
-template <typename T, int MAXV>
+template <typename T, int MAXV, int LT>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                    const float* __restrict__ g, const T* __restrict__ res, int res_ld,
-                   T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int64_t rows, int C, int L) {
+                   T* __restrict__ dx, int dx_ld, float* __restrict__ dg, int rows, int C, int Lrt) {
   pdl_prologue();
+  const int L = LT ? LT : Lrt;
   const int lane = threadIdx.x & 31;
   const int sub = lane / L, sl = lane % L, rpw = 32 / L;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
   const int C8 = C / 8;
   const float sqrtC = sqrtf((float)C);
   float gs[MAXV][8], dgacc[MAXV][8];
@@ -820,39 +852,43 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
       dgacc[k][j] = 0.f;
     }
   }
-  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
-    const int64_t r = r0 + sub;
-    const bool ok = r < rows;
+  const int stride = nwarps * rpw;
+  const int64_t row0 = warp * rpw + sub;
+  const T* xp = x + row0 * x_ld + sl * 8;
+  const T* gp = dy + row0 * dy_ld + sl * 8;
+  const T* rp = res ? res + row0 * res_ld + sl * 8 : nullptr;
+  T* op = dx + row0 * dx_ld + sl * 8;
+  const int64_t xs = (int64_t)stride * x_ld, gsd = (int64_t)stride * dy_ld, rs = (int64_t)stride * res_ld,
+                os = (int64_t)stride * dx_ld;
+  for (int r0 = warp * rpw; r0 < rows; r0 += stride, xp += xs, gp += gsd, rp += rs, op += os) {
+    const bool ok = r0 + sub < rows;
     Raw8<T> rx[MAXV], rg[MAXV], rr[MAXV];
     // input, upstream gradient and skip gradient are all requested before the first reduction
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int cv = sl + L * k;
-      if (ok && cv < C8) {
-        rx[k].load(x + r * x_ld + cv * 8);
-        rg[k].load(dy + r * dy_ld + cv * 8);
-        if (res) rr[k].load(res + r * res_ld + cv * 8);
+      if (ok && sl + L * k < C8) {
+        rx[k].load(xp + k * L * 8);
+        rg[k].load(gp + k * L * 8);
+        if (res) rr[k].load(rp + k * L * 8);
       }
     }
     float u[MAXV][8], gd[MAXV][8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int cv = sl + L * k;
-      if (ok && cv < C8) {
+      if (ok && sl + L * k < C8) {
         rx[k].unpack(u[k]);
         rg[k].unpack(gd[k]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
       }
     }
-    ss = seg_sum(ss, L);
-    const float rn = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    ss = seg_sum<LT>(ss, L);
+    const float rn = rsqrt_ftz(fmaxf(ss, 1e-24f));
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int cv = sl + L * k;
-      if (ok && cv < C8) {
+      if (ok && sl + L * k < C8) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           u[k][j] *= rn;                                       // unit vector
@@ -862,19 +898,19 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
         }
       }
     }
-    dot = seg_sum(dot, L);
+    dot = seg_sum<LT>(dot, L);
+    const float a = rn * sqrtC, nb = -a * dot;                 // dx = a * gd + nb * u (+ skip gradient)
 #pragma unroll
     for (int k = 0; k < MAXV; ++k) {
-      const int cv = sl + L * k;
-      if (ok && cv < C8) {
+      if (ok && sl + L * k < C8) {
         float o[8], rv[8];
         if (res) rr[k].unpack(rv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = rn * sqrtC * (gd[k][j] - u[k][j] * dot);
-          if (res) o[j] += rv[j];
+          const float t = fmaf(nb, u[k][j], a * gd[k][j]);
+          o[j] = res ? t + rv[j] : t;
         }
-        st8(dx + r * dx_ld + cv * 8, o);
+        st8(op + k * L * 8, o);
       }
     }
   }
@@ -991,8 +1027,9 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
   const int lanes = GNC_THREADS / (C / 8);
-  int chunks = (int)(((long long)num_sms() * 4) / B);
-  if (chunks > 16) chunks = 16;
+  static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 4; }();
+  int chunks = (int)(((long long)num_sms() * mult) / B);
+  if (chunks > 32) chunks = 32;
   while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
@@ -1097,23 +1134,37 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   return check_launch("gn_apply_bwd");
 }
 
+// dispatch on (two vectors per lane, lanes per row): the UNet's channel counts get compile-time L
+#define RMS_DISPATCH(CALL)                                   \
+  if (two) { CALL(2, 32); }                                  \
+  else if (L == 32 && C == 256) { CALL(1, 32); }             \
+  else if (L == 16 && C == 128) { CALL(1, 16); }             \
+  else if (L == 8 && C == 64) { CALL(1, 8); }                \
+  else { CALL(1, 0); }
+
 extern "C" int b200dm_rmsnorm_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* g,
                                   const void* res, int32_t res_ld, void* y, int32_t y_ld, int64_t rows,
                                   int32_t C, void* stream) {
-  B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && y_ld % 8 == 0, B200DM_ERR_SHAPE,
-                 "rmsnorm_fwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
+  B200DM_REQUIRE(rows > 0 && rows < (1LL << 31) && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && y_ld % 8 == 0,
+                 B200DM_ERR_SHAPE, "rmsnorm_fwd: need C %% 8 == 0, C <= 512 (C=%d), rows < 2^31", C);
   cudaStream_t st = (cudaStream_t)stream;
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
   unsigned grid = ew_grid(rows * L);
   const bool two = C / 8 > 32;      // 512 channels: two 8-wide vectors per lane
+#define RMS_FWD_T(TT, MV, LT)                                                                                      \
+  launch_k(rmsnorm_fwd_kernel<TT, MV, LT>, grid, 256, 0, st, (const TT*)x, x_ld, g, (const TT*)res, res_ld, (TT*)y, \
+           y_ld, (int)rows, C, L)
+#define RMS_FWD_F32(MV, LT) RMS_FWD_T(float, MV, LT)
+#define RMS_FWD_BF16(MV, LT) RMS_FWD_T(bf16, MV, LT)
   if (dtype == B200DM_F32) {
-    if (two) launch_k(rmsnorm_fwd_kernel<float, 2>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
-    else launch_k(rmsnorm_fwd_kernel<float, 1>, grid, 256, 0, st, (const float*)x, x_ld, g, (const float*)res, res_ld, (float*)y, y_ld, rows, C, L);
+    RMS_DISPATCH(RMS_FWD_F32)
   } else {
-    if (two) launch_k(rmsnorm_fwd_kernel<bf16, 2>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
-    else launch_k(rmsnorm_fwd_kernel<bf16, 1>, grid, 256, 0, st, (const bf16*)x, x_ld, g, (const bf16*)res, res_ld, (bf16*)y, y_ld, rows, C, L);
+    RMS_DISPATCH(RMS_FWD_BF16)
   }
+#undef RMS_FWD_T
+#undef RMS_FWD_F32
+#undef RMS_FWD_BF16
   count_launch();
   return check_launch("rmsnorm_fwd");
 }
@@ -1122,23 +1173,28 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
                                   int32_t x_ld, const float* g, const void* res, int32_t res_ld,
                                   void* dx, int32_t dx_ld, float* dg, int64_t rows, int32_t C,
                                   void* stream) {
-  B200DM_REQUIRE(rows > 0 && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && dy_ld % 8 == 0 && dx_ld % 8 == 0,
-                 B200DM_ERR_SHAPE, "rmsnorm_bwd: need C %% 8 == 0, C <= 512 (C=%d)", C);
+  B200DM_REQUIRE(rows > 0 && rows < (1LL << 31) && C % 8 == 0 && C <= 512 && x_ld % 8 == 0 && dy_ld % 8 == 0 &&
+                     dx_ld % 8 == 0,
+                 B200DM_ERR_SHAPE, "rmsnorm_bwd: need C %% 8 == 0, C <= 512 (C=%d), rows < 2^31", C);
   cudaStream_t st = (cudaStream_t)stream;
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
   int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   const bool two = C / 8 > 32;
-#define RMS_BWD(TT, MV)                                                                                      \
-  launch_k(rmsnorm_bwd_kernel<TT, MV>, grid, 256, 0, st, (const TT*)dy, dy_ld, (const TT*)x, x_ld, g,       \
-           (const TT*)res, res_ld, (TT*)dx, dx_ld, dg, rows, C, L)
+#define RMS_BWD_T(TT, MV, LT)                                                                                \
+  launch_k(rmsnorm_bwd_kernel<TT, MV, LT>, grid, 256, 0, st, (const TT*)dy, dy_ld, (const TT*)x, x_ld, g,   \
+           (const TT*)res, res_ld, (TT*)dx, dx_ld, dg, (int)rows, C, L)
+#define RMS_BWD_F32(MV, LT) RMS_BWD_T(float, MV, LT)
+#define RMS_BWD_BF16(MV, LT) RMS_BWD_T(bf16, MV, LT)
   if (dtype == B200DM_F32) {
-    if (two) RMS_BWD(float, 2); else RMS_BWD(float, 1);
+    RMS_DISPATCH(RMS_BWD_F32)
   } else {
-    if (two) RMS_BWD(bf16, 2); else RMS_BWD(bf16, 1);
+    RMS_DISPATCH(RMS_BWD_BF16)
   }
-#undef RMS_BWD
+#undef RMS_BWD_T
+#undef RMS_BWD_F32
+#undef RMS_BWD_BF16
   count_launch();
   return check_launch("rmsnorm_bwd");
 }

@@ -350,7 +350,7 @@ def test_init_conv_fwd_and_wgrad(dtype, C, S, B):
     assert rel(dw, w.grad) < 2e-5
 
 
-@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 16, 5)])
+@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 16, 5), (3, 64, 2), (2, 8, 3)])
 def test_stem_on_tensor_cores_im2col_gemm_and_wgrad(C, S, B):
     """7x7 stem as im2col + tcgen05 1x1 GEMM, and its weight gradient through conv_wgrad(cin_valid)."""
     if not L.load().b200dm_tc_available():
