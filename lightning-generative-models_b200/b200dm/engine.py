@@ -481,9 +481,12 @@ class Plan:
         self.F("b200dm_final_conv_fwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
                a.ptr("final_conv.bias"), self.out.data_ptr(), B, S * S, dim, ch)
         if tr:
+            # data gradient on the main chain; the (pixel-reduction) parameter gradients overlap it on the side stream
             self.Bk("b200dm_final_conv_bwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
-                    self.d_out.data_ptr(), gy.ptr, gy.ld, a.gptr("final_conv.weight"),
-                    a.gptr("final_conv.bias"), B, S * S, dim, ch, writes=(gy,))
+                    self.d_out.data_ptr(), gy.ptr, gy.ld, None, None, B, S * S, dim, ch, writes=(gy,))
+            self.Bk("b200dm_final_conv_bwd", self.dt, yb.ptr, yb.ld, a.ptr("final_conv.weight"),
+                    self.d_out.data_ptr(), None, 0, a.gptr("final_conv.weight"),
+                    a.gptr("final_conv.bias"), B, S * S, dim, ch, side=True, reads=(yb,))
 
     # ---- execution --------------------------------------------------------------------------------------
     def run_forward(self):

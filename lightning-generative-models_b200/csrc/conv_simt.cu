@@ -759,14 +759,17 @@ extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld,
   int64_t per = (total + nblk - 1) / nblk;
   dim3 block2(Cin, ny);
   size_t smem2 = (size_t)ny * 4 * Cin * sizeof(float);
+  // dx == nullptr or dw == nullptr skips that kernel (the plan issues the parameter gradients on its side stream)
+  int launches = 0;
   if (dtype == B200DM_F32) {
-    launch_k(final_conv_dx_kernel<float>, grid, 256, smem, st, w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
-    launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, block2, smem2, st, (const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    if (dx) launch_k(final_conv_dx_kernel<float>, grid, 256, smem, st, w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
+    if (dw) launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, block2, smem2, st, (const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
   } else {
-    launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, smem, st, w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
-    launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, block2, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    if (dx) launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, smem, st, w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
+    if (dw) launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, block2, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
   }
-  count_launch(2);
+  launches = (dx ? 1 : 0) + (dw ? 1 : 0);
+  count_launch(launches);
   return check_launch("final_conv_bwd");
 }
 

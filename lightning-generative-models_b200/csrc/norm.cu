@@ -331,8 +331,10 @@ template <> struct Raw8<__nv_bfloat16> {
 // STAGE: the chunk's raw vectors are parked in (dynamic) shared memory during phase 1 and phase 2 reads them
 // from there instead of going back to L2 (chunk bytes = ceil(HW/CL) * C * sizeof(T), <= GNC_STAGE_MAX).
 constexpr int GNC_STAGE_MAX = 40 * 1024;
-template <typename T, bool STAGE>
-__global__ void __launch_bounds__(GNC_THREADS, sizeof(T) == 2 ? 3 : 2)
+// PIPE (pre-statistics mode only): phase 2 as a software pipeline whose first loads are requested before the
+// statistics are reduced; 80 registers, so the launcher sizes the grid for three CTAs per SM
+template <typename T, bool STAGE, bool PIPE = false>
+__global__ void __launch_bounds__(GNC_THREADS, PIPE ? 3 : (sizeof(T) == 2 ? 4 : 2))
 gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
@@ -360,20 +362,18 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   Raw8<T>* stage = reinterpret_cast<Raw8<T>*>(gn_stage_raw);     // [pixel of the chunk][C8]
   const T* rp = res ? res + (int64_t)b * HW * res_ld + c0 : nullptr;
   T* yp = y + (int64_t)b * HW * y_ld + c0;
-  const int64_t ys = (int64_t)lanes * y_ld;
-  // phase-2 operands of two pixels (p, p + lanes): input (from the staging buffer when STAGE) and residual
+  // PIPE: phase-2 operands of two pixels (p, p + lanes): input and residual
   Raw8<T> nx[2], nr[2];
   auto fetch2 = [&](int p) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
-        if (STAGE) nx[u] = stage[(p + u * lanes - p0) * C8 + cv];
-        else nx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        nx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
         if (rp) nr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
       }
     }
   };
-  if (part) fetch2(p0 + lane);
+  if (PIPE) fetch2(p0 + lane);
   // ---- phase 1: per-group sum / sum of squares of the chunk
   float s = 0.f, ss = 0.f;
   if (part) {
@@ -475,19 +475,31 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
       Bc[j] = sizeof(T) == 2 ? 0.5f * be : be;
     }
   }
-  // software pipeline: the loads of the next two pixels are in flight while the current two are processed; in the
-  // pre-statistics mode the first two were requested before the statistics were reduced (top of the kernel)
-  if (!part) fetch2(p0 + lane);
   for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    const Raw8<T> cx[2] = {nx[0], nx[1]}, cr[2] = {nr[0], nr[1]};
-    T* const yq = yp + (int64_t)p * y_ld;
-    if (p + 2 * lanes < p1) fetch2(p + 2 * lanes);
+    Raw8<T> rx[2], rr[2];
+    if (PIPE) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        rx[u] = nx[u];
+        rr[u] = nr[u];
+      }
+      if (p + 2 * lanes < p1) fetch2(p + 2 * lanes);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (p + u * lanes < p1) {
+          if (STAGE) rx[u] = stage[(p + u * lanes - p0) * C8 + cv];
+          else rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+          if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
+        }
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (p + u * lanes < p1) {
         float v[8], r[8];
-        cx[u].unpack(v);
-        if (rp) cr[u].unpack(r);
+        rx[u].unpack(v);
+        if (rp) rr[u].unpack(r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float z = fmaf(A[j], v[j], Bc[j]);
@@ -496,7 +508,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
           else o = z * sigmoid_t<T>(z);
           v[j] = rp ? o + r[j] : o;
         }
-        st8(yq + (int64_t)u * ys, v);
+        st8(yp + (int64_t)(p + u * lanes) * y_ld, v);
       }
     }
   }
@@ -504,11 +516,16 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 }
 
 #ifndef GN_BWD_MINB
-#define GN_BWD_MINB 3      // resident CTAs per SM the backward kernel is compiled for (80 registers)
+#define GN_BWD_MINB 2      // resident CTAs per SM the backward kernel is compiled for (register budget 128)
+#endif
+#ifndef GN_BWD_UB
+#define GN_BWD_UB 4        // pixels in flight per thread: the kernel is latency-bound, one wave, ~2 CTAs per SM
 #endif
 
-template <typename T>
-__global__ void __launch_bounds__(GNC_THREADS, GN_BWD_MINB)
+// UB pixels per thread and iteration; PIPE: the next UB are requested before the current UB are processed
+// (software pipeline, twice the raw registers); MINB: resident CTAs per SM the register budget is set for
+template <typename T, int UB, bool PIPE, int MINB>
+__global__ void __launch_bounds__(GNC_THREADS, MINB)
 gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                       const float* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ film, int film_ld,
@@ -532,10 +549,10 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
   const T* gp = dy + (int64_t)b * HW * dy_ld + c0;
   // the first pixels of the chunk are requested before anything else: their latency overlaps the coefficient setup
-  Raw8<T> rx[2], rg[2];
+  Raw8<T> rx[UB], rg[UB];
   auto fetch = [&](int p) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UB; ++u) {
       if (p + u * lanes < p1) {
         rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
         rg[u].load(gp + (int64_t)(p + u * lanes) * dy_ld);
@@ -585,11 +602,17 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk); the loads of the
   //      next two pixels are in flight while the current two are processed
   float s1[8] = {}, s2[8] = {}, s0[8] = {};
-  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    Raw8<T> cx[2] = {rx[0], rx[1]}, cg2[2] = {rg[0], rg[1]};
-    if (p + 2 * lanes < p1) fetch(p + 2 * lanes);
+  for (int p = p0 + lane; p < p1; p += UB * lanes) {
+    Raw8<T> cx[UB], cg2[UB];
+    if (!PIPE && p != p0 + lane) fetch(p);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UB; ++u) {
+      cx[u] = rx[u];
+      cg2[u] = rg[u];
+    }
+    if (PIPE && p + UB * lanes < p1) fetch(p + UB * lanes);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
       if (p + u * lanes < p1) {
         float xv[8], gv[8];
         cx[u].unpack(xv);
@@ -673,11 +696,17 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) P[j] = rstd * sc[j] * gamma[c0 + j];
   T* dp = dx + (int64_t)b * HW * dx_ld + c0;
-  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
-    Raw8<T> cx[2] = {rx[0], rx[1]}, cg2[2] = {rg[0], rg[1]};
-    if (p + 2 * lanes < p1) fetch(p + 2 * lanes);
+  for (int p = p0 + lane; p < p1; p += UB * lanes) {
+    Raw8<T> cx[UB], cg2[UB];
+    if (!PIPE && p != p0 + lane) fetch(p);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UB; ++u) {
+      cx[u] = rx[u];
+      cg2[u] = rg[u];
+    }
+    if (PIPE && p + UB * lanes < p1) fetch(p + UB * lanes);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
       if (p + u * lanes < p1) {
         float xv[8], gv[8];
         cx[u].unpack(xv);
@@ -860,57 +889,66 @@ rmsnorm_bwd_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x,
   T* op = dx + row0 * dx_ld + sl * 8;
   const int64_t xs = (int64_t)stride * x_ld, gsd = (int64_t)stride * dy_ld, rs = (int64_t)stride * res_ld,
                 os = (int64_t)stride * dx_ld;
-  for (int r0 = warp * rpw; r0 < rows; r0 += stride, xp += xs, gp += gsd, rp += rs, op += os) {
-    const bool ok = r0 + sub < rows;
-    Raw8<T> rx[MAXV], rg[MAXV], rr[MAXV];
-    // input, upstream gradient and skip gradient are all requested before the first reduction
+  // the kernel runs as ~2 CTAs per SM (every CTA ends with one dg atomic per channel), so it is latency-bound:
+  // U rows per thread are requested before the first reduction
+  constexpr int U = MAXV == 1 ? 2 : 1;
+  for (int r0 = warp * rpw; r0 < rows; r0 += U * stride, xp += U * xs, gp += U * gsd, rp += U * rs, op += U * os) {
+    Raw8<T> rx[U][MAXV], rg[U][MAXV], rr[U][MAXV];
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (ok && sl + L * k < C8) {
-        rx[k].load(xp + k * L * 8);
-        rg[k].load(gp + k * L * 8);
-        if (res) rr[k].load(rp + k * L * 8);
-      }
-    }
-    float u[MAXV][8], gd[MAXV][8];
-    float ss = 0.f;
+    for (int w = 0; w < U; ++w) {
+      const bool ok = r0 + w * stride + sub < rows;
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (ok && sl + L * k < C8) {
-        rx[k].unpack(u[k]);
-        rg[k].unpack(gd[k]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
-      }
-    }
-    ss = seg_sum<LT>(ss, L);
-    const float rn = rsqrt_ftz(fmaxf(ss, 1e-24f));
-    float dot = 0.f;
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (ok && sl + L * k < C8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          u[k][j] *= rn;                                       // unit vector
-          dgacc[k][j] = fmaf(gd[k][j], u[k][j], dgacc[k][j]);  // dg_c += dy_c*u_c (x sqrtC at the end)
-          gd[k][j] *= gs[k][j];                                // g .* dy
-          dot = fmaf(gd[k][j], u[k][j], dot);
+      for (int k = 0; k < MAXV; ++k) {
+        if (ok && sl + L * k < C8) {
+          rx[w][k].load(xp + w * xs + k * L * 8);
+          rg[w][k].load(gp + w * gsd + k * L * 8);
+          if (res) rr[w][k].load(rp + w * rs + k * L * 8);
         }
       }
     }
-    dot = seg_sum<LT>(dot, L);
-    const float a = rn * sqrtC, nb = -a * dot;                 // dx = a * gd + nb * u (+ skip gradient)
 #pragma unroll
-    for (int k = 0; k < MAXV; ++k) {
-      if (ok && sl + L * k < C8) {
-        float o[8], rv[8];
-        if (res) rr[k].unpack(rv);
+    for (int w = 0; w < U; ++w) {
+      const bool ok = r0 + w * stride + sub < rows;
+      float u[MAXV][8], gd[MAXV][8];
+      float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = fmaf(nb, u[k][j], a * gd[k][j]);
-          o[j] = res ? t + rv[j] : t;
+      for (int k = 0; k < MAXV; ++k) {
+        if (ok && sl + L * k < C8) {
+          rx[w][k].unpack(u[k]);
+          rg[w][k].unpack(gd[k]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss = fmaf(u[k][j], u[k][j], ss);
         }
-        st8(op + k * L * 8, o);
+      }
+      ss = seg_sum<LT>(ss, L);
+      const float rn = rsqrt_ftz(fmaxf(ss, 1e-24f));
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        if (ok && sl + L * k < C8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            u[k][j] *= rn;                                       // unit vector
+            dgacc[k][j] = fmaf(gd[k][j], u[k][j], dgacc[k][j]);  // dg_c += dy_c*u_c (x sqrtC at the end)
+            gd[k][j] *= gs[k][j];                                // g .* dy
+            dot = fmaf(gd[k][j], u[k][j], dot);
+          }
+        }
+      }
+      dot = seg_sum<LT>(dot, L);
+      const float a = rn * sqrtC, nb = -a * dot;                 // dx = a * gd + nb * u (+ skip gradient)
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) {
+        if (ok && sl + L * k < C8) {
+          float o[8], rv[8];
+          if (res) rr[w][k].unpack(rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(nb, u[k][j], a * gd[k][j]);
+            o[j] = res ? t + rv[j] : t;
+          }
+          st8(op + w * os + k * L * 8, o);
+        }
       }
     }
   }
@@ -1027,8 +1065,10 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
   const int lanes = GNC_THREADS / (C / 8);
-  static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 4; }();
-  int chunks = (int)(((long long)num_sms() * mult) / B);
+  static const int fvar = [] { const char* e = getenv("B200DM_GNF_VAR"); return e ? atoi(e) : 0; }();
+  static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 0; }();
+  const bool pipe = fvar == 1 && dtype == B200DM_BF16;
+  int chunks = (int)(((long long)num_sms() * (mult ? mult : (pipe ? 3 : 4))) / B);
   if (chunks > 32) chunks = 32;
   while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
   if (chunks < 1) chunks = 1;
@@ -1036,6 +1076,10 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
   if (dtype == B200DM_F32)
     launch_k(gn_fwd_cluster_kernel<float, false>, grid, GNC_THREADS, 0, st, (const float*)x, (int)x_ld, stats, gamma,
              beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld, (int)HW, (int)C, (int)G,
+             eps, 1, part, (int)slots);
+  else if (pipe)
+    launch_k(gn_fwd_cluster_kernel<bf16, false, true>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
+             beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW, (int)C, (int)G,
              eps, 1, part, (int)slots);
   else
     launch_k(gn_fwd_cluster_kernel<bf16, false>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
@@ -1075,17 +1119,27 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (gn_cluster_ok(C, G)) {
-    const int cl = gn_cluster_size(B, HW, C, GN_BWD_MINB);
+    // variant (experiment knob B200DM_GNB_VAR): pixels in flight per thread / software pipeline / CTAs per SM
+    static const int var = [] { const char* v = getenv("B200DM_GNB_VAR"); return v ? atoi(v) : 1; }();
+    const int minb = (dtype == B200DM_F32 || var == 0 || var == 3 || var == 7) ? 3 : 2;
+    const int cl = gn_cluster_size(B, HW, C, minb);
     dim3 grid(cl, B);
     cudaError_t e;
-    if (dtype == B200DM_F32)
-      e = launch_cluster(gn_bwd_cluster_kernel<float>, grid, cl, 0, st, (const float*)dy, (int)dy_ld,
-                         (const float*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (float*)dx,
-                         (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
-    else
-      e = launch_cluster(gn_bwd_cluster_kernel<bf16>, grid, cl, 0, st, (const bf16*)dy, (int)dy_ld,
-                         (const bf16*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (bf16*)dx,
-                         (int)dx_ld, dgamma, dbeta, dfilm, dbias, (int)HW, (int)C, (int)G);
+#define GN_BWD_LAUNCH(TT, UB, PIPE, MINB)                                                                          \
+  e = launch_cluster(gn_bwd_cluster_kernel<TT, UB, PIPE, MINB>, grid, cl, 0, st, (const TT*)dy, (int)dy_ld,        \
+                     (const TT*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (TT*)dx, (int)dx_ld, dgamma, \
+                     dbeta, dfilm, dbias, (int)HW, (int)C, (int)G)
+    // measured on the training step (B = 128, 32x32): three pixels in flight, pipelined, two CTAs per SM (var 1)
+    // 0.69 ms for the 38 launches; var 0 (two pixels, three CTAs per SM) 0.85; var 4 0.71; var 2 0.79; var 5 0.76
+    if (dtype == B200DM_F32) GN_BWD_LAUNCH(float, 2, true, 3);
+    else if (var == 0) GN_BWD_LAUNCH(bf16, 2, true, 3);
+    else if (var == 2) GN_BWD_LAUNCH(bf16, 4, true, 2);
+    else if (var == 3) GN_BWD_LAUNCH(bf16, 4, false, 3);
+    else if (var == 4) GN_BWD_LAUNCH(bf16, 4, false, 2);
+    else if (var == 5) GN_BWD_LAUNCH(bf16, 8, false, 2);
+    else if (var == 6) GN_BWD_LAUNCH(bf16, 2, true, 2);
+    else GN_BWD_LAUNCH(bf16, 3, true, 2);            // var 1 (default) and var 7 (same kernel, cluster sized for 3 per SM)
+#undef GN_BWD_LAUNCH
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
     count_launch();
     return check_launch("gn_apply_bwd");

@@ -19,7 +19,7 @@ __global__ void sinusoidal_kernel(const int64_t* __restrict__ t, float* __restri
   emb[b * dim + half + k] = cosf(a);
 }
 
-constexpr int GM = 64, GN = 64, GK = 16, GPAD = 4;
+constexpr int GM = 64, GN = 64, GK = 32, GPAD = 4;
 
 __device__ __forceinline__ float act_fwd(int act, float v) {
   if (act == 1) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
@@ -40,57 +40,82 @@ __device__ __forceinline__ float act_grad(int act, float v) {
 }
 
 // C[M,N] (+)= A(M,K) * B(K,N).  AT: A stored [K][M] (else [M][K]);  BT: B stored [N][K] (else [K][N]).
+// M is the batch, so every launch is a handful of CTAs and latency-bound: 32-deep K chunks fetched as float4 and
+// requested one chunk ahead (registers) while the current chunk is multiplied out of shared memory.
+
+// one 64 x 32 operand tile = 512 float4, two per thread.  ROWS_ARE_K: storage rows run along k (64 contiguous
+// m or n per row), else storage rows run along m / n (32 contiguous k per row).
+template <bool ROWS_ARE_K>
+struct TileLoader {
+  const float* base;
+  int ld, lim_row, lim_col;      // extents along the storage row index and the contiguous index
+  bool vec;
+  __device__ __forceinline__ void load(int row0, int col0, int tid, float4 (&r)[2]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = row0 + (ROWS_ARE_K ? (tid >> 4) + 16 * i : (tid >> 3) + 32 * i);
+      const int col = col0 + (ROWS_ARE_K ? (tid & 15) * 4 : (tid & 7) * 4);
+      const float* p = base + (int64_t)row * ld + col;
+      if (row < lim_row && col + 3 < lim_col && vec) {
+        r[i] = *reinterpret_cast<const float4*>(p);
+      } else {
+        r[i].x = (row < lim_row && col < lim_col) ? p[0] : 0.f;
+        r[i].y = (row < lim_row && col + 1 < lim_col) ? p[1] : 0.f;
+        r[i].z = (row < lim_row && col + 2 < lim_col) ? p[2] : 0.f;
+        r[i].w = (row < lim_row && col + 3 < lim_col) ? p[3] : 0.f;
+      }
+    }
+  }
+  // shared tile is [k][64 + pad]
+  __device__ __forceinline__ void store(float (*S)[GM + GPAD], int tid, const float4 (&r)[2]) const {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (ROWS_ARE_K) {
+        *reinterpret_cast<float4*>(&S[(tid >> 4) + 16 * i][(tid & 15) * 4]) = r[i];
+      } else {
+        const int mn = (tid >> 3) + 32 * i, k = (tid & 7) * 4;
+        S[k][mn] = r[i].x;
+        S[k + 1][mn] = r[i].y;
+        S[k + 2][mn] = r[i].z;
+        S[k + 3][mn] = r[i].w;
+      }
+    }
+  }
+};
+
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
              float* __restrict__ C, int ldc, const float* __restrict__ bias, float* __restrict__ pre,
              int M, int N, int K, int act, int beta, int splits) {
   pdl_prologue();
-  __shared__ float As[GK][GM + GPAD];
-  __shared__ float Bs[GK][GN + GPAD];
+  static_assert(GM == GN, "one tile loader serves both operands");
+  __shared__ __align__(16) float As[GK][GM + GPAD];
+  __shared__ __align__(16) float Bs[GK][GN + GPAD];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
   const int ty = tid >> 4, tx = tid & 15;
   float acc[4][4] = {};
-  int kchunks = (K + GK - 1) / GK;
-  int per = (kchunks + splits - 1) / splits;
-  int kb0 = blockIdx.z * per, kb1 = min(kb0 + per, kchunks);
-  for (int kb = kb0; kb < kb1; ++kb) {
+  const int kchunks = (K + GK - 1) / GK;
+  const int per = (kchunks + splits - 1) / splits;
+  const int kb0 = blockIdx.z * per, kb1 = min(kb0 + per, kchunks);
+  // A: AT -> rows are k (extent K), contiguous m (extent M); else rows m, contiguous k
+  const TileLoader<AT> la{A, lda, AT ? K : M, AT ? M : K, (lda & 3) == 0 && ((uintptr_t)A & 15) == 0};
+  // B: BT -> storage [N][K]: rows n, contiguous k; else rows k, contiguous n
+  const TileLoader<!BT> lb{Bm, ldb, BT ? N : K, BT ? K : N, (ldb & 3) == 0 && ((uintptr_t)Bm & 15) == 0};
+  float4 ra[2], rb[2];
+  auto fetch = [&](int kb) {
     const int k0 = kb * GK;
-    float a[4], b[4];
-    if (AT) {  // rows of storage are k; 64 consecutive m
-      int kk = tid >> 4, mm = (tid & 15) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        a[j] = (k0 + kk < K && m0 + mm + j < M) ? A[(int64_t)(k0 + kk) * lda + m0 + mm + j] : 0.f;
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) As[kk][mm + j] = a[j];
-    } else {   // rows of storage are m; 16 consecutive k
-      int mm = tid >> 2, kk = (tid & 3) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        a[j] = (m0 + mm < M && k0 + kk + j < K) ? A[(int64_t)(m0 + mm) * lda + k0 + kk + j] : 0.f;
-      __syncthreads();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) As[kk + j][mm] = a[j];
-    }
-    if (BT) {  // storage [N][K]
-      int nn = tid >> 2, kk = (tid & 3) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        b[j] = (n0 + nn < N && k0 + kk + j < K) ? Bm[(int64_t)(n0 + nn) * ldb + k0 + kk + j] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Bs[kk + j][nn] = b[j];
-    } else {   // storage [K][N]
-      int kk = tid >> 4, nn = (tid & 15) * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        b[j] = (k0 + kk < K && n0 + nn + j < N) ? Bm[(int64_t)(k0 + kk) * ldb + n0 + nn + j] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Bs[kk][nn + j] = b[j];
-    }
+    if (AT) la.load(k0, m0, tid, ra); else la.load(m0, k0, tid, ra);
+    if (BT) lb.load(n0, k0, tid, rb); else lb.load(k0, n0, tid, rb);
+  };
+  if (kb0 < kb1) fetch(kb0);
+  for (int kb = kb0; kb < kb1; ++kb) {
+    __syncthreads();                       // the previous chunk has been multiplied out
+    la.store(As, tid, ra);
+    lb.store(Bs, tid, rb);
     __syncthreads();
+    if (kb + 1 < kb1) fetch(kb + 1);       // in flight during the multiply
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -101,7 +126,6 @@ sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm,
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -177,9 +201,9 @@ extern "C" int b200dm_linear_bwd(const float* X, const float* W, const float* pr
     int tiles = ((M + GM - 1) / GM) * ((K + GN - 1) / GN);
     int chunks = (N + GK - 1) / GK;
     int splits = 1;
-    if (tiles < num_sms() && chunks >= 16) {
-      splits = (num_sms() + tiles - 1) / tiles;
-      if (splits > chunks / 8) splits = chunks / 8;
+    if (tiles < num_sms() && chunks >= 8) {
+      splits = (2 * num_sms() + tiles - 1) / tiles;          // about two CTAs per SM
+      if (splits > chunks / 4) splits = chunks / 4;
       if (splits < 1) splits = 1;
     }
     if (splits > 1) {
