@@ -1513,6 +1513,119 @@ attn_fwd_kernel(const T* __restrict__ qkv, int ld, const float* __restrict__ mem
   }
 }
 
+// ---- bf16 forward on tensor cores (mma.sync m16n8k16, the flash-attention register flow): one CTA per (b, head),
+//      one warp per 16 query rows.  S = Q K^T stays in the accumulator registers, the row softmax is done there
+//      (quad shuffles), and the probabilities are re-packed in place as the A operand of P V.
+constexpr int FA_KVP = 80;     // key/value rows (4 memory rows + up to 64 tokens) padded to a multiple of 16
+struct FaTcSmem {
+  lbf Q[FA_MAXN][LP];
+  lbf K[FA_KVP][LP];
+  lbf V[FA_KVP][LP];
+};
+
+__global__ void __launch_bounds__(128)
+attn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restrict__ mem_kv,
+                   lbf* __restrict__ out, int out_ld, int n) {
+  pdl_prologue();
+  __shared__ __align__(16) FaTcSmem s;
+  const int b = blockIdx.x / HEADS, h = blockIdx.x % HEADS, kv = n + NMEM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const lbf* base = qkv + (int64_t)b * n * ld + h * DH;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < FA_MAXN * 4; i += 128) {            // q, k, v rows as raw 16-byte vectors; zero padding
+    const int r = i >> 2, part = i & 3;
+    uint4 q = zero, k = zero, v = zero;
+    if (r < n) {
+      const lbf* p = base + (int64_t)r * ld + part * 8;
+      q = *reinterpret_cast<const uint4*>(p);
+      k = *reinterpret_cast<const uint4*>(p + HID);
+      v = *reinterpret_cast<const uint4*>(p + 2 * HID);
+    }
+    *reinterpret_cast<uint4*>(&s.Q[r][part * 8]) = q;
+    *reinterpret_cast<uint4*>(&s.K[r + NMEM][part * 8]) = k;
+    *reinterpret_cast<uint4*>(&s.V[r + NMEM][part * 8]) = v;
+  }
+  for (int i = tid; i < (FA_KVP - FA_MAXN - NMEM) * 4; i += 128) {
+    const int r = FA_MAXN + NMEM + (i >> 2), part = i & 3;
+    *reinterpret_cast<uint4*>(&s.K[r][part * 8]) = zero;
+    *reinterpret_cast<uint4*>(&s.V[r][part * 8]) = zero;
+  }
+  for (int i = tid; i < NMEM * DH; i += 128) {              // memory key/values, [2][heads][4][32] fp32
+    const int r = i >> 5, d = i & 31;
+    s.K[r][d] = __float2bfloat16_rn(mem_kv[((0 * HEADS + h) * NMEM + r) * DH + d]);
+    s.V[r][d] = __float2bfloat16_rn(mem_kv[((1 * HEADS + h) * NMEM + r) * DH + d]);
+  }
+  __syncthreads();
+  if (warp * 16 >= n) return;
+  const int mi = lane >> 3, r8 = lane & 7;
+  // S[16][80] = Q K^T
+  float sacc[FA_KVP / 8][4] = {};
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[4];
+    ldsm_x4(a, (uint32_t)__cvta_generic_to_shared(&s.Q[warp * 16 + (mi & 1) * 8 + r8][ks * 16 + (mi >> 1) * 8]));
+#pragma unroll
+    for (int nt = 0; nt < FA_KVP / 8; ++nt) {
+      uint32_t bb[2];
+      ldsm_x2(bb, (uint32_t)__cvta_generic_to_shared(&s.K[nt * 8 + r8][ks * 16 + (mi & 1) * 8]));
+      mma_bf16_16816(sacc[nt], a, bb);
+    }
+  }
+  // softmax over the kv columns of the two rows this thread holds (lane >> 2 and + 8); exp2 with the scale folded in
+  const float sc = kScale * kLog2e;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < FA_KVP / 8; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = nt * 8 + 2 * (lane & 3) + (j & 1);
+      sacc[nt][j] = col < kv ? sacc[nt][j] * sc : -INFINITY;
+    }
+    m0 = fmaxf(m0, fmaxf(sacc[nt][0], sacc[nt][1]));
+    m1 = fmaxf(m1, fmaxf(sacc[nt][2], sacc[nt][3]));
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pa[FA_KVP / 16][4];                               // probabilities as A fragments of P V
+#pragma unroll
+  for (int nt = 0; nt < FA_KVP / 8; ++nt) {
+    const float p0 = ex2_ftz(sacc[nt][0] - m0), p1 = ex2_ftz(sacc[nt][1] - m0);
+    const float p2 = ex2_ftz(sacc[nt][2] - m1), p3 = ex2_ftz(sacc[nt][3] - m1);
+    l0 += p0 + p1;
+    l1 += p2 + p3;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(p0, p1), hi = __floats2bfloat162_rn(p2, p3);
+    pa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<uint32_t*>(&lo);
+    pa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // O[16][32] = P V
+  float oacc[4][4] = {};
+#pragma unroll
+  for (int j = 0; j < FA_KVP / 16; ++j) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bb[2];
+      ldsm_x2_t(bb, (uint32_t)__cvta_generic_to_shared(&s.V[j * 16 + (mi & 1) * 8 + r8][nt * 8]));
+      mma_bf16_16816(oacc[nt], pa[j], bb);
+    }
+  }
+  const float i0 = rcp_ftz(l0), i1 = rcp_ftz(l1);
+  const int row0 = warp * 16 + (lane >> 2), col = 2 * (lane & 3);
+  lbf* o = out + ((int64_t)b * n + row0) * out_ld + h * DH + col;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    if (row0 < n) *reinterpret_cast<__nv_bfloat162*>(o + nt * 8) = __floats2bfloat162_rn(oacc[nt][0] * i0, oacc[nt][1] * i0);
+    if (row0 + 8 < n)
+      *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)8 * out_ld + nt * 8) = __floats2bfloat162_rn(oacc[nt][2] * i1, oacc[nt][3] * i1);
+  }
+}
+
 struct FaBwdSmem {
   FaSmem f;
   float dO[FA_MAXN][DH + 1];
@@ -1658,6 +1771,9 @@ extern "C" int b200dm_attn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, c
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_fwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)qkv, qkv_ld, mem_kv, (float*)out, out_ld, n);
+  } else if (qkv_ld % 8 == 0 && out_ld % 2 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0 &&
+             getenv("B200DM_ATTN_SIMT") == nullptr) {
+    launch_k(attn_fwd_tc_kernel, B * HEADS, 128, 0, st, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)out, out_ld, n);
   } else {
     cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_fwd_kernel<bf16>, B * HEADS, 256, smem, st, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)out, out_ld, n);

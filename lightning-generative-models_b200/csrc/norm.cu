@@ -1233,7 +1233,8 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   cudaStream_t st = (cudaStream_t)stream;
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
-  int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * 2;   // few CTAs: every CTA ends with one dg atomic per channel
+  static const int rmult = [] { const char* e = getenv("B200DM_RMSB_MULT"); return e ? atoi(e) : 2; }();
+  int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * rmult;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   const bool two = C / 8 > 32;
 #define RMS_BWD_T(TT, MV, LT)                                                                                \
