@@ -105,13 +105,18 @@ int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream);
  *   mode 1: pixel-unshuffle(2) + 1x1 == 2x2 stride-2 conv; input [B,2H,2W,Cin], 4 taps (p1,p2)
  *   mode 2: transpose of mode 1 (its data gradient): input [B,H,W,Cin], output [B,2H,2W,Cout],
  *           weight taps (p1,p2) of shape [Cout][Cin]
+ *   mode 3: nn.Upsample(scale_factor=2, mode="nearest") followed by the 3x3 conv (ddpm.py:93-97) as ONE launch
+ *           (tcgen05 path only, inference): input [B,H,W,Cin] at the LOW resolution, output [B,2H,2W,Cout].
+ *           Output phase (a,b) = (oy&1, ox&1) is a 2x2 conv over the source image (rows y+r+a-1, columns
+ *           x+c+b-1 for tap (r,c)) whose weights are sums of the 3x3 taps that land on the same source pixel:
+ *           16 instead of 36 multiply-adds per output.  Packed weights: [4 taps (r,c)][4 phases (a,b)][Cout][Cin]
  * Packed weights: [taps][Cout][Cin] in the activation dtype (Cin contiguous).
  * y = conv(x) + bias (+ res) (+ y if accumulate).  impl: 0 = SIMT (any shape, fp32 or bf16),
  * 1 = tcgen05/TMEM/TMA (bf16; Cin % 64 == 0, Cout % 64 == 0).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t dtype, mode, ksize, impl;
-  int32_t B, H, W; /* OUTPUT spatial size for modes 0/1; INPUT spatial size for mode 2 */
+  int32_t B, H, W; /* OUTPUT spatial size for modes 0/1; INPUT spatial size for modes 2/3 */
   int32_t Cin, Cout;
   const void* x;
   int32_t x_ld;
@@ -165,6 +170,9 @@ int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t rows, int32_
  * s_co = C*49) its weight gradient. */
 int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, void* stream);
 int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream);
+/* Weights of conv_fwd mode 3 (nearest-2x upsample + 3x3 conv in one launch, Upsample ddpm.py:93-97) from the fp32
+ * master weight in [ky*3+kx][Cout][Cin] order: out = bf16 [4 taps][4 phases][Cout][Cin] (see b200dm_conv_desc). */
+int b200dm_pack_upconv_weight(const float* w, void* out, int32_t Cout, int32_t Cin, void* stream);
 
 int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* w, const float* bias, void* y,
                          int32_t y_ld, int32_t B, int32_t C, int32_t H, int32_t W, int32_t Cout,

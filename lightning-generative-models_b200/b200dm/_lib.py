@@ -72,6 +72,7 @@ PROTOTYPES = {
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_pack_stem_weight": [_P, _P, _I, _I, _I, _P],
+    "b200dm_pack_upconv_weight": [_P, _P, _I, _I, _P],
     "b200dm_init_conv_fwd": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200dm_init_conv_wgrad": [_I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_final_conv_fwd": [_I, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -15,6 +15,7 @@ Data-flow decisions:
 from __future__ import annotations
 
 import ctypes as C
+import re
 from typing import Callable, List, Optional
 
 import torch
@@ -51,6 +52,14 @@ class WeightPack:
         self.stem_k = arena.channels * 49
         self.stem_kp = (self.stem_k + 63) // 64 * 64
         self.stem = torch.zeros(arena.dim * self.stem_kp, dtype=tdt, device=dev) if dt == L.BF16 else None
+        # Upsample convs (ddpm.py:93-97) for inference: weights of the fused upsample + 3x3 launch (conv mode 3),
+        # [4 taps][4 phases][Cout][Cin]; packed on demand (inference plans only)
+        self.up = {}
+        if dt == L.BF16:
+            for nm, ci in arena.convs.items():
+                if re.fullmatch(r"ups\.\d+\.3\.1", nm) and ci.mode == 0 and ci.ksize == 3:
+                    self.up[nm] = torch.empty(16 * ci.cout * ci.cin, dtype=tdt, device=dev)
+        self.up_version = None
         # device table for the one-launch batched pack
         entries = (L.PackEntry * len(arena.convs))()
         tile = 0
@@ -71,9 +80,14 @@ class WeightPack:
         raw = bytes(entries)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
 
-    def refresh(self, force: bool = False):
+    def refresh(self, force: bool = False, inference: bool = False):
         """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
         v = self.arena.version
+        if inference and self.up and (force or v != self.up_version):
+            for nm, buf in self.up.items():
+                ci = self.arena.convs[nm]
+                L.call("b200dm_pack_upconv_weight", self.arena.ptr(nm + ".weight"), buf.data_ptr(), ci.cout, ci.cin)
+            self.up_version = v
         if not force and v == self.version:
             return
         L.call("b200dm_pack_conv_weights_batched", self.dt, self.table.data_ptr(), self.n_entries,
@@ -108,6 +122,7 @@ class Plan:
         import os
         self.side_enabled = os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
         self.fuse_gn_stats = os.environ.get("B200DM_FUSE_GN_STATS", "1") != "0"
+        self.fuse_upsample = os.environ.get("B200DM_FUSE_UPSAMPLE", "1") != "0"
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
@@ -345,6 +360,17 @@ class Plan:
 
     def upsample_conv(self, nm, x: View, out: View, gx, gout):
         self.begin_unit()
+        ci = self.arena.convs[nm]
+        if not self.training and nm in self.pack.up and self._impl(ci.cin, ci.cout) == 1 and self.fuse_upsample:
+            # inference: nearest-2x upsample + 3x3 conv as ONE launch over the low-resolution tensor (conv mode 3:
+            # four 2x2 convs, one per output phase; 16 instead of 36 multiply-adds per output, no upsampled copy)
+            d = L.ConvDesc(dtype=self.dt, mode=3, ksize=3, impl=1, B=self.B, H=x.H, W=x.H, Cin=ci.cin, Cout=ci.cout,
+                           x=x.ptr, x_ld=x.ld, w=self.pack.up[nm].data_ptr(), bias=self.arena.ptr(nm + ".bias"),
+                           y=out.ptr, y_ld=out.ld, res=None, res_ld=0, accumulate=0, gn_part=None, gn_groups=0)
+            self.F("b200dm_conv_fwd", C.byref(d), kname="conv_tc_fwd",
+                   flops=2.0 * self.B * x.H * x.H * ci.cout * ci.cin * 16, writes=(out,))
+            self._keep.append(d)
+            return
         xu = self.buf(2 * x.H, x.C)
         self.F("b200dm_upsample2x_fwd", self.dt, x.ptr, x.ld, xu.ptr, xu.ld, self.B, x.H, x.H, x.C)
         self.conv_fwd(self.F, nm, xu, out)

@@ -54,7 +54,7 @@ extern "C" int b200dm_tc_available(void) { return tc_supported() ? 1 : 0; }
 
 static int check_conv_common(int dtype, int mode, int ksize, int B, int H, int W, int Cin, int Cout) {
   B200DM_REQUIRE(dtype == B200DM_F32 || dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "conv: dtype %d", dtype);
-  B200DM_REQUIRE(mode >= 0 && mode <= 2, B200DM_ERR_UNSUPPORTED, "conv: mode %d", mode);
+  B200DM_REQUIRE(mode >= 0 && mode <= 3, B200DM_ERR_UNSUPPORTED, "conv: mode %d", mode);
   B200DM_REQUIRE(mode != 0 || ksize == 1 || ksize == 3, B200DM_ERR_UNSUPPORTED, "conv: ksize %d (1 or 3)", ksize);
   B200DM_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, B200DM_ERR_SHAPE,
                  "conv: empty shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
@@ -72,6 +72,8 @@ extern "C" int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream) {
     return conv_fwd_tc(d, stream);
   }
   B200DM_REQUIRE(d->impl == 0, B200DM_ERR_UNSUPPORTED, "conv_fwd: impl %d", d->impl);
+  B200DM_REQUIRE(d->mode != 3, B200DM_ERR_UNSUPPORTED,
+                 "conv_fwd: mode 3 (fused nearest-2x upsample + 3x3) is built for the tcgen05 path (impl 1) only");
   B200DM_REQUIRE(d->gn_part == nullptr, B200DM_ERR_UNSUPPORTED,
                  "conv_fwd: fused GroupNorm statistics are built for the tcgen05 path (impl 1) only");
   return conv_fwd_simt(d, stream);
@@ -81,7 +83,8 @@ extern "C" int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream) {
   B200DM_REQUIRE(d != nullptr, B200DM_ERR_SHAPE, "conv_wgrad: null descriptor");
   int rc = check_conv_common(d->dtype, d->mode, d->ksize, d->B, d->H, d->W, d->Cin, d->Cout);
   if (rc) return rc;
-  B200DM_REQUIRE(d->mode != 2, B200DM_ERR_UNSUPPORTED, "conv_wgrad: use mode 1 for the down/up-shuffle pair");
+  B200DM_REQUIRE(d->mode != 2 && d->mode != 3, B200DM_ERR_UNSUPPORTED,
+                 "conv_wgrad: mode %d has no weight gradient (use mode 1 for the down/up-shuffle pair)", d->mode);
   B200DM_REQUIRE(d->x && d->dy && d->dw, B200DM_ERR_SHAPE, "conv_wgrad: null tensor pointer");
   if (!d->accumulate) {
     int taps = d->mode == 0 ? d->ksize * d->ksize : 4;

@@ -185,7 +185,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                           n_first);
             else if (p.mode == 0)
               tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
-            else
+            else if (p.mode == 3) {
+              // nearest-2x upsample + 3x3 conv as four 2x2 convs over the SOURCE image: output phase (a, b) =
+              // n0 / Cout reads source rows y + r + a - 1 and columns x + c + b - 1 for tap (r, c)
+              const int ph = n0 / p.Cout;
+              tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, (tap & 1) + (ph & 1) - 1,
+                          y_first + (tap >> 1) + (ph >> 1) - 1, n_first, 0);
+            } else
               tma_load_5d(a_dst, &tmA, full_bar(stage), kc * TC_BK, 0, y_first, n_first, 0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -257,7 +263,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t my_stage = out_stage + (uint32_t)(warp - 2) * 4096u;
     uint8_t* my_row = out_stage_ptr + (warp - 2) * 4096 + lane * 128;
     // bias of all N columns, once per CTA
-    for (int i = threadIdx.x - 64; i < p.Ncols; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x - 64; i < p.Ncols; i += 32 * TC_EPI_WARPS)
+      bias_s[i] = p.bias ? p.bias[p.mode == 3 ? i % p.Cout : i] : 0.f;      // mode 3: one bias per output phase
     named_bar_sync(1, 32 * TC_EPI_WARPS);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -270,7 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = pix < p.M;
       long long opix = pix;
       int co0 = n0, tap2 = 0;
-      if (p.mode == 2) {  // output pixel (2y+p1, 2x+p2) of the [2H,2W] tensor; one tap per N tile
+      if (p.mode >= 2) {  // output pixel (2y+p1, 2x+p2) of the [2H,2W] tensor; one tap / phase per N tile
         tap2 = n0 / p.Cout;
         co0 = n0 - tap2 * p.Cout;
         const int ox = (int)(pix % p.W);
@@ -389,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async();                  // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          if (p.mode == 2)
+          if (p.mode >= 2)
             tma_store_5d(&tmY, my_stage, (tap2 & 1) * p.y_ld + co0 + s * 64, sx, tap2 >> 1, sy, sn);
           else
             tma_store_5d(&tmY, my_stage, co0 + s * 64, sx, sy, sn, 0);
@@ -937,11 +944,11 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   if (rc) return rc;
   TcParams p{};
   p.mode = d->mode; p.ksize = ksize;
-  p.taps = d->mode == 0 ? ksize * ksize : (d->mode == 1 ? 4 : 1);
+  p.taps = d->mode == 0 ? ksize * ksize : (d->mode == 1 || d->mode == 3 ? 4 : 1);
   p.kblocks = d->Cin / TC_BK;
   p.H = d->H; p.W = d->W; p.bh = bh; p.bn = bn;
   p.Cout = d->Cout;
-  p.Ncols = d->mode == 2 ? 4 * d->Cout : d->Cout;
+  p.Ncols = d->mode >= 2 ? 4 * d->Cout : d->Cout;
   p.x_ld = d->x_ld; p.y_ld = d->y_ld;
   p.M = (long long)d->B * d->H * d->W;
   p.y_read = d->accumulate ? (const __nv_bfloat16*)d->y : nullptr;
@@ -970,7 +977,7 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   rc = make_act_map(&tmA, d->mode == 1 ? 1 : 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_fwd(tc) A");
   if (rc) return rc;
   // output: NHWC tensor (modes 0/1) or the unshuffle view of the [2H,2W] tensor (mode 2)
-  rc = make_out_map32(&tmY, d->mode == 2 ? 1 : 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, "conv_fwd(tc) Y");
+  rc = make_out_map32(&tmY, d->mode >= 2 ? 1 : 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, "conv_fwd(tc) Y");
   if (rc) return rc;
   {
     const int wt = d->mode == 2 ? 1 : p.taps;

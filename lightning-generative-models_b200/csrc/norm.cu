@@ -331,10 +331,8 @@ template <> struct Raw8<__nv_bfloat16> {
 // STAGE: the chunk's raw vectors are parked in (dynamic) shared memory during phase 1 and phase 2 reads them
 // from there instead of going back to L2 (chunk bytes = ceil(HW/CL) * C * sizeof(T), <= GNC_STAGE_MAX).
 constexpr int GNC_STAGE_MAX = 40 * 1024;
-// PIPE (pre-statistics mode only): phase 2 as a software pipeline whose first loads are requested before the
-// statistics are reduced; 80 registers, so the launcher sizes the grid for three CTAs per SM
-template <typename T, bool STAGE, bool PIPE = false>
-__global__ void __launch_bounds__(GNC_THREADS, PIPE ? 3 : (sizeof(T) == 2 ? 4 : 2))
+template <typename T, bool STAGE>
+__global__ void __launch_bounds__(GNC_THREADS, sizeof(T) == 2 ? 4 : 2)
 gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ stats,
                       const float* __restrict__ gamma, const float* __restrict__ beta,
                       const float* __restrict__ film, int film_ld, const T* __restrict__ res, int res_ld,
@@ -362,18 +360,6 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   Raw8<T>* stage = reinterpret_cast<Raw8<T>*>(gn_stage_raw);     // [pixel of the chunk][C8]
   const T* rp = res ? res + (int64_t)b * HW * res_ld + c0 : nullptr;
   T* yp = y + (int64_t)b * HW * y_ld + c0;
-  // PIPE: phase-2 operands of two pixels (p, p + lanes): input and residual
-  Raw8<T> nx[2], nr[2];
-  auto fetch2 = [&](int p) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (p + u * lanes < p1) {
-        nx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
-        if (rp) nr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
-      }
-    }
-  };
-  if (PIPE) fetch2(p0 + lane);
   // ---- phase 1: per-group sum / sum of squares of the chunk
   float s = 0.f, ss = 0.f;
   if (part) {
@@ -477,21 +463,12 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   }
   for (int p = p0 + lane; p < p1; p += 2 * lanes) {
     Raw8<T> rx[2], rr[2];
-    if (PIPE) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        rx[u] = nx[u];
-        rr[u] = nr[u];
-      }
-      if (p + 2 * lanes < p1) fetch2(p + 2 * lanes);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (p + u * lanes < p1) {
-          if (STAGE) rx[u] = stage[(p + u * lanes - p0) * C8 + cv];
-          else rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
-          if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
-        }
+    for (int u = 0; u < 2; ++u) {
+      if (p + u * lanes < p1) {
+        if (STAGE) rx[u] = stage[(p + u * lanes - p0) * C8 + cv];
+        else rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+        if (rp) rr[u].load(rp + (int64_t)(p + u * lanes) * res_ld);
       }
     }
 #pragma unroll
@@ -1065,10 +1042,8 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
   cudaStream_t st = (cudaStream_t)stream;
   // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
   const int lanes = GNC_THREADS / (C / 8);
-  static const int fvar = [] { const char* e = getenv("B200DM_GNF_VAR"); return e ? atoi(e) : 0; }();
   static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 0; }();
-  const bool pipe = fvar == 1 && dtype == B200DM_BF16;
-  int chunks = (int)(((long long)num_sms() * (mult ? mult : (pipe ? 3 : 4))) / B);
+  int chunks = (int)(((long long)num_sms() * (mult ? mult : 4)) / B);
   if (chunks > 32) chunks = 32;
   while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
   if (chunks < 1) chunks = 1;
@@ -1076,10 +1051,6 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
   if (dtype == B200DM_F32)
     launch_k(gn_fwd_cluster_kernel<float, false>, grid, GNC_THREADS, 0, st, (const float*)x, (int)x_ld, stats, gamma,
              beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld, (int)HW, (int)C, (int)G,
-             eps, 1, part, (int)slots);
-  else if (pipe)
-    launch_k(gn_fwd_cluster_kernel<bf16, false, true>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
-             beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW, (int)C, (int)G,
              eps, 1, part, (int)slots);
   else
     launch_k(gn_fwd_cluster_kernel<bf16, false>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,

@@ -118,6 +118,25 @@ pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) 
   }
 }
 
+// Weights of the fused nearest-2x upsample + 3x3 conv (conv_fwd mode 3): for output phase (a, b) and 2x2 tap
+// (r, c) the sum of the 3x3 taps that read the same source pixel.  w: master layout [ky*3+kx][Cout][Cin] fp32;
+// out: [tap r*2+c][phase a*2+b][Cout][Cin] bf16.
+__global__ void pack_upconv_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin) {
+  pdl_prologue();
+  const int n = Cout * Cin;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 16 * n) return;
+  const int e = i % n, ph = (i / n) & 3, t = i / (4 * n);
+  const int a = ph >> 1, b = ph & 1, r = t >> 1, c = t & 1;
+  // phase 0: tap 0 <- k {0}, tap 1 <- k {1, 2};  phase 1: tap 0 <- k {0, 1}, tap 1 <- k {2}
+  const int ky0 = a == 0 ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = a == 0 ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+  const int kx0 = b == 0 ? (c == 0 ? 0 : 1) : (c == 0 ? 0 : 2), kx1 = b == 0 ? (c == 0 ? 0 : 2) : (c == 0 ? 1 : 2);
+  float acc = 0.f;
+  for (int ky = ky0; ky <= ky1; ++ky)
+    for (int kx = kx0; kx <= kx1; ++kx) acc += w[(ky * 3 + kx) * n + e];
+  out[i] = __float2bfloat16_rn(acc);
+}
+
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
@@ -178,6 +197,14 @@ extern "C" int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack
     launch_k(pack_weights_batched_kernel<__nv_bfloat16>, total_tiles, block, 0, st, table, n_entries);
   count_launch();
   return check_launch("pack_conv_weights_batched");
+}
+
+extern "C" int b200dm_pack_upconv_weight(const float* w, void* out, int32_t Cout, int32_t Cin, void* stream) {
+  B200DM_REQUIRE(w && out && Cout > 0 && Cin > 0, B200DM_ERR_SHAPE, "pack_upconv_weight: bad arguments");
+  const int total = 16 * Cout * Cin;
+  launch_k(pack_upconv_kernel, (total + 255) / 256, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)out, Cout, Cin);
+  count_launch();
+  return check_launch("pack_upconv_weight");
 }
 
 extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,

@@ -271,6 +271,40 @@ def test_conv_unshuffle_and_its_transpose(impl, dtype, case):
     assert rel(dxv.to_nchw(), x.grad) < tol(dtype)
 
 
+@pytest.mark.parametrize("case", [(2, 32, 128, 64), (3, 16, 256, 128), (5, 8, 512, 256), (2, 4, 64, 64)])
+def test_conv_fused_nearest_upsample_3x3(case):
+    """Upsample (ddpm.py:93-97): nn.Upsample(scale_factor=2, mode='nearest') + Conv2d(3x3, padding=1) as ONE launch
+    over the low-resolution tensor (conv mode 3: one 2x2 conv per output phase, weights summed by
+    b200dm_pack_upconv_weight)."""
+    _skip_tc(1, L.BF16)
+    B, S, Cin, Cout = case                   # input [B, Cin, S, S] -> output [B, Cout, 2S, 2S]
+    x = q(rnd(B, Cin, S, S, seed=31), L.BF16)
+    w = rnd(Cout, Cin, 3, 3, seed=32, scale=1 / math.sqrt(9 * Cin))
+    bias = rnd(Cout, seed=33)
+    master = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous()          # arena layout [ky*3+kx][Cout][Cin]
+    wp = torch.full((16 * Cout * Cin,), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.call("b200dm_pack_upconv_weight", master.data_ptr(), wp.data_ptr(), Cout, Cin)
+    sel = ([[0], [1, 2]], [[0, 1], [2]])      # phase -> 2x2 tap -> 3x3 taps that land on the same source pixel
+    exp = torch.empty(4, 4, Cout, Cin, device=DEV)
+    for a in range(2):
+        for b in range(2):
+            for r in range(2):
+                for c in range(2):
+                    acc = torch.zeros(Cout, Cin, device=DEV)          # same fp32 summation order as the kernel
+                    for ky in sel[a][r]:
+                        for kx in sel[b][c]:
+                            acc = acc + w[:, :, ky, kx]
+                    exp[r * 2 + c, a * 2 + b] = acc
+    assert torch.equal(wp.view(4, 4, Cout, Cin).float(), exp.to(torch.bfloat16).float())
+    xv = nhwc(x, L.BF16, ld=Cin + 64, off=0)
+    yv = View.zeros(B, 2 * S, 2 * S, Cout, torch.bfloat16, DEV, ld=Cout + 64, off=64)
+    run_conv(L.BF16, 1, 3, 3, xv, wp, bias, yv, Cin, Cout, S, S)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, bias, padding=1)
+    assert rel(yv.to_nchw(), ref) < tol(L.BF16)
+    with pytest.raises(L.B200dmError):        # the SIMT path does not build it
+        run_conv(L.BF16, 0, 3, 3, xv, wp, bias, yv, Cin, Cout, S, S)
+
+
 @pytest.mark.parametrize("impl", [0, 1], ids=["simt", "tc"])
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("case", [(2, 32, 64, 64, 3), (3, 8, 128, 64, 3), (4, 4, 256, 128, 3),
