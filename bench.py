@@ -329,7 +329,7 @@ def main():
         B, S = TRAIN_CFG[args.workload]
         model = DDPM(img_channels=3, img_size=S, dim=64, diffusion_timesteps=1000, sampling_timesteps=None,
                      lr=2e-5, betas=(0.9, 0.99), ema_update_every=10, ema_decay=0.995, precision="bf16",
-                     device=dev)
+                     device=dev, overlap_optimizer=os.environ.get("B200DM_OVERLAP_OPT", "1") != "0")
         model.train()
         unet = model.ema.model.model
         opt = model.configure_optimizers()
@@ -383,7 +383,9 @@ def main():
                            "(reference defaults), fwd+loss+bwd+fused Adam+EMA",
                "global_batch": B * world, "parallelism": f"dp{world}",
                "l2": f"per-step working set {plan.nbytes / 1e9:.2f} GB of activations > 126 MB L2 (no flush needed)",
-               "cuda_graph": bool(unet._cuda_graph)}
+               "cuda_graph": bool(unet._cuda_graph),
+               "optimizer": "fused Adam + weight re-pack per gradient bucket, overlapped with backward"
+               if opt.overlap else "fused Adam after backward"}
         step_flops = flop_per_img * B
     else:
         from b200dm import GaussianDiffusion, Unet

@@ -296,7 +296,7 @@ int b200dm_pack_conv_weight(int32_t dtype, const float* w, void* wf, void* wt, i
                             int32_t Cout, int32_t Cin, int32_t flip, int64_t s_tap, int64_t s_co,
                             int64_t s_ci, void* stream);
 /* the same for every conv of the network in one launch.  `table` is a DEVICE array of entries; entry i
- * owns the CTAs [tile_begin, tile_begin + taps*tiles_co*tiles_ci) with tiles_* = ceil(C* / 32). */
+ * owns the CTAs [tile_begin, tile_begin + taps*tiles_co*tiles_ci) with tiles_* = ceil(C* / 64). */
 typedef struct {
   const float* w;
   void* wf;
@@ -307,11 +307,21 @@ typedef struct {
 } b200dm_pack_entry;
 int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack_entry* table, int32_t n_entries,
                                      int32_t total_tiles, void* stream);
+/* a contiguous run of table entries only (`entries` = &table[first]; their tile_begin keep the numbering of the
+ * full table, `tile_first` = entries[0].tile_begin, `n_tiles` = tiles owned by the run): lets the optimiser
+ * re-pack one gradient bucket's convs as soon as their weights are updated. */
+int b200dm_pack_conv_weights_range(int32_t dtype, const b200dm_pack_entry* entries, int32_t n_entries,
+                                   int32_t tile_first, int32_t n_tiles, void* stream);
 /* fused Adam over a flat fp32 arena (torch.optim.Adam semantics, ddpm.py:1053-1059):
  * grad_scale multiplies g first (DDP mean).  step is the 1-based step count. */
 int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
                      void* stream);
+/* the same with a bounded grid (`ctas_per_sm` x SMs CTAs of 256 threads): for running the update of one gradient
+ * bucket on a second stream behind backward without taking every thread slot of the machine. */
+int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                        int32_t ctas_per_sm, void* stream);
 /* ema = ema + (1-decay)*(online-ema)  (ema_pytorch lerp), or copy when decay == 0 */
 int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream);
 int b200dm_fill_f32(float* p, int64_t n, float value, void* stream);

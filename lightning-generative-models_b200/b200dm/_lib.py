@@ -96,7 +96,9 @@ PROTOTYPES = {
     "b200dm_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200dm_pack_conv_weight": [_I, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _P],
     "b200dm_pack_conv_weights_batched": [_I, _P, _I, _I, _P],
+    "b200dm_pack_conv_weights_range": [_I, _P, _I, _I, _I, _P],
     "b200dm_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "b200dm_adam_step_bg": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     "b200dm_ema_update": [_P, _P, _L, _F, _P],
     "b200dm_fill_f32": [_P, _L, _F, _P],
     "b200dm_debug_umma_rate": [_I, _I, _I, _I, _P, _P],

@@ -111,7 +111,8 @@ class DDPM(_Base):
                  diffusion_timesteps: int = 1000, sampling_timesteps: Optional[int] = None,
                  lr: float = 2e-5, betas: Tuple[float, float] = (0.9, 0.99), ema_update_every: int = 10,
                  ema_decay: float = 0.995, *, precision: str = "bf16", objective: str = "pred_v",
-                 beta_schedule: str = "sigmoid", device=None, rng: str = "philox"):
+                 beta_schedule: str = "sigmoid", device=None, rng: str = "philox",
+                 overlap_optimizer: bool = False):
         super().__init__()
         if _HAS_PL:
             self.save_hyperparameters()
@@ -127,6 +128,7 @@ class DDPM(_Base):
         self.img_size = img_size
         self.ema = EMA(diffusion_model, beta=ema_decay, update_every=ema_update_every)
         self._step_count = 0
+        self._overlap_optimizer = bool(overlap_optimizer)     # FusedAdam(overlap_with_backward=...)
         self.logged = {}
 
     # Lightning provides these; minimal stand-ins otherwise
@@ -165,7 +167,7 @@ class DDPM(_Base):
 
     def configure_optimizers(self):
         h = self.hparams_
-        opt = FusedAdam(self.ema.model.model, lr=h.lr, betas=h.betas)
+        opt = FusedAdam(self.ema.model.model, lr=h.lr, betas=h.betas, overlap_with_backward=self._overlap_optimizer)
         # the reference relies on Lightning's DDPStrategy when several GPUs are used
         # (utils/lightning_utils.py:41-43): same semantics here when torch.distributed is initialised
         import torch.distributed as dist

@@ -79,6 +79,14 @@ class WeightPack:
         self.n_entries, self.total_tiles = len(arena.convs), tile
         raw = bytes(entries)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        # host copy of (arena offset of the weight, tile_begin, tiles) per entry: `refresh_range` re-packs the convs
+        # of one gradient bucket (the optimiser-in-backward path)
+        self._entry_size = C.sizeof(L.PackEntry)
+        self._entry_info = []
+        for i, (nm, ci) in enumerate(arena.convs.items()):
+            e = entries[i]
+            self._entry_info.append((arena.offset[nm + ".weight"], e.tile_begin, ci.taps * e.tiles_ci * e.tiles_co))
+        self._range_cache = {}
 
     def refresh(self, force: bool = False, inference: bool = False):
         """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
@@ -96,6 +104,32 @@ class WeightPack:
             L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
                    self.arena.dim, self.stem_k, self.stem_kp)
         self.version = v
+
+
+    def refresh_range(self, begin: int, end: int):
+        """Re-pack the convs whose master weights live in arena elements [begin, end) on the current stream (one
+        launch per contiguous run of table entries; the stem rides with the range that holds it)."""
+        runs = self._range_cache.get((begin, end))
+        if runs is None:
+            idx = [i for i, (off, _, _) in enumerate(self._entry_info) if begin <= off < end]
+            runs, k = [], 0
+            while k < len(idx):
+                j = k
+                while j + 1 < len(idx) and idx[j + 1] == idx[j] + 1:
+                    j += 1
+                first, n = idx[k], j - k + 1
+                tiles = sum(self._entry_info[i][2] for i in range(first, first + n))
+                runs.append((first, n, self._entry_info[first][1], tiles))
+                k = j + 1
+            stem_off = self.arena.offset["init_conv.weight"]
+            runs = (runs, self.stem is not None and begin <= stem_off < end)
+            self._range_cache[(begin, end)] = runs
+        for first, n, tile_first, tiles in runs[0]:
+            L.call("b200dm_pack_conv_weights_range", self.dt, self.table.data_ptr() + first * self._entry_size, n,
+                   tile_first, tiles)
+        if runs[1]:
+            L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
+                   self.arena.dim, self.stem_k, self.stem_kp)
 
 
 class Plan:

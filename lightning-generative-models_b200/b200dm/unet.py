@@ -100,6 +100,8 @@ class Unet(nn.Module):
         self._pack: Optional[WeightPack] = None
         self._plans: Dict[tuple, Plan] = {}
         self.grad_sync = None        # b200dm.distributed.GradSync when training data-parallel
+        self.bucket_hook = None      # callable(i, (begin, end)): gradient bucket i is complete (FusedAdam overlap)
+        self._buckets = None
 
     # ---- reference surface ----------------------------------------------------------------------------
     @property
@@ -230,16 +232,25 @@ class Unet(nn.Module):
         communication stream as soon as its segment has been issued."""
         sync = self.grad_sync
         nseg = len(plan.bwd_segments)
+        hook = self.bucket_hook
+        if hook is not None and self._buckets is None:
+            from .distributed import buckets
+            self._buckets = buckets(self.arena)
+            assert len(self._buckets) == nseg
         if self._cuda_graph and plan.graph_bwd is not None:
             for i in range(nseg):
                 plan.graph_bwd[i].replay()
                 if sync is not None:
                     sync.reduce_bucket(i)
+                if hook is not None:
+                    hook(i, self._buckets[i])
         else:
             for i in range(nseg):
                 plan.run_backward_segment(i)
                 if sync is not None:
                     sync.reduce_bucket(i)
+                if hook is not None:
+                    hook(i, self._buckets[i])
             if self._cuda_graph and plan.warm >= 2 and not torch.cuda.is_current_stream_capturing():
                 # capture for the following steps (stream capture records the launches, it does not run them)
                 graphs = []

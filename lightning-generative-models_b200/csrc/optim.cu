@@ -53,11 +53,11 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a,
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n) {
+pack_weights_batched_kernel(const b200dm_pack_entry* __restrict__ table, int n, int tile_first) {
   pdl_prologue();
   __shared__ float tile[PK][PK + 1];
   int lo = 0, hi = n - 1;
-  const int bid = blockIdx.x;
+  const int bid = blockIdx.x + tile_first;             // tile index in the numbering of the FULL table
   while (lo < hi) {
     int mid = (lo + hi + 1) >> 1;
     if (table[mid].tile_begin <= bid) lo = mid; else hi = mid - 1;
@@ -140,18 +140,60 @@ __global__ void pack_upconv_kernel(const float* __restrict__ w, __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
-            float weight_decay, float bc2_sqrt, float grad_scale) {
+            float weight_decay, float bc2_sqrt, float grad_scale, int vec) {
   pdl_prologue();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * grad_scale;
-    float pi = p[i];
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= grad_scale;
     if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
-    float mi = m[i], vi = v[i];
     mi = mi + (1.f - beta1) * (gi - mi);          // exp_avg.lerp_(grad, 1 - beta1)
     vi = vi * beta2 + (1.f - beta2) * gi * gi;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);         // param.addcdiv_(exp_avg, denom, value=-step_size)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);           // param.addcdiv_(exp_avg, denom, value=-step_size)
+  };
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    // 16-byte accesses with the streaming (evict-first) cache policy: the four arenas are touched once per step, and
+    // when the update runs behind backward it must not push backward's working set out of L2
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += 2 * nthr) {       // two vectors per arena in flight per thread
+      const int64_t j = i + nthr;
+      const bool two = j < n4;
+      float4 pp = __ldcs(p4 + i), mm = __ldcs(m4 + i), vv = __ldcs(v4 + i);
+      const float4 gg = __ldcs(g4 + i);
+      float4 pq = pp, mq = mm, vq = vv, gq = gg;
+      if (two) {
+        pq = __ldcs(p4 + j);
+        mq = __ldcs(m4 + j);
+        vq = __ldcs(v4 + j);
+        gq = __ldcs(g4 + j);
+      }
+      upd(pp.x, gg.x, mm.x, vv.x);
+      upd(pp.y, gg.y, mm.y, vv.y);
+      upd(pp.z, gg.z, mm.z, vv.z);
+      upd(pp.w, gg.w, mm.w, vv.w);
+      __stcs(p4 + i, pp);
+      __stcs(m4 + i, mm);
+      __stcs(v4 + i, vv);
+      if (two) {
+        upd(pq.x, gq.x, mq.x, vq.x);
+        upd(pq.y, gq.y, mq.y, vq.y);
+        upd(pq.z, gq.z, mq.z, vq.z);
+        upd(pq.w, gq.w, mq.w, vq.w);
+        __stcs(p4 + j, pq);
+        __stcs(m4 + j, mq);
+        __stcs(v4 + j, vq);
+      }
+    }
+    return;
+  }
+  for (int64_t i = tid; i < n; i += nthr) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
   }
@@ -192,11 +234,25 @@ extern "C" int b200dm_pack_conv_weights_batched(int32_t dtype, const b200dm_pack
   dim3 block(32, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    launch_k(pack_weights_batched_kernel<float>, total_tiles, block, 0, st, table, n_entries);
+    launch_k(pack_weights_batched_kernel<float>, total_tiles, block, 0, st, table, n_entries, 0);
   else
-    launch_k(pack_weights_batched_kernel<__nv_bfloat16>, total_tiles, block, 0, st, table, n_entries);
+    launch_k(pack_weights_batched_kernel<__nv_bfloat16>, total_tiles, block, 0, st, table, n_entries, 0);
   count_launch();
   return check_launch("pack_conv_weights_batched");
+}
+
+extern "C" int b200dm_pack_conv_weights_range(int32_t dtype, const b200dm_pack_entry* entries, int32_t n_entries,
+                                              int32_t tile_first, int32_t n_tiles, void* stream) {
+  B200DM_REQUIRE(entries && n_entries > 0 && n_tiles > 0 && tile_first >= 0, B200DM_ERR_SHAPE,
+                 "pack_conv_weights_range: empty range");
+  dim3 block(32, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32)
+    launch_k(pack_weights_batched_kernel<float>, n_tiles, block, 0, st, entries, n_entries, tile_first);
+  else
+    launch_k(pack_weights_batched_kernel<__nv_bfloat16>, n_tiles, block, 0, st, entries, n_entries, tile_first);
+  count_launch();
+  return check_launch("pack_conv_weights_range");
 }
 
 extern "C" int b200dm_pack_upconv_weight(const float* w, void* out, int32_t Cout, int32_t Cin, void* stream) {
@@ -210,14 +266,21 @@ extern "C" int b200dm_pack_upconv_weight(const float* w, void* out, int32_t Cout
 extern "C" int b200dm_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                                 float beta1, float beta2, float eps, float weight_decay, int32_t step,
                                 float grad_scale, void* stream) {
-  B200DM_REQUIRE(n > 0 && step >= 1, B200DM_ERR_SHAPE, "adam_step: n=%lld step=%d", (long long)n, step);
+  return b200dm_adam_step_bg(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, 16, stream);
+}
+
+extern "C" int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                                   float grad_scale, int32_t ctas_per_sm, void* stream) {
+  B200DM_REQUIRE(n > 0 && step >= 1 && ctas_per_sm >= 1, B200DM_ERR_SHAPE, "adam_step: n=%lld step=%d", (long long)n, step);
   double bc1 = 1.0 - pow((double)beta1, (double)step);
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   float step_size = (float)((double)lr / bc1);
   float bc2_sqrt = (float)sqrt(bc2);
-  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;
+  const int vec = (n % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  int64_t blocks = ((vec ? n / 4 : n) + 255) / 256, cap = (int64_t)num_sms() * ctas_per_sm;
   launch_k(adam_kernel, (unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream, 
-      p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
+      p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale, vec);
   count_launch();
   return check_launch("adam_step");
 }
