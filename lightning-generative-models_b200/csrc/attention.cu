@@ -1626,6 +1626,212 @@ attn_fwd_tc_kernel(const lbf* __restrict__ qkv, int ld, const float* __restrict_
   }
 }
 
+// ---- bf16 backward on tensor cores.  Per (b, head): every warp recomputes P for its 16 query rows as in the forward,
+//      then dP = dO V^T, dS = P .* (dP - rowsum(P .* dP)) in registers and dQ = scale dS K from the re-packed
+//      fragments; P and dS (bf16) are parked in shared memory and the two products that reduce over the query rows,
+//      dV = P^T dO and dK = scale dS^T Q, are computed as A^T B (ldmatrix.trans), warp w owning output columns 8w..
+constexpr int FA_LPK = FA_KVP + 8;          // row pitch of the parked P / dS tiles: 176 B, conflict-free ldmatrix
+struct FaBwdTcSmem {
+  lbf Q[FA_MAXN][LP];
+  lbf K[FA_KVP][LP];
+  lbf V[FA_KVP][LP];
+  lbf dO[FA_MAXN][LP];
+  lbf P[FA_MAXN][FA_LPK];
+  lbf dS[FA_MAXN][FA_LPK];
+};
+
+__global__ void __launch_bounds__(128)
+attn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __restrict__ qkv, int ld,
+                   const float* __restrict__ mem_kv, lbf* __restrict__ dqkv, int dld,
+                   float* __restrict__ dmem_kv, int n) {
+  pdl_prologue();
+  __shared__ __align__(16) FaBwdTcSmem s;
+  const int b = blockIdx.x / HEADS, h = blockIdx.x % HEADS, kv = n + NMEM;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const lbf* base = qkv + (int64_t)b * n * ld + h * DH;
+  const lbf* gbase = dout + (int64_t)b * n * dout_ld + h * DH;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < FA_MAXN * 4; i += 128) {
+    const int r = i >> 2, part = i & 3;
+    uint4 q = zero, k = zero, v = zero, g = zero;
+    if (r < n) {
+      const lbf* p = base + (int64_t)r * ld + part * 8;
+      q = *reinterpret_cast<const uint4*>(p);
+      k = *reinterpret_cast<const uint4*>(p + HID);
+      v = *reinterpret_cast<const uint4*>(p + 2 * HID);
+      g = *reinterpret_cast<const uint4*>(gbase + (int64_t)r * dout_ld + part * 8);
+    }
+    *reinterpret_cast<uint4*>(&s.Q[r][part * 8]) = q;
+    *reinterpret_cast<uint4*>(&s.K[r + NMEM][part * 8]) = k;
+    *reinterpret_cast<uint4*>(&s.V[r + NMEM][part * 8]) = v;
+    *reinterpret_cast<uint4*>(&s.dO[r][part * 8]) = g;
+  }
+  for (int i = tid; i < (FA_KVP - FA_MAXN - NMEM) * 4; i += 128) {
+    const int r = FA_MAXN + NMEM + (i >> 2), part = i & 3;
+    *reinterpret_cast<uint4*>(&s.K[r][part * 8]) = zero;
+    *reinterpret_cast<uint4*>(&s.V[r][part * 8]) = zero;
+  }
+  for (int i = tid; i < NMEM * DH; i += 128) {
+    const int r = i >> 5, d = i & 31;
+    s.K[r][d] = __float2bfloat16_rn(mem_kv[((0 * HEADS + h) * NMEM + r) * DH + d]);
+    s.V[r][d] = __float2bfloat16_rn(mem_kv[((1 * HEADS + h) * NMEM + r) * DH + d]);
+  }
+  __syncthreads();
+  const int mi = lane >> 3, r8 = lane & 7;
+  const int qrow = lane >> 2, qcol = 2 * (lane & 3);
+  constexpr int NT = FA_KVP / 8;
+  // ---- S = Q K^T, P = softmax(scale S) for this warp's 16 query rows (registers)
+  float pr[NT][4] = {};
+  uint32_t qa[2][4], ga[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    ldsm_x4(qa[ks], (uint32_t)__cvta_generic_to_shared(&s.Q[warp * 16 + (mi & 1) * 8 + r8][ks * 16 + (mi >> 1) * 8]));
+    ldsm_x4(ga[ks], (uint32_t)__cvta_generic_to_shared(&s.dO[warp * 16 + (mi & 1) * 8 + r8][ks * 16 + (mi >> 1) * 8]));
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      uint32_t bb[2];
+      ldsm_x2(bb, (uint32_t)__cvta_generic_to_shared(&s.K[nt * 8 + r8][ks * 16 + (mi & 1) * 8]));
+      mma_bf16_16816(pr[nt], qa[ks], bb);
+    }
+  }
+  {
+    const float sc = kScale * kLog2e;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pr[nt][j] = (nt * 8 + qcol + (j & 1)) < kv ? pr[nt][j] * sc : -INFINITY;
+      m0 = fmaxf(m0, fmaxf(pr[nt][0], pr[nt][1]));
+      m1 = fmaxf(m1, fmaxf(pr[nt][2], pr[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      pr[nt][0] = ex2_ftz(pr[nt][0] - m0);
+      pr[nt][1] = ex2_ftz(pr[nt][1] - m0);
+      pr[nt][2] = ex2_ftz(pr[nt][2] - m1);
+      pr[nt][3] = ex2_ftz(pr[nt][3] - m1);
+      l0 += pr[nt][0] + pr[nt][1];
+      l1 += pr[nt][2] + pr[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = rcp_ftz(l0), i1 = rcp_ftz(l1);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      pr[nt][0] *= i0;
+      pr[nt][1] *= i0;
+      pr[nt][2] *= i1;
+      pr[nt][3] *= i1;
+    }
+  }
+  // ---- dP = dO V^T; dS = P .* (dP - rowsum(P .* dP))
+  float dp[NT][4] = {};
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      uint32_t bb[2];
+      ldsm_x2(bb, (uint32_t)__cvta_generic_to_shared(&s.V[nt * 8 + r8][ks * 16 + (mi & 1) * 8]));
+      mma_bf16_16816(dp[nt], ga[ks], bb);
+    }
+  }
+  float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    t0 = fmaf(pr[nt][0], dp[nt][0], fmaf(pr[nt][1], dp[nt][1], t0));
+    t1 = fmaf(pr[nt][2], dp[nt][2], fmaf(pr[nt][3], dp[nt][3], t1));
+  }
+  t0 += __shfl_xor_sync(0xffffffffu, t0, 1);
+  t0 += __shfl_xor_sync(0xffffffffu, t0, 2);
+  t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+  t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+  uint32_t dsa[NT / 2][4];                               // dS as A fragments of dS K
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const float d0 = pr[nt][0] * (dp[nt][0] - t0), d1 = pr[nt][1] * (dp[nt][1] - t0);
+    const float d2 = pr[nt][2] * (dp[nt][2] - t1), d3 = pr[nt][3] * (dp[nt][3] - t1);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(d0, d1), hi = __floats2bfloat162_rn(d2, d3);
+    dsa[nt >> 1][(nt & 1) * 2] = *reinterpret_cast<uint32_t*>(&lo);
+    dsa[nt >> 1][(nt & 1) * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    // park P and dS (bf16) for the products over the query rows
+    *reinterpret_cast<__nv_bfloat162*>(&s.dS[warp * 16 + qrow][nt * 8 + qcol]) = lo;
+    *reinterpret_cast<__nv_bfloat162*>(&s.dS[warp * 16 + qrow + 8][nt * 8 + qcol]) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(&s.P[warp * 16 + qrow][nt * 8 + qcol]) = __floats2bfloat162_rn(pr[nt][0], pr[nt][1]);
+    *reinterpret_cast<__nv_bfloat162*>(&s.P[warp * 16 + qrow + 8][nt * 8 + qcol]) = __floats2bfloat162_rn(pr[nt][2], pr[nt][3]);
+  }
+  // ---- dQ = scale * dS K
+  {
+    float dq[4][4] = {};
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bb[2];
+        ldsm_x2_t(bb, (uint32_t)__cvta_generic_to_shared(&s.K[j * 16 + (mi & 1) * 8 + r8][nt * 8]));
+        mma_bf16_16816(dq[nt], dsa[j], bb);
+      }
+    }
+    const int row0 = warp * 16 + qrow;
+    lbf* o = dqkv + ((int64_t)b * n + row0) * dld + h * DH + qcol;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (row0 < n)
+        *reinterpret_cast<__nv_bfloat162*>(o + nt * 8) = __floats2bfloat162_rn(dq[nt][0] * kScale, dq[nt][1] * kScale);
+      if (row0 + 8 < n)
+        *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)8 * dld + nt * 8) =
+            __floats2bfloat162_rn(dq[nt][2] * kScale, dq[nt][3] * kScale);
+    }
+  }
+  __syncthreads();
+  // ---- dV = P^T dO, dK = scale * dS^T Q: [80 x 32] each, K = 64 query rows; warp w owns columns 8w .. 8w+7
+  {
+    float dv[FA_KVP / 16][4] = {}, dk[FA_KVP / 16][4] = {};
+#pragma unroll
+    for (int ks = 0; ks < FA_MAXN / 16; ++ks) {
+      uint32_t bg[2], bq[2];
+      ldsm_x2_t(bg, (uint32_t)__cvta_generic_to_shared(&s.dO[ks * 16 + (mi & 1) * 8 + r8][warp * 8]));
+      ldsm_x2_t(bq, (uint32_t)__cvta_generic_to_shared(&s.Q[ks * 16 + (mi & 1) * 8 + r8][warp * 8]));
+#pragma unroll
+      for (int mt = 0; mt < FA_KVP / 16; ++mt) {
+        uint32_t a[4];
+        ldsm_x4_t(a, (uint32_t)__cvta_generic_to_shared(&s.P[ks * 16 + (mi >> 1) * 8 + r8][mt * 16 + (mi & 1) * 8]));
+        mma_bf16_16816(dv[mt], a, bg);
+        ldsm_x4_t(a, (uint32_t)__cvta_generic_to_shared(&s.dS[ks * 16 + (mi >> 1) * 8 + r8][mt * 16 + (mi & 1) * 8]));
+        mma_bf16_16816(dk[mt], a, bq);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < FA_KVP / 16; ++mt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = mt * 16 + qrow + half * 8;            // key/value row
+        const int d = warp * 8 + qcol;
+        const float k0 = dk[mt][half * 2] * kScale, k1 = dk[mt][half * 2 + 1] * kScale;
+        const float v0 = dv[mt][half * 2], v1 = dv[mt][half * 2 + 1];
+        if (c < NMEM) {
+          float* mk = dmem_kv + ((0 * HEADS + h) * NMEM + c) * DH + d;
+          float* mv = dmem_kv + ((1 * HEADS + h) * NMEM + c) * DH + d;
+          atomicAdd(mk, k0);
+          atomicAdd(mk + 1, k1);
+          atomicAdd(mv, v0);
+          atomicAdd(mv + 1, v1);
+        } else if (c < kv) {
+          lbf* p = dqkv + ((int64_t)b * n + (c - NMEM)) * dld + h * DH + d;
+          *reinterpret_cast<__nv_bfloat162*>(p + HID) = __floats2bfloat162_rn(k0, k1);
+          *reinterpret_cast<__nv_bfloat162*>(p + 2 * HID) = __floats2bfloat162_rn(v0, v1);
+        }
+      }
+    }
+  }
+}
+
 struct FaBwdSmem {
   FaSmem f;
   float dO[FA_MAXN][DH + 1];
@@ -1792,6 +1998,10 @@ extern "C" int b200dm_attn_bwd(int32_t dtype, const void* dout, int32_t dout_ld,
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_bwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)dout, dout_ld, (const float*)qkv, qkv_ld, mem_kv, (float*)dqkv, dqkv_ld, dmem_kv, n);
+  } else if (qkv_ld % 8 == 0 && dout_ld % 8 == 0 && dqkv_ld % 2 == 0 && ((uintptr_t)qkv & 15) == 0 &&
+             ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 3) == 0 && getenv("B200DM_ATTN_SIMT") == nullptr) {
+    launch_k(attn_bwd_tc_kernel, B * HEADS, 128, 0, st, (const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, mem_kv,
+             (bf16*)dqkv, dqkv_ld, dmem_kv, n);
   } else {
     cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_bwd_kernel<bf16>, B * HEADS, 256, smem, st, (const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)dqkv, dqkv_ld, dmem_kv, n);

@@ -140,7 +140,7 @@ __global__ void pack_upconv_kernel(const float* __restrict__ w, __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, int64_t n, float step_size, float beta1, float beta2, float eps,
-            float weight_decay, float bc2_sqrt, float grad_scale, int vec) {
+            float weight_decay, float bc2_sqrt, float grad_scale) {
   pdl_prologue();
   auto upd = [&](float& pi, float gi, float& mi, float& vi) {
     gi *= grad_scale;
@@ -151,45 +151,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     pi = pi - step_size * (mi / denom);           // param.addcdiv_(exp_avg, denom, value=-step_size)
   };
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-  if (vec) {
-    // 16-byte accesses with the streaming (evict-first) cache policy: the four arenas are touched once per step, and
-    // when the update runs behind backward it must not push backward's working set out of L2
-    float4* p4 = reinterpret_cast<float4*>(p);
-    const float4* g4 = reinterpret_cast<const float4*>(g);
-    float4* m4 = reinterpret_cast<float4*>(m);
-    float4* v4 = reinterpret_cast<float4*>(v);
-    const int64_t n4 = n >> 2;
-    for (int64_t i = tid; i < n4; i += 2 * nthr) {       // two vectors per arena in flight per thread
-      const int64_t j = i + nthr;
-      const bool two = j < n4;
-      float4 pp = __ldcs(p4 + i), mm = __ldcs(m4 + i), vv = __ldcs(v4 + i);
-      const float4 gg = __ldcs(g4 + i);
-      float4 pq = pp, mq = mm, vq = vv, gq = gg;
-      if (two) {
-        pq = __ldcs(p4 + j);
-        mq = __ldcs(m4 + j);
-        vq = __ldcs(v4 + j);
-        gq = __ldcs(g4 + j);
-      }
-      upd(pp.x, gg.x, mm.x, vv.x);
-      upd(pp.y, gg.y, mm.y, vv.y);
-      upd(pp.z, gg.z, mm.z, vv.z);
-      upd(pp.w, gg.w, mm.w, vv.w);
-      __stcs(p4 + i, pp);
-      __stcs(m4 + i, mm);
-      __stcs(v4 + i, vv);
-      if (two) {
-        upd(pq.x, gq.x, mq.x, vq.x);
-        upd(pq.y, gq.y, mq.y, vq.y);
-        upd(pq.z, gq.z, mq.z, vq.z);
-        upd(pq.w, gq.w, mq.w, vq.w);
-        __stcs(p4 + j, pq);
-        __stcs(m4 + j, mq);
-        __stcs(v4 + j, vq);
-      }
-    }
-    return;
-  }
+  // one element per thread and iteration: measured 5.05 TB/s on the flat arenas; a float4 / streaming-policy version
+  // was slower (4.4 TB/s)
   for (int64_t i = tid; i < n; i += nthr) {
     float pi = p[i], mi = m[i], vi = v[i];
     upd(pi, g[i], mi, vi);
@@ -277,10 +240,9 @@ extern "C" int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v,
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   float step_size = (float)((double)lr / bc1);
   float bc2_sqrt = (float)sqrt(bc2);
-  const int vec = (n % 4 == 0) && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
-  int64_t blocks = ((vec ? n / 4 : n) + 255) / 256, cap = (int64_t)num_sms() * ctas_per_sm;
+  int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * ctas_per_sm;
   launch_k(adam_kernel, (unsigned)(blocks > cap ? cap : blocks), 256, 0, (cudaStream_t)stream, 
-      p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale, vec);
+      p, g, m, v, n, step_size, beta1, beta2, eps, weight_decay, bc2_sqrt, grad_scale);
   count_launch();
   return check_launch("adam_step");
 }

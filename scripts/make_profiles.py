@@ -67,7 +67,8 @@ lines = [f"# Round-1 profiles (evidence run `{tag}`, scripts/gpu_baseline.sh)\n"
 traffic = {}
 for name, title in (("conv", "tcgen05 forward / data-gradient convs (first 12 launches of a training step)"),
                     ("wgrad", "weight-gradient kernels (first 8 launches of the backward pass)"),
-                    ("hbmk", "HBM-bound kernels (first 14 launches)")):
+                    ("hbmk", "HBM-bound kernels (first 14 launches)"),
+                    ("hbmk_ddim", "HBM-bound kernels at the DDIM shape (B=256, 64x64; first level of an evaluation)")):
     recs, labels = raw_table(name)
     if not recs:
         continue
@@ -76,6 +77,8 @@ for name, title in (("conv", "tcgen05 forward / data-gradient convs (first 12 la
     lines.append("|---|---|" + "---|" * len(labels))
     for r in recs:
         lines.append(f"| `{r['kernel']}` | {r['grid']} | " + " | ".join(str(r.get(l, "")) for l in labels) + " |")
+        if name == "hbmk_ddim":
+            continue                                # the roofline traffic JSON describes the training step
         k = r["kernel"].split("<")[0]
         t = traffic.setdefault(k, {"launches": 0, "dram_MB": 0.0, "us": 0.0})
         t["launches"] += 1
@@ -99,11 +102,15 @@ for f, note in ((f"{tag}_bench_train.log", "bench.py (train, N=1)"), (f"{tag}_be
                 (f"{tag}_bench_reference.log", "bench.py --impl reference"), (f"{tag}_hbm.log", "scripts/hbm_microbench.py"),
                 (f"{tag}_umma_rate.log", "scripts/umma_rate.py"), (f"{tag}_conv_micro.log", "scripts/conv_microbench.py"),
                 (f"{tag}_kernels.json", "bench.py --profile-out (per-launch CUDA-event times, training step)"),
-                (f"{tag}_kernels_ddim.json", "bench.py --profile-out (DDIM evaluation)")):
+                (f"{tag}_kernels_ddim.json", "bench.py --profile-out (DDIM evaluation)"),
+                (f"{tag}_bench_ddpm.log", "bench.py --workload ddpm (configs[3]: 1000-step ancestral sampling, batch 1024)"),
+                (f"{tag}_bench_train64.log", "bench.py --workload train64 (configs[4] per GPU: 3x64x64, 64 images)"),
+                (f"{tag}_kernels_train64.json", "bench.py --profile-out (training step at 3x64x64)"),
+                (f"{tag}_opt_cost.log", "scripts/opt_cost.py (optimiser tail inside the loop)")):
     if os.path.isfile(os.path.join(SRC, f)):
         shutil.copy(os.path.join(SRC, f), os.path.join(DST, f.replace(tag, out)))
         lines.append(f"* `{f.replace(tag, out)}` — {note}")
-for name in ("conv", "wgrad", "hbmk"):
+for name in ("conv", "wgrad", "hbmk", "hbmk_ddim"):
     f = os.path.join(SRC, f"{tag}_{name}_raw.csv")
     if os.path.isfile(f):
         shutil.copy(f, os.path.join(DST, f"{out}_{name}_ncu_raw.csv"))

@@ -637,7 +637,7 @@ def test_linear_attention_fwd_bwd(dtype, B, S):
 
 
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
-@pytest.mark.parametrize("B,S", [(3, 4), (2, 8)])
+@pytest.mark.parametrize("B,S", [(3, 4), (2, 8), (2, 5), (1, 7)])
 def test_full_attention_fwd_bwd(dtype, B, S):
     n = S * S
     qkv = q(rnd(B, 384, S, S, seed=111), dtype).requires_grad_(True)
@@ -659,7 +659,7 @@ def test_full_attention_fwd_bwd(dtype, B, S):
     L.call("b200dm_attn_bwd", dtype, dov.ptr, dov.ld, qv.ptr, qv.ld, mem.data_ptr(), dqv.ptr, dqv.ld,
            dmem.data_ptr(), B, n)
     assert rel(dqv.to_nchw(), qkv.grad) < (1e-4 if dtype == L.F32 else 6e-3)
-    assert rel(dmem, mem.grad) < 1e-4
+    assert rel(dmem, mem.grad) < (1e-4 if dtype == L.F32 else 5e-3)     # bf16: P and dS are bf16 MMA operands
     with pytest.raises(L.B200dmError):       # 16x16 softmax attention never occurs
         L.call("b200dm_attn_fwd", dtype, qv.ptr, qv.ld, mem.data_ptr(), ov.ptr, ov.ld, B, 256)
 
