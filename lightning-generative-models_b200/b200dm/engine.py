@@ -106,9 +106,9 @@ class WeightPack:
         self.version = v
 
 
-    def refresh_range(self, begin: int, end: int):
-        """Re-pack the convs whose master weights live in arena elements [begin, end) on the current stream (one
-        launch per contiguous run of table entries; the stem rides with the range that holds it)."""
+    def range_runs(self, begin: int, end: int):
+        """Contiguous runs of table entries (first, n, tile_first, tiles) whose master weights live in arena elements
+        [begin, end), and whether the stem weight does."""
         runs = self._range_cache.get((begin, end))
         if runs is None:
             idx = [i for i, (off, _, _) in enumerate(self._entry_info) if begin <= off < end]
@@ -124,10 +124,16 @@ class WeightPack:
             stem_off = self.arena.offset["init_conv.weight"]
             runs = (runs, self.stem is not None and begin <= stem_off < end)
             self._range_cache[(begin, end)] = runs
-        for first, n, tile_first, tiles in runs[0]:
+        return runs
+
+    def refresh_range(self, begin: int, end: int):
+        """Re-pack the convs whose master weights live in arena elements [begin, end) on the current stream (one
+        launch per contiguous run of table entries; the stem rides with the range that holds it)."""
+        runs, has_stem = self.range_runs(begin, end)
+        for first, n, tile_first, tiles in runs:
             L.call("b200dm_pack_conv_weights_range", self.dt, self.table.data_ptr() + first * self._entry_size, n,
                    tile_first, tiles)
-        if runs[1]:
+        if has_stem:
             L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
                    self.arena.dim, self.stem_k, self.stem_kp)
 

@@ -69,6 +69,26 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_weight_pack_ranges_follow_the_gradient_buckets():
+    """The optimiser-in-backward path re-packs one bucket's conv weights at a time: the per-bucket runs of pack-table
+    entries must cover every conv exactly once, own all tiles of the batched pack, and carry the stem once."""
+    from b200dm import _lib as L
+    from b200dm.engine import WeightPack
+    a = ParamArena(64, 3, "cpu")
+    pack = WeightPack(a, L.BF16, with_dgrad=True)
+    seen, tiles, stems = [], 0, 0
+    for b, e in buckets(a):
+        runs, has_stem = pack.range_runs(b, e)
+        stems += int(has_stem)
+        for first, n, tile_first, nt in runs:
+            assert tile_first == pack._entry_info[first][1]
+            seen.extend(range(first, first + n))
+            tiles += nt
+    assert sorted(seen) == list(range(pack.n_entries)) and tiles == pack.total_tiles and stems == 1
+    # buckets are contiguous arena ranges in table order: a handful of launches per step, not one per conv
+    assert sum(len(pack.range_runs(b, e)[0]) for b, e in buckets(a)) <= 8
+
+
 def test_gloo_world2_bucketed_allreduce_and_broadcast():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
