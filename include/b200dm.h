@@ -106,7 +106,7 @@ int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream);
  *   mode 2: transpose of mode 1 (its data gradient): input [B,H,W,Cin], output [B,2H,2W,Cout],
  *           weight taps (p1,p2) of shape [Cout][Cin]
  *   mode 3: nn.Upsample(scale_factor=2, mode="nearest") followed by the 3x3 conv (ddpm.py:93-97) as ONE launch
- *           (tcgen05 path only, inference): input [B,H,W,Cin] at the LOW resolution, output [B,2H,2W,Cout].
+ *           (tcgen05 path only): input [B,H,W,Cin] at the LOW resolution, output [B,2H,2W,Cout].
  *           Output phase (a,b) = (oy&1, ox&1) is a 2x2 conv over the source image (rows y+r+a-1, columns
  *           x+c+b-1 for tap (r,c)) whose weights are sums of the 3x3 taps that land on the same source pixel:
  *           16 instead of 36 multiply-adds per output.  Packed weights: [4 taps (r,c)][4 phases (a,b)][Cout][Cin]

@@ -217,7 +217,7 @@ class GaussianDiffusion(nn.Module):
         """The sampler state lives in the Unet plan's static input buffer: no per-step copies."""
         unet = self.model
         plan = unet._plan(shape[0], shape[-1], training=False)
-        unet._pack.refresh(inference=True)
+        unet._pack.refresh()
         if init is None:
             if self.rng == "torch":
                 plan.x_in.copy_(torch.randn(shape, device=self.device))
@@ -297,7 +297,7 @@ class GaussianDiffusion(nn.Module):
         shape = (b, self.channels, self.img_size, self.img_size)
         unet = self.model
         plan = unet._plan(b, self.img_size, training=False)
-        unet._pack.refresh(inference=True)
+        unet._pack.refresh()
         n = plan.x_in.numel()
         off = rank * n
         L.call("b200dm_randn", plan.x_in.data_ptr(), n, seed, 1, off)

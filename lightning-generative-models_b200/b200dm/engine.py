@@ -88,10 +88,10 @@ class WeightPack:
             self._entry_info.append((arena.offset[nm + ".weight"], e.tile_begin, ci.taps * e.tiles_ci * e.tiles_co))
         self._range_cache = {}
 
-    def refresh(self, force: bool = False, inference: bool = False):
+    def refresh(self, force: bool = False):
         """Re-pack when the master arena changed (in-place updates bump the tensor version)."""
         v = self.arena.version
-        if inference and self.up and (force or v != self.up_version):
+        if self.up and (force or v != self.up_version):
             for nm, buf in self.up.items():
                 ci = self.arena.convs[nm]
                 L.call("b200dm_pack_upconv_weight", self.arena.ptr(nm + ".weight"), buf.data_ptr(), ci.cout, ci.cin)
@@ -136,6 +136,10 @@ class WeightPack:
         if has_stem:
             L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
                    self.arena.dim, self.stem_k, self.stem_kp)
+        for nm, buf in self.up.items():
+            if begin <= self.arena.offset[nm + ".weight"] < end:
+                ci = self.arena.convs[nm]
+                L.call("b200dm_pack_upconv_weight", self.arena.ptr(nm + ".weight"), buf.data_ptr(), ci.cout, ci.cin)
 
 
 class Plan:
@@ -401,15 +405,25 @@ class Plan:
     def upsample_conv(self, nm, x: View, out: View, gx, gout):
         self.begin_unit()
         ci = self.arena.convs[nm]
-        if not self.training and nm in self.pack.up and self._impl(ci.cin, ci.cout) == 1 and self.fuse_upsample:
-            # inference: nearest-2x upsample + 3x3 conv as ONE launch over the low-resolution tensor (conv mode 3:
-            # four 2x2 convs, one per output phase; 16 instead of 36 multiply-adds per output, no upsampled copy)
+        if nm in self.pack.up and self._impl(ci.cin, ci.cout) == 1 and self.fuse_upsample:
+            # nearest-2x upsample + 3x3 conv as ONE launch over the low-resolution tensor (conv mode 3: four 2x2
+            # convs, one per output phase; 16 instead of 36 multiply-adds per output, no upsampled copy on the chain)
             d = L.ConvDesc(dtype=self.dt, mode=3, ksize=3, impl=1, B=self.B, H=x.H, W=x.H, Cin=ci.cin, Cout=ci.cout,
                            x=x.ptr, x_ld=x.ld, w=self.pack.up[nm].data_ptr(), bias=self.arena.ptr(nm + ".bias"),
                            y=out.ptr, y_ld=out.ld, res=None, res_ld=0, accumulate=0, gn_part=None, gn_groups=0)
             self.F("b200dm_conv_fwd", C.byref(d), kname="conv_tc_fwd",
                    flops=2.0 * self.B * x.H * x.H * ci.cout * ci.cin * 16, writes=(out,))
             self._keep.append(d)
+            if self.training:
+                # backward is the reference's: the weight gradient wants the upsampled tensor as its operand, so it is
+                # materialised there, on the side stream next to the weight-gradient kernel that reads it
+                xu = self.buf(2 * x.H, x.C)
+                self.Bk("b200dm_upsample2x_fwd", self.dt, x.ptr, x.ld, xu.ptr, xu.ld, self.B, x.H, x.H, x.C,
+                        side=True, reads=(x,), writes=(xu,))
+                gxu = self.scratch("gxu", 2 * x.H, x.C)
+                self.conv_bwd(nm, xu, gout, gxu)
+                self.Bk("b200dm_upsample2x_bwd", self.dt, gxu.ptr, gxu.ld, gx.ptr, gx.ld, self.B, x.H, x.H, x.C,
+                        writes=(gx,))
             return
         xu = self.buf(2 * x.H, x.C)
         self.F("b200dm_upsample2x_fwd", self.dt, x.ptr, x.ld, xu.ptr, xu.ld, self.B, x.H, x.H, x.C)

@@ -75,7 +75,7 @@ class FusedAdam(torch.optim.Optimizer):
             torch.cuda.current_stream().wait_stream(self._stream)
             unet.arena.touch()
             if unet._pack is not None:
-                unet._pack.version = unet.arena.version
+                unet._pack.version = unet._pack.up_version = unet.arena.version
         else:
             if self._done:             # partially applied (should not happen): finish the remaining buckets
                 torch.cuda.current_stream().wait_stream(self._stream)

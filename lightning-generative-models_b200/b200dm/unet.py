@@ -200,7 +200,7 @@ class Unet(nn.Module):
         return plan
 
     def _run(self, plan: Plan, x, time) -> torch.Tensor:
-        self._pack.refresh(inference=not plan.training)
+        self._pack.refresh()
         plan.x_in.copy_(x)
         plan.t_in.copy_(time)
         self.run_plan_forward(plan)

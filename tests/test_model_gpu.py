@@ -322,9 +322,11 @@ def test_optimizer_overlapped_with_backward():
     assert (unet.arena.flat - ref_p.detach()).abs().max().item() < 1e-6
     pack = unet._pack
     assert pack.version == unet.arena.version          # the next forward will not re-pack
-    got = [pack.fbuf.clone(), pack.tbuf.clone(), pack.stem.clone()]
+    got = [pack.fbuf.clone(), pack.tbuf.clone(), pack.stem.clone()] + [pack.up[k].clone() for k in sorted(pack.up)]
+    assert len(pack.up) == 3 and pack.up_version == unet.arena.version
     pack.refresh(force=True)
-    assert torch.equal(got[0], pack.fbuf) and torch.equal(got[1], pack.tbuf) and torch.equal(got[2], pack.stem)
+    now = [pack.fbuf, pack.tbuf, pack.stem] + [pack.up[k] for k in sorted(pack.up)]
+    assert all(torch.equal(a, b) for a, b in zip(got, now))
 
 
 def test_reference_configs_load_through_loader_convention():
