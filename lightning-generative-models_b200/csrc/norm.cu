@@ -346,7 +346,8 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   const int rank = part ? (int)blockIdx.x : (int)cluster.block_rank();
   const int b = blockIdx.y;
   const int C8 = C >> 3, gs8 = C8 / G;                 // 8-wide vectors per group
-  const int lanes = GNC_THREADS / C8;
+  const int NT = (int)blockDim.x;                      // 256, or 128 in the pre-statistics mode (finer grid)
+  const int lanes = NT / C8;
   const int cv = threadIdx.x % C8, lane = threadIdx.x / C8;
   const int c0 = cv * 8, g = cv / gs8;
   const int ppb = (HW + CL - 1) / CL;
@@ -365,7 +366,7 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   if (part) {
     // partials: [sample][slot][C/8 chunks][2].  thread = (slot lane, (group, which)): add the sample's slots and the
     // chunks of the group, then the slot lanes through shared memory
-    const int gk = threadIdx.x % (2 * G), sl = threadIdx.x / (2 * G), SL = GNC_THREADS / (2 * G);
+    const int gk = threadIdx.x % (2 * G), sl = threadIdx.x / (2 * G), SL = NT / (2 * G);
     const int gq = gk >> 1, which = gk & 1, cpg = C8 / G;   // chunks per group
     float a = 0.f;
     const float* pp = part + (int64_t)b * slots * 2 * C8 + (gq * cpg) * 2 + which;
@@ -491,13 +492,6 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
   }
   if (!part) cluster.sync();        // peers may still be reading this CTA's gpart
 }
-
-#ifndef GN_BWD_MINB
-#define GN_BWD_MINB 2      // resident CTAs per SM the backward kernel is compiled for (register budget 128)
-#endif
-#ifndef GN_BWD_UB
-#define GN_BWD_UB 4        // pixels in flight per thread: the kernel is latency-bound, one wave, ~2 CTAs per SM
-#endif
 
 // UB pixels per thread and iteration; PIPE: the next UB are requested before the current UB are processed
 // (software pipeline, twice the raw registers); MINB: resident CTAs per SM the register budget is set for
@@ -1041,19 +1035,22 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
                  "gn_fwd_pre: C=%d G=%d not supported", C, G);
   cudaStream_t st = (cudaStream_t)stream;
   // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
-  const int lanes = GNC_THREADS / (C / 8);
+  // CTA size: B200DM_GNF_THREADS=128 gives a finer grid (8 CTAs per SM) that fills the machine more evenly
+  static const int nthr = [] { const char* e = getenv("B200DM_GNF_THREADS"); return e && atoi(e) == 128 ? 128 : GNC_THREADS; }();
+  const int threads = (nthr % (C / 8) == 0 && nthr % (2 * G) == 0) ? nthr : GNC_THREADS;
+  const int lanes = threads / (C / 8);
   static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 0; }();
-  int chunks = (int)(((long long)num_sms() * (mult ? mult : 4)) / B);
+  int chunks = (int)(((long long)num_sms() * (mult ? mult : (threads == 128 ? 8 : 4))) / B);
   if (chunks > 32) chunks = 32;
   while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
   if (dtype == B200DM_F32)
-    launch_k(gn_fwd_cluster_kernel<float, false>, grid, GNC_THREADS, 0, st, (const float*)x, (int)x_ld, stats, gamma,
+    launch_k(gn_fwd_cluster_kernel<float, false>, grid, threads, 0, st, (const float*)x, (int)x_ld, stats, gamma,
              beta, film, (int)film_ld, (const float*)res, (int)res_ld, (float*)y, (int)y_ld, (int)HW, (int)C, (int)G,
              eps, 1, part, (int)slots);
   else
-    launch_k(gn_fwd_cluster_kernel<bf16, false>, grid, GNC_THREADS, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
+    launch_k(gn_fwd_cluster_kernel<bf16, false>, grid, threads, 0, st, (const bf16*)x, (int)x_ld, stats, gamma,
              beta, film, (int)film_ld, (const bf16*)res, (int)res_ld, (bf16*)y, (int)y_ld, (int)HW, (int)C, (int)G,
              eps, 1, part, (int)slots);
   count_launch();
@@ -1090,9 +1087,11 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   B200DM_REQUIRE(C <= 2048, B200DM_ERR_UNSUPPORTED, "gn_apply_bwd: C=%d too large", C);
   cudaStream_t st = (cudaStream_t)stream;
   if (gn_cluster_ok(C, G)) {
-    // variant (experiment knob B200DM_GNB_VAR): pixels in flight per thread / software pipeline / CTAs per SM
+    // measured on the training step (B = 128, 32x32, 38 launches): three pixels in flight, pipelined, cluster sized for
+    // two CTAs per SM: 0.69 ms; two pixels / three CTAs per SM (cluster of 3): 0.85; four pixels unpipelined: 0.71;
+    // four pipelined (spills): 0.79; eight unpipelined: 0.76.  B200DM_GNB_VAR=0 selects the two-pixel variant.
     static const int var = [] { const char* v = getenv("B200DM_GNB_VAR"); return v ? atoi(v) : 1; }();
-    const int minb = (dtype == B200DM_F32 || var == 0 || var == 3 || var == 7) ? 3 : 2;
+    const int minb = (dtype == B200DM_F32 || var == 0) ? 3 : 2;
     const int cl = gn_cluster_size(B, HW, C, minb);
     dim3 grid(cl, B);
     cudaError_t e;
@@ -1100,16 +1099,9 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   e = launch_cluster(gn_bwd_cluster_kernel<TT, UB, PIPE, MINB>, grid, cl, 0, st, (const TT*)dy, (int)dy_ld,        \
                      (const TT*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (TT*)dx, (int)dx_ld, dgamma, \
                      dbeta, dfilm, dbias, (int)HW, (int)C, (int)G)
-    // measured on the training step (B = 128, 32x32): three pixels in flight, pipelined, two CTAs per SM (var 1)
-    // 0.69 ms for the 38 launches; var 0 (two pixels, three CTAs per SM) 0.85; var 4 0.71; var 2 0.79; var 5 0.76
     if (dtype == B200DM_F32) GN_BWD_LAUNCH(float, 2, true, 3);
     else if (var == 0) GN_BWD_LAUNCH(bf16, 2, true, 3);
-    else if (var == 2) GN_BWD_LAUNCH(bf16, 4, true, 2);
-    else if (var == 3) GN_BWD_LAUNCH(bf16, 4, false, 3);
-    else if (var == 4) GN_BWD_LAUNCH(bf16, 4, false, 2);
-    else if (var == 5) GN_BWD_LAUNCH(bf16, 8, false, 2);
-    else if (var == 6) GN_BWD_LAUNCH(bf16, 2, true, 2);
-    else GN_BWD_LAUNCH(bf16, 3, true, 2);            // var 1 (default) and var 7 (same kernel, cluster sized for 3 per SM)
+    else GN_BWD_LAUNCH(bf16, 3, true, 2);
 #undef GN_BWD_LAUNCH
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
     count_launch();
