@@ -189,11 +189,71 @@ def cpu_baseline(workload, budget_s=20.0):
             "sample": f"{n} fp32 UNet evaluations at batch {b}, 3x{S}x{S}, extrapolated x{evals} steps per image"}
 
 
+def run_reference_gpu(args):
+    """`--impl reference --ref-device cuda` (informational, not part of the driver's contract): the same oracle —
+    the reference's algorithm as plain PyTorch ops — run eagerly on the GPU (cuDNN / cuBLAS / ATen kernels), fp32 or
+    under torch.autocast(bf16) like the reference's `--precision bf16-mixed`.  This is the kernel-for-kernel bar on the
+    same B200; full batch, K timed steps."""
+    from oracle import ddpm_oracle as O
+    dev = torch.device("cuda", 0)
+    K, W = args.steps, max(args.warmup, 3)
+    amp = args.ref_autocast
+    ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if amp else (lambda: torch.autocast("cuda", enabled=False))
+    g = torch.Generator(device=dev).manual_seed(10)
+    if args.workload in TRAIN_CFG:
+        B, S = TRAIN_CFG[args.workload]
+        sd = {k: v.to(dev).requires_grad_(True) for k, v in O.synth_state_dict(64, 3, seed=10).items()}
+        orc = O.DiffusionOracle(sd, img_size=S, channels=3)
+        orc.buf = {k: v.to(dev) for k, v in orc.buf.items()}
+        opt = torch.optim.Adam(list(sd.values()), lr=2e-5, betas=(0.9, 0.99))
+        x = torch.rand(B, 3, S, S, generator=g, device=dev)
+
+        def step():
+            t = torch.randint(0, 1000, (B,), generator=g, device=dev)
+            noise = torch.randn(B, 3, S, S, generator=g, device=dev)
+            opt.zero_grad()
+            with ctx():
+                loss = orc.forward(x, t, noise)
+            loss.backward()
+            opt.step()
+        imgs_per_step, what = B, f"DDPM train step 3x{S}x{S} batch {B}"
+    else:
+        B, S, evals = SAMPLE_CFG[args.workload]
+        sd = {k: v.to(dev) for k, v in O.synth_state_dict(64, 3, seed=10).items()}
+        x = torch.randn(B, 3, S, S, generator=g, device=dev)
+        t = torch.full((B,), 500, dtype=torch.long, device=dev)
+
+        def step():
+            with torch.no_grad(), ctx():
+                O.unet_forward(sd, x, t)
+        imgs_per_step, what = B / evals, f"UNet evaluation 3x{S}x{S} batch {B}; img/s = evals/s x batch / {evals}"
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    value = imgs_per_step / (ms / 1e3)
+    kind = "eager PyTorch on the same GPU, " + ("torch.autocast(bf16)" if amp else "fp32 (TF32 off)")
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": value, "unit": "img/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16-autocast" if amp else "f32", "data": "synthetic",
+            "config": {"workload": what, "device": torch.cuda.get_device_name(0), "kind": kind},
+            "cpu_baseline": None, "e2e": None}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own CPU path (oracle port), bounded per-step sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_gpu(args)
     K, W = args.steps, args.warmup
     if args.workload in TRAIN_CFG:
         TRAIN_B, TRAIN_S = TRAIN_CFG[args.workload]
@@ -285,6 +345,9 @@ def main():
     ap.add_argument("--workload", choices=["train", "ddim", "ddpm", "train64"], default="train")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", choices=["cpu", "cuda"], default="cpu",
+                    help="with --impl reference: cuda = the oracle as eager PyTorch on the GPU (informational)")
+    ap.add_argument("--ref-autocast", action="store_true", help="with --ref-device cuda: torch.autocast(bf16)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel time table (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":
