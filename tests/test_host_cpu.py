@@ -1,6 +1,7 @@
 """CPU tests of the host side: C-ABI library loads and exports every declared symbol, schedules match
 the oracle bit-for-bit, the ctypes structs match the C layout."""
 import ctypes
+import json
 import os
 import re
 
@@ -43,3 +44,48 @@ def test_schedules_bit_equal_to_oracle():
     assert all(torch.equal(a[k], b[k]) for k in a)
     o = O.DiffusionOracle({}, img_size=32, sampling_timesteps=50)
     assert S.ddim_time_pairs(1000, 50) == o.ddim_time_pairs()
+
+
+def test_upsample_conv_phase_decomposition_identity():
+    """The algebra behind conv_fwd mode 3 (b200dm_pack_upconv_weight): a 3x3 'same' conv over a nearest-2x upsampled
+    image equals, per output phase (oy&1, ox&1), a 2x2 conv over the SOURCE image whose taps are sums of the 3x3 taps
+    that read the same source pixel (reference Upsample, ddpm.py:93-97).  Exact in fp64."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(7)
+    B, Cin, Cout, H = 2, 5, 4, 6
+    x = torch.randn(B, Cin, H, H, generator=g, dtype=torch.float64)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g, dtype=torch.float64)
+    bias = torch.randn(Cout, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, bias, padding=1)
+    sel = ([[0], [1, 2]], [[0, 1], [2]])          # phase -> 2x2 tap -> 3x3 taps landing on that source pixel
+    out = torch.empty_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))                    # zero padding == TMA out-of-bounds fill
+    for a in range(2):
+        for b in range(2):
+            acc = bias.view(1, Cout, 1, 1).expand(B, Cout, H, H).clone()
+            for r in range(2):
+                for c in range(2):
+                    wsum = sum(w[:, :, ky, kx] for ky in sel[a][r] for kx in sel[b][c])          # [Cout, Cin]
+                    dy, dx = r + a - 1, c + b - 1                                               # source offset
+                    patch = xp[:, :, 1 + dy:1 + dy + H, 1 + dx:1 + dx + H]
+                    acc = acc + torch.einsum("oc,bchw->bohw", wsum, patch)
+            out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max().item() < 1e-12
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs) prints one JSON line with the contract's keys."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([_sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
