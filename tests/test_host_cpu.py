@@ -89,3 +89,53 @@ def test_bench_reference_arm_json_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_groupnorm_film_silu_backward_closed_form():
+    """The closed forms gn_bwd_cluster_kernel evaluates (norm.cu): with z = (gamma*xn + beta)*(scale+1) + shift,
+    y = silu(z), dz = dy*silu'(z), per-channel S1 = sum dz, S2 = sum dz*xn, S0 = sum x and per-group means
+    M1, M2 of a*S1, a*S2 (a = (scale+1)*gamma):  dx = rstd*a*dz - rstd*M1 - rstd^2*M2*(x - mean); the parameter
+    gradients and the gradient of the producing conv's bias follow from the same sums.  Checked against autograd of
+    Block.forward (ddpm.py:164-173) in fp64."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    B, C, G, H = 3, 16, 4, 5
+    HW, gs = H * H, C // G
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    conv, bias = rnd(B, C, H, H), rnd(C).requires_grad_(True)
+    gamma, beta = rnd(C).requires_grad_(True), rnd(C).requires_grad_(True)
+    film = rnd(B, 2 * C).requires_grad_(True)
+    dy = rnd(B, C, H, H)
+    x = (conv + bias.view(1, C, 1, 1))
+    x.retain_grad()
+    sc, sh = film[:, :C].view(B, C, 1, 1), film[:, C:].view(B, C, 1, 1)
+    y = F.silu(F.group_norm(x, G, gamma, beta, eps=1e-5) * (sc + 1) + sh)
+    y.backward(dy)
+    with torch.no_grad():
+        xg = x.view(B, G, gs * HW)
+        mean = xg.mean(-1).repeat_interleave(gs, 1).view(B, C, 1, 1)
+        rstd = (xg.var(-1, unbiased=False) + 1e-5).rsqrt().repeat_interleave(gs, 1).view(B, C, 1, 1)
+        xn = (x - mean) * rstd
+        scale1 = sc + 1
+        z = (gamma.view(1, C, 1, 1) * xn + beta.view(1, C, 1, 1)) * scale1 + sh
+        sg = torch.sigmoid(z)
+        dz = dy * sg * (1 + z * (1 - sg))
+        S1, S2, S0 = dz.sum((2, 3)), (dz * xn).sum((2, 3)), x.sum((2, 3))            # [B, C]
+        a = (scale1 * gamma.view(1, C, 1, 1)).view(B, C)
+        M1 = (a * S1).view(B, G, gs).sum(-1) / (gs * HW)
+        M2 = (a * S2).view(B, G, gs).sum(-1) / (gs * HW)
+        M1c, M2c = M1.repeat_interleave(gs, 1), M2.repeat_interleave(gs, 1)           # [B, C]
+        rs, mu = rstd.view(B, C), mean.view(B, C)
+        P, R = rs * a, -rs * rs * M2c
+        Q = -rs * M1c - R * mu
+        dx = P.view(B, C, 1, 1) * dz + Q.view(B, C, 1, 1) + R.view(B, C, 1, 1) * x
+        assert (dx - x.grad).abs().max().item() < 1e-10
+        assert ((scale1.view(B, C) * S2).sum(0) - gamma.grad).abs().max().item() < 1e-10
+        assert ((scale1.view(B, C) * S1).sum(0) - beta.grad).abs().max().item() < 1e-10
+        dfilm = torch.cat((gamma * S2 + beta * S1, S1), 1)
+        assert (dfilm - film.grad).abs().max().item() < 1e-10
+        sum_xn = (S0 - HW * mu) * rs
+        dbias = (rs * (a * S1 - HW * M1c - M2c * sum_xn)).sum(0)
+        assert (dbias - bias.grad).abs().max().item() < 1e-10
+        # forward: silu(z) = h + h*tanh(h) with h = z/2 (one MUFU per element in the bf16 kernels)
+        assert (z / 2 + z / 2 * torch.tanh(z / 2) - F.silu(z)).abs().max().item() < 1e-12
