@@ -139,3 +139,72 @@ def test_groupnorm_film_silu_backward_closed_form():
         assert (dbias - bias.grad).abs().max().item() < 1e-10
         # forward: silu(z) = h + h*tanh(h) with h = z/2 (one MUFU per element in the bf16 kernels)
         assert (z / 2 + z / 2 * torch.tanh(z / 2) - F.silu(z)).abs().max().item() < 1e-12
+
+
+def test_linear_attention_partial_merge_and_backward_closed_form():
+    """Algebra of the linear-attention kernels (attention.cu) against LinearAttention (ddpm.py:222-238) in fp64:
+    forward — every CTA of a cluster owns a pixel range and produces (column max M_r, exp-sums L_r, unnormalised
+    context C_r); the merge  ctx = sum_r e^{M_r-M} C_r / sum_r e^{M_r-M} L_r  equals the softmax over all n;
+    backward — dctx = scale * softmax_d(q) dout^T, dq = scale * P .* (ctx dout - colsum(P .* ctx dout)),
+    dv = ks^T-weighted dctx, dk = ks .* (v dctx^T - rowsum(dctx .* ctx))."""
+    g = torch.Generator().manual_seed(13)
+    d, n, nm, scale = 8, 37, 4, 8 ** -0.5
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    q, k, v = rnd(d, n).requires_grad_(True), rnd(d, n).requires_grad_(True), rnd(d, n).requires_grad_(True)
+    mk, mv = rnd(d, nm).requires_grad_(True), rnd(d, nm).requires_grad_(True)
+    dout = rnd(d, n)
+    kk, vv = torch.cat((mk, k), 1), torch.cat((mv, v), 1)            # memory key/values are prepended (ddpm.py:225-226)
+    ks = kk.softmax(-1)                                              # over the n + 4 positions
+    qs = q.softmax(0) * scale                                        # over the channels, times dim_head^-0.5
+    ctx = ks @ vv.t()                                                # [d, e]
+    out = ctx.t() @ qs                                               # [e, n]
+    out.backward(dout)
+    with torch.no_grad():
+        # ---- forward: three "CTAs" with uneven pixel ranges, rank 0 also owns the memory rows
+        bounds, parts = [0, 4 + 10, 4 + 25, 4 + n], []
+        for r in range(3):
+            kr, vr = kk[:, bounds[r]:bounds[r + 1]], vv[:, bounds[r]:bounds[r + 1]]
+            M = kr.max(1).values
+            p = torch.exp(kr - M[:, None])
+            parts.append((M, p.sum(1), p @ vr.t()))
+        Mg = torch.stack([p[0] for p in parts]).max(0).values
+        L = sum(torch.exp(M - Mg) * l for M, l, _ in parts)
+        Cm = sum(torch.exp(M - Mg)[:, None] * c for M, _, c in parts) / L[:, None]
+        assert (Cm - ctx).abs().max().item() < 1e-12
+        # ---- backward from (ctx, M, L) as the kernel keeps them
+        P = q.softmax(0)
+        dctx = scale * (P @ dout.t())                                # [d, e]
+        dqs = ctx @ dout                                             # [d, n]
+        dq = scale * P * (dqs - (P * dqs).sum(0, keepdim=True))
+        ksr = torch.exp(kk - Mg[:, None]) / L[:, None]
+        dvv = (ksr.t() @ dctx).t()                                   # [e, n + 4]
+        dks = dctx @ vv                                              # [d, n + 4]
+        Dd = (dctx * ctx).sum(1)
+        dkk = ksr * (dks - Dd[:, None])
+        assert (dq - q.grad).abs().max().item() < 1e-12
+        assert (dkk[:, nm:] - k.grad).abs().max().item() < 1e-12 and (dkk[:, :nm] - mk.grad).abs().max().item() < 1e-12
+        assert (dvv[:, nm:] - v.grad).abs().max().item() < 1e-12 and (dvv[:, :nm] - mv.grad).abs().max().item() < 1e-12
+
+
+def test_softmax_attention_backward_closed_form():
+    """attn_bwd_tc_kernel (attention.cu) against Attention + Attend's math branch (ddpm.py:255-271,
+    models/modules/attend.py:111-126) in fp64: P = softmax(scale Q K^T), dP = dO V^T,
+    dS = P .* (dP - rowsum(P .* dP)), dQ = scale dS K, dK = scale dS^T Q, dV = P^T dO (memory key/values are
+    the first four rows of K and V)."""
+    g = torch.Generator().manual_seed(17)
+    n, nm, d, scale = 9, 4, 8, 8 ** -0.5
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    q, k, v = rnd(n, d).requires_grad_(True), rnd(n, d).requires_grad_(True), rnd(n, d).requires_grad_(True)
+    mk, mv = rnd(nm, d).requires_grad_(True), rnd(nm, d).requires_grad_(True)
+    do = rnd(n, d)
+    K, V = torch.cat((mk, k)), torch.cat((mv, v))
+    out = (q @ K.t() * scale).softmax(-1) @ V
+    out.backward(do)
+    with torch.no_grad():
+        P = (q @ K.t() * scale).softmax(-1)
+        dP = do @ V.t()
+        dS = P * (dP - (P * dP).sum(-1, keepdim=True))
+        dQ, dK, dV = scale * dS @ K, scale * dS.t() @ q, P.t() @ do
+        assert (dQ - q.grad).abs().max().item() < 1e-12
+        assert (dK[nm:] - k.grad).abs().max().item() < 1e-12 and (dK[:nm] - mk.grad).abs().max().item() < 1e-12
+        assert (dV[nm:] - v.grad).abs().max().item() < 1e-12 and (dV[:nm] - mv.grad).abs().max().item() < 1e-12
