@@ -46,6 +46,10 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def _on_bucket(self, i, rng):
         """Backward has issued everything that writes gradient bucket i (and its all-reduce, if any)."""
+        if i in self._done:
+            raise RuntimeError("FusedAdam(overlap_with_backward=True) applies the update during backward and "
+                               "therefore supports exactly one backward() per step(); use the default mode for "
+                               "gradient accumulation")
         unet = self.unet
         flat, gflat = unet.flat_parameters()
         main = torch.cuda.current_stream()
