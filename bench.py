@@ -417,10 +417,27 @@ def main():
         def step_device(i):
             step_core(dev_batches[i % 4])
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
         def step_e2e(i):
+            # public-API step from pinned host memory.  The loss of THIS step is read back on the host before the
+            # next step starts; the read is issued as soon as the loss exists (after the forward pass, on a second
+            # stream) so that the host does not wait for backward + Adam before it can enqueue the next step.
             data = host[i % 4].to(dev, non_blocking=True)       # H2D from pinned memory
-            loss = step_core(data)
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=False)   # D2H + sync (loss.item())
+            opt.zero_grad()
+            loss = model.training_step((data, labels))
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)   # D2H of the step's result
+                done = torch.cuda.Event()
+                done.record()
+            loss.backward()
+            opt.step()
+            model.on_train_batch_end(None, None, 0)
+            done.synchronize()                                  # the host holds this step's loss (loss.item())
+            assert loss_host[0] == loss_host[0]                 # touch the value (and catch a NaN)
 
         # launches per step, counted on an eager (non-graph-replayed) step
         L.load().b200dm_reset_launch_count()
