@@ -112,8 +112,7 @@ class ClockSampler:
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
-                if float(r[7]) >= 50:            # under load
-                    sm.append(float(r[0]))
+                sm.append(float(r[0]))           # taken between mark() and stop(): inside the timed regions
             except (ValueError, IndexError):
                 continue
         use = sm if sm else sm_all
@@ -363,6 +362,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # nvidia-smi needs a few hundred ms before its first line: start it now, samples before mark() are ignored
+    clocks = ClockSampler(local)
+    clocks.start()
     from b200dm import DDPM, _lib as L
     peaks = measured_peaks()
     K, W = args.steps, args.warmup
@@ -444,8 +446,6 @@ def main():
         step_device(0)
         torch.cuda.synchronize()
         launches_per_step = int(L.load().b200dm_launch_count())
-        clocks = ClockSampler(local)
-        clocks.start()
         for i in range(W):
             step_device(i)
         clocks.mark()
@@ -489,8 +489,6 @@ def main():
         step_device(0)
         torch.cuda.synchronize()
         launches_per_step = int(L.load().b200dm_launch_count())
-        clocks = ClockSampler(local)
-        clocks.start()
         W = max(1, min(W, 2)) if args.workload == "ddim" else 1     # a chain is 50 / 1000 warm evaluations
         for i in range(W):
             step_device(i)
