@@ -208,3 +208,30 @@ def test_softmax_attention_backward_closed_form():
         assert (dQ - q.grad).abs().max().item() < 1e-12
         assert (dK[nm:] - k.grad).abs().max().item() < 1e-12 and (dK[:nm] - mk.grad).abs().max().item() < 1e-12
         assert (dV[nm:] - v.grad).abs().max().item() < 1e-12 and (dV[:nm] - mv.grad).abs().max().item() < 1e-12
+
+
+def test_bench_clock_sampler_reports_only_the_timed_region():
+    """bench.py's nvidia-smi sampler: samples before mark() are ignored, throttle reasons inside the region are kept."""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            pass
+    c = b.ClockSampler(0)
+    c.proc = _Proc()
+    t = time.perf_counter()
+    idle = ["1200", "1965", "100", "Not Active", "Not Active", "Not Active", "Not Active", "3"]
+    capped = ["1950", "1965", "700", "Not Active", "Not Active", "Not Active", "Active", "99"]
+    full = ["1965", "1965", "700", "Not Active", "Not Active", "Not Active", "Not Active", "20"]
+    c.rows = [(t - 1, idle), (t + 1, capped), (t + 2, full)]
+    c.t_mark = t
+    r = c.stop()
+    assert r["sm_mhz"] == 1957.5 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"]
+    assert r["samples_under_load"] == 2 and r["samples"] == 3
