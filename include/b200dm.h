@@ -56,27 +56,43 @@ int b200dm_tc_available(void);
  * so results do not depend on how a batch is sharded over GPUs.
  * ---------------------------------------------------------------------------------------------- */
 
-/* normalize + q_sample: x_t = sqrt_ac[t]*(2*img-1 if normalize) + sqrt_1mac[t]*eps.
- * Replaces ddpm.py:945 (normalize), :881 (randn_like), :869-876 (q_sample).
- * Optionally writes eps (noise_out) and the normalised x0 (x0_out) for the loss. */
-int b200dm_q_sample(const float* img, const int64_t* t, const float* noise, float* x_t,
-                    float* noise_out, float* x0_out, const float* sqrt_ac, const float* sqrt_1mac,
-                    int32_t B, int64_t chw, int32_t normalize, uint64_t seed, uint64_t stream_id,
-                    uint64_t elem_offset, void* stream);
+/* Inputs of the forward-noising step, shared by q_sample and the loss (the loss kernel re-derives x0 and eps from
+ * the same description instead of reading stored copies: 8 + 12 B per element in fp32 I/O).
+ *   x0  = normalize ? 2*img - 1 : img                                          ddpm.py:945
+ *   eps = noise ? noise[i] : Philox4x32-10 N(0,1) of element elem_offset + i    ddpm.py:881 (randn_like)
+ *   eps += offset_strength * offset[b, c]      (offset != NULL)                 ddpm.py:889-891 (offset noise)
+ * hw = pixels per channel plane (only needed with offset noise; hw % 4 == 0). */
+typedef struct {
+  const float* img;        /* [B, chw] fp32 */
+  const int64_t* t;        /* [B] */
+  const float* noise;      /* [B, chw] injected normals, or NULL */
+  const float* offset;     /* [B, chw/hw] normals of the offset noise, or NULL */
+  const float* sqrt_ac;    /* sqrt_alphas_cumprod [T] */
+  const float* sqrt_1mac;  /* sqrt_one_minus_alphas_cumprod [T] */
+  float offset_strength;
+  int32_t normalize;
+  int32_t B;
+  int32_t reserved;
+  int64_t chw, hw;
+  uint64_t seed, stream_id, elem_offset;
+} b200dm_noise_desc;
+
+/* normalize + q_sample: x_t = sqrt_ac[t]*x0 + sqrt_1mac[t]*eps.
+ * Replaces ddpm.py:945 (normalize), :881 (randn_like), :889-891 (offset noise), :869-876 (q_sample).
+ * Optionally writes eps (noise_out) and the normalised x0 (x0_out). */
+int b200dm_q_sample(const b200dm_noise_desc* d, float* x_t, float* noise_out, float* x0_out, void* stream);
 
 /* target + MSE + loss weight + mean, and dL/d(model_out).  Replaces ddpm.py:911-925, :684-688.
- * loss_acc: fp32[1] accumulator (must be zeroed by the caller); per-element grad
- * d_out = 2*w[t]*(out-target)/(B*chw) written if d_out != NULL. */
-int b200dm_loss_fwd_bwd(const float* model_out, const float* x0, const float* noise,
-                        const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
-                        const float* loss_weight, float* loss_acc, float* d_out, int32_t B,
-                        int64_t chw, int32_t objective, void* stream);
+ * `d` is the descriptor q_sample was called with.  loss_acc: fp32[1] accumulator (must be zeroed by the caller);
+ * per-element grad d_out = 2*w[t]*(out-target)/(B*chw) written if d_out != NULL. */
+int b200dm_loss_fwd_bwd(const b200dm_noise_desc* d, const float* model_out, const float* loss_weight,
+                        float* loss_acc, float* d_out, int32_t objective, void* stream);
 
 /* DDIM update for one (time, time_next) pair given the UNet output.
  * Replaces model_predictions(clip_x_start=True, rederive_pred_noise=True) ddpm.py:707-734 and the
  * update at :812-827.  coefficient scalars are computed on the host from the fp32 buffers exactly as
  * the reference does (`alpha_next.sqrt()`, `c`, `sigma`).  last != 0: x_next = x0 (time_next < 0).
- * x0_out optional. */
+ * x0_out optional.  x_next may be the same buffer as x_t (in-place update of the sampler state). */
 int b200dm_ddim_step(const float* x_t, const float* model_out, const float* noise, float* x_next,
                      float* x0_out, float c_sqrt_ac, float c_sqrt_1mac, float c_sqrt_recip,
                      float c_sqrt_recipm1, float sqrt_alpha_next, float c, float sigma, int32_t last,
@@ -85,7 +101,7 @@ int b200dm_ddim_step(const float* x_t, const float* model_out, const float* nois
 
 /* DDPM ancestral step.  Replaces p_mean_variance + p_sample, ddpm.py:736-757 (x0 clamped to [-1,1],
  * posterior mean, + noise_std*z with noise_std = exp(0.5*logvar) computed by the host in fp32,
- * z = 0 when add_noise == 0 i.e. t == 0). */
+ * z = 0 when add_noise == 0 i.e. t == 0).  x_prev may be the same buffer as x_t. */
 int b200dm_ddpm_step(const float* x_t, const float* model_out, const float* noise, float* x_prev,
                      float* x0_out, float c_sqrt_ac, float c_sqrt_1mac, float c_sqrt_recip,
                      float c_sqrt_recipm1, float coef1, float coef2, float noise_std,

@@ -48,6 +48,17 @@ class WgradDesc(C.Structure):
     ]
 
 
+class NoiseDesc(C.Structure):
+    """b200dm_noise_desc: inputs of the forward-noising step shared by q_sample and the loss."""
+    _fields_ = [
+        ("img", C.c_void_p), ("t", C.c_void_p), ("noise", C.c_void_p), ("offset", C.c_void_p),
+        ("sqrt_ac", C.c_void_p), ("sqrt_1mac", C.c_void_p),
+        ("offset_strength", C.c_float), ("normalize", C.c_int32), ("B", C.c_int32), ("reserved", C.c_int32),
+        ("chw", C.c_int64), ("hw", C.c_int64),
+        ("seed", C.c_uint64), ("stream_id", C.c_uint64), ("elem_offset", C.c_uint64),
+    ]
+
+
 class PackEntry(C.Structure):
     _fields_ = [
         ("w", C.c_void_p), ("wf", C.c_void_p), ("wt", C.c_void_p),
@@ -61,8 +72,8 @@ _P, _I, _L, _F, _U = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
 # name -> argtypes (restype is int unless listed in _SPECIAL)
 PROTOTYPES = {
-    "b200dm_q_sample": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _U, _U, _U, _P],
-    "b200dm_loss_fwd_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P],
+    "b200dm_q_sample": [C.POINTER(NoiseDesc), _P, _P, _P, _P],
+    "b200dm_loss_fwd_bwd": [C.POINTER(NoiseDesc), _P, _P, _P, _P, _I, _P],
     "b200dm_ddim_step": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I, _I, _L, _U, _U, _U, _P],
     "b200dm_ddpm_step": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _I, _I, _L, _U, _U, _U, _P],
     "b200dm_randn": [_P, _L, _U, _U, _U, _P],

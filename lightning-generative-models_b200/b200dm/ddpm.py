@@ -50,7 +50,14 @@ class EMA(nn.Module):
         self.ema_model.requires_grad_(False)
         self.register_buffer("initted", torch.tensor(False))
         self.register_buffer("step", torch.tensor(0))
+        # host mirrors of the two buffers (update() must not synchronise with the device every step); they are
+        # re-read from the buffers whenever a state dict is loaded (checkpoint resume)
         self._step_host, self._initted_host = 0, False
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._step_host = int(self.step.item())
+        self._initted_host = bool(self.initted.item())
 
     @property
     def model(self):
@@ -96,11 +103,7 @@ def _clone_diffusion(gd: GaussianDiffusion) -> GaussianDiffusion:
     unet = Unet(u.dim, channels=u.channels, precision=u.precision, device=u._device,
                 use_tc=u._use_tc, cuda_graph=u._cuda_graph)
     unet.arena.flat.copy_(u.arena.flat)
-    out = GaussianDiffusion(unet, img_size=gd.img_size, timesteps=gd.num_timesteps,
-                            sampling_timesteps=gd.sampling_timesteps, objective=gd.objective,
-                            beta_schedule=gd._beta_schedule, ddim_sampling_eta=gd.ddim_sampling_eta,
-                            auto_normalize=gd.auto_normalize, rng=gd.rng)
-    return out
+    return GaussianDiffusion(unet, **gd._ctor)          # every constructor argument of the online model
 
 
 class DDPM(_Base):
@@ -133,7 +136,28 @@ class DDPM(_Base):
 
     # Lightning provides these; minimal stand-ins otherwise
     if not _HAS_PL:
-        def log(self, name, value, **kw):
+        def log(self, name, value, sync_dist=False, **kw):
+            """`sync_dist=True` (ddpm.py:1017-1023) averages the logged scalar over the ranks.  The all-reduce is
+            enqueued on the gradient communication stream, i.e. it rides behind the gradient buckets instead of
+            stalling the compute stream; `logged[name]` is a device tensor the caller reads when it wants to."""
+            import torch.distributed as dist
+            if sync_dist and isinstance(value, torch.Tensor) and dist.is_available() and dist.is_initialized() \
+                    and dist.get_world_size() > 1:
+                v = value.detach().clone()
+                sync = self.ema.model.model.grad_sync
+                stream = sync.stream if (sync is not None and sync.stream is not None) else None
+                if stream is not None:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    with torch.cuda.stream(stream):
+                        stream.wait_event(ev)
+                        dist.all_reduce(v)
+                        v.div_(dist.get_world_size())
+                    v.record_stream(stream)
+                else:
+                    dist.all_reduce(v)
+                    v.div_(dist.get_world_size())
+                value = v
             self.logged[name] = value
 
         @property
@@ -164,6 +188,35 @@ class DDPM(_Base):
 
     def validation_step(self, batch) -> torch.Tensor:
         return self._common_step(batch, "val")
+
+    # ---- checkpoints in the layout Lightning writes for the reference module (train.py:113-117,137-141) -------------
+    def checkpoint(self, optimizer=None, epoch: int = 0) -> dict:
+        """{"state_dict": ema.online_model.* / ema.ema_model.* / ema.initted / ema.step, "optimizer_states": [Adam in
+        torch.optim format], "global_step", "epoch", "hyper_parameters"} — the keys of a Lightning `.ckpt` of the
+        reference DDPM (ema_pytorch naming)."""
+        h = self.hparams_
+        ck = {"state_dict": self.state_dict(), "global_step": self.global_step, "epoch": epoch,
+              "hyper_parameters": dict(vars(h)), "pytorch-lightning_version": "b200dm"}
+        if optimizer is not None:
+            ck["optimizer_states"] = [optimizer.state_dict()]
+        return ck
+
+    def save_checkpoint(self, path: str, optimizer=None, epoch: int = 0):
+        torch.save(self.checkpoint(optimizer, epoch), path)
+
+    def load_checkpoint(self, path_or_dict, optimizer=None, strict: bool = True):
+        """Load a checkpoint written by `save_checkpoint` or by Lightning for the reference module."""
+        ck = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location="cpu",
+                                                                            weights_only=False)
+        sd = ck["state_dict"] if "state_dict" in ck else ck
+        out = self.load_state_dict(sd, strict=strict)
+        self.ema.online_model.model.arena.touch()
+        self.ema.ema_model.model.arena.touch()
+        if not _HAS_PL:
+            self._step_count = int(ck.get("global_step", self._step_count))
+        if optimizer is not None and ck.get("optimizer_states"):
+            optimizer.load_state_dict(ck["optimizer_states"][0])
+        return out
 
     def configure_optimizers(self):
         h = self.hparams_

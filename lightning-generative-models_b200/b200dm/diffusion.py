@@ -30,25 +30,23 @@ def _extract(a, t, ndim):
 
 
 class _LossFn(torch.autograd.Function):
-    """target + MSE + loss-weight + mean in one kernel that also emits dL/d(model_out)."""
+    """target + MSE + loss-weight + mean in one kernel that also emits dL/d(model_out).  `desc` is the noise
+    descriptor q_sample ran with: the kernel re-derives x0 and eps from it (Philox block or injected tensor)."""
 
     @staticmethod
-    def forward(ctx, model_out, gd, x0, noise, t):
-        B = model_out.shape[0]
-        chw = model_out[0].numel()
+    def forward(ctx, model_out, gd, desc, keep):
+        import ctypes as C
         acc = torch.zeros(1, device=model_out.device)
         d_out = torch.empty_like(model_out)
-        L.call("b200dm_loss_fwd_bwd", model_out.data_ptr(), x0.data_ptr(), noise.data_ptr(), t.data_ptr(),
-               gd.sqrt_alphas_cumprod.data_ptr(), gd.sqrt_one_minus_alphas_cumprod.data_ptr(),
-               gd.loss_weight.data_ptr(), acc.data_ptr(), d_out.data_ptr(), B, chw,
-               L.OBJECTIVES[gd.objective])
+        L.call("b200dm_loss_fwd_bwd", C.byref(desc), model_out.data_ptr(), gd.loss_weight.data_ptr(), acc.data_ptr(),
+               d_out.data_ptr(), L.OBJECTIVES[gd.objective])
         ctx.save_for_backward(d_out)
         return acc.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         (d_out,) = ctx.saved_tensors
-        return d_out * g, None, None, None, None
+        return d_out * g, None, None, None
 
 
 class GaussianDiffusion(nn.Module):
@@ -68,9 +66,13 @@ class GaussianDiffusion(nn.Module):
             "objective must be either pred_noise (predict noise) or pred_x0 (predict image start) or pred_v"
         if beta_schedule not in ("linear", "cosine", "sigmoid"):
             raise ValueError(f"unknown beta schedule {beta_schedule}")
-        if offset_noise_strength != 0.0:
-            raise NotImplementedError("offset noise is not built (off in every reference config)")
         assert rng in ("philox", "torch")
+        # every constructor argument, for EMA's copy (b200dm.ddpm._clone_diffusion)
+        self._ctor = dict(img_size=img_size, timesteps=timesteps, sampling_timesteps=sampling_timesteps,
+                          objective=objective, beta_schedule=beta_schedule,
+                          schedule_fn_kwargs=dict(schedule_fn_kwargs), ddim_sampling_eta=ddim_sampling_eta,
+                          auto_normalize=auto_normalize, offset_noise_strength=offset_noise_strength,
+                          min_snr_loss_weight=min_snr_loss_weight, min_snr_gamma=min_snr_gamma, rng=rng)
         self.rng = rng
         self._beta_schedule = beta_schedule
         tables = make_buffers(timesteps, beta_schedule, objective, min_snr_loss_weight, min_snr_gamma,
@@ -133,33 +135,62 @@ class GaussianDiffusion(nn.Module):
                 _extract(self.posterior_log_variance_clipped, t, x_t.dim()))
 
     # ---- forward noising + loss ---------------------------------------------------------------------------
-    def _q_sample_kernel(self, img, t, noise, normalize, want_noise, want_x0):
+    def _noise_desc(self, img, t, noise, normalize, offset_strength=0.0):
+        """b200dm_noise_desc over `img` (+ the tensors it points to, which the caller keeps alive)."""
         img = img.contiguous().float()
         B, chw = img.shape[0], img[0].numel()
-        x_t = torch.empty_like(img)
-        noise_out = torch.empty_like(img) if want_noise else None
-        x0_out = torch.empty_like(img) if want_x0 else None
+        keep = [img, t]
         seed, sid = (0, 0) if noise is not None else self._next_stream()
         if noise is not None:
             noise = noise.contiguous().float()
-        L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), L.ptr(noise), x_t.data_ptr(),
-               L.ptr(noise_out), L.ptr(x0_out), self.sqrt_alphas_cumprod.data_ptr(),
-               self.sqrt_one_minus_alphas_cumprod.data_ptr(), B, chw, 1 if normalize else 0, seed, sid, 0)
-        return x_t, noise_out, x0_out
+            keep.append(noise)
+        offset = None
+        if offset_strength and offset_strength > 0.0:
+            # one normal per (sample, channel), ddpm.py:889-891 (drawn after the noise, like the reference)
+            if self.rng == "torch":
+                offset = torch.randn(img.shape[:2], device=img.device)
+            else:
+                offset = torch.empty(B, img.shape[1], device=img.device)
+                n4 = (offset.numel() + 3) // 4 * 4
+                tmp = torch.empty(n4, device=img.device)
+                oseed, osid = self._next_stream()
+                L.call("b200dm_randn", tmp.data_ptr(), n4, oseed, osid, 0)
+                offset.copy_(tmp[:offset.numel()].view_as(offset))
+            keep.append(offset)
+        d = L.NoiseDesc(img=img.data_ptr(), t=t.data_ptr(), noise=L.ptr(noise), offset=L.ptr(offset),
+                        sqrt_ac=self.sqrt_alphas_cumprod.data_ptr(),
+                        sqrt_1mac=self.sqrt_one_minus_alphas_cumprod.data_ptr(),
+                        offset_strength=float(offset_strength or 0.0), normalize=1 if normalize else 0, B=B,
+                        chw=chw, hw=img.shape[-1] * img.shape[-2], seed=seed, stream_id=sid, elem_offset=0)
+        return d, keep
+
+    def _q_sample_kernel(self, img, t, noise, normalize, want_noise=False, want_x0=False, offset_strength=0.0):
+        import ctypes as C
+        d, keep = self._noise_desc(img, t, noise, normalize, offset_strength)
+        x_t = torch.empty_like(keep[0])
+        noise_out = torch.empty_like(x_t) if want_noise else None
+        x0_out = torch.empty_like(x_t) if want_x0 else None
+        L.call("b200dm_q_sample", C.byref(d), x_t.data_ptr(), L.ptr(noise_out), L.ptr(x0_out))
+        return x_t, noise_out, x0_out, d, keep
 
     def q_sample(self, x_start, t, noise=None):
         if noise is None and self.rng == "torch":
             noise = torch.randn_like(x_start)
-        return self._q_sample_kernel(x_start, t, noise, False, False, False)[0]
+        return self._q_sample_kernel(x_start, t, noise, False)[0]
 
     def p_losses(self, x_start, t, noise=None, offset_noise_strength=None, _normalize=False):
-        if offset_noise_strength not in (None, 0.0):
-            raise NotImplementedError("offset noise is not built")
+        """ddpm.py:878-925.  q_sample and the loss are two kernels around the UNet; the loss kernel regenerates eps
+        from the same Philox blocks (or reads the injected tensor), so neither eps nor x0 is stored in between."""
+        if offset_noise_strength is None:
+            offset_noise_strength = self.offset_noise_strength
+        if self.self_condition:
+            raise NotImplementedError("self-conditioning is not built (off in every reference config)")
         if noise is None and self.rng == "torch":
             noise = torch.randn_like(x_start)
-        x_t, eps, x0 = self._q_sample_kernel(x_start, t, noise, _normalize, True, True)
+        x_t, _, _, desc, keep = self._q_sample_kernel(x_start, t, noise, _normalize,
+                                                      offset_strength=offset_noise_strength)
         model_out = self.model(x_t, t)
-        return _LossFn.apply(model_out, self, x0, eps, t)
+        return _LossFn.apply(model_out, self, desc, keep)
 
     def forward(self, img, *args, **kwargs):
         b, c, h, w = img.shape

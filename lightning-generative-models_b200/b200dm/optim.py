@@ -95,11 +95,54 @@ class FusedAdam(torch.optim.Optimizer):
     def zero_grad(self, set_to_none: bool = True):
         self.unet.zero_grad(set_to_none=set_to_none)
 
+    # ---- torch.optim.Adam's checkpoint format (what a Lightning checkpoint of the reference holds) --------------------
+    _TORCH_ADAM_DEFAULTS = dict(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False,
+                                fused=None, decoupled_weight_decay=False)
+
+    def _names(self):
+        return [n for n, p in self.unet.named_parameters() if p.requires_grad]
+
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        """{"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups": [{..., "params": [0..n-1]}]} with
+        per-parameter tensors in the reference (OIHW / [out,in]) layout, cloned out of the flat arenas."""
+        arena, names = self.unet.arena, self._names()
+        state = {}
+        if self.step_count > 0:
+            for i, nm in enumerate(names):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": arena._logical(self.exp_avg, nm).detach().contiguous().clone(),
+                            "exp_avg_sq": arena._logical(self.exp_avg_sq, nm).detach().contiguous().clone()}
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group = dict(self._TORCH_ADAM_DEFAULTS)
+        group.update(g)
+        group["params"] = list(range(len(names)))
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        if "state" not in sd:                      # the flat layout of round 1 ("step", "exp_avg", "exp_avg_sq")
+            self.step_count = int(sd["step"])
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        else:
+            arena, names = self.unet.arena, self._names()
+            groups = sd["param_groups"]
+            ids = [i for g in groups for i in g["params"]]
+            if len(ids) != len(names):
+                raise ValueError(f"optimizer state holds {len(ids)} parameters, the model has {len(names)}")
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            step = 0
+            with torch.no_grad():
+                for pos, pid in enumerate(ids):
+                    st = sd["state"].get(pid)
+                    if st is None:
+                        continue
+                    nm = names[pos]
+                    arena._logical(self.exp_avg, nm).copy_(st["exp_avg"].to(self.exp_avg.device, torch.float32))
+                    arena._logical(self.exp_avg_sq, nm).copy_(st["exp_avg_sq"].to(self.exp_avg.device, torch.float32))
+                    step = max(step, int(float(st["step"])))
+            self.step_count = step
+        for g, ng in zip(self.param_groups, sd.get("param_groups", [])):
+            for k in ("lr", "betas", "eps", "weight_decay"):
+                if k in ng:
+                    g[k] = tuple(ng[k]) if k == "betas" else ng[k]

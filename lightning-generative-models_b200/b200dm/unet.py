@@ -102,6 +102,8 @@ class Unet(nn.Module):
         self.grad_sync = None        # b200dm.distributed.GradSync when training data-parallel
         self.bucket_hook = None      # callable(i, (begin, end)): gradient bucket i is complete (FusedAdam overlap)
         self._buckets = None
+        self._sync_enabled = True    # False inside no_sync(): gradient accumulation micro-batches
+        self._reduced = False        # a gradient all-reduce has been issued since the last zero_grad()
 
     # ---- reference surface ----------------------------------------------------------------------------
     @property
@@ -167,7 +169,22 @@ class Unet(nn.Module):
     def flat_parameters(self):
         return self.arena.flat, self.arena.gflat
 
+    def no_sync(self):
+        """DistributedDataParallel.no_sync(): backward passes inside the context only accumulate local gradients;
+        the first backward outside it all-reduces the accumulated sum (gradient accumulation under data parallel)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self._sync_enabled = self._sync_enabled, False
+            try:
+                yield
+            finally:
+                self._sync_enabled = prev
+        return ctx()
+
     def zero_grad(self, set_to_none: bool = True):
+        self._reduced = False
         self.arena.gflat.zero_()
         for nm, p in self._params.items():
             p.grad = None if set_to_none else self.arena.gviews[nm]
@@ -230,7 +247,15 @@ class Unet(nn.Module):
     def run_plan_backward(self, plan: Plan):
         """Backward launches, one segment per gradient bucket; each bucket's all-reduce is enqueued on the
         communication stream as soon as its segment has been issued."""
-        sync = self.grad_sync
+        sync = self.grad_sync if self._sync_enabled else None
+        if sync is not None and sync.world > 1:
+            if self._reduced:
+                # the arena already holds an all-reduced sum: adding local gradients and reducing again would count
+                # the first micro-batch world_size times
+                raise RuntimeError("b200dm.Unet: second backward() after the gradients were all-reduced; wrap the "
+                                   "accumulation micro-batches in `with unet.no_sync():` (all but the last one) or "
+                                   "call zero_grad() between steps")
+            self._reduced = True
         nseg = len(plan.bwd_segments)
         hook = self.bucket_hook
         if hook is not None and self._buckets is None:

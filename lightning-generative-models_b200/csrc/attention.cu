@@ -1411,10 +1411,6 @@ linattn_bwd_tc_kernel(const lbf* __restrict__ dout, int dout_ld, const lbf* __re
 // reductions and two cluster barriers, so more, smaller CTAs lose), at most 8, at least one chunk each
 static int la_cluster_size(int BH, int n) {
   const int chunks = (n + LA_CHUNK - 1) / LA_CHUNK;
-  {
-    const char* e = getenv("B200DM_LA_CL");      // experiment knob
-    if (e && e[0] >= '1' && e[0] <= '8') return e[0] - '0' > chunks ? chunks : e[0] - '0';
-  }
   int cl = (int)((2LL * num_sms() * 4 + BH / 2) / BH);
   if (cl > 8) cl = 8;
   if (cl > chunks) cl = chunks;
@@ -1977,8 +1973,7 @@ extern "C" int b200dm_attn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, c
   if (dtype == B200DM_F32) {
     cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_fwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)qkv, qkv_ld, mem_kv, (float*)out, out_ld, n);
-  } else if (qkv_ld % 8 == 0 && out_ld % 2 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0 &&
-             getenv("B200DM_ATTN_SIMT") == nullptr) {
+  } else if (qkv_ld % 8 == 0 && out_ld % 2 == 0 && ((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 3) == 0) {
     launch_k(attn_fwd_tc_kernel, B * HEADS, 128, 0, st, (const bf16*)qkv, qkv_ld, mem_kv, (bf16*)out, out_ld, n);
   } else {
     cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1999,7 +1994,7 @@ extern "C" int b200dm_attn_bwd(int32_t dtype, const void* dout, int32_t dout_ld,
     cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     launch_k(attn_bwd_kernel<float>, B * HEADS, 256, smem, st, (const float*)dout, dout_ld, (const float*)qkv, qkv_ld, mem_kv, (float*)dqkv, dqkv_ld, dmem_kv, n);
   } else if (qkv_ld % 8 == 0 && dout_ld % 8 == 0 && dqkv_ld % 2 == 0 && ((uintptr_t)qkv & 15) == 0 &&
-             ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 3) == 0 && getenv("B200DM_ATTN_SIMT") == nullptr) {
+             ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 3) == 0) {
     launch_k(attn_bwd_tc_kernel, B * HEADS, 128, 0, st, (const bf16*)dout, dout_ld, (const bf16*)qkv, qkv_ld, mem_kv,
              (bf16*)dqkv, dqkv_ld, dmem_kv, n);
   } else {

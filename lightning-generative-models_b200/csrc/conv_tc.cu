@@ -439,8 +439,14 @@ struct TcHaloParams {
   const float* bias;
   float* gn_part;              // GroupNorm partial sums [pixel slot][G][2] of the output, or nullptr
   int gn_groups;
-  int dbg;                     // B200DM_HALO_DEBUG bit 0: skip epilogue stores, 1: skip A loads, 2: skip MMAs
+  int dbg;                     // -DB200DM_HALO_DEBUG builds only (scripts/halo_debug.py): bit 0 skip epilogue stores,
+                               // 1 skip A loads, 2 skip MMAs, 3 return at once, 4 no tiles, 5 no resident-weight load
 };
+#ifdef B200DM_HALO_DEBUG
+#define HALO_DBG(p) ((p).dbg)
+#else
+#define HALO_DBG(p) 0          // the production kernel carries none of the experiment branches
+#endif
 
 template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -471,8 +477,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));   // [Cout]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p.dbg & 8) return;
-  const int num_tiles = (p.dbg & 16) ? 0 : p.m_tiles * p.n_tiles;
+  if (HALO_DBG(p) & 8) return;
+  const int num_tiles = (HALO_DBG(p) & 16) ? 0 : p.m_tiles * p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
@@ -498,7 +504,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (B_RESIDENT && !(p.dbg & 32)) {   // the whole [9][N_TILE][Cin] weight, once
+      if (B_RESIDENT && !(HALO_DBG(p) & 32)) {   // the whole [9][N_TILE][Cin] weight, once
         mbar_expect_tx(bres_bar, (uint32_t)(9 * p.kblocks * B_BYTES));
         for (int tap = 0; tap < 9; ++tap)
           for (int kc = 0; kc < p.kblocks; ++kc)
@@ -512,7 +518,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
         for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(aempty(ab), aph ^ 1u);
-          if (p.dbg & 2) {
+          if (HALO_DBG(p) & 2) {
             mbar_arrive(afull(ab));
           } else {
             mbar_expect_tx(afull(ab), HALO_BYTES);
@@ -552,7 +558,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool leader = elect_one();
     int ab = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
-    if (B_RESIDENT && !(p.dbg & 32)) mbar_wait(bres_bar, 0);
+    if (B_RESIDENT && !(HALO_DBG(p) & 32)) mbar_wait(bres_bar, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -562,7 +568,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)ab * (HALO_BYTES >> 4);
         if (B_RESIDENT) {
-          if (leader && !(p.dbg & 4)) {
+          if (leader && !(HALO_DBG(p) & 4)) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int dy = tap / 3, dx = tap - dy * 3;
@@ -655,7 +661,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
           }
-          if (p.dbg & 1) continue;
+          if (HALO_DBG(p) & 1) continue;
           float v[32];
           {
             const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0 + c);
@@ -716,7 +722,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<uint4*>(my_row + chunk * 16) = u;
           }
         }
-        if (p.dbg & 1) continue;
+        if (HALO_DBG(p) & 1) continue;
         if (p.gn_part)
           gn_part_store(gS, gQ, 32, lane, true, p.gn_part, (long long)m_tile * 4 + quarter, p.Cout / 8, (n0 + s2 * 64) / 8);
         fence_proxy_async();
@@ -877,8 +883,10 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
     // MEASURED on B200 (scripts/halo_debug.py): the tensor core derives the 128-B swizzle phase from the
     // absolute shared-memory address bits [7,10), exactly like the TMA unit that wrote the tile, so a
     // window that starts at an arbitrary 128-B row needs base_offset = 0 in the UMMA descriptor.
+#ifdef B200DM_HALO_DEBUG
     const char* e = getenv("B200DM_HALO_DEBUG");
     p.dbg = e ? atoi(e) : 0;
+#endif
   }
   const int sms = num_sms();
   int n_tile = 64;

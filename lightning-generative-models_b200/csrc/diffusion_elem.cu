@@ -30,25 +30,48 @@ __device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.f), 
 
 
 // ---------------------------------------------------------------------------------------------
+// Forward noising inputs shared by q_sample and the loss: the SAME descriptor is given to both, so the loss kernel
+// re-derives x0 (normalize) and eps (Philox block of the element, or the injected tensor, + offset noise) instead
+// of reading copies that q_sample would have had to store: q_sample moves 8 B and the loss 12 B per element in
+// fp32 I/O (SURVEY 8d's fp32-mode byte budgets) instead of 16 + 16.
+struct NoiseIn {
+  const float* img;
+  const int64_t* t;
+  const float* noise;      // injected eps, or nullptr -> Philox
+  const float* offset;     // [B * C] per-(sample, channel) normals of the offset noise (ddpm.py:889-891), or nullptr
+  const float* sqrt_ac;
+  const float* sqrt_1mac;
+  float offset_strength;
+  int normalize;
+  int64_t chw4, hw4;       // float4 vectors per sample / per channel plane
+  uint64_t seed, stream_id, vec_offset;
+};
+
+__device__ __forceinline__ void noise_in_load(const NoiseIn& d, int64_t i, int b, float4& x, float4& e) {
+  x = ld4(d.img, i);
+  if (d.normalize) {
+    x.x = sub_(mul_(x.x, 2.f), 1.f); x.y = sub_(mul_(x.y, 2.f), 1.f);
+    x.z = sub_(mul_(x.z, 2.f), 1.f); x.w = sub_(mul_(x.w, 2.f), 1.f);
+  }
+  e = d.noise ? ld4(d.noise, i) : Philox::normal4(d.seed, d.vec_offset + (uint64_t)i, d.stream_id);
+  if (d.offset) {          // noise += strength * offset[b, c]   (one channel per float4: hw % 4 == 0)
+    const int64_t c = (i - (int64_t)b * d.chw4) / d.hw4;
+    const float o = mul_(d.offset_strength, __ldg(d.offset + (int64_t)b * (d.chw4 / d.hw4) + c));
+    e.x = add_(e.x, o); e.y = add_(e.y, o); e.z = add_(e.z, o); e.w = add_(e.w, o);
+  }
+}
+
 __global__ void __launch_bounds__(kElemThreads)
-q_sample_kernel(const float* __restrict__ img, const int64_t* __restrict__ t,
-                const float* __restrict__ noise, float* __restrict__ x_t,
-                float* __restrict__ noise_out, float* __restrict__ x0_out,
-                const float* __restrict__ sqrt_ac, const float* __restrict__ sqrt_1mac,
-                int64_t nvec, int64_t chw4, int normalize, uint64_t seed, uint64_t stream_id,
-                uint64_t vec_offset) {
+q_sample_kernel(const NoiseIn d, float* __restrict__ x_t, float* __restrict__ noise_out,
+                float* __restrict__ x0_out, int64_t nvec) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / chw4);
-    int64_t tb = t[b];
-    float ca = __ldg(sqrt_ac + tb), cb = __ldg(sqrt_1mac + tb);
-    float4 x = ld4(img, i);
-    if (normalize) {
-      x.x = sub_(mul_(x.x, 2.f), 1.f); x.y = sub_(mul_(x.y, 2.f), 1.f);
-      x.z = sub_(mul_(x.z, 2.f), 1.f); x.w = sub_(mul_(x.w, 2.f), 1.f);
-    }
-    float4 e = noise ? ld4(noise, i) : Philox::normal4(seed, vec_offset + (uint64_t)i, stream_id);
+    int b = (int)(i / d.chw4);
+    int64_t tb = d.t[b];
+    float ca = __ldg(d.sqrt_ac + tb), cb = __ldg(d.sqrt_1mac + tb);
+    float4 x, e;
+    noise_in_load(d, i, b, x, e);
     float4 o;
     o.x = add_(mul_(ca, x.x), mul_(cb, e.x));
     o.y = add_(mul_(ca, x.y), mul_(cb, e.y));
@@ -68,19 +91,18 @@ __device__ __forceinline__ float target_of(int objective, float x0, float e, flo
 }
 
 __global__ void __launch_bounds__(kElemThreads)
-loss_kernel(const float* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ noise,
-            const int64_t* __restrict__ t, const float* __restrict__ sqrt_ac,
-            const float* __restrict__ sqrt_1mac, const float* __restrict__ loss_weight,
-            float* __restrict__ loss_acc, float* __restrict__ d_out, int64_t nvec, int64_t chw4,
-            int objective, float inv_count) {
+loss_kernel(const NoiseIn dsc, const float* __restrict__ out, const float* __restrict__ loss_weight,
+            float* __restrict__ loss_acc, float* __restrict__ d_out, int64_t nvec, int objective,
+            float inv_count) {
   pdl_prologue();
   float acc = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / chw4);
-    int64_t tb = t[b];
-    float ca = __ldg(sqrt_ac + tb), cb = __ldg(sqrt_1mac + tb), w = __ldg(loss_weight + tb);
-    float4 o = ld4(out, i), x = ld4(x0, i), e = ld4(noise, i);
+    int b = (int)(i / dsc.chw4);
+    int64_t tb = dsc.t[b];
+    float ca = __ldg(dsc.sqrt_ac + tb), cb = __ldg(dsc.sqrt_1mac + tb), w = __ldg(loss_weight + tb);
+    float4 o = ld4(out, i), x, e;
+    noise_in_load(dsc, i, b, x, e);
     float4 d;
     d.x = o.x - target_of(objective, x.x, e.x, ca, cb);
     d.y = o.y - target_of(objective, x.y, e.y, ca, cb);
@@ -125,16 +147,18 @@ __device__ __forceinline__ void predict(int objective, const StepCoef& c, float 
   }
 }
 
+// x_t and x_next may be the SAME buffer (the samplers update their state in place): neither is __restrict__ and x_t is
+// read with a plain (coherent) load; every thread reads vector i before it writes vector i.
 __global__ void __launch_bounds__(kElemThreads)
-ddim_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
-                 const float* __restrict__ noise, float* __restrict__ x_next,
+ddim_step_kernel(const float* x_t, const float* __restrict__ out,
+                 const float* __restrict__ noise, float* x_next,
                  float* __restrict__ x0_out, StepCoef c, float sqrt_an, float cc, float sigma,
                  int last, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
                  uint64_t vec_offset) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float4 x = ld4(x_t, i), o = ld4(out, i);
+    float4 x = reinterpret_cast<const float4*>(x_t)[i], o = ld4(out, i);
     float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, r[4], x0s[4];
     float zs[4] = {0.f, 0.f, 0.f, 0.f};
     if (!last && sigma != 0.f) {
@@ -155,15 +179,15 @@ ddim_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
 }
 
 __global__ void __launch_bounds__(kElemThreads)
-ddpm_step_kernel(const float* __restrict__ x_t, const float* __restrict__ out,
-                 const float* __restrict__ noise, float* __restrict__ x_prev,
+ddpm_step_kernel(const float* x_t, const float* __restrict__ out,
+                 const float* __restrict__ noise, float* x_prev,
                  float* __restrict__ x0_out, StepCoef c, float coef1, float coef2, float noise_std,
                  int add_noise, int objective, int64_t nvec, uint64_t seed, uint64_t stream_id,
                  uint64_t vec_offset) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float4 x = ld4(x_t, i), o = ld4(out, i);
+    float4 x = reinterpret_cast<const float4*>(x_t)[i], o = ld4(out, i);
     float xs[4] = {x.x, x.y, x.z, x.w}, os[4] = {o.x, o.y, o.z, o.w}, r[4], x0s[4];
     float zs[4] = {0.f, 0.f, 0.f, 0.f};
     if (add_noise) {
@@ -221,38 +245,52 @@ using namespace b200dm;
 #define CHECK_ALIGN16(p, what) \
   B200DM_REQUIRE(((uintptr_t)(p) & 15) == 0, B200DM_ERR_SHAPE, what ": pointer not 16-byte aligned")
 
-extern "C" int b200dm_q_sample(const float* img, const int64_t* t, const float* noise, float* x_t,
-                               float* noise_out, float* x0_out, const float* sqrt_ac,
-                               const float* sqrt_1mac, int32_t B, int64_t chw, int32_t normalize,
-                               uint64_t seed, uint64_t stream_id, uint64_t elem_offset, void* stream) {
-  B200DM_REQUIRE(B > 0, B200DM_ERR_SHAPE, "q_sample: empty batch");
-  CHECK_VEC(chw, "q_sample");
-  B200DM_REQUIRE(elem_offset % 4 == 0, B200DM_ERR_SHAPE, "q_sample: elem_offset must be a multiple of 4");
-  CHECK_ALIGN16(img, "q_sample img"); CHECK_ALIGN16(x_t, "q_sample x_t");
-  CHECK_ALIGN16(noise, "q_sample noise"); CHECK_ALIGN16(noise_out, "q_sample noise_out");
+static int noise_in_from(const b200dm_noise_desc* d, NoiseIn* o, const char* what) {
+  B200DM_REQUIRE(d != nullptr && d->B > 0, B200DM_ERR_SHAPE, "%s: empty batch", what);
+  B200DM_REQUIRE(d->chw > 0 && d->chw % 4 == 0, B200DM_ERR_SHAPE, "%s: chw=%lld must be a positive multiple of 4", what,
+                 (long long)d->chw);
+  B200DM_REQUIRE(d->elem_offset % 4 == 0, B200DM_ERR_SHAPE, "%s: elem_offset must be a multiple of 4", what);
+  B200DM_REQUIRE(((uintptr_t)d->img & 15) == 0 && ((uintptr_t)d->noise & 15) == 0, B200DM_ERR_SHAPE,
+                 "%s: pointers must be 16-byte aligned", what);
+  B200DM_REQUIRE(d->img && d->t && d->sqrt_ac && d->sqrt_1mac, B200DM_ERR_SHAPE, "%s: null input", what);
+  if (d->offset)
+    B200DM_REQUIRE(d->hw > 0 && d->hw % 4 == 0 && d->chw % d->hw == 0, B200DM_ERR_SHAPE,
+                   "%s: offset noise needs hw %% 4 == 0 and chw %% hw == 0 (hw=%lld)", what, (long long)d->hw);
+  o->img = d->img; o->t = d->t; o->noise = d->noise;
+  o->offset = (d->offset && d->offset_strength != 0.f) ? d->offset : nullptr;
+  o->sqrt_ac = d->sqrt_ac; o->sqrt_1mac = d->sqrt_1mac;
+  o->offset_strength = d->offset_strength; o->normalize = d->normalize;
+  o->chw4 = d->chw / 4; o->hw4 = d->hw > 0 ? d->hw / 4 : d->chw / 4;
+  o->seed = d->seed; o->stream_id = d->stream_id; o->vec_offset = d->elem_offset / 4;
+  return B200DM_OK;
+}
+
+extern "C" int b200dm_q_sample(const b200dm_noise_desc* d, float* x_t, float* noise_out, float* x0_out,
+                               void* stream) {
+  NoiseIn in;
+  int rc = noise_in_from(d, &in, "q_sample");
+  if (rc) return rc;
+  CHECK_ALIGN16(x_t, "q_sample x_t"); CHECK_ALIGN16(noise_out, "q_sample noise_out");
   CHECK_ALIGN16(x0_out, "q_sample x0_out");
-  int64_t nvec = (int64_t)B * chw / 4;
-  launch_k(q_sample_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, 
-      img, t, noise, x_t, noise_out, x0_out, sqrt_ac, sqrt_1mac, nvec, chw / 4, normalize, seed,
-      stream_id, elem_offset / 4);
+  B200DM_REQUIRE(x_t != nullptr, B200DM_ERR_SHAPE, "q_sample: x_t is null");
+  int64_t nvec = (int64_t)d->B * in.chw4;
+  launch_k(q_sample_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, in, x_t, noise_out, x0_out, nvec);
   count_launch();
   return check_launch("q_sample");
 }
 
-extern "C" int b200dm_loss_fwd_bwd(const float* model_out, const float* x0, const float* noise,
-                                   const int64_t* t, const float* sqrt_ac, const float* sqrt_1mac,
-                                   const float* loss_weight, float* loss_acc, float* d_out, int32_t B,
-                                   int64_t chw, int32_t objective, void* stream) {
-  B200DM_REQUIRE(B > 0, B200DM_ERR_SHAPE, "loss: empty batch");
-  CHECK_VEC(chw, "loss");
+extern "C" int b200dm_loss_fwd_bwd(const b200dm_noise_desc* d, const float* model_out, const float* loss_weight,
+                                   float* loss_acc, float* d_out, int32_t objective, void* stream) {
+  NoiseIn in;
+  int rc = noise_in_from(d, &in, "loss");
+  if (rc) return rc;
   B200DM_REQUIRE(objective >= 0 && objective <= 2, B200DM_ERR_UNSUPPORTED, "loss: unknown objective %d", objective);
-  CHECK_ALIGN16(model_out, "loss out"); CHECK_ALIGN16(x0, "loss x0"); CHECK_ALIGN16(noise, "loss noise");
-  CHECK_ALIGN16(d_out, "loss d_out");
-  int64_t nvec = (int64_t)B * chw / 4;
-  float inv_count = 1.f / ((float)B * (float)chw);
-  launch_k(loss_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, 
-      model_out, x0, noise, t, sqrt_ac, sqrt_1mac, loss_weight, loss_acc, d_out, nvec, chw / 4,
-      objective, inv_count);
+  B200DM_REQUIRE(model_out && loss_weight && loss_acc, B200DM_ERR_SHAPE, "loss: null input");
+  CHECK_ALIGN16(model_out, "loss out"); CHECK_ALIGN16(d_out, "loss d_out");
+  int64_t nvec = (int64_t)d->B * in.chw4;
+  float inv_count = 1.f / ((float)d->B * (float)d->chw);
+  launch_k(loss_kernel, elem_grid(nvec), kElemThreads, 0, (cudaStream_t)stream, in, model_out, loss_weight, loss_acc,
+           d_out, nvec, objective, inv_count);
   count_launch();
   return check_launch("loss_fwd_bwd");
 }

@@ -699,10 +699,6 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 // cluster size: as many CTAs per sample as still fit on the machine in ONE wave (a second, partial wave costs
 // more than the smaller chunks save), each chunk at least two passes of the pixel lanes; any size 1..8.
 static int gn_cluster_size(int B, int HW, int C, int ctas_per_sm) {
-  {
-    const char* e = getenv("B200DM_GN_CL");      // experiment knob
-    if (e && e[0] >= '1' && e[0] <= '8') return e[0] - '0';
-  }
   const int lanes = GNC_THREADS / (C / 8);
   const long long slots = (long long)num_sms() * ctas_per_sm;
   int cl = (int)(slots / B);
@@ -1035,12 +1031,10 @@ extern "C" int b200dm_gn_fwd_pre(int32_t dtype, const void* x, int32_t x_ld, con
                  "gn_fwd_pre: C=%d G=%d not supported", C, G);
   cudaStream_t st = (cudaStream_t)stream;
   // plain grid of pixel chunks: about one wave of CTAs, every chunk at least two passes of the pixel lanes
-  // CTA size: B200DM_GNF_THREADS=128 gives a finer grid (8 CTAs per SM) that fills the machine more evenly
-  static const int nthr = [] { const char* e = getenv("B200DM_GNF_THREADS"); return e && atoi(e) == 128 ? 128 : GNC_THREADS; }();
-  const int threads = (nthr % (C / 8) == 0 && nthr % (2 * G) == 0) ? nthr : GNC_THREADS;
+  // (measured: 256-thread CTAs, 4 per SM; finer grids of 128-thread CTAs were within 1 %, grids x2 / x4 slower)
+  const int threads = GNC_THREADS;
   const int lanes = threads / (C / 8);
-  static const int mult = [] { const char* e = getenv("B200DM_GNF_MULT"); return e ? atoi(e) : 0; }();
-  int chunks = (int)(((long long)num_sms() * (mult ? mult : (threads == 128 ? 8 : 4))) / B);
+  int chunks = (int)(((long long)num_sms() * 4) / B);
   if (chunks > 32) chunks = 32;
   while (chunks > 1 && HW / chunks < 2 * lanes) --chunks;
   if (chunks < 1) chunks = 1;
@@ -1089,9 +1083,8 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
   if (gn_cluster_ok(C, G)) {
     // measured on the training step (B = 128, 32x32, 38 launches): three pixels in flight, pipelined, cluster sized for
     // two CTAs per SM: 0.69 ms; two pixels / three CTAs per SM (cluster of 3): 0.85; four pixels unpipelined: 0.71;
-    // four pipelined (spills): 0.79; eight unpipelined: 0.76.  B200DM_GNB_VAR=0 selects the two-pixel variant.
-    static const int var = [] { const char* v = getenv("B200DM_GNB_VAR"); return v ? atoi(v) : 1; }();
-    const int minb = (dtype == B200DM_F32 || var == 0) ? 3 : 2;
+    // four pipelined (spills): 0.79; eight unpipelined: 0.76.
+    const int minb = dtype == B200DM_F32 ? 3 : 2;
     const int cl = gn_cluster_size(B, HW, C, minb);
     dim3 grid(cl, B);
     cudaError_t e;
@@ -1100,7 +1093,6 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
                      (const TT*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (TT*)dx, (int)dx_ld, dgamma, \
                      dbeta, dfilm, dbias, (int)HW, (int)C, (int)G)
     if (dtype == B200DM_F32) GN_BWD_LAUNCH(float, 2, true, 3);
-    else if (var == 0) GN_BWD_LAUNCH(bf16, 2, true, 3);
     else GN_BWD_LAUNCH(bf16, 3, true, 2);
 #undef GN_BWD_LAUNCH
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
@@ -1196,7 +1188,7 @@ extern "C" int b200dm_rmsnorm_bwd(int32_t dtype, const void* dy, int32_t dy_ld, 
   cudaStream_t st = (cudaStream_t)stream;
   int L = 1;
   while (L < C / 8 && L < 32) L <<= 1;
-  static const int rmult = [] { const char* e = getenv("B200DM_RMSB_MULT"); return e ? atoi(e) : 2; }();
+  constexpr int rmult = 2;     // measured: 1x / 3x / 4x SMs CTAs are 13-26 % slower
   int64_t blocks = (rows * L + 255) / 256, cap = (int64_t)num_sms() * rmult;   // few CTAs: every CTA ends with one dg atomic per channel
   unsigned grid = (unsigned)(blocks > cap ? cap : blocks);
   const bool two = C / 8 > 32;

@@ -410,6 +410,13 @@ class DiffusionOracle:
         self.is_ddim_sampling = self.sampling_timesteps < timesteps
         self.eta = ddim_sampling_eta
 
+    def to(self, device):
+        """Move weights and schedule buffers (tests run the oracle on cuda, fp32 or under torch.autocast(bf16),
+        as the yardstick BASELINE.md section 3 defines); created tensors follow the input's device."""
+        self.sd = {k: v.to(device) for k, v in self.sd.items()}
+        self.buf = {k: v.to(device) for k, v in self.buf.items()}
+        return self
+
     def model(self, x, t):
         return unet_forward(self.sd, x, t, dim=self.dim, emulate=self.emulate)
 
@@ -464,7 +471,7 @@ class DiffusionOracle:
     # ddpm.py:736-757 — `noise` is what randn_like would have returned (ignored at t == 0)
     def p_sample(self, x, t: int, noise, model_out=None):
         b = self.buf
-        bt = torch.full((x.shape[0],), t, dtype=torch.long)
+        bt = torch.full((x.shape[0],), t, dtype=torch.long, device=x.device)
         x0 = self.model_predictions(x, bt, model_out=model_out).pred_x_start.clamp(-1.0, 1.0)
         mean = (extract(b["posterior_mean_coef1"], bt, 4) * x0
                 + extract(b["posterior_mean_coef2"], bt, 4) * x)
@@ -490,7 +497,7 @@ class DiffusionOracle:
         b = self.buf
         img = init_noise
         for time, time_next in self.ddim_time_pairs():
-            tc = torch.full((img.shape[0],), time, dtype=torch.long)
+            tc = torch.full((img.shape[0],), time, dtype=torch.long, device=img.device)
             pred_noise, x0 = self.model_predictions(img, tc, clip_x_start=True,
                                                     rederive_pred_noise=True)
             if time_next < 0:

@@ -51,14 +51,17 @@ for tag, B, C, S in (("bench C2", 128, 3, 32), ("saturating", 8192, 3, 64)):
     xt, eps, x0, out, dout = (torch.empty_like(img) for _ in range(5))
     out.normal_()
     acc = torch.zeros(1, device=dev)
-    us = timeit(lambda: L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), None, xt.data_ptr(), None, None,
-                               buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
-                               B, chw, 1, 1234, 1, 0))
-    report("q_sample (normalize + Philox + q_sample)", f"{tag} [{B},{C},{S},{S}] fp32", 8 * n, us)
-    us = timeit(lambda: L.call("b200dm_loss_fwd_bwd", out.data_ptr(), img.data_ptr(), xt.data_ptr(), t.data_ptr(),
-                               buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
-                               buf["loss_weight"].data_ptr(), acc.data_ptr(), dout.data_ptr(), B, chw, 2))
-    report("loss_fwd_bwd (target + MSE + weight + grad)", f"{tag} [{B},{C},{S},{S}] fp32", 16 * n, us)
+    import ctypes
+    nd = L.NoiseDesc(img=img.data_ptr(), t=t.data_ptr(), noise=None, offset=None,
+                     sqrt_ac=buf["sqrt_alphas_cumprod"].data_ptr(),
+                     sqrt_1mac=buf["sqrt_one_minus_alphas_cumprod"].data_ptr(), offset_strength=0.0, normalize=1,
+                     B=B, chw=chw, hw=S * S, seed=1234, stream_id=1, elem_offset=0)
+    us = timeit(lambda: L.call("b200dm_q_sample", ctypes.byref(nd), xt.data_ptr(), None, None))
+    report("q_sample (normalize + Philox + q_sample: read img, write x_t)", f"{tag} [{B},{C},{S},{S}] fp32", 8 * n, us)
+    us = timeit(lambda: L.call("b200dm_loss_fwd_bwd", ctypes.byref(nd), out.data_ptr(), buf["loss_weight"].data_ptr(),
+                               acc.data_ptr(), dout.data_ptr(), 2))
+    report("loss_fwd_bwd (Philox eps regenerated: read out + img, write grad)", f"{tag} [{B},{C},{S},{S}] fp32",
+           12 * n, us)
     us = timeit(lambda: L.call("b200dm_ddim_step", xt.data_ptr(), out.data_ptr(), None, x0.data_ptr(), None, 0.7, 0.7,
                                1.4, 1.0, 0.8, 0.6, 0.0, 0, 2, n, 1234, 1, 0))
     report("ddim_step", f"{tag} [{B},{C},{S},{S}] fp32", 12 * n, us)

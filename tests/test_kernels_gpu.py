@@ -6,6 +6,7 @@ Tolerances: fp32 kernels 1e-5..1e-4 relative (accumulation order only); bf16 ker
 the fp32 expression evaluated on the bf16-rounded inputs, so the only differences are the fp32
 accumulation order and the final bf16 rounding of the output (rel-L2 <= 4e-3).
 """
+import ctypes
 import math
 
 import pytest
@@ -50,6 +51,17 @@ def nhwc(x_nchw, dtype, ld=None, off=0):
 # ------------------------------------------------------------------------------------------------
 # scheduler / loss kernels
 # ------------------------------------------------------------------------------------------------
+def noise_desc(buf, img, t, noise, normalize, seed=0, stream_id=0, offset=None, strength=0.0):
+    d = L.NoiseDesc(img=img.data_ptr(), t=t.data_ptr(), noise=None if noise is None else noise.data_ptr(),
+                    offset=None if offset is None else offset.data_ptr(),
+                    sqrt_ac=buf["sqrt_alphas_cumprod"].data_ptr(),
+                    sqrt_1mac=buf["sqrt_one_minus_alphas_cumprod"].data_ptr(), offset_strength=strength,
+                    normalize=normalize, B=img.shape[0], chw=img[0].numel(), hw=img.shape[-1] * img.shape[-2],
+                    seed=seed, stream_id=stream_id, elem_offset=0)
+    d._keep = (img, t, noise, offset)
+    return d
+
+
 def _buffers(schedule="sigmoid", objective="pred_v"):
     from b200dm.schedule import make_buffers
     return {k: v.to(DEV) for k, v in make_buffers(1000, schedule, objective).items()}
@@ -61,9 +73,8 @@ def test_q_sample_injected_noise_exact():
     img, noise = torch.rand(B, C, S, S, device=DEV), rnd(B, C, S, S, seed=1)
     t = torch.tensor([0, 999, 17, 500, 998], device=DEV)
     xt, eo, x0 = (torch.empty_like(img) for _ in range(3))
-    L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), noise.data_ptr(), xt.data_ptr(), eo.data_ptr(),
-           x0.data_ptr(), buf["sqrt_alphas_cumprod"].data_ptr(),
-           buf["sqrt_one_minus_alphas_cumprod"].data_ptr(), B, C * S * S, 1, 0, 0, 0)
+    d = noise_desc(buf, img, t, noise, normalize=1)
+    L.call("b200dm_q_sample", ctypes.byref(d), xt.data_ptr(), eo.data_ptr(), x0.data_ptr())
     xs = img * 2 - 1
     ref = (buf["sqrt_alphas_cumprod"][t].view(B, 1, 1, 1) * xs
            + buf["sqrt_one_minus_alphas_cumprod"][t].view(B, 1, 1, 1) * noise)
@@ -91,10 +102,15 @@ def test_philox_noise_statistics_and_shard_invariance():
     img = torch.rand(4, 3, 32, 32, device=DEV)
     t = torch.tensor([10, 20, 30, 40], device=DEV)
     xt, eo = torch.empty_like(img), torch.empty_like(img)
-    L.call("b200dm_q_sample", img.data_ptr(), t.data_ptr(), None, xt.data_ptr(), eo.data_ptr(), None,
-           buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
-           4, 3 * 32 * 32, 1, 1234, 7, 0)
+    d = noise_desc(buf, img, t, None, normalize=1, seed=1234, stream_id=7)
+    L.call("b200dm_q_sample", ctypes.byref(d), xt.data_ptr(), eo.data_ptr(), None)
     assert torch.equal(eo.flatten(), a[:eo.numel()])
+    # ... and the loss kernel regenerates exactly that eps from the descriptor (nothing stored in between):
+    # with out = target of pred_noise = eps the loss is exactly 0
+    acc = torch.zeros(1, device=DEV)
+    L.call("b200dm_loss_fwd_bwd", ctypes.byref(d), eo.data_ptr(), buf["loss_weight"].data_ptr(), acc.data_ptr(), None,
+           L.OBJECTIVES["pred_noise"])
+    assert acc.item() == 0.0
 
 
 @pytest.mark.parametrize("objective", ["pred_noise", "pred_x0", "pred_v"])
@@ -111,12 +127,35 @@ def test_loss_fwd_bwd(objective):
     loss.backward()
     acc = torch.zeros(1, device=DEV)
     dout = torch.empty_like(out)
-    L.call("b200dm_loss_fwd_bwd", out.data_ptr(), x0.data_ptr(), noise.data_ptr(), t.data_ptr(),
-           buf["sqrt_alphas_cumprod"].data_ptr(), buf["sqrt_one_minus_alphas_cumprod"].data_ptr(),
-           buf["loss_weight"].data_ptr(), acc.data_ptr(), dout.data_ptr(), B, C * S * S,
-           L.OBJECTIVES[objective])
+    d = noise_desc(buf, x0, t, noise, normalize=0)
+    L.call("b200dm_loss_fwd_bwd", ctypes.byref(d), out.data_ptr(), buf["loss_weight"].data_ptr(), acc.data_ptr(),
+           dout.data_ptr(), L.OBJECTIVES[objective])
     assert abs(acc.item() - loss.item()) <= 2e-6 * abs(loss.item()) + 1e-9
     assert rel(dout, out.grad) < 1e-6
+
+
+def test_offset_noise_q_sample_and_loss():
+    """ddpm.py:889-891: noise += strength * randn(b, c)[:, :, None, None], used by q_sample AND the target."""
+    buf = _buffers(objective="pred_v")
+    B, Cc, S = 4, 3, 32
+    img, noise, out = torch.rand(B, Cc, S, S, device=DEV), rnd(B, Cc, S, S, seed=11), rnd(B, Cc, S, S, seed=12)
+    off = rnd(B, Cc, seed=13)
+    t = torch.tensor([3, 999, 400, 77], device=DEV)
+    d = noise_desc(buf, img, t, noise, normalize=1, offset=off, strength=0.1)
+    xt, eo = torch.empty_like(img), torch.empty_like(img)
+    L.call("b200dm_q_sample", ctypes.byref(d), xt.data_ptr(), eo.data_ptr(), None)
+    n2 = noise + 0.1 * off.view(B, Cc, 1, 1)
+    sa = buf["sqrt_alphas_cumprod"][t].view(B, 1, 1, 1)
+    sb = buf["sqrt_one_minus_alphas_cumprod"][t].view(B, 1, 1, 1)
+    xs = img * 2 - 1
+    assert (eo - n2).abs().max().item() <= 1e-6
+    assert (xt - (sa * xs + sb * n2)).abs().max().item() <= 2e-6
+    acc = torch.zeros(1, device=DEV)
+    L.call("b200dm_loss_fwd_bwd", ctypes.byref(d), out.data_ptr(), buf["loss_weight"].data_ptr(), acc.data_ptr(), None,
+           L.OBJECTIVES["pred_v"])
+    target = sa * n2 - sb * xs
+    ref = (F.mse_loss(out, target, reduction="none").flatten(1).mean(1) * buf["loss_weight"][t]).mean()
+    assert abs(acc.item() - ref.item()) <= 1e-5 * abs(ref.item())
 
 
 @pytest.mark.parametrize("objective", ["pred_noise", "pred_x0", "pred_v"])

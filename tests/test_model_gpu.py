@@ -1,12 +1,16 @@
 """End-to-end GPU parity: b200dm.Unet / GaussianDiffusion / DDPM against the oracle (oracle/ddpm_oracle.py,
 itself pinned to the reference by tests/golden) and against the committed golden fixtures.
 
-Tolerances (BASELINE.json north_star; yardsticks measured in DESIGN.md §5):
+Tolerances (BASELINE.json north_star / BASELINE.md §3):
   fp32 mode : UNet output and loss rel <= 1e-4, gradients rel-L2 <= 1e-3 per tensor
-  bf16 mode : UNet output rel-L2 <= 1e-2 and loss rel <= 1e-2 vs the fp32 reference; the distance to
-              the oracle's emulation of the B200 rounding points is reported beside it (bf16 rounding is
-              chaotic, so two correct bf16 evaluations sit ~7e-3 apart: it is a yardstick, not a tighter gate)
-  samplers  : DDIM / DDPM images in [0,1]: fp32 PSNR >= 80 dB; bf16 PSNR >= 40 dB and L-inf <= 0.05
+  bf16 mode : UNet output rel-L2 <= 1e-2 and loss rel <= 1e-2 vs the fp32 reference (every case, 1-channel included).
+              The yardstick is the reference's own bf16 arithmetic: the oracle run on this GPU under
+              torch.autocast(bf16) (tests/_refcuda.py); its distance to fp32 is reported beside ours.
+  samplers  : DDIM / DDPM images in [0,1]: fp32 PSNR >= 80 dB; bf16 PSNR >= 40 dB and L-inf <= 0.05.  One fixture
+              (c3s64: pred_noise + linear schedule, 4 DDIM steps from t=999) multiplies the UNet error by
+              sqrt(1/abar - 1) ~ 158 before the clamp, so NO bf16 evaluation meets 40 dB there, the reference's own
+              included; `sampler_gate` therefore demands the absolute bound whenever the autocast reference meets
+              it, and otherwise "at least as close to fp32 as the autocast reference is" (-1 dB, x1.25 L-inf).
 """
 import json
 import math
@@ -17,6 +21,7 @@ import pytest
 import torch
 
 from oracle import ddpm_oracle as O
+from _refcuda import cuda_oracle, precision_ctx
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -41,6 +46,15 @@ def rel(a, b):
 def psnr(a, b):
     mse = (a.detach().float().cpu() - b.detach().float().cpu()).pow(2).mean().item()
     return 10 * math.log10(1.0 / max(mse, 1e-20))
+
+
+def sampler_gate(p, li, yard_p, yard_li, what):
+    """bf16 sampler bound: absolute (>= 40 dB, L-inf <= 0.05) whenever the reference's own bf16-autocast run meets
+    it; otherwise no further from the fp32 reference than that run is."""
+    if yard_p >= 40 and yard_li <= 0.05:
+        assert p >= 40 and li <= 0.05, (what, p, li, yard_p, yard_li)
+    else:
+        assert p >= yard_p - 1.0 and li <= 1.25 * yard_li + 0.01, (what, p, li, yard_p, yard_li)
 
 
 def seeded_inputs(b, c, s, seed=1234):
@@ -109,14 +123,13 @@ def test_unet_forward_vs_golden_and_oracle(name, precision):
     if precision == "fp32":
         assert r <= 1e-4, r
     else:
-        # the 1-channel case sits at the bf16 noise floor: an independent bf16 evaluation of the reference
-        # (the oracle's rounding emulation) is itself 1.02e-2 away from fp32 there
-        assert r <= (1e-2 if ch == 3 else 1.25e-2), r
-        with torch.no_grad():
-            emu = O.unet_forward(synth(ch), x * 2 - 1, t, emulate="bf16")
-        r2, r3 = rel(out, emu), rel(emu, ref)
-        report(test="unet_fwd_emu", case=name, rel_vs_emulation=r2, emulation_vs_reference=r3)
-        assert r2 <= 1.2e-2, r2
+        assert r <= 1e-2, r
+        orc = cuda_oracle(ch, s)
+        with torch.no_grad(), precision_ctx("autocast"):
+            ac = orc.model((x * 2 - 1).to(DEV), t.to(DEV)).float()
+        r2, r3 = rel(out, ac), rel(ac, ref)
+        report(test="unet_fwd_autocast", case=name, rel_vs_autocast=r2, autocast_vs_reference=r3)
+        assert r2 <= 1e-2 + r3, (r2, r3)
 
 
 @pytest.mark.parametrize("name", ["c3s32", "c1s32", "c3s64", "c3s32_x0"])
@@ -156,7 +169,22 @@ def test_loss_and_all_gradients(name, precision):
         np.testing.assert_allclose(gn, gold["grad_norms"], rtol=5e-3, atol=1e-7)
     else:
         assert lrel <= 1e-2, lrel
-        assert total <= 3e-2 and worst <= 0.15, (total, worst, worst_name)
+        # yardstick: the reference's bf16-autocast gradients on this GPU against the same fp32 gradients
+        orc = cuda_oracle(ch, s, grads=True, objective=objective, beta_schedule=sched)
+        with precision_ctx("autocast"):
+            la = orc.forward(x.to(DEV), t.to(DEV), noise.to(DEV))
+        la.backward()
+        ynum = yworst = 0.0
+        for k, _ in O.unet_param_spec(64, ch):
+            gr, ga = sd[k].grad, orc.sd[k].grad.float().cpu()
+            e = (ga - gr).norm().item()
+            ynum += e * e
+            if gr.norm().item() > 1e-6:
+                yworst = max(yworst, e / gr.norm().item())
+        ytotal = math.sqrt(ynum / den)
+        report(test="loss_grads_autocast_yardstick", case=name, grad_rel_total=ytotal, grad_rel_worst=yworst)
+        assert total <= max(2e-2, 1.5 * ytotal) and worst <= max(5e-2, 2.0 * yworst), \
+            (total, worst, worst_name, ytotal, yworst)
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -172,26 +200,50 @@ def test_samplers_vs_golden(name, precision):
     report(test="ddim4", case=name, precision=precision, psnr=p, linf=linf)
     if precision == "fp32":
         assert p >= 80 and linf <= 1e-3, (p, linf)
-    elif name == "c3s64":
-        # 4 DDIM steps from t=999 with pred_noise/linear multiply the UNet error by sqrt(1/abar - 1) ~ 158
-        # before the clamp: the oracle's own bf16 emulation reaches PSNR 41 dB / L-inf 0.35 here
-        assert p >= 37, (p, linf)
     else:
-        assert p >= 40 and linf <= 0.05, (p, linf)
+        orc = cuda_oracle(ch, s, sampling_timesteps=4, objective=objective, beta_schedule=sched)
+        with torch.no_grad(), precision_ctx("autocast"):
+            ac = orc.sample(init.to(DEV)).float().cpu()
+        yp, yl = psnr(ac, ref), (ac - ref).abs().max().item()
+        report(test="ddim4_autocast_yardstick", case=name, psnr=yp, linf=yl)
+        sampler_gate(p, linf, yp, yl, "ddim4 " + name)
     for tt in (999, 500, 0):
         im, x0 = gd.p_sample(init.to(DEV), tt, noise=noise.to(DEV))
         d = (im.cpu() - torch.from_numpy(gold[f"p_sample_{tt}"])).abs()
         d0 = (x0.cpu() - torch.from_numpy(gold[f"p_sample_{tt}_x0"])).abs()
         report(test="p_sample", case=name, precision=precision, t=tt, linf=d.max().item(),
                linf_x0=d0.max().item(), mean=d.mean().item(), mean_x0=d0.mean().item())
-        # x0 = sqrt(1/abar) x - ... amplifies UNet error by up to ~160x at t=999 (then clamped to [-1,1]):
-        # fp32 is held to L-inf, bf16 to the mean absolute error
         if precision == "fp32":
             assert d.max().item() <= 2e-3 and d0.max().item() <= 2e-3, (tt, d.max().item(), d0.max().item())
         else:
-            assert d.mean().item() <= 0.03 and d0.mean().item() <= 0.03, (tt, d.mean().item(), d0.mean().item())
+            # x0 = sqrt(1/abar) x - ... amplifies the UNet error by up to ~160x at t=999 (then clamps): bounded by
+            # what the reference's own bf16-autocast step does on the same inputs (x1.5, + 0.01 absolute)
+            with torch.no_grad(), precision_ctx("autocast"):
+                ai, a0 = orc.p_sample(init.to(DEV), tt, noise.to(DEV))
+            yd = (ai.float().cpu() - torch.from_numpy(gold[f"p_sample_{tt}"])).abs()
+            yd0 = (a0.float().cpu() - torch.from_numpy(gold[f"p_sample_{tt}_x0"])).abs()
+            report(test="p_sample_autocast_yardstick", case=name, t=tt, linf=yd.max().item(),
+                   linf_x0=yd0.max().item(), mean=yd.mean().item(), mean_x0=yd0.mean().item())
+            assert d.mean().item() <= 1.5 * yd.mean().item() + 1e-3, (tt, d.mean().item(), yd.mean().item())
+            assert d0.mean().item() <= 1.5 * yd0.mean().item() + 1e-3, (tt, d0.mean().item(), yd0.mean().item())
+            assert d.max().item() <= 1.5 * yd.max().item() + 0.01, (tt, d.max().item(), yd.max().item())
+            assert d0.max().item() <= 1.5 * yd0.max().item() + 0.01, (tt, d0.max().item(), yd0.max().item())
+    # model_predictions (ddpm.py:707-734) against the reference's values
     mp = gd.model_predictions(init.to(DEV), t.to(DEV), clip_x_start=True, rederive_pred_noise=True)
     assert type(mp).__name__ == "ModelPrediction" and mp._fields == ("pred_noise", "pred_x_start")
+    gn_, g0_ = torch.from_numpy(gold["mp_noise"]), torch.from_numpy(gold["mp_x0"])
+    dn, d0 = (mp.pred_noise.float().cpu() - gn_).abs(), (mp.pred_x_start.float().cpu() - g0_).abs()
+    report(test="model_predictions", case=name, precision=precision, noise_linf=dn.max().item(),
+           x0_linf=d0.max().item(), noise_rel=rel(mp.pred_noise, gn_), x0_rel=rel(mp.pred_x_start, g0_))
+    if precision == "fp32":
+        assert rel(mp.pred_noise, gn_) <= 1e-4 and d0.max().item() <= 2e-3, (rel(mp.pred_noise, gn_), d0.max().item())
+    else:
+        with torch.no_grad(), precision_ctx("autocast"):
+            amp = orc.model_predictions(init.to(DEV), t.to(DEV), clip_x_start=True, rederive_pred_noise=True)
+        yn, y0 = rel(amp.pred_noise.float(), gn_), rel(amp.pred_x_start.float(), g0_)
+        report(test="model_predictions_autocast_yardstick", case=name, noise_rel=yn, x0_rel=y0)
+        assert rel(mp.pred_noise, gn_) <= max(1e-2, 1.25 * yn), (rel(mp.pred_noise, gn_), yn)
+        assert rel(mp.pred_x_start, g0_) <= max(1e-2, 1.25 * y0), (rel(mp.pred_x_start, g0_), y0)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
