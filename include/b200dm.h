@@ -153,6 +153,32 @@ typedef struct {
 
 int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream);
 
+/* Block.forward in one launch (ddpm.py:164-173, :189-200), tcgen05 path:
+ *   y = SiLU( GroupNorm_groups(conv3x3(x) + bias) * (scale + 1) + shift ) (+ res)
+ * `d` describes the 3x3 'same' conv (mode 0, ksize 3, impl 1; d->y receives the ACTIVATED output, d->res is added after
+ * the SiLU, d->gn_part / d->accumulate must be 0).  A CTA (or thread-block cluster) owns one sample, the conv
+ * accumulators stay in TMEM until the sample's statistics are known, and the norm is applied straight out of TMEM:
+ * the conv -> norm intermediate never makes an HBM round trip and is never rounded to bf16 before the norm.
+ *   gamma, beta [Cout]; film = FiLM (scale | shift) rows [B][film_ld] with scale at column c and shift at Cout + c,
+ *   or NULL; stats (optional, out) [B][groups][2] = (mean, rstd); raw (optional, out) = conv(x) + bias in bf16
+ *   [B,H,W,raw_ld] (what b200dm_gn_apply_bwd reads in training).
+ * b200dm_conv_gn_supported returns 1 when the layer fits (bf16, Cin % 64 == 0, Cout in {64,128,256}, 8 groups,
+ * 16 <= W <= 128, H % 16 == 0, W % 8 == 0), else 0: use b200dm_conv_fwd + b200dm_gn_fwd_pre there. */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  const float* film;
+  int32_t film_ld;
+  int32_t groups;
+  float eps;
+  int32_t raw_ld;
+  float* stats;
+  void* raw;
+} b200dm_gn_desc;
+
+int b200dm_conv_gn_supported(const b200dm_conv_desc* d, const b200dm_gn_desc* gn);
+int b200dm_conv_gn_fwd(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* stream);
+
 /* weight gradient of a mode-0/mode-1 conv:  dW[tap][co][ci] (+)= sum_pix dY[pix,co] * X[pix+tap,ci]
  * (fp32, same packed order as the master weights).  Uses `ws` (fp32, ws_bytes) for split-K partials
  * when needed.  impl as above. */
@@ -341,6 +367,9 @@ int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v, int64_t n,
 /* ema = ema + (1-decay)*(online-ema)  (ema_pytorch lerp), or copy when decay == 0 */
 int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream);
 int b200dm_fill_f32(float* p, int64_t n, float value, void* stream);
+/* fp32 <-> bf16 copies of a gradient bucket for the opt-in bf16 all-reduce (n % 4 == 0). */
+int b200dm_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+int b200dm_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

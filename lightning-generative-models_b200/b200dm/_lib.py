@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200dm.so")
+# B200DM_LIB selects another build of the same ABI (the phase-timing debug build of scripts/phase_timing.py)
+LIB_PATH = os.environ.get("B200DM_LIB") or os.path.join(_HERE, "libb200dm.so")
 
 F32, BF16 = 0, 1
 PRED_NOISE, PRED_X0, PRED_V = 0, 1, 2
@@ -32,6 +33,15 @@ class ConvDesc(C.Structure):
         ("res", C.c_void_p), ("res_ld", C.c_int32),
         ("accumulate", C.c_int32),
         ("gn_part", C.c_void_p), ("gn_groups", C.c_int32),
+    ]
+
+
+class GnDesc(C.Structure):
+    """b200dm_gn_desc: GroupNorm + FiLM + SiLU fused behind a 3x3 conv (b200dm_conv_gn_fwd)."""
+    _fields_ = [
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("film", C.c_void_p),
+        ("film_ld", C.c_int32), ("groups", C.c_int32), ("eps", C.c_float), ("raw_ld", C.c_int32),
+        ("stats", C.c_void_p), ("raw", C.c_void_p),
     ]
 
 
@@ -79,6 +89,7 @@ PROTOTYPES = {
     "b200dm_randn": [_P, _L, _U, _U, _U, _P],
     "b200dm_unnormalize": [_P, _P, _L, _P],
     "b200dm_conv_fwd": [C.POINTER(ConvDesc), _P],
+    "b200dm_conv_gn_fwd": [C.POINTER(ConvDesc), C.POINTER(GnDesc), _P],
     "b200dm_conv_wgrad": [C.POINTER(WgradDesc), _P],
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -112,6 +123,8 @@ PROTOTYPES = {
     "b200dm_adam_step_bg": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P],
     "b200dm_ema_update": [_P, _P, _L, _F, _P],
     "b200dm_fill_f32": [_P, _L, _F, _P],
+    "b200dm_cast_f32_bf16": [_P, _P, _L, _P],
+    "b200dm_cast_bf16_f32": [_P, _P, _L, _P],
     "b200dm_debug_umma_rate": [_I, _I, _I, _I, _P, _P],
 }
 _SPECIAL = {
@@ -121,6 +134,7 @@ _SPECIAL = {
     "b200dm_gn_bwd_ws_floats": ([_I, _I, _I], C.c_int64),
     "b200dm_reset_launch_count": ([], None),
     "b200dm_tc_available": ([], C.c_int),
+    "b200dm_conv_gn_supported": ([C.POINTER(ConvDesc), C.POINTER(GnDesc)], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
 

@@ -6,7 +6,7 @@ backward, and rank 0's initial weights are broadcast at construction.  Here the 
 in ONE flat fp32 arena, so synchronisation is a handful of all-reduces over contiguous slices:
 
   * `buckets()` cuts the arena into regions in the order the backward pass finishes them
-    (final block -> up path -> middle -> down path -> stem + time embedding), each a contiguous slice;
+    (final block -> up path -> middle -> down path level 3 .. 0 -> stem + time embedding), each a contiguous slice;
   * `GradSync.reduce_bucket(i)` enqueues the all-reduce of bucket i on a side stream as soon as the
     compute stream has produced it (event), so communication overlaps the rest of backward;
   * `GradSync.finish()` makes the compute stream wait for the collectives before the optimiser step.
@@ -39,22 +39,28 @@ def init_from_env(backend: str | None = None):
     return rank, local, world
 
 
+# Backward-completion order of the gradient regions (= Plan.bwd_segments): the down path is cut per level so that only
+# the gradients of the last (level-0) blocks and of the arena head remain to be reduced when backward ends — the big
+# level-3 / level-2 tensors of the down path are on the wire while the slow level-0 layers are still computing.
+REGIONS = ("final", "ups", "mid", "downs.3", "downs.2", "downs.1", "downs.0", "head")
+
+
 def buckets(arena) -> List[Tuple[int, int]]:
-    """Contiguous [begin, end) element ranges of the flat arena, listed in backward-completion order."""
+    """Contiguous [begin, end) element ranges of the flat arena, listed in backward-completion order (REGIONS)."""
     names = [nm for nm, _ in arena.spec]
 
     def span(pred):
         offs = [(arena.offset[n], arena.offset[n] + arena._numel(n)) for n in names if pred(n)]
         return min(o[0] for o in offs), max(o[1] for o in offs)
 
-    named = {
-        "final": span(lambda n: n.startswith("final_") and ".mlp.1." not in n),
-        "ups": span(lambda n: n.startswith("ups.") and ".mlp.1." not in n),
-        "mid": span(lambda n: n.startswith("mid_") and ".mlp.1." not in n),
-        "downs": span(lambda n: n.startswith("downs.") and ".mlp.1." not in n),
-        # stem, time MLP and the concatenated FiLM projections (arena head) are finished last
-        "head": (0, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1]),
-    }
+    def region(prefix):
+        return span(lambda n: n.startswith(prefix) and ".mlp.1." not in n)
+
+    named = {"final": region("final_"), "ups": region("ups."), "mid": region("mid_")}
+    for i in range(4):
+        named[f"downs.{i}"] = region(f"downs.{i}.")
+    # stem, time MLP and the concatenated FiLM projections (arena head) are finished last
+    named["head"] = (0, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1])
     # make the regions tile the arena exactly (alignment padding goes to the following region)
     by_mem = sorted(named.items(), key=lambda kv: kv[1][0])
     tiled, prev = {}, 0
@@ -63,20 +69,27 @@ def buckets(arena) -> List[Tuple[int, int]]:
         prev = e
     last = by_mem[-1][0]
     tiled[last] = (tiled[last][0], arena.numel)
-    # order in which Plan.bwd_segments completes them
-    return [tiled[k] for k in ("final", "ups", "mid", "downs", "head")]
+    return [tiled[k] for k in REGIONS]
 
 
 class GradSync:
     """Bucketed, overlapped gradient all-reduce over the flat gradient arena."""
 
-    def __init__(self, arena, group=None):
+    def __init__(self, arena, group=None, wire: str | None = None):
+        """wire: "fp32" (default; what DistributedDataParallel does for the reference) or "bf16" (opt-in, also
+        B200DM_GRAD_WIRE=bf16): every bucket is rounded to bf16 for the all-reduce — half the bytes on NVLink — and
+        widened back into the fp32 arena, like torch's bf16_compress_hook."""
         self.arena, self.group = arena, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buckets = buckets(arena)
         self.cuda = arena.gflat.is_cuda
         self.stream = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
         self.handles = []
+        self.wire = wire or os.environ.get("B200DM_GRAD_WIRE", "fp32")
+        assert self.wire in ("fp32", "bf16")
+        self._wire_buf = None
+        if self.wire == "bf16" and self.cuda and self.world > 1:
+            self._wire_buf = torch.empty(arena.numel, dtype=torch.bfloat16, device=arena.gflat.device)
 
     def reduce_bucket(self, i: int):
         """Call once bucket i's gradients have been enqueued on the current stream."""
@@ -91,7 +104,14 @@ class GradSync:
         ev.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            dist.all_reduce(g, group=self.group)
+            if self._wire_buf is not None and (e - b) % 4 == 0:
+                from . import _lib as L
+                w = self._wire_buf[b:e]
+                L.call("b200dm_cast_f32_bf16", g.data_ptr(), w.data_ptr(), e - b)
+                dist.all_reduce(w, group=self.group)
+                L.call("b200dm_cast_bf16_f32", w.data_ptr(), g.data_ptr(), e - b)
+            else:
+                dist.all_reduce(g, group=self.group)
 
     def reduce_all(self):
         for i in range(len(self.buckets)):

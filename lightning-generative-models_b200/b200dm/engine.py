@@ -167,6 +167,7 @@ class Plan:
         self.side_enabled = os.environ.get("B200DM_SIDE_STREAM", "1") != "0"
         self.fuse_gn_stats = os.environ.get("B200DM_FUSE_GN_STATS", "1") != "0"
         self.fuse_upsample = os.environ.get("B200DM_FUSE_UPSAMPLE", "1") != "0"
+        self.fuse_gn = os.environ.get("B200DM_FUSE_GN", "1") != "0"       # conv + GroupNorm + FiLM + SiLU in one launch
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
@@ -177,7 +178,8 @@ class Plan:
         # backward segments in gradient-bucket order (b200dm.distributed.buckets): after segment i has run,
         # bucket i of the gradient arena is final and can be all-reduced while the rest of backward runs
         self.bwd_segments: List[List[Callable[[int], None]]] = []
-        for region in ("final", "ups", "mid", "downs", "head"):
+        from .distributed import REGIONS
+        for region in REGIONS:
             seg = [op for g, r in zip(reversed(self.bwd_groups), reversed(self.unit_regions)) if r == region
                    for op in g]
             self.bwd_segments.append(seg)
@@ -269,6 +271,26 @@ class Plan:
                reads=(x, res) if side else ())
         self._keep.append(d)
 
+    def conv_gn(self, nm, norm, x: View, y: View, *, film_ptr=None, res: Optional[View] = None,
+                raw: Optional[View] = None, stats: Optional[torch.Tensor] = None, emit=True, reads=()):
+        """Block.forward as ONE launch (b200dm_conv_gn_fwd): y = SiLU(GN(conv(x)+b)*(scale+1)+shift) (+ res); the
+        conv accumulators stay in TMEM across the norm.  emit=False only asks whether the layer is supported."""
+        a, ci = self.arena, self.arena.convs[nm]
+        d = L.ConvDesc(dtype=self.dt, mode=0, ksize=3, impl=self._impl(ci.cin, ci.cout), B=self.B, H=y.H, W=y.H,
+                       Cin=ci.cin, Cout=ci.cout, x=x.ptr, x_ld=x.ld, w=self.pack.fwd[nm].data_ptr(),
+                       bias=a.ptr(nm + ".bias"), y=y.ptr, y_ld=y.ld, res=None if res is None else res.ptr,
+                       res_ld=0 if res is None else res.ld, accumulate=0, gn_part=None, gn_groups=0)
+        g = L.GnDesc(gamma=a.ptr(norm + ".weight"), beta=a.ptr(norm + ".bias"), film=film_ptr,
+                     film_ld=a.film_cols if film_ptr else 0, groups=GROUPS, eps=GN_EPS,
+                     raw_ld=0 if raw is None else raw.ld, stats=None if stats is None else stats.data_ptr(),
+                     raw=None if raw is None else raw.ptr)
+        if not emit:
+            return self.lib.b200dm_conv_gn_supported(C.byref(d), C.byref(g)) == 1
+        self.F("b200dm_conv_gn_fwd", C.byref(d), C.byref(g), kname="conv_gn_fwd",
+               flops=2.0 * self.B * y.H * y.H * ci.cout * ci.cin * 9, writes=(y, raw), reads=reads)
+        self._keep.append((d, g))
+        return True
+
     def conv_bwd(self, nm, x: View, dy: View, dx: Optional[View], *, dx_acc=0, dx_res: Optional[View] = None,
                  bias_grad=True, dgrad_side=False):
         """wgrad + bias grad + (optional) dgrad of conv `nm` whose forward was x -> y, given dy."""
@@ -299,6 +321,7 @@ class Plan:
         cin, cout = a.blocks[nm]
         H, HW = x.H, x.H * x.H
         has_res_conv = cin != cout
+        tr = self.training
         self.begin_unit()
         c1, h1, c2 = self.buf(H, cout), self.buf(H, cout), self.buf(H, cout)
         st1, st2 = self.f32(self.B, GROUPS, 2), self.f32(self.B, GROUPS, 2)
@@ -312,7 +335,17 @@ class Plan:
         gs = cout // GROUPS
         fused = (self.fuse_gn_stats and self._impl(cin, cout) == 1 and self._impl(cout, cout) == 1
                  and gs % 8 == 0)
-        if fused:
+        one_launch = (fused and self.fuse_gn
+                      and self.conv_gn(b1 + ".proj", b1 + ".norm", x, h1, emit=False)
+                      and self.conv_gn(b2 + ".proj", b2 + ".norm", h1, out, emit=False))
+        if one_launch:
+            # conv -> GroupNorm -> FiLM -> SiLU (-> + residual) per launch; the raw conv outputs c1 / c2 and the
+            # statistics are only written when the backward pass will read them
+            self.conv_gn(b1 + ".proj", b1 + ".norm", x, h1, film_ptr=film_ptr, raw=c1 if tr else None,
+                         stats=st1 if tr else None, reads=(self.film,))
+            self.conv_gn(b2 + ".proj", b2 + ".norm", h1, out, res=res, raw=c2 if tr else None,
+                         stats=st2 if tr else None, reads=(res,))
+        elif fused:
             # GroupNorm statistics come out of the conv epilogues as per-slot partial sums; the norm is one pass
             slots = HW // min(32, HW)
             pt1, pt2 = self.f32(self.B, slots, cout // 8, 2), self.f32(self.B, slots, cout // 8, 2)
@@ -511,8 +544,8 @@ class Plan:
 
         x, gx = r, gr
         x_prior = True        # gcatF[dim:] also receives the final block's gradient first
-        self._region = "downs"
         for i in range(4):
+            self._region = f"downs.{i}"          # one gradient bucket per level of the down path
             d_in, d_out, H = dims[i], dims[i + 1], res[i]
             last = i == 3
             x1, gx1 = catA[i].slice(d_out, d_in), sl(gcatA[i], d_out, d_in)

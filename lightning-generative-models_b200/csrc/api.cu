@@ -40,6 +40,8 @@ int conv_fwd_simt(const b200dm_conv_desc* d, void* stream);
 int conv_wgrad_simt(const b200dm_wgrad_desc* d, void* stream);
 int conv_fwd_tc(const b200dm_conv_desc* d, void* stream);
 int conv_wgrad_tc(const b200dm_wgrad_desc* d, void* stream);
+int conv_gn_fwd_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* stream);
+int conv_gn_supported_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn);
 bool tc_supported();
 
 }  // namespace b200dm
@@ -77,6 +79,22 @@ extern "C" int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream) {
   B200DM_REQUIRE(d->gn_part == nullptr, B200DM_ERR_UNSUPPORTED,
                  "conv_fwd: fused GroupNorm statistics are built for the tcgen05 path (impl 1) only");
   return conv_fwd_simt(d, stream);
+}
+
+extern "C" int b200dm_conv_gn_supported(const b200dm_conv_desc* d, const b200dm_gn_desc* gn) {
+  if (!d || !gn || d->impl != 1 || d->gn_part) return 0;
+  return conv_gn_supported_tc(d, gn);
+}
+
+extern "C" int b200dm_conv_gn_fwd(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* stream) {
+  B200DM_REQUIRE(d != nullptr && gn != nullptr, B200DM_ERR_SHAPE, "conv_gn_fwd: null descriptor");
+  int rc = check_conv_common(d->dtype, d->mode, d->ksize, d->B, d->H, d->W, d->Cin, d->Cout);
+  if (rc) return rc;
+  B200DM_REQUIRE(d->x && d->w && d->y, B200DM_ERR_SHAPE, "conv_gn_fwd: null tensor pointer");
+  B200DM_REQUIRE(d->x_ld >= d->Cin && d->y_ld >= d->Cout, B200DM_ERR_SHAPE, "conv_gn_fwd: ld smaller than channel count");
+  B200DM_REQUIRE(d->impl == 1 && d->dtype == B200DM_BF16 && !d->gn_part && !d->accumulate, B200DM_ERR_UNSUPPORTED,
+                 "conv_gn_fwd: tcgen05 path (impl 1, bf16) only, without gn_part / accumulate");
+  return conv_gn_fwd_tc(d, gn, stream);
 }
 
 extern "C" int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream) {

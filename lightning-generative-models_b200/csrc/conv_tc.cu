@@ -245,6 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            b_lo0 + so + (uint32_t)((k * 32) >> 4), b_hi, idesc, (k > 0) ? 1u : (kb > 0 ? 1u : 0u));
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
         }
+        __syncwarp();   // the other lanes wait here, not in the next try_wait (see conv3x3_halo_kernel)
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(tmem_full_bar(acc));  // accumulator complete
@@ -425,8 +426,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // shared-memory address (measured), so the shifted rows read back exactly what the TMA unit wrote.  For 64->64 layers the whole 3x3 weight
 // (72 KiB) stays resident in shared memory for the life of the persistent CTA.
 // =====================================================================================================
-constexpr int HALO_W = 16, HALO_H = 18;
-constexpr int HALO_BYTES = HALO_W * HALO_H * 128;  // 36 KiB per 64-channel block
+// Row pitch of the staged halo = the box width: 10 pixels (tile 8 + 2 halo).  The 8-row groups of the A operand are
+// then 1280 B apart — not a multiple of the 1024-B swizzle atom — which is fine because both the TMA unit and the
+// tensor core derive the swizzle phase from the absolute shared-memory address (measured, see conv3x3_halo below).
+// Against the 16-pixel pitch of round 1 this moves 23 KB instead of 36 KB per tile through L2 -> SM, the link that
+// bounds the 64-channel layers (one 128-pixel tile every 0.88 us per SM = 6 TB/s at 36 KB).  -DB200DM_HALO_W=16
+// restores the padded pitch for A/B runs.
+#ifndef B200DM_HALO_W
+#define B200DM_HALO_W 10
+#endif
+constexpr int HALO_W = B200DM_HALO_W, HALO_H = 18;
+constexpr int HALO_TX = HALO_W * HALO_H * 128;                 // bytes one halo box brings (mbarrier expect_tx)
+constexpr int HALO_BYTES = (HALO_TX + 1023) / 1024 * 1024;     // buffer stride: 23 KiB (36 KiB at pitch 16)
+
+// -DB200DM_PHASE_TIMING (scripts/phase_timing.py, a separate libb200dm_timing.so): CTA 0 of the halo kernel records
+// SM-clock stamps of its pipeline phases into a global buffer.  Not compiled into the production library.
+#ifdef B200DM_PHASE_TIMING
+__device__ long long* g_tbuf = nullptr;
+#define TSTAMP(slot) do { if (g_tbuf && blockIdx.x == 0) g_tbuf[(slot)] = clock64(); } while (0)
+#else
+#define TSTAMP(slot) do { } while (0)
+#endif
 
 struct TcHaloParams {
   int kblocks;                 // Cin / 64
@@ -456,6 +476,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
   constexpr int SUBTILES = N_TILE / 64;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) TSTAMP(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -499,7 +520,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TSTAMP(1);
   pdl_wait();   // everything above is on-chip setup; global memory is touched only below
+  if (threadIdx.x == 0) TSTAMP(2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -518,10 +541,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
         for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(aempty(ab), aph ^ 1u);
+          if (kc == 0 && (tile - (int)blockIdx.x) / (int)gridDim.x < 16) TSTAMP(150 + (tile - (int)blockIdx.x) / (int)gridDim.x);
           if (HALO_DBG(p) & 2) {
             mbar_arrive(afull(ab));
           } else {
-            mbar_expect_tx(afull(ab), HALO_BYTES);
+            mbar_expect_tx(afull(ab), HALO_TX);
             tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
           }
           if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
@@ -559,34 +583,56 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int ab = 0, bs = 0, acc = 0;
     uint32_t aph = 0, bph = 0, acc_phase = 0;
     if (B_RESIDENT && !(HALO_DBG(p) & 32)) mbar_wait(bres_bar, 0);
+    // `pre`: the barriers of the coming tile (its accumulator, its first halo) were already waited for while the last
+    // MMAs of the previous tile were still queued, so the tensor pipe does not drain between tiles (measured with the
+    // phase-timing build: ~0.4 us of waits per 1.5 us tile on the 64-channel layers otherwise)
+    bool pre = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
-      for (int kc = 0; kc < p.kblocks; ++kc) {
-        mbar_wait(afull(ab), aph);
+      if (!pre) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+      }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      const int ti_ = (tile - (int)blockIdx.x) / (int)gridDim.x;
+      if (leader && ti_ < 16) TSTAMP(200 + ti_);          // accumulator free
+      for (int kc = 0; kc < p.kblocks; ++kc) {
+        // (no tcgen05 fence after a TMA-full wait: the operands were written by the async proxy and complete_tx
+        // orders them for the MMA; the fence is for barriers signalled by other threads' tcgen05 operations)
+        if (!(pre && kc == 0)) mbar_wait(afull(ab), aph);
+        if (leader && kc == 0 && ti_ < 16) TSTAMP(10 + 2 * ti_);   // first halo of the tile has landed
         const uint32_t a_lo = a_lo0 + (uint32_t)ab * (HALO_BYTES >> 4);
         if (B_RESIDENT) {
-          if (leader && !(HALO_DBG(p) & 4)) {
+          const bool more = kc == p.kblocks - 1 && tile + (int)gridDim.x < num_tiles;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              const uint32_t b_lo = b_lo0 + (uint32_t)(tap * p.kblocks + kc) * (B_BYTES >> 4);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t b_lo = b_lo0 + (uint32_t)(tap * p.kblocks + kc) * (B_BYTES >> 4);
+            if (tap == 8) {
+              pre = more;
+              if (more) {     // the coming tile's barriers, behind the queue of the 32 MMAs just issued
+                const int nacc = acc ^ 1, nab = ab + 1 == A_BUFS ? 0 : ab + 1;
+                mbar_wait(tmem_empty_bar(nacc), (nacc == 0 ? acc_phase ^ 1u : acc_phase) ^ 1u);
+                tc_fence_after();
+                mbar_wait(afull(nab), nab == 0 ? aph ^ 1u : aph);
+              }
+            }
+            if (leader && !(HALO_DBG(p) & 4)) {
 #pragma unroll
               for (int k = 0; k < TC_BK / 16; ++k)
                 umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4), a_hi,
                                b_lo + (uint32_t)((k * 32) >> 4), b_hi, idesc,
                                (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
             }
+            // the 31 other lanes wait HERE for the issuing lane: left to run ahead they would sit in the next
+            // mbarrier try_wait of the loop, and the warp would alternate between that spin and the MMA issue
+            __syncwarp();
           }
         } else {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            // tap window: rows (tx + dx) + 16*(ty + dy) of the halo buffer; 8-row groups = image rows
+            // tap window: rows (tx + dx) + pitch*(ty + dy) of the halo buffer; 8-row groups = image rows
             const int dy = tap / 3, dx = tap - dy * 3;
             mbar_wait(bfull(bs), bph);
-            tc_fence_after();
             const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_BYTES >> 4);
             if (leader) {
 #pragma unroll
@@ -596,6 +642,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
               umma_commit(bempty(bs));
             }
+            __syncwarp();
             if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
           }
         }
@@ -603,6 +650,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
       }
       if (leader) umma_commit(tmem_full_bar(acc));
+      if (leader && ti_ < 16) TSTAMP(11 + 2 * ti_);       // all MMAs of the tile issued
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -643,12 +691,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       const int s_first = SUBTILES == 1 ? 0 : wset;
       prefetch_src(s_first * 64);
+      const int eb_ = (quarter == 0 && lane == 0 && (it >> 1) < 8) ? 50 + wset * 50 + 4 * (it >> 1) : -1;
+      if (eb_ >= 0) TSTAMP(eb_);                            // starts waiting for the accumulator
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
+      if (eb_ >= 0) TSTAMP(eb_ + 1);                        // accumulator complete
 #pragma unroll 1
       for (int s2 = s_first; s2 < SUBTILES; s2 += 2) {
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        if (eb_ >= 0 && s2 == s_first) TSTAMP(eb_ + 2);     // staging block free
         float gS[8], gQ[8];
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
@@ -731,13 +783,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_5d(&tmY, my_stage, n0 + s2 * 64, x0, y0 + 4 * quarter, b, 0);
           tma_store_commit();
         }
+        if (eb_ >= 0) TSTAMP(eb_ + 3);                      // store issued
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
+    if (warp == 2 && lane == 0) TSTAMP(3);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TSTAMP(4);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -923,9 +978,10 @@ static int conv3x3_halo(const b200dm_conv_desc* d, cudaStream_t st) {
     int rc = encode_map(&tmB, d->w, 3, dims, str, box, "conv3x3_halo B");
     if (rc) return rc;
   }
-  if (resident) return launch_halo<64, 3, 1, true>(tmA, tmB, tmY, p, st);
-  if (n_tile == 128) return launch_halo<128, 2, 6, false>(tmA, tmB, tmY, p, st);
-  return launch_halo<64, 3, 6, false>(tmA, tmB, tmY, p, st);
+  // halo buffers in flight (23 KiB each): as many as shared memory holds next to the weights and the store staging
+  if (resident) return launch_halo<64, HALO_W <= 10 ? 5 : 3, 1, true>(tmA, tmB, tmY, p, st);
+  if (n_tile == 128) return launch_halo<128, HALO_W <= 10 ? 4 : 2, 6, false>(tmA, tmB, tmY, p, st);
+  return launch_halo<64, HALO_W <= 10 ? 5 : 3, 6, false>(tmA, tmB, tmY, p, st);
 }
 
 int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
@@ -999,6 +1055,654 @@ int conv_fwd_tc(const b200dm_conv_desc* d, void* stream) {
   if (n_tile == 256) return launch_tc<256, 3>(tmA, tmB, tmY, p, st);
   if (n_tile == 128) return launch_tc<128, 5>(tmA, tmB, tmY, p, st);
   return launch_tc<64, 6>(tmA, tmB, tmY, p, st);
+}
+
+// =====================================================================================================
+// Block.forward in ONE launch (ddpm.py:164-173, :189-200): 3x3 conv -> GroupNorm -> FiLM -> SiLU (+ residual).
+//
+// The halo kernel above, re-organised so that the GroupNorm never sees HBM: a CTA - or a thread-block cluster of
+// CL CTAs - owns ONE sample, and every accumulator tile of the sample stays resident in TMEM (512 columns x 128
+// lanes = the conv output of 1024 pixels x 64 channels in fp32) until the sample's statistics are known:
+//   MMA warp      all tiles of the CTA back to back, one TMEM accumulator each (no drain / reuse)
+//   epilogue 1    as each accumulator completes: tcgen05.ld -> + bias -> per-(8-channel chunk) sum / sum of squares
+//                 (overlaps the MMAs of the following tiles); training also stores the raw conv output (bf16) that
+//                 the GroupNorm backward wants
+//   reduce        warp shuffles -> shared memory -> (clusters) distributed shared memory; deterministic, no atomics
+//   epilogue 2    tcgen05.ld again -> z = A_c * acc + B_c (gamma, beta, mean, rstd, FiLM scale/shift and the conv
+//                 bias folded into two per-channel coefficients) -> SiLU via one tanh.approx -> (+ residual) ->
+//                 bf16 -> swizzled staging -> TMA store
+// The statistics are taken from the fp32 accumulators, i.e. the conv output is never rounded to bf16 before the norm,
+// and the conv -> norm intermediate makes no HBM round trip (inference) / is written once and never re-read (training).
+// =====================================================================================================
+constexpr int GN_STAGE_BYTES = TC_EPI_WARPS * 2 * 4096;     // 64 KiB
+struct TcGnParams {
+  int kblocks;                       // Cin / 64
+  int H, W, tiles_x, tpc;            // 8x16-pixel tiles per image row; pixel tiles per CTA
+  int Cout, n_tiles, gs_shift;       // channels per group = 1 << gs_shift
+  int res_ld, film_ld;
+  int store_raw, tmem_cols, B;
+  const __nv_bfloat16* res;
+  const float *bias, *gamma, *beta, *film;
+  float* stats;                      // [B][8][2] (mean, rstd) or nullptr
+  float eps, inv_count;              // 1 / (H*W*channels per group)
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// release-arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// acquire-wait (cluster scope) on a local mbarrier the peers arrive on; bounded like mbar_wait
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 8000000000LL) {
+      printf("b200dm: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 16 per-thread values (8 chunk sums, 8 chunk sums of squares) reduced over the 32 lanes of a warp by recursive
+// halving (16 shuffles + 1): afterwards lane l holds the warp total of value index (idx & 7) + 8 * (idx >> 3), where
+// idx is returned; lanes with an odd lane id hold a duplicate.
+__device__ __forceinline__ float warp_reduce16(const float (&S)[8], const float (&Q)[8], int lane, int& idx_out) {
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] = S[k]; v[8 + k] = Q[k]; }
+  int idx = 0;
+#pragma unroll
+  for (int n = 8, step = 0; n >= 1; n >>= 1, ++step) {
+    const int m = 16 >> step;
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float keep = up ? v[i + n] : v[i];
+      const float send = up ? v[i] : v[i + n];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+    idx = idx * 2 + (up ? 1 : 0);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  idx_out = idx;
+  return v[0];
+}
+
+template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRaw,
+                  const TcGnParams p) {
+  constexpr int B_BYTES = N_TILE * TC_BK * 2;
+  constexpr int SUBTILES = N_TILE / 64;
+  constexpr int MAX_ACC = 8;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + A_BUFS * HALO_BYTES;
+  const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
+  const uint32_t out_stage = b_base + b_slots * B_BYTES;        // two private 4 KiB staging blocks per epilogue warp
+  const uint32_t bar_base = out_stage + GN_STAGE_BYTES;
+  auto afull = [&](int a) { return bar_base + 8u * a; };
+  auto aempty = [&](int a) { return bar_base + 8u * (A_BUFS + a); };
+  auto bfull = [&](int s) { return bar_base + 8u * (2 * A_BUFS + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (2 * A_BUFS + B_STAGES + s); };
+  auto acc_full = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + a); };
+  auto acc_empty = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + MAX_ACC + a); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC);
+  const uint32_t xbar = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 1);   // cluster exchange of the sums
+  const uint32_t tmem_slot = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 2);
+  uint8_t* const sm = smem_raw + (base - smem_u32(smem_raw));         // generic pointer to `base`
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+  uint8_t* out_stage_ptr = sm + (out_stage - base);
+  // fp32 scratch after the barriers: bias | coefA | coefB [Cout each] | wpart[2][4][4][8][2] | gpart[2][16] | gall[8][16]
+  const uint32_t f_base = bar_base + 512u;
+  float* bias_s = reinterpret_cast<float*>(sm + (f_base - base));
+  float* coefA = bias_s + p.Cout;
+  float* coefB = coefA + p.Cout;
+  float* wpart = coefB + p.Cout;                 // [wset][quarter][unit slot][chunk][sum, sumsq]
+  float* gpart = wpart + 2 * 4 * 4 * 8 * 2;      // [sample parity][group][sum, sumsq] of this CTA: read by the peers
+  float* gall = gpart + 32;                      // [cluster rank][16]: the peers' sums of the current sample
+  const uint32_t gpart_addr = f_base + (uint32_t)((3 * p.Cout + 2 * 4 * 4 * 8 * 2) * 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank(), CL = (int)cluster_nctarank();
+  const int n_clusters = (int)gridDim.x / CL, cluster_id = (int)blockIdx.x / CL;
+  const int NA = p.tpc * p.n_tiles;              // accumulators of this CTA (<= 8)
+  const int NU = NA * SUBTILES;                  // 64-column units
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+    if (p.store_raw) prefetch_tmap(&tmRaw);
+    for (int a = 0; a < A_BUFS; ++a) { mbar_init(afull(a), 1); mbar_init(aempty(a), 1); }
+    for (int s2 = 0; s2 < B_STAGES; ++s2) { mbar_init(bfull(s2), 1); mbar_init(bempty(s2), 1); }
+    for (int a = 0; a < MAX_ACC; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4 * SUBTILES); }
+    mbar_init(bres_bar, 1);
+    mbar_init(xbar, 16 * CL);                    // 16 publishing threads of every CTA of the cluster
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  // the peers' exchange barriers must be initialised before anybody arrives on them
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above is on-chip setup; global memory is touched only below
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation halos of every sample of this cluster =====================
+    if (lane == 0) {
+      if (B_RESIDENT) {
+        mbar_expect_tx(bres_bar, (uint32_t)(9 * p.kblocks * B_BYTES));
+        for (int tap = 0; tap < 9; ++tap)
+          for (int kc = 0; kc < p.kblocks; ++kc)
+            tma_load_3d(b_base + (tap * p.kblocks + kc) * B_BYTES, &tmB, bres_bar, kc * TC_BK, 0, tap);
+      }
+      int ab = 0;
+      uint32_t aph = 0;
+      for (int b = cluster_id; b < p.B; b += n_clusters)
+        for (int mi = 0; mi < p.tpc; ++mi) {
+          const int m = rank * p.tpc + mi;
+          const int y0 = (m / p.tiles_x) * 16, x0 = (m % p.tiles_x) * 8;
+          for (int n = 0; n < p.n_tiles; ++n)
+            for (int kc = 0; kc < p.kblocks; ++kc) {
+              mbar_wait(aempty(ab), aph ^ 1u);
+              mbar_expect_tx(afull(ab), HALO_TX);
+              tma_load_5d(a_base + ab * HALO_BYTES, &tmA, afull(ab), kc * TC_BK, x0 - 1, y0 - 1, b, 0);
+              if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
+            }
+        }
+    }
+  } else if (warp == TC_BWARP) {
+    // ===================== TMA producer: weight tiles (streamed variant) =====================
+    if (lane == 0 && !B_RESIDENT) {
+      int bs = 0;
+      uint32_t bph = 0;
+      for (int b = cluster_id; b < p.B; b += n_clusters)
+        for (int mi = 0; mi < p.tpc; ++mi)
+          for (int n = 0; n < p.n_tiles; ++n)
+            for (int kc = 0; kc < p.kblocks; ++kc)
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(bempty(bs), bph ^ 1u);
+                mbar_expect_tx(bfull(bs), B_BYTES);
+                tma_load_3d(b_base + bs * B_BYTES, &tmB, bfull(bs), kc * TC_BK, n * N_TILE, tap);
+                if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+              }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // Accumulator a of the NEXT sample is started as soon as epilogue 2 of the current sample has read it
+    // (acc_empty), so the apply pass of one sample overlaps the MMAs of the following one, tile by tile.
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc(a_base, 16, HALO_W * 128);
+    const uint64_t b_desc0 = make_smem_desc(b_base, 16, 1024);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+    const bool leader = elect_one();
+    int ab = 0, bs = 0;
+    uint32_t aph = 0, bph = 0, sph = 0;          // sph: parity of the sample iteration
+    if (B_RESIDENT) mbar_wait(bres_bar, 0);
+    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u) {
+      for (int a = 0; a < NA; ++a) {
+        mbar_wait(acc_empty(a), sph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * N_TILE);
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(afull(ab), aph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)ab * (HALO_BYTES >> 4);
+          if (B_RESIDENT) {
+            if (leader) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap - dy * 3;
+                const uint32_t b_lo = b_lo0 + (uint32_t)(tap * p.kblocks + kc) * (B_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4), a_hi,
+                                 b_lo + (uint32_t)((k * 32) >> 4), b_hi, idesc,
+                                 (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
+              }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after();
+              const uint32_t b_lo = b_lo0 + (uint32_t)bs * (B_BYTES >> 4);
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)
+                  umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4), a_hi,
+                                 b_lo + (uint32_t)((k * 32) >> 4), b_hi, idesc,
+                                 (tap > 0 || k > 0) ? 1u : (kc > 0 ? 1u : 0u));
+                umma_commit(bempty(bs));
+              }
+              __syncwarp();
+              if (++bs == B_STAGES) { bs = 0; bph ^= 1u; }
+            }
+          }
+          if (leader) umma_commit(aempty(ab));
+          if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
+        }
+        if (leader) umma_commit(acc_full(a));
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..9 =====================
+    const int quarter = warp & 3;
+    const int wset = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const int tx = row & 7, ty = row >> 3;
+    const int te = threadIdx.x - 64;
+    uint8_t* const stage_ptr0 = out_stage_ptr + (warp - 2) * 8192;
+    const uint32_t stage0 = out_stage + (uint32_t)(warp - 2) * 8192u;
+    uint32_t nst = 0;                            // TMA stores issued by this warp: staging block = nst & 1
+    for (int i = te; i < p.Cout; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    named_bar_sync(1, 32 * TC_EPI_WARPS);
+    uint32_t sph = 0;
+    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u) {
+      // ---------- epilogue 1: statistics (+ raw conv output when training), as the accumulators complete ----------
+      for (int u = wset; u < NU; u += 2) {
+        const int a = u / SUBTILES, s2 = u - a * SUBTILES;
+        const int mi = a / p.n_tiles, n = a - mi * p.n_tiles;
+        const int m = rank * p.tpc + mi;
+        const int y0 = (m / p.tiles_x) * 16, x0 = (m % p.tiles_x) * 8;
+        uint8_t* my_row = stage_ptr0 + (nst & 1u) * 4096 + lane * 128;
+        mbar_wait(acc_full(a), sph);
+        tc_fence_after();
+        if (p.store_raw) {
+          if (lane == 0) tma_store_wait_read<1>();                  // the block used two stores ago is free again
+          __syncwarp();
+        }
+        float gS[8], gQ[8];
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = s2 * 64 + hh * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * N_TILE + c), r);
+          tmem_ld_wait();
+          float v[32];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n * N_TILE + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+              v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+              v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+              v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float sa = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sa += v[8 * k + j];
+              q = fmaf(v[8 * k + j], v[8 * k + j], q);
+            }
+            if (hh == 0) { gS[k] = sa; gQ[k] = q; } else { gS[4 + k] = sa; gQ[4 + k] = q; }
+          }
+          if (p.store_raw) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 uu;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uu);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+              const int chunk = (hh * 4 + g) ^ (lane & 7);
+              *reinterpret_cast<uint4*>(my_row + chunk * 16) = uu;
+            }
+          }
+        }
+        if (p.store_raw) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmRaw, stage0 + (nst & 1u) * 4096u, n * N_TILE + s2 * 64, x0, y0 + 4 * quarter, b, 0);
+            tma_store_commit();
+          }
+          ++nst;
+        }
+        int idx;
+        const float tot = warp_reduce16(gS, gQ, lane, idx);
+        if ((lane & 1) == 0)
+          wpart[((((wset * 4 + quarter) * 4 + (u >> 1)) * 8) + (idx & 7)) * 2 + (idx >> 3)] = tot;
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);
+      // CTA totals per group in a fixed order: thread = (group, which); the entries of a group are enumerated directly
+      float* gmine = gpart + sph * 16;
+      if (te < 16) {
+        const int g = te >> 1, which = te & 1;
+        const int gs = 1 << p.gs_shift;
+        float acc = 0.f;
+        for (int mi = 0; mi < p.tpc; ++mi)
+          for (int c = g * gs; c < (g + 1) * gs; c += 8) {
+            const int n = c / N_TILE, cc = c - n * N_TILE;
+            const int u = (mi * p.n_tiles + n) * SUBTILES + (cc >> 6);
+            const int k = (cc & 63) >> 3;
+            for (int q = 0; q < 4; ++q)
+              acc += wpart[(((((u & 1) * 4 + q) * 4 + (u >> 1)) * 8) + k) * 2 + which];
+          }
+        gmine[te] = acc;
+        if (CL > 1) {
+          // publish: one release-arrive on the exchange barrier of every CTA of the cluster (this thread's own write)
+          for (int r = 0; r < CL; ++r) mbar_arrive_cluster(xbar, (uint32_t)r);
+        }
+      }
+      if (CL > 1) {
+        mbar_wait_cluster(xbar, sph);
+        // one distributed-shared-memory load per thread (independent loads, all in flight together)
+        if (te < 16 * CL)
+          gall[te] = ld_dsmem_f32(gpart_addr + (uint32_t)(sph * 16 + (te & 15)) * 4u, (uint32_t)(te >> 4));
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);          // gmine (CL == 1) / gall (CL > 1) complete
+      // ---------- statistics -> per-channel coefficients ----------
+      const float* gsrc = CL > 1 ? gall : gmine;
+      for (int c = te; c < p.Cout; c += 32 * TC_EPI_WARPS) {
+        const int g = c >> p.gs_shift;
+        float sum = 0.f, sq = 0.f;
+        for (int r = 0; r < CL; ++r) {
+          sum += gsrc[r * 16 + g * 2];
+          sq += gsrc[r * 16 + g * 2 + 1];
+        }
+        const float mean = sum * p.inv_count;
+        const float var = fmaxf(sq * p.inv_count - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        float ga = p.gamma[c] * rstd;
+        float be = p.beta[c] - mean * ga;
+        if (p.film) {
+          const float sc = p.film[(long long)b * p.film_ld + c] + 1.f;
+          const float sh = p.film[(long long)b * p.film_ld + p.Cout + c];
+          ga *= sc;
+          be = be * sc + sh;
+        }
+        // z = ga * (acc + bias) + be; silu(z) = h + h * tanh(h) with h = z / 2: the halves are folded in
+        coefA[c] = 0.5f * ga;
+        coefB[c] = 0.5f * fmaf(ga, bias_s[c], be);
+        if (p.stats && rank == 0 && (c & ((1 << p.gs_shift) - 1)) == 0) {
+          p.stats[((long long)b * 8 + g) * 2] = mean;
+          p.stats[((long long)b * 8 + g) * 2 + 1] = rstd;
+        }
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);
+      // ---------- epilogue 2: apply straight out of TMEM; each accumulator is handed back to the MMA warp ----------
+      for (int u = wset; u < NU; u += 2) {
+        const int a = u / SUBTILES, s2 = u - a * SUBTILES;
+        const int mi = a / p.n_tiles, n = a - mi * p.n_tiles;
+        const int m = rank * p.tpc + mi;
+        const int y0 = (m / p.tiles_x) * 16, x0 = (m % p.tiles_x) * 8;
+        const long long opix = ((long long)b * p.H + y0 + ty) * p.W + x0 + tx;
+        const int cbase = n * N_TILE + s2 * 64;
+        uint8_t* my_row = stage_ptr0 + (nst & 1u) * 4096 + lane * 128;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int c = cbase + hh * 32;
+          uint4 src_res[4];
+          if (p.res) {
+            const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + c);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) src_res[g] = rr[g];
+          }
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * N_TILE + s2 * 64 + hh * 32), r);
+          tmem_ld_wait();
+          if (hh == 1) {                 // last read of this unit: the accumulator may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(a));
+          }
+          float v[32];
+          {
+            const float4* a4 = reinterpret_cast<const float4*>(coefA + c);
+            const float4* b4 = reinterpret_cast<const float4*>(coefB + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 aa = a4[j], bb = b4[j];
+              const float z0 = fmaf(aa.x, __uint_as_float(r[4 * j]), bb.x);
+              const float z1 = fmaf(aa.y, __uint_as_float(r[4 * j + 1]), bb.y);
+              const float z2 = fmaf(aa.z, __uint_as_float(r[4 * j + 2]), bb.z);
+              const float z3 = fmaf(aa.w, __uint_as_float(r[4 * j + 3]), bb.w);
+              v[4 * j] = fmaf(z0, tanh_approx_f(z0), z0);
+              v[4 * j + 1] = fmaf(z1, tanh_approx_f(z1), z1);
+              v[4 * j + 2] = fmaf(z2, tanh_approx_f(z2), z2);
+              v[4 * j + 3] = fmaf(z3, tanh_approx_f(z3), z3);
+            }
+          }
+          if (p.res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 uu;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uu);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            const int chunk = (hh * 4 + g) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(my_row + chunk * 16) = uu;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_5d(&tmY, stage0 + (nst & 1u) * 4096u, cbase, x0, y0 + 4 * quarter, b, 0);
+          tma_store_commit();
+        }
+        ++nst;
+      }
+    }
+    // the staging blocks must outlive the TMA engine's reads; the global writes themselves complete before the grid
+    // does (bulk-async stores are flushed at kernel completion), so the CTA does not wait for them
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  // nobody leaves while a peer may still read its group sums or arrive on its exchange barrier
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
+static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmRaw,
+                     const TcGnParams& p, int B, int CL, cudaStream_t st) {
+  const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
+  const int smem = A_BUFS * HALO_BYTES + b_slots * (N_TILE * TC_BK * 2) + GN_STAGE_BYTES + 1024 + 512 +
+                   (3 * p.Cout + 2 * 4 * 4 * 8 * 2 + 32 + 16 * 8) * 4;
+  B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv_gn: %d B of shared memory", smem);
+  static int configured = 0;
+  auto kernel = conv3x3_gn_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT>;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_gn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // persistent grid: as many clusters as the machine holds at once (one CTA per SM; a cluster lives inside one GPC, so
+  // this is not simply SMs / CL), each walking samples cluster_id, cluster_id + n_clusters, ...
+  static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (max_clusters[CL] == 0) {
+    cfg.gridDim = dim3(CL * 64);
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / CL;
+    }
+    max_clusters[CL] = n;
+  }
+  const int n_clusters = B < max_clusters[CL] ? B : max_clusters[CL];
+  cfg.gridDim = dim3(n_clusters * CL);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmY, tmRaw, p);
+  B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_gn: launch failed: %s", cudaGetErrorString(e));
+  count_launch();
+  return check_launch("conv_gn");
+}
+
+// Geometry of the fused launch: tile shape, cluster size and TMEM columns; false if the layer does not fit.
+struct GnGeom { int n_tile, n_tiles, tiles, cl, tpc, tmem_cols; };
+static bool conv_gn_geometry(const b200dm_conv_desc* d, int groups, GnGeom* g) {
+  if (d->dtype != B200DM_BF16 || d->mode != 0 || d->ksize != 3 || d->accumulate) return false;
+  if (d->Cin % 64 || d->Cout % 64 || d->Cout > 256 || groups != 8) return false;
+  if (d->W < 16 || d->W % 8 || d->H % 16 || d->W > 128 || d->H > 128) return false;
+  const int gs = d->Cout / groups;
+  if (gs < 8 || (gs & (gs - 1))) return false;
+  g->n_tile = d->Cout % 128 == 0 ? 128 : 64;
+  g->n_tiles = d->Cout / g->n_tile;
+  g->tiles = (d->W / 8) * (d->H / 16);
+  // cluster size: the smallest power of two for which the sample's accumulators fit the CTAs' TMEM (512 columns
+  // each); then doubled while that still divides the tiles and the machine is less than ~85 % full
+  int cl = 1;
+  while (cl <= 8 && (g->tiles % cl || (g->tiles / cl) * d->Cout > 512 || (g->tiles / cl) * g->n_tiles > 8)) cl *= 2;
+  if (cl > 8) return false;
+  const int sms = num_sms();
+  while (cl * 2 <= 8 && g->tiles % (cl * 2) == 0 && (long long)d->B * cl * 2 <= sms && g->tiles / (cl * 2) >= 1 &&
+         (g->tiles / (cl * 2)) * g->n_tiles * (g->n_tile / 64) >= 2)
+    cl *= 2;
+  g->cl = cl;
+  g->tpc = g->tiles / cl;
+  const int cols = g->tpc * d->Cout;
+  g->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  return true;
+}
+
+// MEASURED (scripts/conv_microbench.py --what gn, profiles/r2_conv_gn_micro.log): against conv (statistics in the
+// epilogue) + one-pass norm, the fused launch is 10-30 % faster when one wave of CTAs covers the batch (training and
+// 8-way sharded sampling) and within +-7 % when the persistent clusters walk several samples (batch 256 at 64x64), so the
+// launch plan uses it wherever the layer fits: results then do not depend on how the batch is sharded either.
+int conv_gn_supported_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn) {
+  GnGeom g;
+  return (tc_supported() && halo_enabled() && gn && conv_gn_geometry(d, gn->groups, &g)) ? 1 : 0;
+}
+
+int conv_gn_fwd_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* stream) {
+  B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_gn_fwd: needs an sm_100 device and a TMA-capable driver");
+  GnGeom g;
+  B200DM_REQUIRE(gn && conv_gn_geometry(d, gn->groups, &g), B200DM_ERR_UNSUPPORTED,
+                 "conv_gn_fwd: unsupported layer (bf16 3x3 'same', Cin %% 64 == 0, Cout in {64,128,256}, 8 groups, "
+                 "16 <= W <= 128, H %% 16 == 0): Cin=%d Cout=%d H=%d W=%d", d->Cin, d->Cout, d->H, d->W);
+  B200DM_REQUIRE(d->x_ld % 8 == 0 && d->y_ld % 8 == 0 && (!d->res || d->res_ld % 8 == 0) &&
+                     (!gn->raw || gn->raw_ld % 8 == 0), B200DM_ERR_SHAPE, "conv_gn_fwd: ld must be a multiple of 8");
+  B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->y & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
+                     ((uintptr_t)d->res & 15) == 0 && ((uintptr_t)gn->raw & 15) == 0,
+                 B200DM_ERR_SHAPE, "conv_gn_fwd: pointers must be 16-byte aligned");
+  B200DM_REQUIRE(gn->gamma && gn->beta, B200DM_ERR_SHAPE, "conv_gn_fwd: gamma / beta required");
+  TcGnParams p{};
+  p.kblocks = d->Cin / TC_BK;
+  p.H = d->H; p.W = d->W; p.tiles_x = d->W / 8; p.tpc = g.tpc;
+  p.Cout = d->Cout; p.n_tiles = g.n_tiles;
+  int gs = d->Cout / gn->groups, sh = 0;
+  while ((1 << sh) < gs) ++sh;
+  p.gs_shift = sh;
+  p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
+  p.film = gn->film; p.film_ld = gn->film_ld;
+  p.store_raw = gn->raw ? 1 : 0;
+  p.B = d->B;
+  p.tmem_cols = g.tmem_cols;
+  p.bias = d->bias; p.gamma = gn->gamma; p.beta = gn->beta;
+  p.stats = gn->stats;
+  p.eps = gn->eps;
+  p.inv_count = 1.f / ((float)d->H * (float)d->W * (float)gs);
+
+  CUtensorMap tmA, tmB, tmY, tmRaw;
+  const cuuint64_t e = 2;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)d->x_ld * e, (cuuint64_t)d->W * d->x_ld * e,
+                         (cuuint64_t)d->H * d->W * d->x_ld * e, (cuuint64_t)d->B * d->H * d->W * d->x_ld * e};
+    cuuint32_t box[5] = {TC_BK, HALO_W, HALO_H, 1, 1};
+    int rc = encode_map(&tmA, d->x, 5, dims, str, box, "conv_gn A");
+    if (rc) return rc;
+  }
+  auto out_map = [&](CUtensorMap* m, const void* ptr, int ld, const char* what) {
+    cuuint64_t dims[5] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->B, 1};
+    cuuint64_t str[4] = {(cuuint64_t)ld * e, (cuuint64_t)d->W * ld * e, (cuuint64_t)d->H * d->W * ld * e,
+                         (cuuint64_t)d->B * d->H * d->W * ld * e};
+    cuuint32_t box[5] = {64, 8, 4, 1, 1};
+    return encode_map(m, ptr, 5, dims, str, box, what);
+  };
+  int rc = out_map(&tmY, d->y, d->y_ld, "conv_gn Y");
+  if (rc) return rc;
+  rc = out_map(&tmRaw, gn->raw ? gn->raw : d->y, gn->raw ? gn->raw_ld : d->y_ld, "conv_gn raw");
+  if (rc) return rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout, 9};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout * d->Cin * 2};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)g.n_tile, 1};
+    rc = encode_map(&tmB, d->w, 3, dims, str, box, "conv_gn B");
+    if (rc) return rc;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool resident = (d->Cout == 64 && d->Cin == 64);
+  if (resident) return launch_gn<64, HALO_W <= 10 ? 3 : 2, 1, true>(tmA, tmB, tmY, tmRaw, p, d->B, g.cl, st);
+  if (g.n_tile == 128) return launch_gn<128, HALO_W <= 10 ? 3 : 2, HALO_W <= 10 ? 5 : 4, false>(tmA, tmB, tmY, tmRaw, p, d->B, g.cl, st);
+  return launch_gn<64, HALO_W <= 10 ? 4 : 2, 6, false>(tmA, tmB, tmY, tmRaw, p, d->B, g.cl, st);
 }
 
 // =====================================================================================================
@@ -1125,6 +1829,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                            (k > 0) ? 1u : (kt > kt0 ? 1u : 0u));
           umma_commit(empty_bar(stage));
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(tmem_full_bar);
@@ -1264,7 +1969,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int b = t / tiles_per_img, rem = t - b * tiles_per_img;
         const int y0 = (rem / p.tiles_x) * 16, x0 = (rem % p.tiles_x) * 8;
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        mbar_expect_tx(full_bar(stage), HALO_TX + DY_BYTES);
         const uint32_t x_dst = base + stage * STAGE_BYTES;
         tma_load_5d(x_dst, &tmX, full_bar(stage), cib * TC_BK, x0 - 1, y0 - 1, b, 0);
         tma_load_5d(x_dst + HALO_BYTES, &tmDY, full_bar(stage), cob * TC_BK, x0, y0, b, 0);
@@ -1302,6 +2007,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
           umma_commit(empty_bar(stage));
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (leader) umma_commit(tmem_full_bar);
@@ -1350,7 +2056,7 @@ static bool wgrad_halo_enabled() {
 }
 
 static int conv_wgrad_halo(const b200dm_wgrad_desc* d, cudaStream_t st) {
-  constexpr int STAGES = 4;
+  constexpr int STAGES = HALO_W <= 10 ? 5 : 4;
   TcWgradHaloParams p{};
   p.H = d->H; p.W = d->W; p.tiles_x = d->W / 8; p.tiles_y = d->H / 16;
   p.m_tiles = d->B * p.tiles_x * p.tiles_y;
@@ -1454,12 +2160,12 @@ umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base, b_base = base + 64 * 1024;     // 64 KiB A region, up to 32 KiB B region
-  const uint32_t bar = b_base + 64 * 1024, tmem_slot = bar + 8;
+  const uint32_t bar = b_base + 64 * 1024, tmem_slot = bar + 8;      // bar + 16: scratch barrier of modes 3 / 4
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x * 16; i < 128 * 1024; i += blockDim.x * 16)
     *reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)) + i) = make_uint4(0, 0, 0, 0);
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 16, 1); fence_barrier_init(); }
   fence_proxy_async();
   if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
@@ -1476,7 +2182,26 @@ umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
     const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
     const uint32_t a_lo = (uint32_t)a_desc0, b_lo = (uint32_t)b_desc0;
     const long long t0 = clock64();
-    if (leader) {
+    if (leader && mode >= 3) {
+      // modes 3 / 4: the issue pattern of one conv3x3_halo tile with resident weights (N = 64): 36 MMAs over nine
+      // shifted halo windows and nine weight tiles, followed (mode 3) by the two tcgen05.commit of a tile boundary;
+      // `iters` tiles back to back.  Cycles are reported per MMA like the other modes.
+      const uint64_t ah = make_smem_desc(a_base, 16, HALO_W * 128);
+      const uint32_t ah_lo = (uint32_t)ah, ah_hi = (uint32_t)(ah >> 32);
+      const uint32_t bar2 = bar + 16;
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lohi(tmem_base + (uint32_t)((it & 1) * 64), ah_lo + (uint32_t)(((dx + HALO_W * dy) * 128 + k * 32) >> 4),
+                           ah_hi, b_lo + (uint32_t)(((tap % 7) * 8192 + k * 32) >> 4), b_hi, idesc, (tap | k) ? 1u : 0u);
+        }
+        if (mode == 3) { umma_commit(bar2); umma_commit(bar2); }
+      }
+      umma_commit(bar);
+    } else if (leader) {
       for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1496,6 +2221,12 @@ umma_rate_kernel(int iters, int mode, long long* __restrict__ out_cycles) {
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 }  // namespace b200dm
+
+#ifdef B200DM_PHASE_TIMING
+extern "C" int b200dm_debug_set_timing_buf(long long* buf) {
+  return cudaMemcpyToSymbol(b200dm::g_tbuf, &buf, sizeof(buf)) == cudaSuccess ? 0 : -4;
+}
+#endif
 
 extern "C" int b200dm_debug_umma_rate(int32_t n_tile, int32_t iters, int32_t mode, int32_t ctas, long long* out_cycles,
                                       void* stream) {

@@ -247,6 +247,54 @@ extern "C" int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v,
   return check_launch("adam_step");
 }
 
+// ---- gradient compression for the wire (opt-in bf16 all-reduce, b200dm.distributed.GradSync(wire="bf16")) ----------
+namespace b200dm {
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            int64_t n4) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 o;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
+                                                            int64_t n4) {
+  pdl_prologue();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(x)[i];
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    reinterpret_cast<float4*>(y)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+}  // namespace b200dm
+
+extern "C" int b200dm_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  B200DM_REQUIRE(n >= 0 && n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0, B200DM_ERR_SHAPE,
+                 "cast_f32_bf16: n %% 4 == 0 and aligned pointers required");
+  if (n == 0) return B200DM_OK;
+  int64_t blocks = (n / 4 + 255) / 256, cap = (int64_t)b200dm::num_sms() * 8;
+  launch_k(b200dm::cast_f32_bf16_kernel, (int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, x,
+           (__nv_bfloat16*)y, n / 4);
+  b200dm::count_launch();
+  return b200dm::check_launch("cast_f32_bf16");
+}
+
+extern "C" int b200dm_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream) {
+  B200DM_REQUIRE(n >= 0 && n % 4 == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)x & 7) == 0, B200DM_ERR_SHAPE,
+                 "cast_bf16_f32: n %% 4 == 0 and aligned pointers required");
+  if (n == 0) return B200DM_OK;
+  int64_t blocks = (n / 4 + 255) / 256, cap = (int64_t)b200dm::num_sms() * 8;
+  launch_k(b200dm::cast_bf16_f32_kernel, (int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream,
+           (const __nv_bfloat16*)x, y, n / 4);
+  b200dm::count_launch();
+  return b200dm::check_launch("cast_bf16_f32");
+}
+
 extern "C" int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream) {
   B200DM_REQUIRE(n > 0, B200DM_ERR_SHAPE, "ema_update: empty");
   int64_t blocks = (n + 255) / 256, cap = (int64_t)num_sms() * 16;

@@ -3,8 +3,12 @@
 SURVEY.md Appendix A at B=128, S=32), through the C ABI.  Launches are issued back-to-back behind a
 device-side sleep so CUDA events measure GPU time, not host launch rate.
 
-  python scripts/conv_microbench.py [--what fwd|wgrad|both] [--reps 20] [--batch 128] [--size 32] [--only i]
+  python scripts/conv_microbench.py [--what fwd|wgrad|both|gn] [--reps 20] [--batch 128] [--size 32] [--only i]
+
+--what gn: the fused conv + GroupNorm + FiLM + SiLU launch (b200dm_conv_gn_fwd) next to the two launches it replaces
+(b200dm_conv_fwd with statistics in the epilogue + b200dm_gn_fwd_pre), for every 3x3 layer the fused kernel supports.
 """
+import ctypes
 import argparse
 import json
 import os
@@ -54,6 +58,45 @@ def main():
         wd = L.WgradDesc(dtype=L.BF16, mode=0, ksize=k, impl=1, B=B, H=H, W=H, Cin=cin, Cout=cout, x=x.ptr,
                          x_ld=x.ld, dy=dy.ptr, dy_ld=dy.ld, dw=dw.data_ptr(), accumulate=1)
         rec = {"level": lvl, "H": H, "Cin": cin, "Cout": cout, "k": k, "gflop": flops / 1e9}
+        if a.what == "gn":
+            gamma, beta = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+            film = torch.randn(B, 2 * cout, device=dev) * 0.1
+            stats = torch.zeros(B, 8, 2, device=dev)
+            h = View.zeros(B, H, H, cout, torch.bfloat16, dev)
+            gd = L.GnDesc(gamma=gamma.data_ptr(), beta=beta.data_ptr(), film=film.data_ptr(), film_ld=2 * cout,
+                          groups=8, eps=1e-5, raw_ld=0, stats=None, raw=None)
+            gd_tr = L.GnDesc(gamma=gamma.data_ptr(), beta=beta.data_ptr(), film=film.data_ptr(), film_ld=2 * cout,
+                             groups=8, eps=1e-5, raw_ld=y.ld, stats=stats.data_ptr(), raw=y.ptr)
+            cg = L.ConvDesc(dtype=L.BF16, mode=0, ksize=k, impl=1, B=B, H=H, W=H, Cin=cin, Cout=cout, x=x.ptr,
+                            x_ld=x.ld, w=w.data_ptr(), bias=bias.data_ptr(), y=h.ptr, y_ld=h.ld, res=None,
+                            res_ld=0, accumulate=0)
+            if k != 3 or not L.load().b200dm_conv_gn_supported(ctypes.byref(cg), ctypes.byref(gd)):
+                continue
+            slots = H * H // min(32, H * H)
+            part = torch.zeros(B, slots, cout // 8, 2, device=dev)
+            cd.gn_part, cd.gn_groups = part.data_ptr(), 8
+
+            def two():
+                L.call("b200dm_conv_fwd", cd)
+                L.call("b200dm_gn_fwd_pre", L.BF16, y.ptr, y.ld, part.data_ptr(), slots, stats.data_ptr(),
+                       gamma.data_ptr(), beta.data_ptr(), film.data_ptr(), 2 * cout, None, 0, h.ptr, h.ld, B, H * H,
+                       cout, 8, 1e-5)
+            for nm, fn in (("conv+gn", two), ("fused_infer", lambda: L.call("b200dm_conv_gn_fwd", cg, gd)),
+                           ("fused_train", lambda: L.call("b200dm_conv_gn_fwd", cg, gd_tr))):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda._sleep(4_000_000)
+                e0.record()
+                for _ in range(a.reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                rec[nm + "_us"] = round(e0.elapsed_time(e1) * 1e3 / a.reps, 2)
+            rows.append(rec)
+            print(json.dumps(rec), flush=True)
+            continue
         for what, name, desc in (("fwd", "b200dm_conv_fwd", cd), ("wgrad", "b200dm_conv_wgrad", wd)):
             if a.what not in (what, "both"):
                 continue

@@ -7,7 +7,7 @@ O=gpurun_out
 mkdir -p $O
 rm -f $O/parity_report.jsonl
 if [ "$WHAT" = "tests" ] || [ "$WHAT" = "all" ]; then
-  timeout 2400 python -m pytest tests -m gpu -q -x --timeout=1500 > $O/${TAG}_pytest.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest.log
+  timeout 2400 python -m pytest tests -m gpu -q --timeout=1500 > $O/${TAG}_pytest.log 2>&1; echo "exit $?" >> $O/${TAG}_pytest.log
   tail -25 $O/${TAG}_pytest.log
   cp $O/parity_report.jsonl $O/${TAG}_parity_report.jsonl 2>/dev/null
 fi

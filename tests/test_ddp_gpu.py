@@ -50,8 +50,30 @@ def _worker(rank, world, port, q):
         loss.backward()
     torch.cuda.synchronize()
     grads = (unet.arena.gflat * sync.grad_scale).cpu()
+    # gradient accumulation under data parallel: micro-batches inside no_sync() only accumulate locally,
+    # the last one all-reduces the sum; a second synchronising backward without zero_grad() is refused
+    unet.zero_grad()
+    xs, ts, ns = x[sl].to(dev), t[sl].to(dev), noise[sl].to(dev)
+    with unet.no_sync():
+        (gd.p_losses(xs[:1], ts[:1], noise=ns[:1], _normalize=True) / 2).backward()
+    (gd.p_losses(xs[1:], ts[1:], noise=ns[1:], _normalize=True) / 2).backward()
+    torch.cuda.synchronize()
+    acc = (unet.arena.gflat * sync.grad_scale).cpu()
+    refused = False
+    try:
+        (gd.p_losses(xs[1:], ts[1:], noise=ns[1:], _normalize=True) / 2).backward()
+    except RuntimeError:
+        refused = True
+    # opt-in bf16 wire: same sums within bf16 rounding
+    from b200dm.distributed import GradSync
+    unet.grad_sync = GradSync(unet.arena, wire="bf16")
+    unet.zero_grad()
+    gd.p_losses(xs, ts, noise=ns, _normalize=True).backward()
+    torch.cuda.synchronize()
+    g16 = (unet.arena.gflat * sync.grad_scale).cpu()
+    unet.grad_sync = sync
     imgs = gd.sample_shard(4, rank, world, seed=7).cpu()
-    q.put((rank, grads, imgs))
+    q.put((rank, grads, imgs, acc, refused, g16))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,8 +96,11 @@ def test_two_rank_gradients_and_sharded_samples_match_single_gpu():
     x, t, noise = _inputs()
     gd.p_losses(x.to(dev), t.to(dev), noise=noise.to(dev), _normalize=True).backward()
     ref = unet.arena.gflat.cpu()
-    for rank, grads, _ in res:
+    for rank, grads, _, acc, refused, g16 in res:
         assert ((grads - ref).norm() / ref.norm()).item() < 1e-5, rank
+        assert ((acc - ref).norm() / ref.norm()).item() < 1e-5, rank          # accumulation == one big batch
+        assert refused, rank
+        assert ((g16 - ref).norm() / ref.norm()).item() < 5e-3, rank          # bf16 on the wire
     full = gd.sample_shard(4, 0, 1, seed=7).cpu()
     both = torch.cat([res[0][2], res[1][2]], 0)
     assert (full - both).abs().max().item() < 1e-5

@@ -608,6 +608,68 @@ def test_conv_epilogue_groupnorm_statistics_and_one_pass_norm(B, S, Cin, Cout, f
     assert torch.equal(part, part2)
 
 
+@pytest.mark.parametrize("B,S,Cin,Cout,film,res,raw", [
+    (3, 32, 64, 64, True, False, True),        # resident weights, cluster of 4 (small batch)
+    (80, 32, 64, 64, False, True, False),      # one CTA per sample, all 8 accumulators (512 TMEM columns)
+    (2, 16, 128, 128, True, False, True),      # N = 128 tiles
+    (2, 16, 192, 128, False, True, True),      # Cin = 192 (concat input), streamed weights
+    (2, 64, 64, 64, False, False, True),       # 64x64: cluster of 8, four tiles per CTA
+    (2, 32, 256, 128, True, True, False),      # cluster, N = 128, residual
+    (2, 16, 256, 256, True, True, True),       # two N tiles per pixel tile
+    (100, 16, 64, 64, True, True, True),       # two accumulators per CTA
+    (40, 64, 128, 64, False, True, True),      # cluster of 4 x 8 tiles at 64x64, Cin = 128
+])
+def test_conv_groupnorm_film_silu_one_launch(B, S, Cin, Cout, film, res, raw):
+    """b200dm_conv_gn_fwd: Block.forward (ddpm.py:164-173) + the residual of ResnetBlock (:200) in ONE launch, with the
+    conv accumulators resident in TMEM; against conv2d -> group_norm -> FiLM -> SiLU (+ res) in fp32."""
+    if not L.load().b200dm_tc_available():
+        pytest.skip("needs the tcgen05 path")
+    G = 8
+    x = q(rnd(B, Cin, S, S, seed=191), L.BF16)
+    w = q(rnd(Cout, Cin, 3, 3, seed=192, scale=1 / math.sqrt(Cin * 9)), L.BF16)
+    bias = rnd(Cout, seed=193, scale=0.3)
+    gamma, beta = 1 + 0.1 * rnd(Cout, seed=194), 0.1 * rnd(Cout, seed=195)
+    fm = rnd(B, 2 * Cout + 8, seed=196, scale=0.3) if film else None
+    r = q(rnd(B, Cout, S, S, seed=197), L.BF16) if res else None
+    conv = F.conv2d(x, w, bias, padding=1)
+    h = F.group_norm(conv, G, gamma, beta, eps=1e-5)
+    if film:
+        h = h * (fm[:, :Cout, None, None] + 1) + fm[:, Cout:2 * Cout, None, None]
+    ref = F.silu(h) + (r if res else 0)
+    xv = nhwc(x, L.BF16, ld=Cin + 64, off=64)            # channel slice of a wider (concat) buffer
+    yv = View.zeros(B, S, S, Cout, torch.bfloat16, DEV, ld=2 * Cout, off=Cout)
+    cv = View.zeros(B, S, S, Cout, torch.bfloat16, DEV) if raw else None
+    rv = nhwc(r, L.BF16) if res else None
+    stats = torch.full((B, G, 2), float("nan"), device=DEV)
+    wp = w.permute(2, 3, 0, 1).reshape(9, Cout, Cin).contiguous().to(torch.bfloat16)
+    d = L.ConvDesc(dtype=L.BF16, mode=0, ksize=3, impl=1, B=B, H=S, W=S, Cin=Cin, Cout=Cout, x=xv.ptr, x_ld=xv.ld,
+                   w=wp.data_ptr(), bias=bias.data_ptr(), y=yv.ptr, y_ld=yv.ld, res=None if rv is None else rv.ptr,
+                   res_ld=0 if rv is None else rv.ld, accumulate=0, gn_part=None, gn_groups=0)
+    gnd = L.GnDesc(gamma=gamma.data_ptr(), beta=beta.data_ptr(), film=None if fm is None else fm.data_ptr(),
+                   film_ld=0 if fm is None else fm.shape[1], groups=G, eps=1e-5, raw_ld=0 if cv is None else cv.ld,
+                   stats=stats.data_ptr(), raw=None if cv is None else cv.ptr)
+    assert L.load().b200dm_conv_gn_supported(ctypes.byref(d), ctypes.byref(gnd)) == 1
+    L.call("b200dm_conv_gn_fwd", ctypes.byref(d), ctypes.byref(gnd))
+    cg = conv.reshape(B, G, -1)
+    assert rel(stats[..., 0], cg.mean(-1)) < 1e-3
+    assert rel(stats[..., 1], (cg.var(-1, unbiased=False) + 1e-5).rsqrt()) < 1e-3
+    out = yv.to_nchw()
+    assert rel(out, ref) < 4e-3, rel(out, ref)            # one bf16 rounding of the output + tanh.approx
+    assert (out - ref).abs().max().item() < 0.06
+    assert torch.equal(yv.buf[..., :Cout], torch.zeros_like(yv.buf[..., :Cout]))     # the other slice is untouched
+    if raw:
+        assert rel(cv.to_nchw(), conv) < 4e-3
+    # deterministic (no atomics anywhere on the statistics path): bit-identical on a second run
+    first, st1 = yv.buf.clone(), stats.clone()
+    L.call("b200dm_conv_gn_fwd", ctypes.byref(d), ctypes.byref(gnd))
+    assert torch.equal(first, yv.buf) and torch.equal(st1, stats)
+    # unsupported layers are reported, not mis-executed
+    d2 = L.ConvDesc(dtype=L.BF16, mode=0, ksize=3, impl=1, B=B, H=8, W=8, Cin=Cin, Cout=Cout, x=xv.ptr, x_ld=xv.ld,
+                    w=wp.data_ptr(), bias=bias.data_ptr(), y=yv.ptr, y_ld=yv.ld, res=None, res_ld=0, accumulate=0,
+                    gn_part=None, gn_groups=0)
+    assert L.load().b200dm_conv_gn_supported(ctypes.byref(d2), ctypes.byref(gnd)) == 0
+
+
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
 @pytest.mark.parametrize("Cc,res", [(64, False), (128, True), (256, True), (512, False)])
 def test_rmsnorm_fwd_bwd(dtype, Cc, res):
