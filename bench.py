@@ -424,7 +424,10 @@ class Ctx:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=self.dev)
+            from b200dm.distributed import nccl_options
+            opts = nccl_options()               # caps the collective's CTAs (the backward kernels leave those SMs free)
+            kw = {"pg_options": opts} if opts is not None else {}
+            dist.init_process_group("nccl", device_id=self.dev, **kw)
             self.dist = dist
         self.peaks = measured_peaks()
 

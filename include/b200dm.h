@@ -323,6 +323,11 @@ int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* d
                       float* dW, float* db, int32_t M, int32_t N, int32_t K, int32_t act,
                       void* stream);
 
+/* The same for a column range of a layer without activation: dY = [M, N] window of a [M, ldy] matrix, W / dW = the
+ * matching N rows ([N, K]); dX = dY W is overwritten, or added to when dx_accumulate != 0; no bias gradient. */
+int b200dm_linear_bwd_cols(const float* X, const float* W, const float* dY, int32_t ldy, float* dX,
+                           int32_t dx_accumulate, float* dW, int32_t M, int32_t N, int32_t K, void* stream);
+
 /* Diagnostic (scripts/umma_rate.py): cycles for `iters` x 8 tcgen05.mma (M=128, N=n_tile, K=16) issued by one
  * thread per CTA on resident shared-memory operands; mode 0 = K-major SW128, 1 = shifted halo view,
  * 2 = MN-major (wgrad).  out_cycles: int64 [ctas]. */
@@ -367,6 +372,9 @@ int b200dm_adam_step_bg(float* p, const float* g, float* m, float* v, int64_t n,
 /* ema = ema + (1-decay)*(online-ema)  (ema_pytorch lerp), or copy when decay == 0 */
 int b200dm_ema_update(float* ema, const float* online, int64_t n, float decay, void* stream);
 int b200dm_fill_f32(float* p, int64_t n, float value, void* stream);
+/* Launches issued after this call size their persistent grids for (SM count - n) SMs: set while a collective with n
+ * CTAs (NCCL_MAX_CTAS / ProcessGroupNCCL max_ctas) runs next to the backward pass, 0 otherwise.  Process-wide. */
+int b200dm_set_reserved_sms(int32_t n);
 /* fp32 <-> bf16 copies of a gradient bucket for the opt-in bf16 all-reduce (n % 4 == 0). */
 int b200dm_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 int b200dm_cast_bf16_f32(const void* x, float* y, int64_t n, void* stream);

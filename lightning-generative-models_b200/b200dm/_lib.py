@@ -116,6 +116,7 @@ PROTOTYPES = {
     "b200dm_sinusoidal": [_P, _P, _I, _I, _F, _P],
     "b200dm_linear_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200dm_linear_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "b200dm_linear_bwd_cols": [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P],
     "b200dm_pack_conv_weight": [_I, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _P],
     "b200dm_pack_conv_weights_batched": [_I, _P, _I, _I, _P],
     "b200dm_pack_conv_weights_range": [_I, _P, _I, _I, _I, _P],
@@ -134,6 +135,7 @@ _SPECIAL = {
     "b200dm_gn_bwd_ws_floats": ([_I, _I, _I], C.c_int64),
     "b200dm_reset_launch_count": ([], None),
     "b200dm_tc_available": ([], C.c_int),
+    "b200dm_set_reserved_sms": ([C.c_int32], C.c_int),
     "b200dm_conv_gn_supported": ([C.POINTER(ConvDesc), C.POINTER(GnDesc)], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))

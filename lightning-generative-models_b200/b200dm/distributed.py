@@ -23,6 +23,24 @@ import torch
 import torch.distributed as dist
 
 
+# CTAs NCCL may use for the gradient all-reduce = SMs the backward kernels leave free while it runs.  The step needs
+# only ~60 GB/s of all-reduce bandwidth to hide 143 MB behind a 2.8 ms backward pass; every NCCL CTA costs a whole SM,
+# because a conv CTA (>= 200 KiB of shared memory) cannot share one with it.
+COMM_CTAS = int(os.environ.get("B200DM_COMM_CTAS", "8"))
+
+
+def nccl_options():
+    """ProcessGroupNCCL options that cap the collective at COMM_CTAS CTAs (None if this torch cannot express it)."""
+    try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = COMM_CTAS
+        opts.config.min_ctas = min(COMM_CTAS, 4)
+        return opts
+    except Exception:                                   # noqa: BLE001
+        os.environ.setdefault("NCCL_MAX_CTAS", str(COMM_CTAS))
+        return None
+
+
 def init_from_env(backend: str | None = None):
     """Initialise torch.distributed from torchrun's environment (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -35,6 +53,9 @@ def init_from_env(backend: str | None = None):
         if backend == "nccl":
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
+            opts = nccl_options()
+            if opts is not None:
+                kw["pg_options"] = opts
         dist.init_process_group(backend, **kw)
     return rank, local, world
 
@@ -42,7 +63,9 @@ def init_from_env(backend: str | None = None):
 # Backward-completion order of the gradient regions (= Plan.bwd_segments): the down path is cut per level so that only
 # the gradients of the last (level-0) blocks and of the arena head remain to be reduced when backward ends — the big
 # level-3 / level-2 tensors of the down path are on the wire while the slow level-0 layers are still computing.
-REGIONS = ("final", "ups", "mid", "downs.3", "downs.2", "downs.1", "downs.0", "head")
+# "film" = the rows of the FiLM projection that belong to every block but the two level-0 blocks of the down path:
+# their gradient GEMM runs (second stream) as soon as level 1 of the down path is done.
+REGIONS = ("final", "ups", "mid", "downs.3", "downs.2", "downs.1", "film", "downs.0", "head")
 
 
 def buckets(arena) -> List[Tuple[int, int]]:
@@ -59,8 +82,11 @@ def buckets(arena) -> List[Tuple[int, int]]:
     named = {"final": region("final_"), "ups": region("ups."), "mid": region("mid_")}
     for i in range(4):
         named[f"downs.{i}"] = region(f"downs.{i}.")
-    # stem, time MLP and the concatenated FiLM projections (arena head) are finished last
-    named["head"] = (0, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1])
+    # arena head: [FiLM weight rows of all but the level-0 down blocks | level-0 rows, FiLM biases, stem, time MLP];
+    # the second part is finished last
+    cut = arena.film_early_cols * arena.time_dim
+    named["film"] = (0, cut)
+    named["head"] = (cut, span(lambda n: n.startswith("init_conv") or n.startswith("time_mlp"))[1])
     # make the regions tile the arena exactly (alignment padding goes to the following region)
     by_mem = sorted(named.items(), key=lambda kv: kv[1][0])
     tiled, prev = {}, 0
@@ -83,8 +109,12 @@ class GradSync:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buckets = buckets(arena)
         self.cuda = arena.gflat.is_cuda
-        self.stream = torch.cuda.Stream() if (self.cuda and self.world > 1) else None
+        # high priority: the collective's CTAs are dispatched ahead of pending compute blocks whenever an SM frees up
+        # (the conv kernels are persistent one-CTA-per-SM grids launched back to back, which otherwise starve NCCL)
+        self.stream = torch.cuda.Stream(priority=-1) if (self.cuda and self.world > 1) else None
         self.handles = []
+        # SMs the backward kernels leave to the collective while it is in flight (b200dm_set_reserved_sms)
+        self.reserved_sms = COMM_CTAS if (self.cuda and self.world > 1) else 0
         self.wire = wire or os.environ.get("B200DM_GRAD_WIRE", "fp32")
         assert self.wire in ("fp32", "bf16")
         self._wire_buf = None

@@ -491,9 +491,13 @@ class Plan:
                self.tact.data_ptr(), self.pre3.data_ptr(), B, td, td, 2, side=True)
         self.F("b200dm_linear_fwd", self.tact.data_ptr(), a.film_weight_ptr, a.film_bias_ptr,
                self.film.data_ptr(), None, B, a.film_cols, td, 0, side=True, writes=(self.film,))
-        if tr:  # runs LAST in backward (dfilm is complete once every block has run)
-            self.Bk("b200dm_linear_bwd", self.tact.data_ptr(), a.film_weight_ptr, None, self.dfilm.data_ptr(),
-                    self.dtact.data_ptr(), a.film_weight_gptr, a.film_bias_gptr, B, a.film_cols, td, 0)
+        if tr:  # runs LAST in backward (dfilm is complete once every block has run): the FiLM rows of the two level-0
+            # down blocks (+ the bias gradient of all rows); the other rows were done behind level 1 (see below)
+            ec = a.film_early_cols
+            self.Bk("b200dm_linear_bwd_cols", self.tact.data_ptr(), a.film_weight_ptr + 4 * ec * td,
+                    self.dfilm.data_ptr() + 4 * ec, a.film_cols, self.dtact.data_ptr(), 1,
+                    a.film_weight_gptr + 4 * ec * td, B, a.film_cols - ec, td)
+            self.Bk("b200dm_colsum", L.F32, self.dfilm.data_ptr(), a.film_cols, B, a.film_cols, a.film_bias_gptr, 1)
             self.Bk("b200dm_linear_bwd", self.h.data_ptr(), a.ptr("time_mlp.3.weight"), self.pre3.data_ptr(),
                     self.dtact.data_ptr(), self.dh.data_ptr(), a.gptr("time_mlp.3.weight"),
                     a.gptr("time_mlp.3.bias"), B, td, td, 2)
@@ -558,6 +562,16 @@ class Plan:
             x4, gx4 = self.buf(Hn, d_out), G(Hn, d_out)
             self.plain_conv(f"downs.{i}.3" if last else f"downs.{i}.3.1", x3, x4, gx3, gx4, gx_prior=True)
             x, gx, x_prior = x4, gx4, False
+            if i == 0 and tr:
+                # backward reaches this unit when levels 3..1 of the down path (and everything above) are done: all
+                # FiLM gradients except those of the two level-0 blocks are final -> their share of the projection's
+                # weight gradient and of d(time activation) now, on the second stream, and its bucket on the wire
+                self._region = "film"
+                self.begin_unit()
+                ec = a.film_early_cols
+                self.Bk("b200dm_linear_bwd_cols", self.tact.data_ptr(), a.film_weight_ptr, self.dfilm.data_ptr(),
+                        a.film_cols, self.dtact.data_ptr(), 0, a.film_weight_gptr, B, ec, td, side=True,
+                        reads=(self.dfilm,), writes=(self.dtact,))
 
         mid = dims[4]
         Hm = res[3]

@@ -120,16 +120,22 @@ class ParamArena:
         self.spec, self.convs, self.block_order, self.blocks = build_spec(dim, channels)
         self.shapes = dict(self.spec)
         self.time_dim = 4 * dim
-        # FiLM column offsets
+        # FiLM column layout: every block's (scale | shift) columns, the two level-0 blocks of the down path LAST.
+        # Those two are the last ResnetBlocks of the backward pass, so the rows [0, film_early_cols) of the projection's
+        # weight gradient are complete — and their all-reduce can start — while level 0 is still computing.
+        self.film_order = ([b for b in self.block_order if not b.startswith("downs.0.")]
+                           + [b for b in self.block_order if b.startswith("downs.0.")])
         self.film_off: Dict[str, int] = {}
         col = 0
-        for b in self.block_order:
+        for b in self.film_order:
+            if b.startswith("downs.0.") and not hasattr(self, "film_early_cols"):
+                self.film_early_cols = col
             self.film_off[b] = col
             col += 2 * self.blocks[b][1]
         self.film_cols = col
         # arena placement
-        film_w = [b + ".mlp.1.weight" for b in self.block_order]
-        film_b = [b + ".mlp.1.bias" for b in self.block_order]
+        film_w = [b + ".mlp.1.weight" for b in self.film_order]
+        film_b = [b + ".mlp.1.bias" for b in self.film_order]
         placed = film_w + film_b
         placed_set = set(placed)
         placed += [nm for nm, _ in self.spec if nm not in placed_set]
@@ -187,19 +193,19 @@ class ParamArena:
 
     @property
     def film_weight_ptr(self):
-        return self.ptr(self.block_order[0] + ".mlp.1.weight")
+        return self.ptr(self.film_order[0] + ".mlp.1.weight")
 
     @property
     def film_bias_ptr(self):
-        return self.ptr(self.block_order[0] + ".mlp.1.bias")
+        return self.ptr(self.film_order[0] + ".mlp.1.bias")
 
     @property
     def film_weight_gptr(self):
-        return self.gptr(self.block_order[0] + ".mlp.1.weight")
+        return self.gptr(self.film_order[0] + ".mlp.1.weight")
 
     @property
     def film_bias_gptr(self):
-        return self.gptr(self.block_order[0] + ".mlp.1.bias")
+        return self.gptr(self.film_order[0] + ".mlp.1.bias")
 
     def load(self, sd: Dict[str, torch.Tensor], prefix: str = ""):
         missing = [nm for nm, _ in self.spec if prefix + nm not in sd]

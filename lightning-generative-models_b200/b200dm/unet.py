@@ -258,6 +258,9 @@ class Unet(nn.Module):
             self._reduced = True
         nseg = len(plan.bwd_segments)
         hook = self.bucket_hook
+        reserve = sync.reserved_sms if sync is not None else 0
+        if reserve:          # the launches below (eager or captured) size their grids for the SMs NCCL leaves free
+            L.load().b200dm_set_reserved_sms(reserve)
         if hook is not None and self._buckets is None:
             from .distributed import buckets
             self._buckets = buckets(self.arena)
@@ -285,6 +288,8 @@ class Unet(nn.Module):
                         plan.run_backward_segment(i)
                     graphs.append(g)
                 plan.graph_bwd = graphs
+        if reserve:
+            L.load().b200dm_set_reserved_sms(0)
         if sync is not None:
             sync.finish()
 

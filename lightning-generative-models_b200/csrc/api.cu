@@ -17,6 +17,9 @@ bool pdl_enabled() {
 }
 
 
+static std::atomic<int> g_reserved_sms{0};
+int reserved_sms() { return g_reserved_sms.load(std::memory_order_relaxed); }
+
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread
 
@@ -53,6 +56,11 @@ extern "C" const char* b200dm_last_error(void) { return g_err; }
 extern "C" int64_t b200dm_launch_count(void) { return g_launches.load(); }
 extern "C" void b200dm_reset_launch_count(void) { g_launches = 0; }
 extern "C" int b200dm_tc_available(void) { return tc_supported() ? 1 : 0; }
+extern "C" int b200dm_set_reserved_sms(int32_t n) {
+  B200DM_REQUIRE(n >= 0 && n <= 64, B200DM_ERR_SHAPE, "set_reserved_sms: n=%d out of range [0, 64]", n);
+  g_reserved_sms.store(n);
+  return B200DM_OK;
+}
 
 static int check_conv_common(int dtype, int mode, int ksize, int B, int H, int W, int Cin, int Cout) {
   B200DM_REQUIRE(dtype == B200DM_F32 || dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "conv: dtype %d", dtype);

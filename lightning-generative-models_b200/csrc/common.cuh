@@ -52,6 +52,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// SMs the persistent grids size themselves for: the device's SM count minus the SMs set aside for a concurrent
+// collective (b200dm_set_reserved_sms).  A conv CTA needs a whole SM (>= 200 KiB of shared memory), so while NCCL's
+// CTAs hold SMs a 148-CTA grid runs as two waves; sizing it to the free SMs keeps it at one.
+int reserved_sms();
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -60,7 +64,8 @@ inline int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return n;
+  const int r = reserved_sms();
+  return n - r > 16 ? n - r : n;
 }
 
 // ---- element access templated on the activation dtype -----------------------------------------

@@ -183,6 +183,42 @@ extern "C" int b200dm_linear_fwd(const float* X, const float* W, const float* b,
   return check_launch("linear_fwd");
 }
 
+// Backward of a COLUMN RANGE of a linear layer without activation: dY is a [M, N] window of a wider [M, ldy] matrix,
+// W / dW the matching N rows.  dX is overwritten or (dx_accumulate) added to.  Lets the FiLM projection of the Unet
+// finish the gradients of most of its 8064 rows long before the last two ResnetBlocks of the backward pass are done.
+extern "C" int b200dm_linear_bwd_cols(const float* X, const float* W, const float* dY, int32_t ldy, float* dX,
+                                      int32_t dx_accumulate, float* dW, int32_t M, int32_t N, int32_t K,
+                                      void* stream) {
+  B200DM_REQUIRE(M > 0 && N > 0 && K > 0 && ldy >= N, B200DM_ERR_SHAPE, "linear_bwd_cols: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  if (dX) {
+    int tiles = ((M + GM - 1) / GM) * ((K + GN - 1) / GN);
+    int chunks = (N + GK - 1) / GK;
+    int splits = 1;
+    if (tiles < num_sms() && chunks >= 8) {
+      splits = (2 * num_sms() + tiles - 1) / tiles;
+      if (splits > chunks / 4) splits = chunks / 4;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > 1 && !dx_accumulate) {
+      int rc = b200dm_fill_f32(dX, (int64_t)M * K, 0.f, stream);
+      if (rc) return rc;
+    }
+    dim3 grid((M + GM - 1) / GM, (K + GN - 1) / GN, splits);
+    launch_k(sgemm_kernel<false, false>, grid, 256, 0, st, dY, ldy, W, K, dX, K, nullptr, nullptr, M, K, N, 0,
+             dx_accumulate ? 1 : 0, splits);
+    ++launches;
+  }
+  if (dW) {
+    dim3 grid((N + GM - 1) / GM, (K + GN - 1) / GN, 1);
+    launch_k(sgemm_kernel<true, false>, grid, 256, 0, st, dY, ldy, X, K, dW, K, nullptr, nullptr, N, K, M, 0, 1, 1);
+    ++launches;
+  }
+  count_launch(launches);
+  return check_launch("linear_bwd_cols");
+}
+
 extern "C" int b200dm_linear_bwd(const float* X, const float* W, const float* pre, float* dY,
                                  float* dX, float* dW, float* db, int32_t M, int32_t N, int32_t K,
                                  int32_t act, void* stream) {

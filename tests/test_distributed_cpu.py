@@ -21,7 +21,7 @@ def _free_port():
 def test_buckets_tile_the_arena_in_backward_order():
     a = ParamArena(64, 3, "cpu")
     bs = buckets(a)
-    assert len(bs) == 8
+    assert len(bs) == 9
     covered = sorted(bs)
     assert covered[0][0] == 0 and covered[-1][1] == a.numel
     assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
@@ -29,10 +29,16 @@ def test_buckets_tile_the_arena_in_backward_order():
     fb, fe = bs[0]
     assert fb <= a.offset["final_conv.weight"] < fe and fb <= a.offset["final_res_block.block1.proj.weight"] < fe
     hb, he = bs[-1]
-    assert hb == 0 and a.offset["init_conv.weight"] < he and a.offset["time_mlp.3.bias"] < he
-    assert a.offset["downs.0.0.mlp.1.weight"] < he          # FiLM projections live at the arena head
+    assert a.offset["init_conv.weight"] < he and a.offset["time_mlp.3.bias"] < he
+    # FiLM projections live at the arena head: the rows of the two level-0 down blocks (the last ResnetBlocks of the
+    # backward pass) in the last bucket, all other rows in the "film" bucket that is reduced behind level 1
+    assert hb <= a.offset["downs.0.0.mlp.1.weight"] < he and hb <= a.offset["downs.0.1.mlp.1.weight"] < he
+    fb2, fe2 = bs[6]
+    assert fb2 == 0 and fe2 == hb == a.film_early_cols * a.time_dim
+    assert all(fb2 <= a.offset[b + ".mlp.1.weight"] < fe2 for b in a.film_order[:-2])
     # bucket i must hold exactly the parameters whose gradients Plan.bwd_segments[i] produces
-    for i, prefix in enumerate(("final_", "ups.", "mid_", "downs.3.", "downs.2.", "downs.1.", "downs.0.")):
+    for i, prefix in ((0, "final_"), (1, "ups."), (2, "mid_"), (3, "downs.3."), (4, "downs.2."), (5, "downs.1."),
+                      (7, "downs.0.")):
         b, e = bs[i]
         for nm, _ in a.spec:
             if nm.startswith(prefix) and ".mlp.1." not in nm:

@@ -364,7 +364,7 @@ def test_optimizer_overlapped_with_backward():
         opt.zero_grad()
         loss = m.training_step(batch)
         loss.backward()
-        assert len(opt._done) == 8        # every bucket was applied behind backward
+        assert len(opt._done) == 9        # every bucket was applied behind backward
         ref_p.grad = unet.arena.gflat.clone()
         opt.step()
         ref_opt.step()
