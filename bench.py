@@ -42,14 +42,16 @@ SAMPLE_CFG = {"ddim": (256, 64, 50), "ddpm": (1024, 32, 1000)}         # global 
 
 def profiled_traffic(family):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of a kernel family from the committed
-    `ncu --set full` capture (profiles/r1_roofline_traffic.json, scripts/make_profiles.py); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    `ncu --set full` captures (profiles/r2_roofline_traffic.json, scripts/make_profiles_r2.py; the conv / weight-gradient
+    families at the training shape, the fused conv+GroupNorm launch at the DDIM shape); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
     if not os.path.isfile(p):
         return None
     d = json.load(open(p))
     names = {"wgrad_tc": ("wgrad3x3_halo_kernel", "wgrad_tc_kernel"),
              "conv_tc_fwd": ("conv3x3_halo_kernel", "conv_tc_kernel"),
-             "conv_tc_dgrad": ("conv3x3_halo_kernel", "conv_tc_kernel")}.get(family, (family,))
+             "conv_tc_dgrad": ("conv3x3_halo_kernel", "conv_tc_kernel"),
+             "conv_gn_fwd": ("conv3x3_gn_kernel",)}.get(family, (family,))
     n = sum(d[k]["launches"] for k in names if k in d)
     if n == 0:
         return None

@@ -265,29 +265,47 @@ class Unet(nn.Module):
             from .distributed import buckets
             self._buckets = buckets(self.arena)
             assert len(self._buckets) == nseg
-        if self._cuda_graph and plan.graph_bwd is not None:
-            for i in range(nseg):
-                plan.graph_bwd[i].replay()
-                if sync is not None:
-                    sync.reduce_bucket(i)
-                if hook is not None:
-                    hook(i, self._buckets[i])
+        # launch groups: with a collective to overlap every gradient bucket is its own group (its all-reduce starts
+        # as soon as the segment is issued); single-GPU runs fuse the per-level segments of the down path and the
+        # early FiLM GEMM into one group (fewer graph launches, no break in the programmatic-launch chain)
+        from .distributed import REGIONS
+        if sync is not None:
+            groups = [[i] for i in range(nseg)]
         else:
-            for i in range(nseg):
-                plan.run_backward_segment(i)
-                if sync is not None:
-                    sync.reduce_bucket(i)
-                if hook is not None:
-                    hook(i, self._buckets[i])
+            mid = [i for i, r in enumerate(REGIONS) if r.startswith("downs.") or r == "film"]
+            groups = [[i] for i in range(mid[0])] + [mid] + [[i] for i in range(mid[-1] + 1, nseg)]
+        key = "sync" if sync is not None else "solo"
+        graphs = plan.graph_bwd.get(key) if isinstance(plan.graph_bwd, dict) else None
+
+        def after(i):
+            if sync is not None:
+                sync.reduce_bucket(i)
+            if hook is not None:
+                hook(i, self._buckets[i])
+
+        if self._cuda_graph and graphs is not None:
+            for g, grp in zip(graphs, groups):
+                g.replay()
+                for i in grp:
+                    after(i)
+        else:
+            for grp in groups:
+                for i in grp:
+                    plan.run_backward_segment(i)
+                for i in grp:
+                    after(i)
             if self._cuda_graph and plan.warm >= 2 and not torch.cuda.is_current_stream_capturing():
                 # capture for the following steps (stream capture records the launches, it does not run them)
                 graphs = []
-                for i in range(nseg):
+                for grp in groups:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        plan.run_backward_segment(i)
+                        for i in grp:
+                            plan.run_backward_segment(i)
                     graphs.append(g)
-                plan.graph_bwd = graphs
+                if not isinstance(plan.graph_bwd, dict):
+                    plan.graph_bwd = {}
+                plan.graph_bwd[key] = graphs
         if reserve:
             L.load().b200dm_set_reserved_sms(0)
         if sync is not None:
