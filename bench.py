@@ -619,10 +619,15 @@ def run_sample(ctx, workload, K, profile_out=None):
         return B, step_device, step_e2e
 
     B, step_device, step_e2e = runner(GB)
-    L.load().b200dm_reset_launch_count()
     step_device(0)
     torch.cuda.synchronize()
-    launches_per_step = int(L.load().b200dm_launch_count())
+    # kernels per chain: graph replays bypass the library's launch counter, so one UNet evaluation is counted on an
+    # eager pass of the plan and multiplied out (evaluations x (UNet + scheduler-step kernel) + the initial randn)
+    L.load().b200dm_reset_launch_count()
+    unet._plan(B, S, training=False).run_forward()
+    torch.cuda.synchronize()
+    launches_per_eval = int(L.load().b200dm_launch_count())
+    launches_per_step = STEPS * (launches_per_eval + 1) + 1
     for i in range(W if workload == "ddim" else 1):
         step_device(i)
     clocks.mark()
