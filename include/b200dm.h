@@ -162,8 +162,11 @@ int b200dm_conv_fwd(const b200dm_conv_desc* d, void* stream);
  *   gamma, beta [Cout]; film = FiLM (scale | shift) rows [B][film_ld] with scale at column c and shift at Cout + c,
  *   or NULL; stats (optional, out) [B][groups][2] = (mean, rstd); raw (optional, out) = conv(x) + bias in bf16
  *   [B,H,W,raw_ld] (what b200dm_gn_apply_bwd reads in training).
- * b200dm_conv_gn_supported returns 1 when the layer fits (bf16, Cin % 64 == 0, Cout in {64,128,256}, 8 groups,
- * 16 <= W <= 128, H % 16 == 0, W % 8 == 0), else 0: use b200dm_conv_fwd + b200dm_gn_fwd_pre there. */
+ * Images of 8x8 / 4x4 pixels take a second kernel: a 128-pixel tile holds whole samples and a 64-column sub-tile whole
+ * groups, so the statistics are tile-local (no cluster).
+ * b200dm_conv_gn_supported returns 1 when the layer fits (bf16, Cin % 64 == 0, 8 groups, and either 16 <= W <= 128,
+ * H % 16 == 0, W % 8 == 0 with Cout in {64,128,256}, or 8x8 / 4x4 images with Cout in {128,256,512}), else 0: use
+ * b200dm_conv_fwd + b200dm_gn_fwd_pre there. */
 typedef struct {
   const float* gamma;
   const float* beta;

@@ -1607,6 +1607,379 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// =====================================================================================================
+// Block.forward in one launch for the SMALL levels (8x8 and 4x4 images): a 128-pixel M tile of conv_tc_kernel holds
+// whole samples (2 or 8) and a 64-column sub-tile holds whole GroupNorm groups (16, 32 or 64 channels each), so the
+// statistics are tile-local: no cluster, no second kernel.  Same producer / MMA pipeline as conv_tc_kernel (mode 0,
+// 3x3); the epilogue reads its 32 x 64 accumulator block twice (statistics, then apply), reduces over the lanes of a
+// sample by shuffles (and, at 8x8 where a sample spans two warps, through shared memory between the two warps), turns
+// (gamma, beta, mean, rstd, FiLM, bias) into two coefficients per (sample, channel) in a per-warp shared-memory table
+// and applies z = A*acc + B, SiLU, + residual straight out of TMEM.
+// =====================================================================================================
+struct TcGnSmallParams {
+  int kblocks, H, W, bh, bn;
+  int Cout, n_tiles, m_tiles, gs_shift, hw;      // hw = pixels per sample (16 or 64)
+  int res_ld, film_ld, store_raw, B;
+  long long M;
+  const __nv_bfloat16* res;
+  const float *bias, *gamma, *beta, *film;
+  float* stats;
+  float eps, inv_count;
+};
+
+template <int N_TILE, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_gn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmRaw,
+                  const TcGnSmallParams p) {
+  constexpr int B_STAGE_BYTES = N_TILE * TC_BK * 2;
+  constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * N_TILE <= 128 ? 128 : 2 * N_TILE <= 256 ? 256 : 512;
+  constexpr int SUBTILES = N_TILE / 64;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_stage = base + STAGES * STAGE_BYTES;        // one 4 KiB staging block per epilogue warp
+  const uint32_t bar_base = out_stage + 2 * OUT_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  uint8_t* const sm = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + (tmem_slot - base));
+  uint8_t* out_stage_ptr = sm + (out_stage - base);
+  // fp32 scratch: bias[Cout] | coef[8 warps][2 samples][64][2] | xch[2 parities][2 warp sets][4 quarters][8]
+  float* bias_s = reinterpret_cast<float*>(sm + (bar_base + 256u - base));
+  float* coef_s = bias_s + p.Cout;
+  float* xch = coef_s + TC_EPI_WARPS * 2 * 64 * 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = 9 * p.kblocks;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+    if (p.store_raw) prefetch_tmap(&tmRaw);
+    for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(full_bar(s2), 1); mbar_init(empty_bar(s2), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), SUBTILES == 1 ? TC_EPI_WARPS / 2 : TC_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: activation boxes, one per (tap, channel block) =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const long long first = (long long)m_tile * TC_BM;
+      const int n_first = (int)(first / ((long long)p.H * p.W));
+      const int y_first = (int)((first / p.W) % p.H);
+      int dy = -1, dx = -1;
+      for (int tap = 0; tap < 9; ++tap) {
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader) {
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_5d(base + stage * STAGE_BYTES, &tmA, full_bar(stage), kc * TC_BK, dx, y_first + dy, n_first, 0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++dx > 1) { dx = -1; ++dy; }
+      }
+    }
+  } else if (warp == TC_BWARP) {
+    // ===================== TMA producer: weight tiles =====================
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < p.kblocks; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader)
+            tma_load_3d(base + stage * STAGE_BYTES + A_STAGE_BYTES, &tmB, full_bar(stage), kc * TC_BK, n0, tap);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(TC_BM, N_TILE, 0, 0);
+    const uint64_t a_desc0 = make_smem_desc(base, 16, 1024);
+    const uint64_t b_desc0 = make_smem_desc(base + A_STAGE_BYTES, 16, 1024);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+    const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
+    const bool leader = elect_one();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_TILE);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        if (leader) {
+          const uint32_t so = (uint32_t)stage * (STAGE_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16_lohi(d_tmem, a_lo0 + so + (uint32_t)((k * 32) >> 4), a_hi,
+                           b_lo0 + so + (uint32_t)((k * 32) >> 4), b_hi, idesc, (k > 0) ? 1u : (kb > 0 ? 1u : 0u));
+          umma_commit(empty_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      if (leader) umma_commit(tmem_full_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;
+    const int wset = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t my_stage = out_stage + (uint32_t)(warp - 2) * 4096u;
+    uint8_t* my_row = out_stage_ptr + (warp - 2) * 4096 + lane * 128;
+    float* my_coef = coef_s + (warp - 2) * 256;           // [sample in warp][64][A, B]
+    const int R = p.hw;                                   // rows (pixels) per sample: 16 or 64
+    const int seg = R >= 32 ? 32 : R;                     // lanes of this warp that belong to one sample
+    const int sloc = lane / seg, lseg = lane - sloc * seg;
+    const int gs = 1 << p.gs_shift;
+    for (int i = threadIdx.x - 64; i < p.Cout; i += 32 * TC_EPI_WARPS) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    named_bar_sync(1, 32 * TC_EPI_WARPS);
+    int it = 0, unit = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (SUBTILES == 1 && (it & 1) != wset) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int m_tile = tile / p.n_tiles, n0 = (tile - m_tile * p.n_tiles) * N_TILE;
+      const long long first = (long long)m_tile * TC_BM;
+      const long long pix = first + row;
+      const int bsm = (int)(pix / R);                     // this row's sample
+      const bool valid = pix < p.M;
+      const unsigned slice = (unsigned)first + 32u * (unsigned)quarter;
+      const unsigned hw = (unsigned)(p.H * p.W);
+      const int sn = (int)(slice / hw);
+      const unsigned srem = slice - (unsigned)sn * hw;
+      const int sy = (int)(srem / (unsigned)p.W), sx = (int)(srem - (unsigned)sy * (unsigned)p.W);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int s_first = SUBTILES == 1 ? 0 : wset;
+#pragma unroll 1
+      for (int s = s_first; s < SUBTILES; s += 2, ++unit) {
+        const int cb = n0 + s * 64;                       // first output channel of this 64-column unit
+        // ---------- pass 1: statistics (+ raw conv output when training) ----------
+        if (p.store_raw) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        float Sg[4] = {0.f, 0.f, 0.f, 0.f}, Qg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + s * 64 + hh * 32), r);
+          tmem_ld_wait();
+          float v[32];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + cb + hh * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float sa = 0.f, q = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              sa += v[8 * k + j];
+              q = fmaf(v[8 * k + j], v[8 * k + j], q);
+            }
+            const int gi = (hh * 32 + 8 * k) >> p.gs_shift;          // group of this 8-channel chunk inside the unit
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              Sg[g] += gi == g ? sa : 0.f;
+              Qg[g] += gi == g ? q : 0.f;
+            }
+          }
+          if (p.store_raw) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 uu;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uu);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+              const int chunk = (hh * 4 + g) ^ (lane & 7);
+              *reinterpret_cast<uint4*>(my_row + chunk * 16) = uu;
+            }
+          }
+        }
+        if (p.store_raw) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(&tmRaw, my_stage, cb, sx, sy, sn, 0);
+            tma_store_commit();
+          }
+        }
+        // sums over the lanes of a sample (16 or 32 lanes), then over the two warps of a 64-pixel sample
+        for (int off = seg >> 1; off > 0; off >>= 1) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            Sg[g] += __shfl_xor_sync(0xffffffffu, Sg[g], off);
+            Qg[g] += __shfl_xor_sync(0xffffffffu, Qg[g], off);
+          }
+        }
+        if (R > 32) {
+          float* mine = xch + (((unit & 1) * 2 + wset) * 4 + quarter) * 8;
+          if (lane == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { mine[g] = Sg[g]; mine[4 + g] = Qg[g]; }
+          }
+          named_bar_sync(2 + wset, 128);                  // the four quarter-warps of this warp set, once per unit
+          const float* other = xch + (((unit & 1) * 2 + wset) * 4 + (quarter ^ 1)) * 8;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) { Sg[g] += other[g]; Qg[g] += other[4 + g]; }
+        }
+        float mean[4], rstd[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          mean[g] = Sg[g] * p.inv_count;
+          rstd[g] = rsqrtf(fmaxf(Qg[g] * p.inv_count - mean[g] * mean[g], 0.f) + p.eps);
+        }
+        const int ngrp = 64 >> p.gs_shift;                // groups inside this unit (1, 2 or 4)
+        if (p.stats && valid && lseg == 0 && (R <= 32 || (quarter & 1) == 0)) {
+          for (int g = 0; g < ngrp; ++g) {
+            float* st = p.stats + ((long long)bsm * 8 + (cb >> p.gs_shift) + g) * 2;
+            st[0] = mean[g];
+            st[1] = rstd[g];
+          }
+        }
+        // coefficients of this lane's sample for the 64 channels of the unit, split over the lanes of the sample
+        __syncwarp();
+        for (int cc = lseg; cc < 64; cc += seg) {
+          const int c = cb + cc, gi = cc >> p.gs_shift;
+          float mu = mean[0], rs = rstd[0];
+#pragma unroll
+          for (int g = 1; g < 4; ++g) { mu = gi == g ? mean[g] : mu; rs = gi == g ? rstd[g] : rs; }
+          float ga = p.gamma[c] * rs;
+          float be = p.beta[c] - mu * ga;
+          if (p.film && valid) {
+            const float sc = p.film[(long long)bsm * p.film_ld + c] + 1.f;
+            const float sh = p.film[(long long)bsm * p.film_ld + p.Cout + c];
+            ga *= sc;
+            be = be * sc + sh;
+          }
+          my_coef[(sloc * 64 + cc) * 2] = 0.5f * ga;
+          my_coef[(sloc * 64 + cc) * 2 + 1] = 0.5f * fmaf(ga, bias_s[c], be);
+        }
+        __syncwarp();
+        // ---------- pass 2: apply straight out of TMEM ----------
+        const long long opix = pix;
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint4 src_res[4];
+          if (valid && p.res) {
+            const uint4* rr = reinterpret_cast<const uint4*>(p.res + opix * p.res_ld + cb + hh * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) src_res[g] = rr[g];
+          }
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * N_TILE + s * 64 + hh * 32), r);
+          tmem_ld_wait();
+          if (hh == 1 && s + 2 >= SUBTILES) {   // last read of this accumulator by this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          }
+          float v[32];
+          const float4* c4 = reinterpret_cast<const float4*>(my_coef + (sloc * 64 + hh * 32) * 2);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 ab = c4[j];              // (A, B) of two channels
+            const float z0 = fmaf(ab.x, __uint_as_float(r[2 * j]), ab.y);
+            const float z1 = fmaf(ab.z, __uint_as_float(r[2 * j + 1]), ab.w);
+            v[2 * j] = fmaf(z0, tanh_approx_f(z0), z0);
+            v[2 * j + 1] = fmaf(z1, tanh_approx_f(z1), z1);
+          }
+          if (valid && p.res) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&src_res[g]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h2[j]);
+                v[g * 8 + 2 * j] += f.x;
+                v[g * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 uu;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&uu);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1]);
+            const int chunk = (hh * 4 + g) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(my_row + chunk * 16) = uu;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_5d(&tmY, my_stage, cb, sx, sy, sn, 0);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int N_TILE, int STAGES>
+static int launch_tc_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                        const CUtensorMap& tmRaw, const TcGnSmallParams& p, cudaStream_t st) {
+  const int smem = STAGES * (A_STAGE_BYTES + N_TILE * TC_BK * 2) + 2 * OUT_STAGE_BYTES + 1024 + 256 +
+                   (p.Cout + TC_EPI_WARPS * 256 + 2 * 2 * 4 * 8) * 4;
+  B200DM_REQUIRE(smem <= 227 * 1024, B200DM_ERR_UNSUPPORTED, "conv_gn(small): %d B of shared memory", smem);
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_gn_kernel<N_TILE, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "conv_gn(small): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  launch_k(conv_tc_gn_kernel<N_TILE, STAGES>, grid, TC_THREADS, smem, st, tmA, tmB, tmY, tmRaw, p);
+  count_launch();
+  return check_launch("conv_gn(small)");
+}
+
 template <int N_TILE, int A_BUFS, int B_STAGES, bool B_RESIDENT>
 static int launch_gn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmRaw,
                      const TcGnParams& p, int B, int CL, cudaStream_t st) {
@@ -1687,23 +2060,91 @@ static bool conv_gn_geometry(const b200dm_conv_desc* d, int groups, GnGeom* g) {
 // epilogue) + one-pass norm, the fused launch is 10-30 % faster when one wave of CTAs covers the batch (training and
 // 8-way sharded sampling) and within +-7 % when the persistent clusters walk several samples (batch 256 at 64x64), so the
 // launch plan uses it wherever the layer fits: results then do not depend on how the batch is sharded either.
+// small levels (conv_tc_gn_kernel): 8x8 or 4x4 images, groups of 16 / 32 / 64 channels
+static bool conv_gn_small_geometry(const b200dm_conv_desc* d, int groups) {
+  if (d->dtype != B200DM_BF16 || d->mode != 0 || d->ksize != 3 || d->accumulate || groups != 8) return false;
+  if (d->Cin % 64 || d->Cout % 64 || d->Cout > 512) return false;
+  if (d->H != d->W || (d->H != 4 && d->H != 8)) return false;
+  const int gs = d->Cout / groups;
+  return gs == 16 || gs == 32 || gs == 64;
+}
+
 int conv_gn_supported_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn) {
   GnGeom g;
-  return (tc_supported() && halo_enabled() && gn && conv_gn_geometry(d, gn->groups, &g)) ? 1 : 0;
+  if (!tc_supported() || !gn) return 0;
+  if (halo_enabled() && conv_gn_geometry(d, gn->groups, &g)) return 1;
+  return conv_gn_small_geometry(d, gn->groups) ? 1 : 0;
+}
+
+static int conv_gn_fwd_small(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, cudaStream_t st) {
+  int bh, bn;
+  int rc = tile_geometry(d->H, d->W, &bh, &bn, "conv_gn_fwd");
+  if (rc) return rc;
+  TcGnSmallParams p{};
+  p.kblocks = d->Cin / TC_BK;
+  p.H = d->H; p.W = d->W; p.bh = bh; p.bn = bn;
+  p.Cout = d->Cout; p.hw = d->H * d->W; p.B = d->B;
+  int gs = d->Cout / gn->groups, sh = 0;
+  while ((1 << sh) < gs) ++sh;
+  p.gs_shift = sh;
+  p.M = (long long)d->B * d->H * d->W;
+  p.m_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  p.res = (const __nv_bfloat16*)d->res; p.res_ld = d->res_ld;
+  p.film = gn->film; p.film_ld = gn->film_ld;
+  p.store_raw = gn->raw ? 1 : 0;
+  p.bias = d->bias; p.gamma = gn->gamma; p.beta = gn->beta; p.stats = gn->stats;
+  p.eps = gn->eps;
+  p.inv_count = 1.f / ((float)p.hw * (float)gs);
+  // N tile as in conv_fwd_tc: tile-shape efficiency x fill of the last wave
+  const int sms = num_sms();
+  int n_tile = 64;
+  double best = -1.0;
+  const int cand[3] = {256, 128, 64};
+  const double eff[3] = {1.0, 0.85, 0.6};
+  for (int i = 0; i < 3; ++i) {
+    if (d->Cout % cand[i]) continue;
+    const long long tiles = (long long)p.m_tiles * (d->Cout / cand[i]);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double score = eff[i] * (double)tiles / (double)(waves * sms);
+    if (score > best) { best = score; n_tile = cand[i]; }
+  }
+  p.n_tiles = d->Cout / n_tile;
+  CUtensorMap tmA, tmB, tmY, tmRaw;
+  rc = make_act_map(&tmA, 0, d->x, d->x_ld, d->Cin, d->B, d->H, d->W, bh, bn, "conv_gn_fwd A");
+  if (rc) return rc;
+  rc = make_out_map32(&tmY, 0, d->y, d->y_ld, d->Cout, d->B, d->H, d->W, "conv_gn_fwd Y");
+  if (rc) return rc;
+  rc = make_out_map32(&tmRaw, 0, gn->raw ? gn->raw : d->y, gn->raw ? gn->raw_ld : d->y_ld, d->Cout, d->B, d->H, d->W,
+                      "conv_gn_fwd raw");
+  if (rc) return rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout, 9};
+    cuuint64_t str[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout * d->Cin * 2};
+    cuuint32_t box[3] = {TC_BK, (cuuint32_t)n_tile, 1};
+    rc = encode_map(&tmB, d->w, 3, dims, str, box, "conv_gn_fwd B");
+    if (rc) return rc;
+  }
+  if (n_tile == 256) return launch_tc_gn<256, 3>(tmA, tmB, tmY, tmRaw, p, st);
+  if (n_tile == 128) return launch_tc_gn<128, 5>(tmA, tmB, tmY, tmRaw, p, st);
+  return launch_tc_gn<64, 6>(tmA, tmB, tmY, tmRaw, p, st);
 }
 
 int conv_gn_fwd_tc(const b200dm_conv_desc* d, const b200dm_gn_desc* gn, void* stream) {
   B200DM_REQUIRE(tc_supported(), B200DM_ERR_UNSUPPORTED, "conv_gn_fwd: needs an sm_100 device and a TMA-capable driver");
   GnGeom g;
-  B200DM_REQUIRE(gn && conv_gn_geometry(d, gn->groups, &g), B200DM_ERR_UNSUPPORTED,
-                 "conv_gn_fwd: unsupported layer (bf16 3x3 'same', Cin %% 64 == 0, Cout in {64,128,256}, 8 groups, "
-                 "16 <= W <= 128, H %% 16 == 0): Cin=%d Cout=%d H=%d W=%d", d->Cin, d->Cout, d->H, d->W);
+  B200DM_REQUIRE(gn != nullptr, B200DM_ERR_SHAPE, "conv_gn_fwd: null norm descriptor");
+  const bool big = halo_enabled() && conv_gn_geometry(d, gn->groups, &g);
+  B200DM_REQUIRE(big || conv_gn_small_geometry(d, gn->groups), B200DM_ERR_UNSUPPORTED,
+                 "conv_gn_fwd: unsupported layer (bf16 3x3 'same', Cin %% 64 == 0, 8 groups; 16 <= W <= 128 with Cout in "
+                 "{64,128,256}, or 8x8 / 4x4 images with Cout in {128,256,512}): Cin=%d Cout=%d H=%d W=%d", d->Cin,
+                 d->Cout, d->H, d->W);
   B200DM_REQUIRE(d->x_ld % 8 == 0 && d->y_ld % 8 == 0 && (!d->res || d->res_ld % 8 == 0) &&
                      (!gn->raw || gn->raw_ld % 8 == 0), B200DM_ERR_SHAPE, "conv_gn_fwd: ld must be a multiple of 8");
   B200DM_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->y & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
                      ((uintptr_t)d->res & 15) == 0 && ((uintptr_t)gn->raw & 15) == 0,
                  B200DM_ERR_SHAPE, "conv_gn_fwd: pointers must be 16-byte aligned");
   B200DM_REQUIRE(gn->gamma && gn->beta, B200DM_ERR_SHAPE, "conv_gn_fwd: gamma / beta required");
+  if (!big) return conv_gn_fwd_small(d, gn, (cudaStream_t)stream);
   TcGnParams p{};
   p.kblocks = d->Cin / TC_BK;
   p.H = d->H; p.W = d->W; p.tiles_x = d->W / 8; p.tpc = g.tpc;

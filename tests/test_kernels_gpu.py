@@ -618,6 +618,12 @@ def test_conv_epilogue_groupnorm_statistics_and_one_pass_norm(B, S, Cin, Cout, f
     (2, 16, 256, 256, True, True, True),       # two N tiles per pixel tile
     (100, 16, 64, 64, True, True, True),       # two accumulators per CTA
     (40, 64, 128, 64, False, True, True),      # cluster of 4 x 8 tiles at 64x64, Cin = 128
+    # small levels: tile-local statistics (conv_tc_gn_kernel)
+    (5, 8, 128, 256, True, True, True),        # 8x8: a sample spans two epilogue warps; 2.5 tiles of samples
+    (3, 8, 128, 128, False, False, True),      # groups of 16 channels: four per 64-column unit
+    (9, 4, 256, 512, True, False, True),       # 4x4: two samples per warp, groups of 64; last tile partly empty
+    (16, 4, 512, 512, False, True, False),     # two full tiles of 8 samples
+    (130, 8, 256, 256, True, True, True),      # persistent CTAs walk several tiles (65 x 1 tiles at N = 256)
 ])
 def test_conv_groupnorm_film_silu_one_launch(B, S, Cin, Cout, film, res, raw):
     """b200dm_conv_gn_fwd: Block.forward (ddpm.py:164-173) + the residual of ResnetBlock (:200) in ONE launch, with the
@@ -664,7 +670,7 @@ def test_conv_groupnorm_film_silu_one_launch(B, S, Cin, Cout, film, res, raw):
     L.call("b200dm_conv_gn_fwd", ctypes.byref(d), ctypes.byref(gnd))
     assert torch.equal(first, yv.buf) and torch.equal(st1, stats)
     # unsupported layers are reported, not mis-executed
-    d2 = L.ConvDesc(dtype=L.BF16, mode=0, ksize=3, impl=1, B=B, H=8, W=8, Cin=Cin, Cout=Cout, x=xv.ptr, x_ld=xv.ld,
+    d2 = L.ConvDesc(dtype=L.BF16, mode=0, ksize=3, impl=1, B=B, H=2, W=2, Cin=Cin, Cout=Cout, x=xv.ptr, x_ld=xv.ld,
                     w=wp.data_ptr(), bias=bias.data_ptr(), y=yv.ptr, y_ld=yv.ld, res=None, res_ld=0, accumulate=0,
                     gn_part=None, gn_groups=0)
     assert L.load().b200dm_conv_gn_supported(ctypes.byref(d2), ctypes.byref(gnd)) == 0
