@@ -2419,6 +2419,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   constexpr int STAGE_BYTES = HALO_BYTES + DY_BYTES;           // 52 KiB
   constexpr int TMEM_COLS = 512;                               // 6 x 64 accumulator columns
   pdl_launch_dependents();
+  if (threadIdx.x == 0) TSTAMP(300);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + STAGES * STAGE_BYTES;
@@ -2452,7 +2453,9 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TSTAMP(301);
   pdl_wait();   // everything above is on-chip setup; global memory is touched only below
+  if (threadIdx.x == 0) TSTAMP(302);
 
   if (warp == 0) {
     if (lane == 0 && has_work) {
@@ -2486,6 +2489,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int t = t0; t < t1; ++t) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        if (leader && t - t0 < 8) TSTAMP(310 + 2 * (t - t0));
         if (leader) {
           const uint32_t so = (uint32_t)stage * (STAGE_BYTES >> 4);
 #pragma unroll
@@ -2511,6 +2515,7 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int m = quarter * 32 + lane, slot = m >> 6, ci = cib * TC_BK + (m & 63);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (warp == 2 && lane == 0) TSTAMP(304);
 #pragma unroll 1
     for (int g = 0; g < WgPairs<PAIRING>::G; ++g) {
       const int tap = slot ? WgPairs<PAIRING>::t1(g) : WgPairs<PAIRING>::t0(g);
@@ -2531,8 +2536,10 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   }
 
+  if (warp == 2 && lane == 0) TSTAMP(305);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TSTAMP(306);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
