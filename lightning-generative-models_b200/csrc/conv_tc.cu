@@ -1100,13 +1100,7 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// release-arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
-}
-// acquire-wait (cluster scope) on a local mbarrier the peers arrive on; bounded like mbar_wait
+// acquire-wait (cluster scope) on a local mbarrier whose transactions come from the peers (st.async); bounded like mbar_wait
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   for (;;) {
@@ -1133,13 +1127,6 @@ __device__ __forceinline__ void st_async_f32_cluster(uint32_t local_addr, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
-}
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank) {
-  uint32_t remote;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-  return v;
 }
 __device__ __forceinline__ float tanh_approx_f(float x) {
   float y;
