@@ -208,6 +208,18 @@ int b200dm_conv_wgrad(const b200dm_wgrad_desc* d, void* stream);
 int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t rows, int32_t C, float* out,
                   int32_t accumulate, void* stream);
 
+/* n (1..16) independent column sums in one launch: items[i].out[c] += sum_rows items[i].x[row*ld + c] (always
+ * accumulating; all items of one dtype; C and ld multiples of 8, x 16-byte aligned).  The bias gradients of the
+ * convs of one gradient bucket (autograd of the `bias=True` nn.Conv2d's, ddpm.py:96,103,160,252-253,377,413). */
+typedef struct {
+  const void* x;
+  float* out;
+  int64_t rows;
+  int32_t ld;
+  int32_t C;
+} b200dm_colsum_item;
+int b200dm_colsum_batched(int32_t dtype, const b200dm_colsum_item* items, int32_t n, void* stream);
+
 /* init_conv 7x7, pad 3 (ddpm.py:304,437): NCHW fp32 in -> NHWC out; weight OIHW fp32. */
 /* Stem on tensor cores (bf16): P [B*H*W][KP] bf16 = im2col of the 7x7 patches of x (NCHW fp32), columns in the
  * OIHW order of init_conv.weight, zero-padded to KP (multiple of 64); wp [Cout][KP] bf16 = zero-padded weight

@@ -58,6 +58,11 @@ class WgradDesc(C.Structure):
     ]
 
 
+class ColsumItem(C.Structure):
+    """b200dm_colsum_item: one column sum of b200dm_colsum_batched."""
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("ld", C.c_int32), ("C", C.c_int32)]
+
+
 class NoiseDesc(C.Structure):
     """b200dm_noise_desc: inputs of the forward-noising step shared by q_sample and the loss."""
     _fields_ = [
@@ -92,6 +97,7 @@ PROTOTYPES = {
     "b200dm_conv_gn_fwd": [C.POINTER(ConvDesc), C.POINTER(GnDesc), _P],
     "b200dm_conv_wgrad": [C.POINTER(WgradDesc), _P],
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
+    "b200dm_colsum_batched": [_I, _P, _I, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_pack_stem_weight": [_P, _P, _I, _I, _I, _P],
     "b200dm_pack_upconv_weight": [_P, _P, _I, _I, _P],

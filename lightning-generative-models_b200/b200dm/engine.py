@@ -154,11 +154,14 @@ class Plan:
         self.fwd_names: List[str] = []
         self.fwd_flops: List[float] = []
         self.bwd_groups: List[List[Callable[[int], None]]] = []
+        self.unit_colsums: List[list] = []     # per unit: bias column sums deferred to the end of its segment
+        self._cur_colsums: list = []
         self._cur_bwd: Optional[List[Callable[[int], None]]] = None
         self._region = "head"        # which gradient bucket the current unit's parameters belong to
         self.unit_regions: List[str] = []
         self._keep = []              # ctypes structs / tensors referenced by raw pointers
         self._scratch = {}
+        self._scratch_ptrs = set()
         self.lib = L.load()
         self.nbytes = 0
         dim, ch = arena.dim, arena.channels
@@ -168,22 +171,24 @@ class Plan:
         self.fuse_gn_stats = os.environ.get("B200DM_FUSE_GN_STATS", "1") != "0"
         self.fuse_upsample = os.environ.get("B200DM_FUSE_UPSAMPLE", "1") != "0"
         self.fuse_gn = os.environ.get("B200DM_FUSE_GN", "1") != "0"       # conv + GroupNorm + FiLM + SiLU in one launch
+        self.batch_colsum = os.environ.get("B200DM_BATCH_COLSUM", "1") != "0"   # one bias-gradient launch per bucket
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
+        # forward: the second stream only carries the 1x1 residual convs, which the main chain needs a few kernels
+        # later -> high priority (measured, B=128 32x32 forward: 1.467 -> 1.440 ms).  In backward equal priorities are
+        # best: with either stream preferred the step is slower (main chain first: 4.95 -> 5.27 ms, the parameter
+        # gradients pile up at the segment joins; second stream first: 5.13 ms)
+        self.side_stream_fwd = torch.cuda.Stream(device=self.dev, priority=-1) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
         self.out = torch.zeros(B, ch, S, S, device=self.dev)
         self.d_out = torch.zeros(B, ch, S, S, device=self.dev) if training else None
         self._build(dim, ch)
-        self.bwd: List[Callable[[int], None]] = [op for g in reversed(self.bwd_groups) for op in g]
         # backward segments in gradient-bucket order (b200dm.distributed.buckets): after segment i has run,
         # bucket i of the gradient arena is final and can be all-reduced while the rest of backward runs
-        self.bwd_segments: List[List[Callable[[int], None]]] = []
-        from .distributed import REGIONS
-        for region in REGIONS:
-            seg = [op for g, r in zip(reversed(self.bwd_groups), reversed(self.unit_regions)) if r == region
-                   for op in g]
-            self.bwd_segments.append(seg)
-        assert sum(len(sg) for sg in self.bwd_segments) == len(self.bwd)
+        n_unit_ops = sum(len(g) for g in self.bwd_groups)
+        self.bwd_segments: List[List[Callable[[int], None]]] = self._finish_segments()
+        self.bwd: List[Callable[[int], None]] = [op for seg in self.bwd_segments for op in seg]
+        assert len(self.bwd) >= n_unit_ops       # every unit belongs to a region of distributed.REGIONS
         self.bwd_names = [op.kname for op in self.bwd]
         self.bwd_flops = [op.flops for op in self.bwd]
         self.fwd_names = [op.kname for op in self.fwd]
@@ -202,6 +207,7 @@ class Plan:
         k = (key, H, C)
         if k not in self._scratch:
             self._scratch[k] = self.buf(H, C)
+            self._scratch_ptrs.add(self._scratch[k].buf.data_ptr())
         return self._scratch[k]
 
     def f32(self, *shape) -> torch.Tensor:
@@ -238,8 +244,32 @@ class Plan:
 
     def begin_unit(self):
         self._cur_bwd = []
+        self._cur_colsums = []
         self.bwd_groups.append(self._cur_bwd)
+        self.unit_colsums.append(self._cur_colsums)
         self.unit_regions.append(self._region)
+
+    def _finish_segments(self):
+        """Backward segments in gradient-bucket order.  The bias column sums deferred by conv_bwd go to the END of
+        their segment, at most 16 per launch (b200dm_colsum_batched), on the second stream."""
+        from .distributed import REGIONS
+        segs = []
+        for region in REGIONS:
+            seg, items = [], []
+            for g, cs, r in zip(reversed(self.bwd_groups), reversed(self.unit_colsums), reversed(self.unit_regions)):
+                if r == region:
+                    seg.extend(g)
+                    items.extend(cs)
+            for k in range(0, len(items), 16):
+                chunk = items[k:k + 16]
+                arr = (L.ColsumItem * len(chunk))()
+                for q, (dy, rows, cout, gptr) in zip(arr, chunk):
+                    q.x, q.out, q.rows, q.ld, q.C = dy.ptr, gptr, rows, dy.ld, cout
+                self._cur_bwd = seg
+                self.Bk("b200dm_colsum_batched", self.dt, arr, len(chunk), kname="colsum", side=True,
+                        reads=tuple(dy for dy, _, _, _ in chunk))
+            segs.append(seg)
+        return segs
 
     def _impl(self, cin, cout):
         return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
@@ -310,8 +340,13 @@ class Plan:
                 flops=2.0 * self.B * H * H * ci.cout * ci.cin * ci.taps, side=True, reads=(x, dy))
         self._keep.append(d)
         if ci.bias and bias_grad:
-            self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
-                    self.arena.gptr(nm + ".bias"), 1, side=True, reads=(dy,))
+            if self.batch_colsum and dy.buf.data_ptr() not in self._scratch_ptrs and ci.cout % 8 == 0:
+                # dy is a per-unit gradient buffer, final until the next step: its column sum joins the bucket's one
+                # batched launch at the end of the segment (see _finish_segments)
+                self._cur_colsums.append((dy, self.B * H * H, ci.cout, self.arena.gptr(nm + ".bias")))
+            else:
+                self.Bk("b200dm_colsum", self.dt, dy.ptr, dy.ld, self.B * H * H, ci.cout,
+                        self.arena.gptr(nm + ".bias"), 1, side=True, reads=(dy,))
         if dx is not None:
             self.conv_fwd(self.Bk, nm, dy, dx, dgrad=True, res=dx_res, accumulate=dx_acc, side=dgrad_side)
 
@@ -417,7 +452,7 @@ class Plan:
             self.Bk("b200dm_attn_bwd", self.dt, dao.ptr, dao.ld, qkv.ptr, qkv.ld, a.ptr(nm + ".mem_kv"),
                     dqkv.ptr, dqkv.ld, a.gptr(nm + ".mem_kv"), self.B, n, writes=(dqkv,))
         else:
-            dto = self.scratch("dto", H, Cc)
+            dto = self.buf(H, Cc)      # per unit (not shared scratch): its column sum is deferred to the segment end
             self.Bk("b200dm_rmsnorm_bwd", self.dt, gout.ptr, gout.ld, to.ptr, to.ld, a.ptr(nm + ".to_out.1.g"),
                     None, 0, dto.ptr, dto.ld, a.gptr(nm + ".to_out.1.g"), rows, Cc, writes=(dto,))
             self.conv_bwd(nm + ".to_out.0", ao, dto, dao)
@@ -644,7 +679,7 @@ class Plan:
                 op(st)
             return
         main = torch.cuda.current_stream()
-        side = self.side_stream
+        side = self.side_stream_fwd if ops is self.fwd else self.side_stream
         main_ptr, side_ptr = main.cuda_stream, side.cuda_stream
         pending_r, pending_w = {}, {}      # buffer -> event of the last side kernel reading / writing it
         dirty = True

@@ -243,6 +243,70 @@ colsum8_kernel(const T* __restrict__ x, int ld, int64_t rows, int C8, float* __r
   }
 }
 
+// batched variant: up to COLSUM_MAX_ITEMS independent column sums in ONE launch (the bias gradients of a gradient
+// bucket: each is a few microseconds of HBM traffic, so one launch per tensor is all launch latency).  The block
+// range [first[i], first[i+1]) belongs to item i and is split into column blocks x row blocks like colsum8.
+constexpr int COLSUM_MAX_ITEMS = 16;
+struct ColsumBatch {
+  const void* x[COLSUM_MAX_ITEMS];
+  float* out[COLSUM_MAX_ITEMS];
+  long long rows[COLSUM_MAX_ITEMS];
+  int per[COLSUM_MAX_ITEMS];    // rows per row block
+  int ld[COLSUM_MAX_ITEMS];
+  int C8[COLSUM_MAX_ITEMS];
+  int VL[COLSUM_MAX_ITEMS];
+  int cb[COLSUM_MAX_ITEMS];     // column blocks
+  int first[COLSUM_MAX_ITEMS + 1];
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum8_batched_kernel(const __grid_constant__ ColsumBatch bt) {
+  pdl_prologue();
+  __shared__ float red[256][8];
+  int it = 0;
+  while (it + 1 < bt.n && (int)blockIdx.x >= bt.first[it + 1]) ++it;
+  const int local = (int)blockIdx.x - bt.first[it];
+  const int cbs = bt.cb[it], VL = bt.VL[it], C8 = bt.C8[it], ld = bt.ld[it];
+  const int bx = local % cbs, by = local / cbs;
+  const T* x = reinterpret_cast<const T*>(bt.x[it]);
+  float* out = bt.out[it];
+  const long long rows = bt.rows[it];
+  const int vl = threadIdx.x % VL, rl = threadIdx.x / VL, RL = 256 / VL;
+  const int cv = bx * VL + vl;
+  const long long r0 = (long long)by * bt.per[it];
+  const long long r1 = r0 + bt.per[it] < rows ? r0 + bt.per[it] : rows;
+  float acc[8] = {};
+  if (cv < C8)
+    for (long long r = r0 + rl; r < r1; r += 8 * RL) {
+      float v[8][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (r + u * RL < r1) {
+          ld8(x + (r + u * RL) * ld + cv * 8, v[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[j] += ((v[0][j] + v[1][j]) + (v[2][j] + v[3][j])) + ((v[4][j] + v[5][j]) + (v[6][j] + v[7][j]));
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && cv < C8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sum = 0.f;
+      for (int k = 0; k < RL; ++k) sum += red[k * VL + vl][j];
+      atomicAdd(out + cv * 8 + j, sum);
+    }
+  }
+}
+
 // ---- init conv 7x7 (C -> Cout=64), NCHW fp32 in, NHWC out -----------------------------------------
 constexpr int IC_ROWS = 4;   // output rows per CTA
 constexpr int IC_SEG = 32;   // output columns per CTA
@@ -375,98 +439,159 @@ init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, in
 }
 
 // ---- final 1x1 conv (Cin -> C<=4), NHWC in, NCHW fp32 out ------------------------------------------
+// All three kernels are HBM-bound streams over the [pixels][Cin] activation: a thread owns one 8-channel vector
+// (16 B of bf16) of a pixel, the Cin/8 vector lanes of a pixel sit in one warp (coalesced 16*Cin/8-byte rows), and
+// every thread has FC_U pixels in flight.
+constexpr int FC_U = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w,
-                  const float* __restrict__ bias, float* __restrict__ y, int64_t total, int HW,
-                  int Cin, int C) {
+                  const float* __restrict__ bias, float* __restrict__ y, int total, int HW, int Cin, int C) {
   pdl_prologue();
-  extern __shared__ float wsm[];  // [C][Cin]
-  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
-  __syncthreads();
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const T* xr = x + p * x_ld;
-  for (int k = 0; k < Cin; k += 8) {
-    float v[8];
-    ld8(xr + k, v);
+  const int C8 = Cin >> 3, PL = 256 / C8;
+  const int vl = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float wr[4][8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < C) {
+  for (int c = 0; c < 4; ++c) {
+    if (c < C) {
+      ld8(w + c * Cin + vl * 8, wr[c]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c] = fmaf(v[j], wsm[c * Cin + k + j], acc[c]);
-      }
+      for (int j = 0; j < 8; ++j) wr[c][j] = 0.f;
+    }
   }
-  int64_t b = p / HW;
-  int pix = (int)(p - b * HW);
-  for (int c = 0; c < C; ++c) y[(b * C + c) * HW + pix] = acc[c] + (bias ? bias[c] : 0.f);
+  const int p0 = blockIdx.x * (PL * FC_U) + pl;
+  float v[FC_U][8];
+#pragma unroll
+  for (int u = 0; u < FC_U; ++u) {
+    const int p = p0 + u * PL;
+    if (p < total) {
+      ld8(x + (int64_t)p * x_ld + vl * 8, v[u]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < FC_U; ++u) {
+    float acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a = fmaf(v[u][j], wr[c][j], a);
+      for (int o = 1; o < C8; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);   // C8 is a power of two <= 32
+      acc[c] = a;
+    }
+    const int p = p0 + u * PL;
+    if (p < total) {
+      const int b = p / HW, pix = p - b * HW;
+      if (C8 >= 4) {                // vector lane c writes channel c
+        if (vl < C) {
+          const float a = vl == 0 ? acc[0] : vl == 1 ? acc[1] : vl == 2 ? acc[2] : acc[3];
+          y[((int64_t)b * C + vl) * HW + pix] = a + (bias ? bias[vl] : 0.f);
+        }
+      } else if (vl == 0) {
+        for (int c = 0; c < C; ++c) y[((int64_t)b * C + c) * HW + pix] = acc[c] + (bias ? bias[c] : 0.f);
+      }
+    }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
-                     int dx_ld, int64_t total, int HW, int Cin, int C) {
+                     int dx_ld, int total, int HW, int Cin, int C) {
   pdl_prologue();
-  extern __shared__ float wsm[];
-  for (int i = threadIdx.x; i < C * Cin; i += blockDim.x) wsm[i] = w[i];
-  __syncthreads();
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  int64_t b = p / HW;
-  int pix = (int)(p - b * HW);
-  float g[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < C; ++c) g[c] = dy[(b * C + c) * HW + pix];
-  T* dr = dx + p * dx_ld;
-  for (int k = 0; k < Cin; k += 8) {
+  const int C8 = Cin >> 3, PL = 256 / C8;
+  const int vl = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float wr[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < C) {
+      ld8(w + c * Cin + vl * 8, wr[c]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wr[c][j] = 0.f;
+    }
+  }
+  const int p0 = blockIdx.x * (PL * FC_U) + pl;
+  float g[FC_U][4];
+#pragma unroll
+  for (int u = 0; u < FC_U; ++u) {
+    const int p = p0 + u * PL;
+    const int b = p / HW, pix = p - b * HW;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) g[u][c] = (c < C && p < total) ? dy[((int64_t)b * C + c) * HW + pix] : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < FC_U; ++u) {
+    const int p = p0 + u * PL;
+    if (p >= total) continue;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) s = fmaf(g[c], wsm[c * Cin + k + j], s);
-      v[j] = s;
-    }
-    st8(dr + k, v);
+    for (int j = 0; j < 8; ++j)
+      v[j] = fmaf(g[u][0], wr[0][j], fmaf(g[u][1], wr[1][j], fmaf(g[u][2], wr[2][j], g[u][3] * wr[3][j])));
+    st8(dx + (int64_t)p * dx_ld + vl * 8, v);
   }
 }
 
-// dW[c][ci] += sum_p dy[b,c,p]*x[p,ci];  db[c] += sum dy.  blockDim = (Cin, 256/Cin)
+// dW[c][ci] += sum_p dy[b,c,p]*x[p,ci];  db[c] += sum dy.  One wave of CTAs, each over a contiguous pixel range.
 template <typename T>
-__global__ void final_conv_dw_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ dy,
-                                     float* __restrict__ dw, float* __restrict__ db, int64_t total,
-                                     int HW, int Cin, int C, int64_t per_block) {
+__global__ void __launch_bounds__(256)
+final_conv_dw_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ dy, float* __restrict__ dw,
+                     float* __restrict__ db, int total, int HW, int Cin, int C, int per_block) {
   pdl_prologue();
-  extern __shared__ float red[];  // [blockDim.y][5][Cin]
-  const int ci = threadIdx.x, ly = threadIdx.y, ny = blockDim.y;
-  int64_t p0 = (int64_t)blockIdx.x * per_block;
-  int64_t p1 = p0 + per_block < total ? p0 + per_block : total;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t p = p0 + ly; p < p1; p += ny) {
-    int64_t b = p / HW;
-    int pix = (int)(p - b * HW);
-    float xv = Elem<T>::ld(x + p * x_ld + ci);
+  extern __shared__ float red[];  // [PL][4][Cin] + [PL][4]
+  const int C8 = Cin >> 3, PL = 256 / C8;
+  const int vl = threadIdx.x % C8, pl = threadIdx.x / C8;
+  const int p0 = blockIdx.x * per_block, p1 = min(p0 + per_block, total);
+  float acc[4][8] = {}, accb[4] = {};
+  for (int pb = p0 + pl; pb < p1; pb += PL * FC_U) {
+    float v[FC_U][8], g[FC_U][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < C) {
-        float g = dy[(b * C + c) * HW + pix];
-        acc[c] = fmaf(g, xv, acc[c]);
-        accb[c] += g;
+    for (int u = 0; u < FC_U; ++u) {
+      const int p = pb + u * PL;
+      const bool ok = p < p1;
+      const int b = p / HW, pix = p - b * HW;
+      if (ok) {
+        ld8(x + (int64_t)p * x_ld + vl * 8, v[u]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) g[u][c] = (ok && c < C) ? dy[((int64_t)b * C + c) * HW + pix] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < FC_U; ++u)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        accb[c] += g[u][c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(g[u][c], v[u][j], acc[c][j]);
       }
   }
-  for (int c = 0; c < C; ++c) red[(ly * 4 + c) * Cin + ci] = acc[c];
-  __syncthreads();
-  if (ly == 0) {
-    for (int c = 0; c < C; ++c) {
-      float s = 0.f;
-      for (int j = 0; j < ny; ++j) s += red[(j * 4 + c) * Cin + ci];
-      atomicAdd(dw + c * Cin + ci, s);
-    }
+  float* redb = red + PL * 4 * Cin;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(pl * 4 + c) * Cin + vl * 8 + j] = acc[c][j];
+    if (vl == 0) redb[pl * 4 + c] = accb[c];
   }
-  // bias: every (ci == 0) lane holds the column sum of its pixel subset
-  if (ci == 0)
-    for (int c = 0; c < C; ++c) atomicAdd(db + c, accb[c]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * Cin; i += 256) {
+    const int c = i / Cin, ci = i - c * Cin;
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += red[(l * 4 + c) * Cin + ci];
+    atomicAdd(dw + i, s);
+  }
+  if (db != nullptr && threadIdx.x < C) {
+    float s = 0.f;
+    for (int l = 0; l < PL; ++l) s += redb[l * 4 + threadIdx.x];
+    atomicAdd(db + threadIdx.x, s);
+  }
 }
 
 // ---- nearest x2 upsample and its gradient ------------------------------------------------------------
@@ -606,6 +731,50 @@ extern "C" int b200dm_colsum(int32_t dtype, const void* x, int32_t ld, int64_t r
   return check_launch("colsum");
 }
 
+extern "C" int b200dm_colsum_batched(int32_t dtype, const b200dm_colsum_item* items, int32_t n, void* stream) {
+  B200DM_REQUIRE(items != nullptr && n >= 1 && n <= COLSUM_MAX_ITEMS, B200DM_ERR_SHAPE,
+                 "colsum_batched: n=%d must be 1..%d", n, COLSUM_MAX_ITEMS);
+  B200DM_REQUIRE(dtype == B200DM_F32 || dtype == B200DM_BF16, B200DM_ERR_UNSUPPORTED, "colsum_batched: dtype");
+  ColsumBatch bt{};
+  bt.n = n;
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const b200dm_colsum_item& q = items[i];
+    B200DM_REQUIRE(q.x != nullptr && q.out != nullptr && q.rows > 0 && q.C > 0, B200DM_ERR_SHAPE,
+                   "colsum_batched: item %d is empty", i);
+    B200DM_REQUIRE(q.C % 8 == 0 && q.ld % 8 == 0 && q.ld >= q.C && ((uintptr_t)q.x & 15) == 0, B200DM_ERR_SHAPE,
+                   "colsum_batched: item %d: C, ld must be multiples of 8, x 16-byte aligned", i);
+    total += (double)q.rows * q.C;
+  }
+  // about two waves of CTAs, shared out by size (at least one each); every CTA wants at least 4 passes of its row lanes
+  const int budget = 2 * num_sms();
+  int nblk = 0;
+  for (int i = 0; i < n; ++i) {
+    const b200dm_colsum_item& q = items[i];
+    const int C8 = q.C / 8;
+    int VL = 1;
+    while (VL < C8 && VL < 64) VL <<= 1;
+    const int cb = (C8 + VL - 1) / VL, RL = 256 / VL;
+    long long rb = (long long)((double)budget * ((double)q.rows * q.C / total) / cb + 0.5);
+    const long long rbmax = (q.rows + 4 * RL - 1) / (4 * RL);
+    if (rb > rbmax) rb = rbmax;
+    if (rb < 1) rb = 1;
+    const long long per = (q.rows + rb - 1) / rb;
+    B200DM_REQUIRE(per < (1ll << 31), B200DM_ERR_SHAPE, "colsum_batched: item %d has too many rows", i);
+    rb = (q.rows + per - 1) / per;
+    bt.x[i] = q.x; bt.out[i] = q.out; bt.rows[i] = q.rows; bt.per[i] = (int)per; bt.ld[i] = q.ld;
+    bt.C8[i] = C8; bt.VL[i] = VL; bt.cb[i] = cb;
+    bt.first[i] = nblk;
+    nblk += (int)(rb * cb);
+  }
+  bt.first[n] = nblk;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B200DM_F32) launch_k(colsum8_batched_kernel<float>, nblk, 256, 0, st, bt);
+  else launch_k(colsum8_batched_kernel<__nv_bfloat16>, nblk, 256, 0, st, bt);
+  count_launch();
+  return check_launch("colsum_batched");
+}
+
 // ---- stem on tensor cores: im2col of the 7x7 patches + zero-padded weight rows -------------------------------
 // P[pix][k] = x[b, ch, y + ky - 3, x + kx - 3], k = (ch*7 + ky)*7 + kx (the OIHW order of the master weight),
 // columns [C*49, KP) are zero.  The 7x7 conv (ddpm.py:304) then IS a 1x1 conv with Cin = KP over P, and its
@@ -728,18 +897,24 @@ extern "C" int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void*
   return check_launch("init_conv_wgrad");
 }
 
+// Cin/8 vector lanes must tile a warp: Cin in {8, 16, 32, 64, 128, 256}
+static bool final_conv_cin_ok(int Cin) { return Cin >= 8 && Cin <= 256 && (Cin & (Cin - 1)) == 0; }
+
 extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
                                      const float* bias, float* y, int32_t B, int32_t HW, int32_t Cin,
                                      int32_t C, void* stream) {
-  B200DM_REQUIRE(C >= 1 && C <= 4 && Cin % 8 == 0, B200DM_ERR_UNSUPPORTED, "final_conv: C=%d Cin=%d", C, Cin);
-  int64_t total = (int64_t)B * HW;
-  size_t smem = (size_t)C * Cin * sizeof(float);
-  unsigned grid = (unsigned)((total + 255) / 256);
+  B200DM_REQUIRE(C >= 1 && C <= 4 && final_conv_cin_ok(Cin), B200DM_ERR_UNSUPPORTED, "final_conv: C=%d Cin=%d", C, Cin);
+  B200DM_REQUIRE(x_ld % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, B200DM_ERR_SHAPE,
+                 "final_conv: x and w must be 16-byte aligned, ld a multiple of 8");
+  const int64_t total = (int64_t)B * HW;
+  B200DM_REQUIRE(total > 0 && total < (1ll << 31), B200DM_ERR_SHAPE, "final_conv: B*HW out of range");
+  const int per = (256 / (Cin / 8)) * FC_U;
+  unsigned grid = (unsigned)((total + per - 1) / per);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    launch_k(final_conv_kernel<float>, grid, 256, smem, st, (const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<float>, grid, 256, 0, st, (const float*)x, x_ld, w, bias, y, (int)total, HW, Cin, C);
   else
-    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, smem, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, (int)total, HW, Cin, C);
   count_launch();
   return check_launch("final_conv_fwd");
 }
@@ -747,29 +922,31 @@ extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld,
 extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
                                      const float* dy, void* dx, int32_t dx_ld, float* dw, float* db,
                                      int32_t B, int32_t HW, int32_t Cin, int32_t C, void* stream) {
-  B200DM_REQUIRE(C >= 1 && C <= 4 && Cin % 8 == 0 && Cin <= 256 && 256 % Cin == 0, B200DM_ERR_UNSUPPORTED,
+  B200DM_REQUIRE(C >= 1 && C <= 4 && final_conv_cin_ok(Cin), B200DM_ERR_UNSUPPORTED,
                  "final_conv_bwd: C=%d Cin=%d", C, Cin);
-  int64_t total = (int64_t)B * HW;
-  size_t smem = (size_t)C * Cin * sizeof(float);
-  unsigned grid = (unsigned)((total + 255) / 256);
+  B200DM_REQUIRE(((uintptr_t)w & 15) == 0 && (!dx || (dx_ld % 8 == 0 && ((uintptr_t)dx & 15) == 0)) &&
+                     (!dw || (x_ld % 8 == 0 && ((uintptr_t)x & 15) == 0)),
+                 B200DM_ERR_SHAPE, "final_conv_bwd: 16-byte alignment, ld a multiple of 8");
+  const int64_t total = (int64_t)B * HW;
+  B200DM_REQUIRE(total > 0 && total < (1ll << 31), B200DM_ERR_SHAPE, "final_conv_bwd: B*HW out of range");
+  const int PL = 256 / (Cin / 8);
+  unsigned grid = (unsigned)((total + PL * FC_U - 1) / (PL * FC_U));
   cudaStream_t st = (cudaStream_t)stream;
-  int ny = 256 / Cin;
-  int64_t nblk = 2 * num_sms();
-  if (nblk > (total + 63) / 64) nblk = (total + 63) / 64;
-  int64_t per = (total + nblk - 1) / nblk;
-  dim3 block2(Cin, ny);
-  size_t smem2 = (size_t)ny * 4 * Cin * sizeof(float);
+  // parameter gradients: one wave of CTAs (the atomics of every CTA hit the same C*Cin addresses)
+  int64_t nblk = num_sms();
+  if (nblk > (total + PL * FC_U - 1) / (PL * FC_U)) nblk = (total + PL * FC_U - 1) / (PL * FC_U);
+  const int per = (int)((total + nblk - 1) / nblk);
+  nblk = (total + per - 1) / per;
+  size_t smem2 = (size_t)(PL * 4 * Cin + PL * 4) * sizeof(float);
   // dx == nullptr or dw == nullptr skips that kernel (the plan issues the parameter gradients on its side stream)
-  int launches = 0;
   if (dtype == B200DM_F32) {
-    if (dx) launch_k(final_conv_dx_kernel<float>, grid, 256, smem, st, w, dy, (float*)dx, dx_ld, total, HW, Cin, C);
-    if (dw) launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, block2, smem2, st, (const float*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    if (dx) launch_k(final_conv_dx_kernel<float>, grid, 256, 0, st, w, dy, (float*)dx, dx_ld, (int)total, HW, Cin, C);
+    if (dw) launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, 256, smem2, st, (const float*)x, x_ld, dy, dw, db, (int)total, HW, Cin, C, per);
   } else {
-    if (dx) launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, smem, st, w, dy, (__nv_bfloat16*)dx, dx_ld, total, HW, Cin, C);
-    if (dw) launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, block2, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, total, HW, Cin, C, per);
+    if (dx) launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, 0, st, w, dy, (__nv_bfloat16*)dx, dx_ld, (int)total, HW, Cin, C);
+    if (dw) launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, 256, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, (int)total, HW, Cin, C, per);
   }
-  launches = (dx ? 1 : 0) + (dw ? 1 : 0);
-  count_launch(launches);
+  count_launch((dx ? 1 : 0) + (dw ? 1 : 0));
   return check_launch("final_conv_bwd");
 }
 

@@ -501,6 +501,55 @@ def test_upsample_and_colsum(dtype):
     assert rel(out, dy.sum((0, 2, 3))) < 2e-5
 
 
+@pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
+def test_colsum_batched_ragged_items(dtype):
+    """One launch, items of very different sizes (one with a single row, one strided slice of a wider buffer, one with
+    more than 512 channels = several column blocks); every item accumulates onto what `out` already holds."""
+    shapes = [(2, 32, 64, 0), (1, 1, 8, 0), (3, 8, 512, 0), (2, 16, 128, 8), (1, 4, 1024, 0), (5, 2, 64, 0)]
+    arr = (L.ColsumItem * len(shapes))()
+    keep, want, outs = [], [], []
+    for i, (B, S, Cc, off) in enumerate(shapes):
+        dy = q(rnd(B, Cc, S, S, seed=300 + i), dtype)
+        v = nhwc(dy, dtype, ld=Cc + off, off=off) if off else nhwc(dy, dtype)
+        out = torch.full((Cc,), float(i), device=DEV)
+        arr[i].x, arr[i].out, arr[i].rows, arr[i].ld, arr[i].C = v.ptr, out.data_ptr(), B * S * S, v.ld, Cc
+        keep.append(v)
+        outs.append(out)
+        want.append(dy.double().sum((0, 2, 3)) + i)
+    L.call("b200dm_colsum_batched", dtype, arr, len(shapes))
+    torch.cuda.synchronize()
+    for out, w in zip(outs, want):
+        assert rel(out, w) < 2e-5
+    # refusals: too many items, a channel count that is not a multiple of 8
+    big = (L.ColsumItem * 17)()
+    with pytest.raises(L.B200dmError):
+        L.call("b200dm_colsum_batched", dtype, big, 17)
+    arr[0].C = 12
+    with pytest.raises(L.B200dmError):
+        L.call("b200dm_colsum_batched", dtype, arr, 1)
+
+
+def test_final_conv_large_and_ragged_pixel_count():
+    """B*HW that is not a multiple of the pixels one CTA covers, bf16, against the fp32 definition."""
+    B, S, C = 5, 24, 3
+    x = q(rnd(B, 64, S, S, seed=65), L.BF16).requires_grad_(True)
+    w = rnd(C, 64, 1, 1, seed=66, scale=0.125).requires_grad_(True)
+    bias = rnd(C, seed=67).requires_grad_(True)
+    ref = F.conv2d(x, w, bias)
+    xv = nhwc(x.detach(), L.BF16)
+    y = torch.empty(B, C, S, S, device=DEV)
+    L.call("b200dm_final_conv_fwd", L.BF16, xv.ptr, xv.ld, w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, S * S, 64, C)
+    assert rel(y, ref) < 2e-5
+    dy = rnd(B, C, S, S, seed=68)
+    ref.backward(dy)
+    dxv = View.zeros(B, S, S, 64, DT[L.BF16], DEV)
+    dw, db = torch.zeros(C, 64, device=DEV), torch.zeros(C, device=DEV)
+    L.call("b200dm_final_conv_bwd", L.BF16, xv.ptr, xv.ld, w.data_ptr(), dy.data_ptr(), dxv.ptr, dxv.ld,
+           dw.data_ptr(), db.data_ptr(), B, S * S, 64, C)
+    assert rel(dxv.to_nchw(), x.grad) < tol(L.BF16)
+    assert rel(dw, w.grad.view(C, 64)) < 2e-5 and rel(db, bias.grad) < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------
 # norms
 # ------------------------------------------------------------------------------------------------
