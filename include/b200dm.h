@@ -315,6 +315,30 @@ int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const v
                        int32_t qkv_ld, const float* mem_kv, const float* ctx, const float* kstat,
                        float* dctx, void* dqkv, int32_t dqkv_ld, float* dmem_kv, int32_t B,
                        int32_t n, void* stream);
+
+/* LinearAttention block for inference in three launches that never store q, k, v (csrc/linattn_tc.cu):
+ *   y = RMSNorm(to_out(LinearAttention(to_qkv(RMSNorm(x))))) + x
+ * reference ddpm.py:205-238 (LinearAttention.forward), :184-191 (RMSNorm), :449,:464 (`attn(x) + x`).  bf16 only.
+ * wqkv is to_qkv.weight with the first RMSNorm's gain folded in (b200dm_pack_linattn_qkv); wout is to_out.0.weight as
+ * bf16 [C][128]; gout is to_out.1.g.  n must be a multiple of 128 and C 64 or 128 (b200dm_linattn_block_supported);
+ * ws holds b200dm_linattn_block_ws_floats(B, n) floats of scratch. */
+typedef struct {
+  int32_t B, n, C;
+  int32_t x_ld, y_ld;
+  int32_t reserved;
+  const void* x;
+  void* y;
+  const void* wqkv;
+  const void* wout;
+  const float* bout;
+  const float* gout;
+  const float* mem_kv;
+  float* ws;
+} b200dm_linattn_block_desc;
+int b200dm_pack_linattn_qkv(const float* w, const float* g, void* out, int32_t C, void* stream);
+int64_t b200dm_linattn_block_ws_floats(int32_t B, int32_t n);
+int b200dm_linattn_block_supported(const b200dm_linattn_block_desc* d);
+int b200dm_linattn_block_fwd(const b200dm_linattn_block_desc* d, void* stream);
 /* Attention + Attend.forward (math branch), ddpm.py:255-271, models/modules/attend.py:111-126.
  * mem_kv fp32 [2][4][4][32]; n <= 64. */
 int b200dm_attn_fwd(int32_t dtype, const void* qkv, int32_t qkv_ld, const float* mem_kv, void* out,

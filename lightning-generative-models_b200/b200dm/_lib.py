@@ -63,6 +63,16 @@ class ColsumItem(C.Structure):
     _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int64), ("ld", C.c_int32), ("C", C.c_int32)]
 
 
+class LinAttnBlockDesc(C.Structure):
+    """b200dm_linattn_block_desc: the fused inference LinearAttention block (csrc/linattn_tc.cu)."""
+    _fields_ = [
+        ("B", C.c_int32), ("n", C.c_int32), ("C", C.c_int32), ("x_ld", C.c_int32), ("y_ld", C.c_int32),
+        ("reserved", C.c_int32),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("wqkv", C.c_void_p), ("wout", C.c_void_p),
+        ("bout", C.c_void_p), ("gout", C.c_void_p), ("mem_kv", C.c_void_p), ("ws", C.c_void_p),
+    ]
+
+
 class NoiseDesc(C.Structure):
     """b200dm_noise_desc: inputs of the forward-noising step shared by q_sample and the loss."""
     _fields_ = [
@@ -98,6 +108,8 @@ PROTOTYPES = {
     "b200dm_conv_wgrad": [C.POINTER(WgradDesc), _P],
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
     "b200dm_colsum_batched": [_I, _P, _I, _P],
+    "b200dm_pack_linattn_qkv": [_P, _P, _P, _I, _P],
+    "b200dm_linattn_block_fwd": [_P, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200dm_pack_stem_weight": [_P, _P, _I, _I, _I, _P],
     "b200dm_pack_upconv_weight": [_P, _P, _I, _I, _P],
@@ -143,6 +155,8 @@ _SPECIAL = {
     "b200dm_tc_available": ([], C.c_int),
     "b200dm_set_reserved_sms": ([C.c_int32], C.c_int),
     "b200dm_conv_gn_supported": ([C.POINTER(ConvDesc), C.POINTER(GnDesc)], C.c_int),
+    "b200dm_linattn_block_ws_floats": ([_I, _I], C.c_int64),
+    "b200dm_linattn_block_supported": ([_P], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
 

@@ -60,6 +60,10 @@ class WeightPack:
                 if re.fullmatch(r"ups\.\d+\.3\.1", nm) and ci.mode == 0 and ci.ksize == 3:
                     self.up[nm] = torch.empty(16 * ci.cout * ci.cin, dtype=tdt, device=dev)
         self.up_version = None
+        # LinearAttention blocks for inference (b200dm_linattn_block_fwd): to_qkv weights with the PreNorm gain folded
+        # in, bf16 [384][C]; registered by the inference plans that use them
+        self.la = {}
+        self.la_version = None
         # device table for the one-launch batched pack
         entries = (L.PackEntry * len(arena.convs))()
         tile = 0
@@ -96,6 +100,11 @@ class WeightPack:
                 ci = self.arena.convs[nm]
                 L.call("b200dm_pack_upconv_weight", self.arena.ptr(nm + ".weight"), buf.data_ptr(), ci.cout, ci.cin)
             self.up_version = v
+        if self.la and (force or v != self.la_version):
+            for nm, buf in self.la.items():
+                L.call("b200dm_pack_linattn_qkv", self.arena.ptr(nm + ".to_qkv.weight"), self.arena.ptr(nm + ".norm.g"),
+                       buf.data_ptr(), self.arena.convs[nm + ".to_qkv"].cin)
+            self.la_version = v
         if not force and v == self.version:
             return
         L.call("b200dm_pack_conv_weights_batched", self.dt, self.table.data_ptr(), self.n_entries,
@@ -105,6 +114,14 @@ class WeightPack:
                    self.arena.dim, self.stem_k, self.stem_kp)
         self.version = v
 
+
+    def linattn_qkv(self, nm: str) -> torch.Tensor:
+        """Folded to_qkv weight of LinearAttention block `nm` (packed at the next refresh)."""
+        if nm not in self.la:
+            ci = self.arena.convs[nm + ".to_qkv"]
+            self.la[nm] = torch.empty(ci.cout * ci.cin, dtype=torch.bfloat16, device=self.arena.flat.device)
+            self.la_version = None
+        return self.la[nm]
 
     def range_runs(self, begin: int, end: int):
         """Contiguous runs of table entries (first, n, tile_first, tiles) whose master weights live in arena elements
@@ -172,6 +189,9 @@ class Plan:
         self.fuse_upsample = os.environ.get("B200DM_FUSE_UPSAMPLE", "1") != "0"
         self.fuse_gn = os.environ.get("B200DM_FUSE_GN", "1") != "0"       # conv + GroupNorm + FiLM + SiLU in one launch
         self.batch_colsum = os.environ.get("B200DM_BATCH_COLSUM", "1") != "0"   # one bias-gradient launch per bucket
+        self.fuse_linattn = os.environ.get("B200DM_FUSE_LINATTN", "1") != "0"   # inference: LinearAttention block fused
+        self._la_ws = None
+        self._la_descs = []
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
         # forward: the second stream only carries the 1x1 residual convs, which the main chain needs a few kernels
         # later -> high priority (measured, B=128 32x32 forward: 1.467 -> 1.440 ms).  In backward equal priorities are
@@ -430,6 +450,25 @@ class Plan:
         Cc, H = x.C, x.H
         n, rows = H * H, self.B * H * H
         self.begin_unit()
+        if not full and not self.training and self.fuse_linattn and self.dt == L.BF16 and self.use_tc:
+            # inference: RMSNorm -> to_qkv -> LinearAttention -> to_out -> RMSNorm -> + x in three launches that keep
+            # q, k, v on chip (csrc/linattn_tc.cu)
+            d = L.LinAttnBlockDesc(B=self.B, n=n, C=Cc, x_ld=x.ld, y_ld=out.ld, x=x.ptr, y=out.ptr,
+                                   wqkv=self.pack.linattn_qkv(nm).data_ptr(),
+                                   wout=self.pack.fwd[nm + ".to_out.0"].data_ptr(), bout=a.ptr(nm + ".to_out.0.bias"),
+                                   gout=a.ptr(nm + ".to_out.1.g"), mem_kv=a.ptr(nm + ".mem_kv"))
+            if self.lib.b200dm_linattn_block_supported(C.byref(d)) == 1:
+                need = self.lib.b200dm_linattn_block_ws_floats(self.B, n)
+                if self._la_ws is None or self._la_ws.numel() < need:
+                    self._la_ws = self.f32(need)        # the blocks run one after the other: one scratch for all
+                    for dd in self._la_descs:
+                        dd.ws = self._la_ws.data_ptr()
+                d.ws = self._la_ws.data_ptr()
+                self._la_descs.append(d)
+                self.F("b200dm_linattn_block_fwd", C.byref(d), kname="linattn_block", writes=(out,),
+                       flops=2.0 * rows * (Cc * 3 * HIDDEN + 2 * HIDDEN * 32 + HIDDEN * Cc))
+                self._keep.append(d)
+                return
         xn, qkv, ao = self.buf(H, Cc), self.buf(H, 3 * HIDDEN), self.buf(H, HIDDEN)
         self.F("b200dm_rmsnorm_fwd", self.dt, x.ptr, x.ld, a.ptr(nm + ".norm.g"), None, 0, xn.ptr, xn.ld, rows, Cc)
         self.conv_fwd(self.F, nm + ".to_qkv", xn, qkv)

@@ -447,7 +447,8 @@ constexpr int FC_U = 4;
 template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w,
-                  const float* __restrict__ bias, float* __restrict__ y, int total, int HW, int Cin, int C) {
+                  const float* __restrict__ bias, float* __restrict__ y, int total, int HW, int Cin, int C,
+                  int iters) {
   pdl_prologue();
   const int C8 = Cin >> 3, PL = 256 / C8;
   const int vl = threadIdx.x % C8, pl = threadIdx.x / C8;
@@ -461,7 +462,11 @@ final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w
       for (int j = 0; j < 8; ++j) wr[c][j] = 0.f;
     }
   }
-  const int p0 = blockIdx.x * (PL * FC_U) + pl;
+  // `iters` groups of PL * FC_U pixels per CTA: the weight rows (4 x 32 B per thread) are loaded once per CTA
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+  const int p0 = (blockIdx.x * iters + it) * (PL * FC_U) + pl;
+  if (p0 - pl >= total) break;
   float v[FC_U][8];
 #pragma unroll
   for (int u = 0; u < FC_U; ++u) {
@@ -497,12 +502,13 @@ final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w
       }
     }
   }
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 final_conv_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy, T* __restrict__ dx,
-                     int dx_ld, int total, int HW, int Cin, int C) {
+                     int dx_ld, int total, int HW, int Cin, int C, int iters) {
   pdl_prologue();
   const int C8 = Cin >> 3, PL = 256 / C8;
   const int vl = threadIdx.x % C8, pl = threadIdx.x / C8;
@@ -516,24 +522,28 @@ final_conv_dx_kernel(const float* __restrict__ w, const float* __restrict__ dy, 
       for (int j = 0; j < 8; ++j) wr[c][j] = 0.f;
     }
   }
-  const int p0 = blockIdx.x * (PL * FC_U) + pl;
-  float g[FC_U][4];
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    const int p0 = (blockIdx.x * iters + it) * (PL * FC_U) + pl;
+    if (p0 - pl >= total) break;
+    float g[FC_U][4];
 #pragma unroll
-  for (int u = 0; u < FC_U; ++u) {
-    const int p = p0 + u * PL;
-    const int b = p / HW, pix = p - b * HW;
+    for (int u = 0; u < FC_U; ++u) {
+      const int p = p0 + u * PL;
+      const int b = p / HW, pix = p - b * HW;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) g[u][c] = (c < C && p < total) ? dy[((int64_t)b * C + c) * HW + pix] : 0.f;
-  }
+      for (int c = 0; c < 4; ++c) g[u][c] = (c < C && p < total) ? dy[((int64_t)b * C + c) * HW + pix] : 0.f;
+    }
 #pragma unroll
-  for (int u = 0; u < FC_U; ++u) {
-    const int p = p0 + u * PL;
-    if (p >= total) continue;
-    float v[8];
+    for (int u = 0; u < FC_U; ++u) {
+      const int p = p0 + u * PL;
+      if (p >= total) continue;
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = fmaf(g[u][0], wr[0][j], fmaf(g[u][1], wr[1][j], fmaf(g[u][2], wr[2][j], g[u][3] * wr[3][j])));
-    st8(dx + (int64_t)p * dx_ld + vl * 8, v);
+      for (int j = 0; j < 8; ++j)
+        v[j] = fmaf(g[u][0], wr[0][j], fmaf(g[u][1], wr[1][j], fmaf(g[u][2], wr[2][j], g[u][3] * wr[3][j])));
+      st8(dx + (int64_t)p * dx_ld + vl * 8, v);
+    }
   }
 }
 
@@ -899,6 +909,12 @@ extern "C" int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void*
 
 // Cin/8 vector lanes must tile a warp: Cin in {8, 16, 32, 64, 128, 256}
 static bool final_conv_cin_ok(int Cin) { return Cin >= 8 && Cin <= 256 && (Cin & (Cin - 1)) == 0; }
+// pixel groups per CTA of the forward / dx kernels: up to 8, as long as the grid keeps >= 4 CTAs per SM
+static int final_conv_iters(int64_t total, int Cin) {
+  const int64_t groups = (total + (256 / (Cin / 8)) * FC_U - 1) / ((256 / (Cin / 8)) * FC_U);
+  int64_t it = groups / (4 * (int64_t)num_sms());
+  return it < 1 ? 1 : it > 8 ? 8 : (int)it;
+}
 
 extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld, const float* w,
                                      const float* bias, float* y, int32_t B, int32_t HW, int32_t Cin,
@@ -908,13 +924,14 @@ extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld,
                  "final_conv: x and w must be 16-byte aligned, ld a multiple of 8");
   const int64_t total = (int64_t)B * HW;
   B200DM_REQUIRE(total > 0 && total < (1ll << 31), B200DM_ERR_SHAPE, "final_conv: B*HW out of range");
-  const int per = (256 / (Cin / 8)) * FC_U;
+  const int iters = final_conv_iters(total, Cin);
+  const int per = (256 / (Cin / 8)) * FC_U * iters;
   unsigned grid = (unsigned)((total + per - 1) / per);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    launch_k(final_conv_kernel<float>, grid, 256, 0, st, (const float*)x, x_ld, w, bias, y, (int)total, HW, Cin, C);
+    launch_k(final_conv_kernel<float>, grid, 256, 0, st, (const float*)x, x_ld, w, bias, y, (int)total, HW, Cin, C, iters);
   else
-    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, (int)total, HW, Cin, C);
+    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, (int)total, HW, Cin, C, iters);
   count_launch();
   return check_launch("final_conv_fwd");
 }
@@ -930,7 +947,8 @@ extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld,
   const int64_t total = (int64_t)B * HW;
   B200DM_REQUIRE(total > 0 && total < (1ll << 31), B200DM_ERR_SHAPE, "final_conv_bwd: B*HW out of range");
   const int PL = 256 / (Cin / 8);
-  unsigned grid = (unsigned)((total + PL * FC_U - 1) / (PL * FC_U));
+  const int iters = final_conv_iters(total, Cin);
+  unsigned grid = (unsigned)((total + PL * FC_U * iters - 1) / (PL * FC_U * iters));
   cudaStream_t st = (cudaStream_t)stream;
   // parameter gradients: one wave of CTAs (the atomics of every CTA hit the same C*Cin addresses)
   int64_t nblk = num_sms();
@@ -940,10 +958,10 @@ extern "C" int b200dm_final_conv_bwd(int32_t dtype, const void* x, int32_t x_ld,
   size_t smem2 = (size_t)(PL * 4 * Cin + PL * 4) * sizeof(float);
   // dx == nullptr or dw == nullptr skips that kernel (the plan issues the parameter gradients on its side stream)
   if (dtype == B200DM_F32) {
-    if (dx) launch_k(final_conv_dx_kernel<float>, grid, 256, 0, st, w, dy, (float*)dx, dx_ld, (int)total, HW, Cin, C);
+    if (dx) launch_k(final_conv_dx_kernel<float>, grid, 256, 0, st, w, dy, (float*)dx, dx_ld, (int)total, HW, Cin, C, iters);
     if (dw) launch_k(final_conv_dw_kernel<float>, (unsigned)nblk, 256, smem2, st, (const float*)x, x_ld, dy, dw, db, (int)total, HW, Cin, C, per);
   } else {
-    if (dx) launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, 0, st, w, dy, (__nv_bfloat16*)dx, dx_ld, (int)total, HW, Cin, C);
+    if (dx) launch_k(final_conv_dx_kernel<__nv_bfloat16>, grid, 256, 0, st, w, dy, (__nv_bfloat16*)dx, dx_ld, (int)total, HW, Cin, C, iters);
     if (dw) launch_k(final_conv_dw_kernel<__nv_bfloat16>, (unsigned)nblk, 256, smem2, st, (const __nv_bfloat16*)x, x_ld, dy, dw, db, (int)total, HW, Cin, C, per);
   }
   count_launch((dx ? 1 : 0) + (dw ? 1 : 0));

@@ -799,7 +799,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
                       const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
   EncodeTiledFn enc = get_encoder();
   B200DM_REQUIRE(enc != nullptr, B200DM_ERR_UNSUPPORTED, "%s: cuTensorMapEncodeTiled unavailable", what);

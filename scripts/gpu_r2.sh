@@ -32,7 +32,7 @@ if [ "$WHAT" = "evidence" ] || [ "$WHAT" = "all" ]; then
   M="gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread"
   python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_plain_ddim.log 2>&1 &&
   NEV=$(grep "eval 1" $O/${TAG}_plain_ddim.log | sed 's/.*, \([0-9]*\) launches/\1/') &&
-  ncu --metrics $M --clock-control none -k 'regex:attn_fwd|conv3x3|conv_tc|final_conv|gn_fwd|im2col7|linattn|rmsnorm|sgemm|sinusoidal' -s $NEV -c $NEV --csv --log-file $O/${TAG}_eval_ddim_metrics.csv python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_ncu3.log 2>&1
+  ncu --metrics $M --clock-control none -k 'regex:attn_fwd|conv3x3|conv_tc|final_conv|gn_fwd|im2col7|linattn|la_ctx|la_out|rmsnorm|sgemm|sinusoidal' -s $NEV -c $NEV --csv --log-file $O/${TAG}_eval_ddim_metrics.csv python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_ncu3.log 2>&1
   grep -c b200dm $O/${TAG}_eval_ddim_metrics.csv; cat $O/${TAG}_plain_ddim.log
   ls $O | grep ${TAG}_ | tr '\n' ' '
 fi

@@ -13,6 +13,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from _refcuda import report
 from b200dm import _lib as L
 from b200dm.tensor import View
 
@@ -548,6 +549,63 @@ def test_final_conv_large_and_ragged_pixel_count():
            dw.data_ptr(), db.data_ptr(), B, S * S, 64, C)
     assert rel(dxv.to_nchw(), x.grad) < tol(L.BF16)
     assert rel(dw, w.grad.view(C, 64)) < 2e-5 and rel(db, bias.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# fused inference LinearAttention block (csrc/linattn_tc.cu) against the oracle's linear_attention + skip
+# ------------------------------------------------------------------------------------------------
+def _linattn_block_case(B, S, Cc, seed, big_k=False, ld_extra=0):
+    from oracle import ddpm_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Cc, S, S, generator=g).to(DEV)
+    x = x.to(torch.bfloat16).float()                                   # the activation tensor is bf16
+    sd = {
+        "a.norm.g": (1 + 0.2 * torch.randn(1, Cc, 1, 1, generator=g)).to(DEV),
+        "a.to_qkv.weight": (torch.randn(384, Cc, 1, 1, generator=g) * (3.0 if big_k else 1.0) / Cc ** 0.5).to(DEV),
+        "a.mem_kv": torch.randn(2, 4, 32, 4, generator=g).to(DEV),
+        "a.to_out.0.weight": (torch.randn(Cc, 128, 1, 1, generator=g) / 128 ** 0.5).to(DEV),
+        "a.to_out.0.bias": (0.1 * torch.randn(Cc, generator=g)).to(DEV),
+        "a.to_out.1.g": (1 + 0.2 * torch.randn(1, Cc, 1, 1, generator=g)).to(DEV),
+    }
+    ref = O.linear_attention(sd, "a", x, O.Emu(None)) + x
+    n = S * S
+    xv = nhwc(x, L.BF16, ld=Cc + ld_extra, off=ld_extra) if ld_extra else nhwc(x, L.BF16)
+    yv = View.zeros(B, S, S, Cc, DT[L.BF16], DEV)
+    wq = torch.empty(384 * Cc, dtype=torch.bfloat16, device=DEV)
+    L.call("b200dm_pack_linattn_qkv", sd["a.to_qkv.weight"].data_ptr(), sd["a.norm.g"].data_ptr(), wq.data_ptr(), Cc)
+    wo = sd["a.to_out.0.weight"].view(Cc, 128).to(torch.bfloat16).contiguous()
+    ws = torch.zeros(L.load().b200dm_linattn_block_ws_floats(B, n), device=DEV)
+    d = L.LinAttnBlockDesc(B=B, n=n, C=Cc, x_ld=xv.ld, y_ld=yv.ld, x=xv.ptr, y=yv.ptr, wqkv=wq.data_ptr(),
+                           wout=wo.data_ptr(), bout=sd["a.to_out.0.bias"].data_ptr(),
+                           gout=sd["a.to_out.1.g"].data_ptr(), mem_kv=sd["a.mem_kv"].data_ptr(), ws=ws.data_ptr())
+    assert L.load().b200dm_linattn_block_supported(ctypes.byref(d)) == 1
+    L.call("b200dm_linattn_block_fwd", ctypes.byref(d))
+    torch.cuda.synchronize()
+    return yv.to_nchw().float(), ref, ws, d, (xv, wq, wo, sd)
+
+
+@pytest.mark.parametrize("B,S,Cc", [(2, 16, 64), (3, 32, 64), (2, 16, 128), (5, 32, 128), (150, 16, 64)])
+def test_linattn_block_fused_inference(B, S, Cc):
+    y, ref, _, _, _ = _linattn_block_case(B, S, Cc, seed=500 + B + S + Cc)
+    e = rel(y, ref)
+    report(test="linattn_block", B=B, S=S, C=Cc, rel=e)
+    assert e < 1.5e-2, e            # bf16 operands (x, q, k-softmax, v, context, out) against the fp32 definition
+
+
+def test_linattn_block_large_logits_and_strided_input():
+    """Keys whose exp would overflow without the exact row maximum (|k| up to ~40), input as a channel slice."""
+    y, ref, _, _, _ = _linattn_block_case(2, 32, 64, seed=77, big_k=True, ld_extra=64)
+    assert torch.isfinite(y).all()
+    assert rel(y, ref) < 3e-2
+
+
+def test_linattn_block_refuses_unsupported_shapes():
+    d = L.LinAttnBlockDesc(B=1, n=64, C=64, x_ld=64, y_ld=64)
+    assert L.load().b200dm_linattn_block_supported(ctypes.byref(d)) == 0          # n not a multiple of 128
+    d = L.LinAttnBlockDesc(B=1, n=256, C=256, x_ld=256, y_ld=256)
+    assert L.load().b200dm_linattn_block_supported(ctypes.byref(d)) == 0          # C = 256 does not fit
+    with pytest.raises(L.B200dmError):
+        L.call("b200dm_linattn_block_fwd", ctypes.byref(d))
 
 
 # ------------------------------------------------------------------------------------------------
