@@ -321,7 +321,7 @@ int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const v
  * reference ddpm.py:205-238 (LinearAttention.forward), :184-191 (RMSNorm), :449,:464 (`attn(x) + x`).  bf16 only.
  * wqkv is to_qkv.weight with the first RMSNorm's gain folded in (b200dm_pack_linattn_qkv); wout is to_out.0.weight as
  * bf16 [C][128]; gout is to_out.1.g.  n must be a multiple of 128 and C 64 or 128 (b200dm_linattn_block_supported);
- * ws holds b200dm_linattn_block_ws_floats(B, n) floats of scratch. */
+ * ws holds b200dm_linattn_block_ws_floats(B, n, C) floats of scratch (16-byte aligned). */
 typedef struct {
   int32_t B, n, C;
   int32_t x_ld, y_ld;
@@ -336,7 +336,7 @@ typedef struct {
   float* ws;
 } b200dm_linattn_block_desc;
 int b200dm_pack_linattn_qkv(const float* w, const float* g, void* out, int32_t C, void* stream);
-int64_t b200dm_linattn_block_ws_floats(int32_t B, int32_t n);
+int64_t b200dm_linattn_block_ws_floats(int32_t B, int32_t n, int32_t C);
 int b200dm_linattn_block_supported(const b200dm_linattn_block_desc* d);
 int b200dm_linattn_block_fwd(const b200dm_linattn_block_desc* d, void* stream);
 /* Attention + Attend.forward (math branch), ddpm.py:255-271, models/modules/attend.py:111-126.

@@ -155,7 +155,7 @@ _SPECIAL = {
     "b200dm_tc_available": ([], C.c_int),
     "b200dm_set_reserved_sms": ([C.c_int32], C.c_int),
     "b200dm_conv_gn_supported": ([C.POINTER(ConvDesc), C.POINTER(GnDesc)], C.c_int),
-    "b200dm_linattn_block_ws_floats": ([_I, _I], C.c_int64),
+    "b200dm_linattn_block_ws_floats": ([_I, _I, _I], C.c_int64),
     "b200dm_linattn_block_supported": ([_P], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))

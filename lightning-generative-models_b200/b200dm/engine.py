@@ -457,8 +457,10 @@ class Plan:
                                    wqkv=self.pack.linattn_qkv(nm).data_ptr(),
                                    wout=self.pack.fwd[nm + ".to_out.0"].data_ptr(), bout=a.ptr(nm + ".to_out.0.bias"),
                                    gout=a.ptr(nm + ".to_out.1.g"), mem_kv=a.ptr(nm + ".mem_kv"))
-            if self.lib.b200dm_linattn_block_supported(C.byref(d)) == 1:
-                need = self.lib.b200dm_linattn_block_ws_floats(self.B, n)
+            # below 1024 pixels per sample the four launches' fixed costs outweigh the saved traffic (measured at
+            # batch 256: n = 256 fused 127 us, unfused chain ~75 us; n = 1024 fused 136 / 208 us, unfused ~190 / 235)
+            if n >= 1024 and self.lib.b200dm_linattn_block_supported(C.byref(d)) == 1:
+                need = self.lib.b200dm_linattn_block_ws_floats(self.B, n, Cc)
                 if self._la_ws is None or self._la_ws.numel() < need:
                     self._la_ws = self.f32(need)        # the blocks run one after the other: one scratch for all
                     for dd in self._la_descs:

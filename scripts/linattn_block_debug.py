@@ -25,10 +25,13 @@ def main():
     from b200dm import _lib as L
     y, ref, ws, d, (xv, wq, wo, sd) = T._linattn_block_case(a.B, a.S, a.C, seed=1)
     B, n, C = a.B, a.S * a.S, a.C
-    split = ws.numel() // (B * 4480)
-    w = ws.view(B, split, 4480)
+    split = (ws.numel() - B * n - B * C * 64) // (B * 4736)
+    w = ws[:B * split * 4736].view(B, split, 4736)
+    rn = ws[B * split * 4736:B * split * 4736 + B * n]
     x = xv.to_nchw().float()
     xn = torch.nn.functional.normalize(x, dim=1) * sd["a.norm.g"] * C ** 0.5
+    rn_ref = 1.0 / x.permute(0, 2, 3, 1).reshape(B * n, C).norm(dim=1)
+    print("rn rel err", ((rn - rn_ref).abs().max() / rn_ref.abs().max()).item())
     qkv = torch.nn.functional.conv2d(xn, sd["a.to_qkv.weight"])
     q, k, v = (t.reshape(B, 128, n) for t in qkv.chunk(3, dim=1))
     kmax = w[:, :, :128].max(dim=1).values
@@ -37,10 +40,10 @@ def main():
     m = torch.maximum(k.max(dim=2).values, mk.max(dim=1).values[None])
     p = torch.exp(k - m[:, :, None])
     s_ref = p.sum(dim=2)
-    s = w[:, :, 128:384].reshape(B, split, 2, 128).sum(dim=(1, 2))
+    s = w[:, :, 128:640].reshape(B, split, 4, 128).sum(dim=(1, 2))
     print("s rel err", ((s - s_ref).abs().max() / s_ref.abs().max()).item())
     ctx_ref = torch.einsum("bhdn,bhen->bhed", p.view(B, 4, 32, n), v.reshape(B, 4, 32, n))
-    ctx = w[:, :, 384:].reshape(B, split, 4, 32, 32).sum(dim=1)
+    ctx = w[:, :, 640:].reshape(B, split, 4, 32, 32).sum(dim=1)
     print("ctx rel err", ((ctx - ctx_ref).abs().max() / ctx_ref.abs().max()).item())
     print("y rel err", ((y - ref).norm() / ref.norm()).item(), "finite", bool(torch.isfinite(y).all()))
     bad = (y - ref).abs().amax(dim=(1,))        # [B, S, S]

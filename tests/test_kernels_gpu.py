@@ -574,7 +574,7 @@ def _linattn_block_case(B, S, Cc, seed, big_k=False, ld_extra=0):
     wq = torch.empty(384 * Cc, dtype=torch.bfloat16, device=DEV)
     L.call("b200dm_pack_linattn_qkv", sd["a.to_qkv.weight"].data_ptr(), sd["a.norm.g"].data_ptr(), wq.data_ptr(), Cc)
     wo = sd["a.to_out.0.weight"].view(Cc, 128).to(torch.bfloat16).contiguous()
-    ws = torch.zeros(L.load().b200dm_linattn_block_ws_floats(B, n), device=DEV)
+    ws = torch.zeros(L.load().b200dm_linattn_block_ws_floats(B, n, Cc), device=DEV)
     d = L.LinAttnBlockDesc(B=B, n=n, C=Cc, x_ld=xv.ld, y_ld=yv.ld, x=xv.ptr, y=yv.ptr, wqkv=wq.data_ptr(),
                            wout=wo.data_ptr(), bout=sd["a.to_out.0.bias"].data_ptr(),
                            gout=sd["a.to_out.1.g"].data_ptr(), mem_kv=sd["a.mem_kv"].data_ptr(), ws=ws.data_ptr())
