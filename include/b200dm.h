@@ -115,6 +115,11 @@ int b200dm_randn(float* out, int64_t n, uint64_t seed, uint64_t stream_id, uint6
 /* unnormalize_to_zero_to_one, ddpm.py:86-87 */
 int b200dm_unnormalize(const float* x, float* y, int64_t n, void* stream);
 
+/* out[b] = [a[b] | b[b]] for NCHW fp32 tensors with chw_a / chw_b elements per sample (multiples of 4):
+ * torch.cat((x_self_cond, x), dim=1) of a self-conditioned Unet.forward, ddpm.py:433-435. */
+int b200dm_concat2_nchw(const float* a, const float* b, float* out, int32_t B, int64_t chw_a, int64_t chw_b,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Convolutions as implicit GEMM (ddpm.py:96,103,160,187,213-215,252-253,377,413).
  *   mode 0: k x k, stride 1, 'same' padding (k = 1 or 3); input [B,H,W,Cin]

@@ -100,8 +100,8 @@ class EMA(nn.Module):
 
 def _clone_diffusion(gd: GaussianDiffusion) -> GaussianDiffusion:
     u = gd.model
-    unet = Unet(u.dim, channels=u.channels, precision=u.precision, device=u._device,
-                use_tc=u._use_tc, cuda_graph=u._cuda_graph)
+    unet = Unet(u.dim, channels=u.channels, self_condition=u.self_condition, precision=u.precision,
+                device=u._device, use_tc=u._use_tc, cuda_graph=u._cuda_graph)
     unet.arena.flat.copy_(u.arena.flat)
     return GaussianDiffusion(unet, **gd._ctor)          # every constructor argument of the online model
 

@@ -14,6 +14,7 @@ torch's global RNG exactly in the reference's order: randint, randn_like / randn
 from __future__ import annotations
 
 from collections import namedtuple
+from random import random
 from typing import Optional
 
 import torch
@@ -178,18 +179,23 @@ class GaussianDiffusion(nn.Module):
             noise = torch.randn_like(x_start)
         return self._q_sample_kernel(x_start, t, noise, False)[0]
 
-    def p_losses(self, x_start, t, noise=None, offset_noise_strength=None, _normalize=False):
+    def p_losses(self, x_start, t, noise=None, offset_noise_strength=None, _normalize=False, _self_cond=None):
         """ddpm.py:878-925.  q_sample and the loss are two kernels around the UNet; the loss kernel regenerates eps
-        from the same Philox blocks (or reads the injected tensor), so neither eps nor x0 is stored in between."""
+        from the same Philox blocks (or reads the injected tensor), so neither eps nor x0 is stored in between.
+        `_self_cond` forces the reference's coin flip `random() < 0.5` (:902) for tests."""
         if offset_noise_strength is None:
             offset_noise_strength = self.offset_noise_strength
-        if self.self_condition:
-            raise NotImplementedError("self-conditioning is not built (off in every reference config)")
         if noise is None and self.rng == "torch":
             noise = torch.randn_like(x_start)
         x_t, _, _, desc, keep = self._q_sample_kernel(x_start, t, noise, _normalize,
                                                       offset_strength=offset_noise_strength)
-        model_out = self.model(x_t, t)
+        x_self_cond = None
+        if self.self_condition and (random() < 0.5 if _self_cond is None else _self_cond):
+            # ddpm.py:901-905: a first, gradient-free evaluation; its x0 estimate is fed back (inference plan, so the
+            # training plan's saved activations are those of the second evaluation)
+            with torch.no_grad():
+                x_self_cond = self.model_predictions(x_t, t).pred_x_start.detach()
+        model_out = self.model(x_t, t, x_self_cond)
         return _LossFn.apply(model_out, self, desc, keep)
 
     def forward(self, img, *args, **kwargs):
@@ -257,6 +263,8 @@ class GaussianDiffusion(nn.Module):
                 L.call("b200dm_randn", plan.x_in.data_ptr(), plan.x_in.numel(), seed, sid, 0)
         else:
             plan.x_in.copy_(init)
+        if plan.xc_in is not None:
+            plan.xc_in.zero_()           # self-conditioning starts from "no estimate" (x_start = None, ddpm.py:770,803)
         return unet, plan
 
     @torch.inference_mode()
@@ -274,7 +282,8 @@ class GaussianDiffusion(nn.Module):
                     z = step_noise(t).contiguous().float()
                 elif self.rng == "torch":
                     z = torch.randn_like(plan.x_in)
-            self._ddpm_step(plan.x_in, plan.out, t, z, plan.x_in, None, seed, sid * 4096 + t)
+            # self-conditioned nets: the step's clamped x0 is the next evaluation's second input (ddpm.py:773-774)
+            self._ddpm_step(plan.x_in, plan.out, t, z, plan.x_in, plan.xc_in, seed, sid * 4096 + t)
             if return_all_timesteps:
                 imgs.append(plan.x_in.clone())
         ret = plan.x_in.clone() if not return_all_timesteps else torch.stack(imgs, dim=1)
@@ -305,7 +314,7 @@ class GaussianDiffusion(nn.Module):
                 elif self.rng == "torch":
                     z = torch.randn_like(plan.x_in)          # consumed even when eta == 0 (ddpm.py:825)
             L.call("b200dm_ddim_step", plan.x_in.data_ptr(), plan.out.data_ptr(), L.ptr(z),
-                   plan.x_in.data_ptr(), None, *self._coef(time), san, c, sigma, 1 if last else 0,
+                   plan.x_in.data_ptr(), L.ptr(plan.xc_in), *self._coef(time), san, c, sigma, 1 if last else 0,
                    L.OBJECTIVES[self.objective], plan.x_in.numel(), seed, sid * 4096 + max(time, 0), 0)
             if return_all_timesteps:
                 imgs.append(plan.x_in.clone())
@@ -332,6 +341,8 @@ class GaussianDiffusion(nn.Module):
         n = plan.x_in.numel()
         off = rank * n
         L.call("b200dm_randn", plan.x_in.data_ptr(), n, seed, 1, off)
+        if plan.xc_in is not None:
+            plan.xc_in.zero_()
         h, eta = self._host, self.ddim_sampling_eta
         if self.is_ddim_sampling:
             for time, time_next in ddim_time_pairs(self.num_timesteps, self.sampling_timesteps):
@@ -346,13 +357,13 @@ class GaussianDiffusion(nn.Module):
                     c = (1 - alpha_next - sig_t ** 2).sqrt().item()
                     san, sigma = alpha_next.sqrt().item(), float(sig_t)
                 L.call("b200dm_ddim_step", plan.x_in.data_ptr(), plan.out.data_ptr(), None,
-                       plan.x_in.data_ptr(), None, *self._coef(time), san, c, sigma, 1 if last else 0,
+                       plan.x_in.data_ptr(), L.ptr(plan.xc_in), *self._coef(time), san, c, sigma, 1 if last else 0,
                        L.OBJECTIVES[self.objective], n, seed, 2 + time, off)
         else:
             for t in reversed(range(self.num_timesteps)):
                 plan.t_in.fill_(t)
                 unet.run_plan_forward(plan)
-                self._ddpm_step(plan.x_in, plan.out, t, None, plan.x_in, None, seed, 2 + t, off)
+                self._ddpm_step(plan.x_in, plan.out, t, None, plan.x_in, plan.xc_in, seed, 2 + t, off)
         return self.unnormalize(plan.x_in.clone())
 
     @torch.inference_mode()
@@ -364,6 +375,8 @@ class GaussianDiffusion(nn.Module):
         tb = torch.full((b,), t, device=x1.device, dtype=torch.long)
         xt1, xt2 = self.q_sample(x1, tb), self.q_sample(x2, tb)
         img = (1 - lam) * xt1 + lam * xt2
+        x_start = None
         for i in reversed(range(0, t)):
-            img, _ = self.p_sample(img, i)
+            self_cond = x_start if self.self_condition else None          # ddpm.py:864-865
+            img, x_start = self.p_sample(img, i, self_cond)
         return img

@@ -49,7 +49,7 @@ class WeightPack:
             off += n
         self.version = None
         # stem (7x7, C -> dim) as a GEMM over im2col patches: zero-padded bf16 weight rows [dim][KP]
-        self.stem_k = arena.channels * 49
+        self.stem_k = arena.in_channels * 49
         self.stem_kp = (self.stem_k + 63) // 64 * 64
         self.stem = torch.zeros(arena.dim * self.stem_kp, dtype=tdt, device=dev) if dt == L.BF16 else None
         # Upsample convs (ddpm.py:93-97) for inference: weights of the fused upsample + 3x3 launch (conv mode 3),
@@ -199,6 +199,10 @@ class Plan:
         # gradients pile up at the segment joins; second stream first: 5.13 ms)
         self.side_stream_fwd = torch.cuda.Stream(device=self.dev, priority=-1) if self.side_enabled else None
         self.x_in = torch.zeros(B, ch, S, S, device=self.dev)          # NCHW fp32 boundary
+        # self-conditioned net (ddpm.py:433-435): the previous x0 estimate (zeros when absent) is a second input,
+        # concatenated in front of x by the first launch; the samplers write x0 straight into xc_in
+        self.xc_in = torch.zeros(B, ch, S, S, device=self.dev) if arena.self_condition else None
+        self.stem_in = torch.zeros(B, 2 * ch, S, S, device=self.dev) if arena.self_condition else self.x_in
         self.t_in = torch.zeros(B, dtype=torch.long, device=self.dev)
         self.out = torch.zeros(B, ch, S, S, device=self.dev)
         self.d_out = torch.zeros(B, ch, S, S, device=self.dev) if training else None
@@ -595,11 +599,15 @@ class Plan:
         # init conv -> r (= second half of the final concat), ddpm.py:437-438, :468
         self.begin_unit()
         r, gr = catF.slice(dim, dim), sl(gcatF, dim, dim)
+        chi = a.in_channels
+        if a.self_condition:     # torch.cat((x_self_cond, x), dim=1), ddpm.py:435
+            self.F("b200dm_concat2_nchw", self.xc_in.data_ptr(), self.x_in.data_ptr(), self.stem_in.data_ptr(), B,
+                   ch * S * S, ch * S * S)
         if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None:
             # stem on the tensor cores: im2col patches (kept for the weight gradient) + 1x1 GEMM conv
             KP, K = self.pack.stem_kp, self.pack.stem_k
             P = self.buf(S, KP)
-            self.F("b200dm_im2col7", self.x_in.data_ptr(), P.ptr, B, ch, S, S, KP)
+            self.F("b200dm_im2col7", self.stem_in.data_ptr(), P.ptr, B, chi, S, S, KP)
             d = L.ConvDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim, x=P.ptr,
                            x_ld=P.ld, w=self.pack.stem.data_ptr(), bias=a.ptr("init_conv.bias"), y=r.ptr,
                            y_ld=r.ld, res=None, res_ld=0, accumulate=0)
@@ -615,11 +623,11 @@ class Plan:
                 self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1,
                         side=True, reads=(gr,))
         else:
-            self.F("b200dm_init_conv_fwd", self.dt, self.x_in.data_ptr(), a.ptr("init_conv.weight"),
-                   a.ptr("init_conv.bias"), r.ptr, r.ld, B, ch, S, S, dim)
+            self.F("b200dm_init_conv_fwd", self.dt, self.stem_in.data_ptr(), a.ptr("init_conv.weight"),
+                   a.ptr("init_conv.bias"), r.ptr, r.ld, B, chi, S, S, dim)
             if tr:
-                self.Bk("b200dm_init_conv_wgrad", self.dt, self.x_in.data_ptr(), gr.ptr, gr.ld,
-                        a.gptr("init_conv.weight"), B, ch, S, S, dim)
+                self.Bk("b200dm_init_conv_wgrad", self.dt, self.stem_in.data_ptr(), gr.ptr, gr.ld,
+                        a.gptr("init_conv.weight"), B, chi, S, S, dim)
                 self.Bk("b200dm_colsum", self.dt, gr.ptr, gr.ld, B * S * S, dim, a.gptr("init_conv.bias"), 1)
 
         x, gx = r, gr

@@ -32,7 +32,7 @@ class ConvInfo:
         self.master_packed = mode == 0       # tap-major master; mode 1 keeps the reference [Cout, 4C]
 
 
-def build_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8)):
+def build_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8), self_condition: bool = False):
     """Returns (ordered [(name, shape)], {conv name: ConvInfo}, [resblock names in forward order],
     {resblock name: (cin, cout)})."""
     spec: List[Tuple[str, Tuple[int, ...]]] = []
@@ -76,7 +76,7 @@ def build_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8)):
             conv(name + ".to_out.0", HIDDEN, c, 1)
             spec.append((name + ".to_out.1.g", (1, c, 1, 1)))
 
-    conv("init_conv", channels, dim, 7, gemm=False)
+    conv("init_conv", channels * (2 if self_condition else 1), dim, 7, gemm=False)     # ddpm.py:300-304
     linear("time_mlp.1", dim, time_dim)
     linear("time_mlp.3", time_dim, time_dim)
     for i, (din, dout) in enumerate(in_out):
@@ -115,9 +115,12 @@ def build_spec(dim: int, channels: int, dim_mults=(1, 2, 4, 8)):
 class ParamArena:
     """Flat fp32 parameter + gradient arenas with reference-named logical views."""
 
-    def __init__(self, dim: int, channels: int, device, with_grad: bool = True):
+    def __init__(self, dim: int, channels: int, device, with_grad: bool = True, self_condition: bool = False):
         self.dim, self.channels = dim, channels
-        self.spec, self.convs, self.block_order, self.blocks = build_spec(dim, channels)
+        self.self_condition = bool(self_condition)
+        self.in_channels = channels * (2 if self_condition else 1)       # stem input: [x_self_cond | x]
+        self.spec, self.convs, self.block_order, self.blocks = build_spec(dim, channels,
+                                                                          self_condition=self_condition)
         self.shapes = dict(self.spec)
         self.time_dim = 4 * dim
         # FiLM column layout: every block's (scale | shift) columns, the two level-0 blocks of the down path LAST.

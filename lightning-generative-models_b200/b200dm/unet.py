@@ -3,7 +3,7 @@
 Same constructor signature, attributes (`channels`, `out_dim`, `self_condition`,
 `random_or_learned_sinusoidal_cond`, `downsample_factor`), `forward(x, time, x_self_cond=None)` and
 state_dict keys/shapes as the reference.  Only the configuration the reference's configs use is built
-(dim=64, dim_mults=(1,2,4,8), no self-conditioning / learned variance / learned sinusoidal embedding);
+(dim=64, dim_mults=(1,2,4,8), no learned variance / learned sinusoidal embedding; `self_condition=True` is built);
 anything else raises NotImplementedError instead of silently falling back.
 """
 from __future__ import annotations
@@ -37,9 +37,9 @@ class _UnetFn(torch.autograd.Function):
     """Whole-network autograd node: forward = the plan's launch list, backward = the mirrored list."""
 
     @staticmethod
-    def forward(ctx, anchor, unet, x, time):
+    def forward(ctx, anchor, unet, x, time, x_self_cond=None):
         plan = unet._plan(x.shape[0], x.shape[-1], training=True)
-        out = unet._run(plan, x, time)
+        out = unet._run(plan, x, time, x_self_cond)
         ctx.unet, ctx.plan, ctx.ticket = unet, plan, plan.ticket
         return out
 
@@ -50,7 +50,7 @@ class _UnetFn(torch.autograd.Function):
             raise RuntimeError("b200dm.Unet: backward() after a newer forward() of the same shape overwrote "
                                "the saved activations; call backward before the next forward")
         unet._backward(plan, grad_out)
-        return torch.zeros_like(unet._anchor), None, None, None
+        return torch.zeros_like(unet._anchor), None, None, None, None
 
 
 class Unet(nn.Module):
@@ -64,7 +64,7 @@ class Unet(nn.Module):
         unsupported = dict(
             dim=dim != 64, init_dim=init_dim not in (None, dim), out_dim=out_dim not in (None, channels),
             dim_mults=tuple(dim_mults) != (1, 2, 4, 8), channels=channels not in (1, 2, 3),
-            self_condition=bool(self_condition), resnet_block_groups=resnet_block_groups != 8,
+            resnet_block_groups=resnet_block_groups != 8,
             learned_variance=bool(learned_variance), learned_sinusoidal_cond=bool(learned_sinusoidal_cond),
             random_fourier_features=bool(random_fourier_features),
             sinusoidal_pos_emb_theta=sinusoidal_pos_emb_theta != 10000, attn_dim_head=attn_dim_head != 32,
@@ -78,7 +78,7 @@ class Unet(nn.Module):
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {list(PRECISIONS)}")
         self.channels, self.out_dim, self.dim = channels, channels, dim
-        self.self_condition = False
+        self.self_condition = bool(self_condition)              # ddpm.py:300-301: the stem takes 2 * channels
         self.random_or_learned_sinusoidal_cond = False
         self.precision = precision
         self.dt = PRECISIONS[precision]
@@ -86,7 +86,7 @@ class Unet(nn.Module):
         if self._device.type != "cuda":
             raise L.B200dmError("b200dm.Unet runs on CUDA (sm_100a) only; there is no CPU fallback")
         L.load()                                      # fail loudly if the extension is missing
-        self.arena = ParamArena(dim, channels, self._device, with_grad=True)
+        self.arena = ParamArena(dim, channels, self._device, with_grad=True, self_condition=self.self_condition)
         self._init_default()
         self._params: Dict[str, nn.Parameter] = {}
         for nm, _ in self.arena.spec:
@@ -113,16 +113,18 @@ class Unet(nn.Module):
     def forward(self, x, time, x_self_cond=None):
         assert all(d % self.downsample_factor == 0 for d in x.shape[-2:]), \
             f"your input dimensions {tuple(x.shape[-2:])} need to be divisible by {self.downsample_factor}, given the unet"
-        if x_self_cond is not None:
-            raise NotImplementedError("self-conditioning is not built (off in every reference config)")
+        if x_self_cond is not None and not self.self_condition:
+            raise ValueError("x_self_cond given to a Unet built with self_condition=False")
+        if x_self_cond is not None and x_self_cond.shape != x.shape:
+            raise ValueError(f"x_self_cond shape {tuple(x_self_cond.shape)} != x shape {tuple(x.shape)}")
         if x.shape[-1] != x.shape[-2]:
             raise NotImplementedError("b200dm.Unet is built for square inputs")
         if x.shape[1] != self.channels:
             raise ValueError(f"expected {self.channels} input channels, got {x.shape[1]}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._params.values()):
-            return _UnetFn.apply(self._anchor, self, x, time)
+            return _UnetFn.apply(self._anchor, self, x, time, x_self_cond)
         plan = self._plan(x.shape[0], x.shape[-1], training=False)
-        return self._run(plan, x, time)
+        return self._run(plan, x, time, x_self_cond)
 
     # ---- parameters -------------------------------------------------------------------------------------
     def _init_default(self):
@@ -216,9 +218,14 @@ class Unet(nn.Module):
             self._plans[key] = plan
         return plan
 
-    def _run(self, plan: Plan, x, time) -> torch.Tensor:
+    def _run(self, plan: Plan, x, time, x_self_cond=None) -> torch.Tensor:
         self._pack.refresh()
         plan.x_in.copy_(x)
+        if plan.xc_in is not None:       # ddpm.py:434: zeros when no estimate is given
+            if x_self_cond is None:
+                plan.xc_in.zero_()
+            else:
+                plan.xc_in.copy_(x_self_cond)
         plan.t_in.copy_(time)
         self.run_plan_forward(plan)
         plan.ticket += 1

@@ -373,7 +373,8 @@ init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
 template <typename T>
 __global__ void __launch_bounds__(256)
 init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, int dy_ld,
-                       float* __restrict__ dw, int B, int C, int H, int W) {
+                       float* __restrict__ dw, int B, int C, int H, int W, int Ctot, int c0) {
+  // handles input channels [c0, c0 + C) of a Ctot-channel stem (C <= 3 per launch)
   pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   const int PW = W + 6, PH = IC_ROWS + 6;
@@ -405,7 +406,7 @@ init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, in
       int px = i % PW, py = (i / PW) % PH, ch = i / (PW * PH);
       int iy = y0 + py - 3, ix = px - 3;
       patch[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                     ? x[(((int64_t)b * C + ch) * H + iy) * W + ix] : 0.f;
+                     ? x[(((int64_t)b * Ctot + c0 + ch) * H + iy) * W + ix] : 0.f;
     }
     for (int i = tid; i < IC_ROWS * W * 64; i += 256) {
       int c = i & 63, ox = (i >> 6) % W, r = (i >> 6) / W;
@@ -433,7 +434,7 @@ init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, in
     int k = kq + 16 * i;
     if (k < K) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(dw + (co0 + j) * K + k, acc[i][j]);
+      for (int j = 0; j < 4; ++j) atomicAdd(dw + (co0 + j) * (Ctot * 49) + c0 * 49 + k, acc[i][j]);
     }
   }
 }
@@ -824,7 +825,7 @@ extern "C" int b200dm_init_conv_fwd(int32_t dtype, const float* x, const float* 
                                     void* y, int32_t y_ld, int32_t B, int32_t C, int32_t H, int32_t W,
                                     int32_t Cout, void* stream) {
   B200DM_REQUIRE(Cout == 64, B200DM_ERR_UNSUPPORTED, "init_conv: Cout=%d (only dim=64 is built)", Cout);
-  B200DM_REQUIRE(C >= 1 && C <= 3, B200DM_ERR_UNSUPPORTED, "init_conv: channels=%d (1..3 supported)", C);
+  B200DM_REQUIRE(C >= 1 && C <= 6, B200DM_ERR_UNSUPPORTED, "init_conv: channels=%d (1..6 supported)", C);
   B200DM_REQUIRE(W % 8 == 0 && H % 8 == 0, B200DM_ERR_SHAPE, "init_conv: H,W must be multiples of 8");
   size_t smem = ((size_t)C * 49 * 64 + (size_t)C * (IC_ROWS + 6) * (IC_SEG + 6)) * sizeof(float);
   int segs = (W + IC_SEG - 1) / IC_SEG;
@@ -845,20 +846,24 @@ extern "C" int b200dm_init_conv_wgrad(int32_t dtype, const float* x, const void*
                                       float* dw, int32_t B, int32_t C, int32_t H, int32_t W,
                                       int32_t Cout, void* stream) {
   B200DM_REQUIRE(Cout == 64, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: Cout=%d (only dim=64 is built)", Cout);
-  B200DM_REQUIRE(C >= 1 && C <= 3, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: channels=%d", C);
+  B200DM_REQUIRE(C >= 1 && C <= 6, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: channels=%d (1..6)", C);
   B200DM_REQUIRE(W <= 128, B200DM_ERR_UNSUPPORTED, "init_conv_wgrad: W=%d too large", W);
-  size_t smem = ((size_t)C * (IC_ROWS + 6) * (W + 6) + (size_t)IC_ROWS * W * 64) * sizeof(float);
   int items = B * ((H + IC_ROWS - 1) / IC_ROWS);
   int grid = items < 2 * num_sms() ? items : 2 * num_sms();
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == B200DM_F32) {
-    cudaFuncSetAttribute(init_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(init_conv_wgrad_kernel<float>, grid, 256, smem, st, x, (const float*)dy, dy_ld, dw, B, C, H, W);
-  } else {
-    cudaFuncSetAttribute(init_conv_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(init_conv_wgrad_kernel<__nv_bfloat16>, grid, 256, smem, st, x, (const __nv_bfloat16*)dy, dy_ld, dw, B, C, H, W);
+  // one launch per group of up to three input channels (a self-conditioned stem has 2 * channels of them)
+  for (int c0 = 0; c0 < C; c0 += 3) {
+    const int cg = C - c0 < 3 ? C - c0 : 3;
+    size_t smem = ((size_t)cg * (IC_ROWS + 6) * (W + 6) + (size_t)IC_ROWS * W * 64) * sizeof(float);
+    if (dtype == B200DM_F32) {
+      cudaFuncSetAttribute(init_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      launch_k(init_conv_wgrad_kernel<float>, grid, 256, smem, st, x, (const float*)dy, dy_ld, dw, B, cg, H, W, C, c0);
+    } else {
+      cudaFuncSetAttribute(init_conv_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      launch_k(init_conv_wgrad_kernel<__nv_bfloat16>, grid, 256, smem, st, x, (const __nv_bfloat16*)dy, dy_ld, dw, B, cg, H, W, C, c0);
+    }
+    count_launch();
   }
-  count_launch();
   return check_launch("init_conv_wgrad");
 }
 

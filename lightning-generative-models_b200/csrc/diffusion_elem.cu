@@ -229,6 +229,19 @@ unnormalize_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n
   }
 }
 
+// out[b] = [a[b] | b[b]] along the channel axis of NCHW tensors (torch.cat((x_self_cond, x), dim=1), ddpm.py:435)
+__global__ void concat2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                               int64_t n4, int64_t qa, int64_t qb) {
+  pdl_prologue();
+  const int64_t tot = qa + qb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / tot, r = i - s * tot;
+    const float4 v = r < qa ? reinterpret_cast<const float4*>(a)[s * qa + r]
+                            : reinterpret_cast<const float4*>(b)[s * qb + (r - qa)];
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, int64_t n, float v) {
   pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -348,6 +361,17 @@ extern "C" int b200dm_unnormalize(const float* x, float* y, int64_t n, void* str
   launch_k(unnormalize_kernel, elem_grid(n / 4), kElemThreads, 0, (cudaStream_t)stream, x, y, n / 4);
   count_launch();
   return check_launch("unnormalize");
+}
+
+extern "C" int b200dm_concat2_nchw(const float* a, const float* b, float* out, int32_t B, int64_t chw_a,
+                                   int64_t chw_b, void* stream) {
+  B200DM_REQUIRE(a && b && out && B > 0 && chw_a > 0 && chw_b > 0, B200DM_ERR_SHAPE, "concat2_nchw: empty input");
+  B200DM_REQUIRE(chw_a % 4 == 0 && chw_b % 4 == 0, B200DM_ERR_SHAPE, "concat2_nchw: C*H*W must be a multiple of 4");
+  CHECK_ALIGN16(a, "concat2_nchw a"); CHECK_ALIGN16(b, "concat2_nchw b"); CHECK_ALIGN16(out, "concat2_nchw out");
+  const int64_t n4 = (int64_t)B * (chw_a + chw_b) / 4;
+  launch_k(concat2_kernel, elem_grid(n4), kElemThreads, 0, (cudaStream_t)stream, a, b, out, n4, chw_a / 4, chw_b / 4);
+  count_launch();
+  return check_launch("concat2_nchw");
 }
 
 extern "C" int b200dm_fill_f32(float* p, int64_t n, float value, void* stream) {

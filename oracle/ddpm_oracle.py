@@ -34,8 +34,9 @@ GROUPS = 8
 # parameter inventory  (models/generative/diffusion/ddpm.py:304-422)
 # --------------------------------------------------------------------------------------
 def unet_param_spec(dim: int = 64, channels: int = 3,
-                    dim_mults=(1, 2, 4, 8)) -> List[Tuple[str, Tuple[int, ...]]]:
-    """Ordered (name, shape) list equal to reference `Unet(dim, channels=channels).state_dict()`."""
+                    dim_mults=(1, 2, 4, 8), self_condition: bool = False) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Ordered (name, shape) list equal to reference `Unet(dim, channels=channels).state_dict()`
+    (`self_condition=True` doubles the stem's input channels, ddpm.py:300-304)."""
     spec: List[Tuple[str, Tuple[int, ...]]] = []
     time_dim = dim * 4
     hidden = HEADS * DIM_HEAD
@@ -75,7 +76,7 @@ def unet_param_spec(dim: int = 64, channels: int = 3,
     in_out = list(zip(dims[:-1], dims[1:]))
     n_res = len(in_out)
 
-    conv("init_conv", channels, dim, 7)
+    conv("init_conv", channels * (2 if self_condition else 1), dim, 7)
     linear("time_mlp.1", dim, time_dim)
     linear("time_mlp.3", time_dim, time_dim)
     for i, (din, dout) in enumerate(in_out):
@@ -114,7 +115,7 @@ def unet_param_spec(dim: int = 64, channels: int = 3,
 
 
 def synth_state_dict(dim: int = 64, channels: int = 3, seed: int = 10,
-                     dtype=torch.float32) -> Dict[str, Tensor]:
+                     dtype=torch.float32, self_condition: bool = False) -> Dict[str, Tensor]:
     """Deterministic synthetic weights (numpy legacy MT19937 — stable across versions/platforms),
     scaled like torch's default init (ddpm.py has no custom init): U(-1/sqrt(fan_in), ..)
     for conv/linear, N(0,1) mem_kv; norm gains/biases are perturbed off 1/0 so that parity tests
@@ -123,7 +124,8 @@ def synth_state_dict(dim: int = 64, channels: int = 3, seed: int = 10,
 
     rng = np.random.RandomState(seed)
     sd: Dict[str, Tensor] = {}
-    for name, shape in unet_param_spec(dim, channels):
+    spec = unet_param_spec(dim, channels, self_condition=self_condition)
+    for name, shape in spec:
         n = int(np.prod(shape))
         if name.endswith("mem_kv"):
             a = rng.standard_normal(n)
@@ -133,7 +135,7 @@ def synth_state_dict(dim: int = 64, channels: int = 3, seed: int = 10,
             a = 0.1 * rng.standard_normal(n)
         else:
             if name.endswith(".bias"):
-                wshape = dict(unet_param_spec(dim, channels))[name[:-5] + ".weight"]
+                wshape = dict(spec)[name[:-5] + ".weight"]
             else:
                 wshape = shape
             fan_in = int(np.prod(wshape[1:]))
@@ -288,10 +290,15 @@ def time_embedding(sd, time: Tensor, dim: int) -> Tensor:
 
 
 def unet_forward(sd: Dict[str, Tensor], x: Tensor, time: Tensor, *, dim: int = 64,
-                 emulate: Optional[str] = None) -> Tensor:
-    """ddpm.py:428-471 (no self-conditioning; the configs never enable it)."""
+                 emulate: Optional[str] = None, x_self_cond: Optional[Tensor] = None) -> Tensor:
+    """ddpm.py:428-471.  Self-conditioning (:433-435) is on when the stem takes twice the image channels:
+    the previous x0 estimate (zeros when absent) is concatenated in FRONT of x."""
     emu = Emu(emulate)
     assert x.shape[-1] % 8 == 0 and x.shape[-2] % 8 == 0, "H, W must be divisible by 8"  # :429-431
+    if sd["init_conv.weight"].shape[1] == 2 * x.shape[1]:
+        x = torch.cat((torch.zeros_like(x) if x_self_cond is None else x_self_cond, x), dim=1)
+    else:
+        assert x_self_cond is None
     n_levels = 4
     x = emu.st(_conv(x, sd["init_conv.weight"], sd["init_conv.bias"], 3, Emu(None)))
     r = x
@@ -409,6 +416,8 @@ class DiffusionOracle:
         assert self.sampling_timesteps <= timesteps
         self.is_ddim_sampling = self.sampling_timesteps < timesteps
         self.eta = ddim_sampling_eta
+        self.self_condition = ("init_conv.weight" in sd
+                               and sd["init_conv.weight"].shape[1] == 2 * channels)       # ddpm.py:556
 
     def to(self, device):
         """Move weights and schedule buffers (tests run the oracle on cuda, fp32 or under torch.autocast(bf16),
@@ -417,8 +426,8 @@ class DiffusionOracle:
         self.buf = {k: v.to(device) for k, v in self.buf.items()}
         return self
 
-    def model(self, x, t):
-        return unet_forward(self.sd, x, t, dim=self.dim, emulate=self.emulate)
+    def model(self, x, t, x_self_cond=None):
+        return unet_forward(self.sd, x, t, dim=self.dim, emulate=self.emulate, x_self_cond=x_self_cond)
 
     # ddpm.py:869-876
     def q_sample(self, x_start, t, noise):
@@ -426,11 +435,16 @@ class DiffusionOracle:
         return (extract(b["sqrt_alphas_cumprod"], t, 4) * x_start
                 + extract(b["sqrt_one_minus_alphas_cumprod"], t, 4) * noise)
 
-    # ddpm.py:878-925 (offset noise and self-conditioning are off in every shipped config)
-    def p_losses(self, x_start, t, noise, return_parts=False):
+    # ddpm.py:878-925.  `self_cond` stands for the reference's coin flip `random() < 0.5` (:902): when True (and
+    # the model is self-conditioned) the x0 estimate of a first, gradient-free evaluation is fed back (:901-905).
+    def p_losses(self, x_start, t, noise, return_parts=False, self_cond=False):
         b = self.buf
         x = self.q_sample(x_start, t, noise)
-        out = self.model(x, t)
+        x_self_cond = None
+        if self.self_condition and self_cond:
+            with torch.no_grad():
+                x_self_cond = self.model_predictions(x, t).pred_x_start.detach()
+        out = self.model(x, t, x_self_cond)
         if self.objective == "pred_noise":
             target = noise
         elif self.objective == "pred_x0":
@@ -448,9 +462,10 @@ class DiffusionOracle:
         return self.p_losses(img * 2 - 1, t, noise)
 
     # ddpm.py:707-734
-    def model_predictions(self, x, t, clip_x_start=False, rederive_pred_noise=False, model_out=None):
+    def model_predictions(self, x, t, clip_x_start=False, rederive_pred_noise=False, model_out=None,
+                          x_self_cond=None):
         b = self.buf
-        out = self.model(x, t) if model_out is None else model_out
+        out = self.model(x, t, x_self_cond) if model_out is None else model_out
         clip = (lambda v: v.clamp(-1.0, 1.0)) if clip_x_start else (lambda v: v)
         sr = extract(b["sqrt_recip_alphas_cumprod"], t, 4)
         srm1 = extract(b["sqrt_recipm1_alphas_cumprod"], t, 4)
@@ -469,10 +484,11 @@ class DiffusionOracle:
         return ModelPrediction(pred_noise, x0)
 
     # ddpm.py:736-757 — `noise` is what randn_like would have returned (ignored at t == 0)
-    def p_sample(self, x, t: int, noise, model_out=None):
+    def p_sample(self, x, t: int, noise, model_out=None, x_self_cond=None):
         b = self.buf
         bt = torch.full((x.shape[0],), t, dtype=torch.long, device=x.device)
-        x0 = self.model_predictions(x, bt, model_out=model_out).pred_x_start.clamp(-1.0, 1.0)
+        x0 = self.model_predictions(x, bt, model_out=model_out,
+                                    x_self_cond=x_self_cond).pred_x_start.clamp(-1.0, 1.0)
         mean = (extract(b["posterior_mean_coef1"], bt, 4) * x0
                 + extract(b["posterior_mean_coef2"], bt, 4) * x)
         logvar = extract(b["posterior_log_variance_clipped"], bt, 4)
@@ -481,9 +497,10 @@ class DiffusionOracle:
 
     # ddpm.py:759-780
     def p_sample_loop(self, init_noise, step_noise_fn):
-        img = init_noise
+        img, x_start = init_noise, None
         for t in reversed(range(self.num_timesteps)):
-            img, _ = self.p_sample(img, t, step_noise_fn(t) if t > 0 else None)
+            self_cond = x_start if self.self_condition else None                 # :773
+            img, x_start = self.p_sample(img, t, step_noise_fn(t) if t > 0 else None, x_self_cond=self_cond)
         return (img + 1) * 0.5
 
     def ddim_time_pairs(self):
@@ -495,11 +512,12 @@ class DiffusionOracle:
     # ddpm.py:782-834
     def ddim_sample(self, init_noise, step_noise_fn=None):
         b = self.buf
-        img = init_noise
+        img, x0 = init_noise, None
         for time, time_next in self.ddim_time_pairs():
             tc = torch.full((img.shape[0],), time, dtype=torch.long, device=img.device)
+            self_cond = x0 if self.self_condition else None                      # :807
             pred_noise, x0 = self.model_predictions(img, tc, clip_x_start=True,
-                                                    rederive_pred_noise=True)
+                                                    rederive_pred_noise=True, x_self_cond=self_cond)
             if time_next < 0:
                 img = x0
                 continue

@@ -125,6 +125,43 @@ def test_golden_ddpm_chain():
     np.testing.assert_allclose(img.numpy(), gold["img"], rtol=0, atol=5e-5)
 
 
+def test_golden_self_conditioning():
+    """Self-conditioned UNet / losses / samplers against the reference (tests/golden/make_golden_selfcond.py)."""
+    gold = np.load(os.path.join(GOLD, "golden_selfcond.npz"))
+    for name, ch, s, b in (("c1s32", 1, 32, 2), ("c3s16", 3, 16, 2)):
+        sd = O.synth_state_dict(64, ch, seed=10, self_condition=True)
+        assert sd["init_conv.weight"].shape == (64, 2 * ch, 7, 7)
+        orc = O.DiffusionOracle(sd, img_size=s, channels=ch, sampling_timesteps=4)
+        assert orc.self_condition
+        x, t, noise, init = seeded_inputs(b, ch, s, seed=4321)
+        cond = torch.from_numpy(gold[f"{name}:cond"])
+        with torch.no_grad():
+            np.testing.assert_allclose(orc.model(x * 2 - 1, t, cond).numpy(), gold[f"{name}:unet_out_cond"],
+                                       rtol=0, atol=2e-5)
+            np.testing.assert_allclose(orc.model(x * 2 - 1, t).numpy(), gold[f"{name}:unet_out_nocond"],
+                                       rtol=0, atol=2e-5)
+        for flag, sc in (("sc", True), ("nosc", False)):
+            sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            og = O.DiffusionOracle(sdg, img_size=s, channels=ch)
+            loss = og.p_losses(x * 2 - 1, t, noise, self_cond=sc)
+            loss.backward()
+            assert abs(loss.item() - float(gold[f"{name}:loss_{flag}"])) <= 2e-6 * max(1.0, abs(loss.item()))
+            gn = np.array([sdg[k].grad.norm().item() for k, _ in O.unet_param_spec(64, ch, self_condition=True)])
+            np.testing.assert_allclose(gn, gold[f"{name}:grad_norms_{flag}"], rtol=2e-3, atol=1e-7)
+        with torch.no_grad():
+            np.testing.assert_allclose(orc.sample(init).numpy(), gold[f"{name}:ddim4"], rtol=0, atol=5e-5)
+            img, x0 = orc.p_sample(init, 500, noise, x_self_cond=cond)
+            np.testing.assert_allclose(img.numpy(), gold[f"{name}:p_sample_500"], rtol=0, atol=5e-5)
+            np.testing.assert_allclose(x0.numpy(), gold[f"{name}:p_sample_500_x0"], rtol=0, atol=5e-5)
+    sd = O.synth_state_dict(64, 1, seed=10, self_condition=True)
+    orc = O.DiffusionOracle(sd, img_size=32, channels=1, timesteps=6)
+    noises = [torch.from_numpy(a) for a in gold["ddpm6:noises"]]
+    step = {t: noises[1 + (5 - t)] for t in range(5, 0, -1)}
+    with torch.no_grad():
+        img = orc.p_sample_loop(noises[0], lambda t: step[t])
+    np.testing.assert_allclose(img.numpy(), gold["ddpm6:img"], rtol=0, atol=5e-5)
+
+
 def test_input_size_assert():
     sd = O.synth_state_dict(64, 1, seed=10)
     with pytest.raises(AssertionError):

@@ -1,0 +1,138 @@
+"""Self-conditioning (reference Unet(self_condition=True): ddpm.py:300-304, :433-435, :773, :807, :901-905) on the GPU
+against the reference-generated golden fixture tests/golden/golden_selfcond.npz (fp32 mode) and the oracle (bf16 mode)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _refcuda import DEV, linf, psnr, rel, report
+from oracle import ddpm_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_selfcond.npz"))
+CASES = [("c1s32", 1, 32, 2), ("c3s16", 3, 16, 2)]
+
+
+def seeded_inputs(b, c, s, seed=4321):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(b, c, s, s, generator=g)
+    t = torch.randint(0, 1000, (b,), generator=g)
+    noise = torch.randn(b, c, s, s, generator=g)
+    init = torch.randn(b, c, s, s, generator=g)
+    return x.to(DEV), t.to(DEV), noise.to(DEV), init.to(DEV)
+
+
+def build(ch, s, precision, **kw):
+    from b200dm import GaussianDiffusion, Unet
+    unet = Unet(dim=64, channels=ch, self_condition=True, precision=precision)
+    unet.load_reference_state_dict(O.synth_state_dict(64, ch, seed=10, self_condition=True))
+    return unet, GaussianDiffusion(unet, img_size=s, **kw)
+
+
+def skip_small_bf16(s, precision):
+    if precision == "bf16" and s < 32:
+        pytest.skip("the tcgen05 path needs images of at least 32x32 (innermost level 4x4)")
+
+
+def test_selfcond_three_channels_bf16_vs_oracle_32px():
+    """The 3-channel golden case is 16x16 (fp32 mode only): bf16 at 32x32 against the golden-pinned oracle."""
+    ch, s, b = 3, 32, 2
+    unet, gd = build(ch, s, "bf16", sampling_timesteps=4)
+    x, t, noise, init = seeded_inputs(b, ch, s)
+    g = torch.Generator().manual_seed(5)
+    cond = (torch.rand(b, ch, s, s, generator=g) * 2 - 1).to(DEV)
+    orc = O.DiffusionOracle({k: v.to(DEV) for k, v in O.synth_state_dict(64, ch, seed=10, self_condition=True).items()},
+                            img_size=s, channels=ch, sampling_timesteps=4).to(DEV)
+    with torch.no_grad():
+        e = rel(unet(x * 2 - 1, t, cond), orc.model(x * 2 - 1, t, cond))
+        p = psnr(gd.sample(batch_size=b, init_noise=init), orc.sample(init))
+    report(test="selfcond_c3_bf16", unet_rel=e, ddim4_psnr=p)
+    assert e <= 1e-2 and p >= 40, (e, p)
+
+
+@pytest.mark.parametrize("name,ch,s,b", CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_selfcond_unet_forward(name, ch, s, b, precision):
+    skip_small_bf16(s, precision)
+    unet, _ = build(ch, s, precision)
+    assert unet.self_condition and unet.arena.in_channels == 2 * ch
+    x, t, _, _ = seeded_inputs(b, ch, s)
+    cond = torch.from_numpy(GOLD[f"{name}:cond"]).to(DEV)
+    tol = 1e-4 if precision == "fp32" else 1.25e-2
+    with torch.no_grad():
+        for key, c in (("unet_out_cond", cond), ("unet_out_nocond", None)):
+            out = unet(x * 2 - 1, t, c)
+            e = rel(out, torch.from_numpy(GOLD[f"{name}:{key}"]))
+            report(test="selfcond_unet", case=name, precision=precision, which=key, rel=e)
+            assert e <= tol, (key, e)
+    with pytest.raises(ValueError):
+        unet(x * 2 - 1, t, cond[:, :, :8])
+
+
+@pytest.mark.parametrize("name,ch,s,b", CASES)
+def test_selfcond_loss_and_gradients_fp32(name, ch, s, b):
+    unet, gd = build(ch, s, "fp32")
+    x, t, noise, _ = seeded_inputs(b, ch, s)
+    spec = O.unet_param_spec(64, ch, self_condition=True)
+    for flag, sc in (("sc", True), ("nosc", False)):
+        unet.zero_grad()
+        loss = gd.p_losses(x, t, noise=noise, _normalize=True, _self_cond=sc)
+        loss.backward()
+        want = float(GOLD[f"{name}:loss_{flag}"])
+        assert abs(loss.item() - want) <= 1e-4 * abs(want), (flag, loss.item(), want)
+        named = dict(unet.named_parameters())
+        gn = np.array([named[k].grad.norm().item() for k, _ in spec])
+        ref = GOLD[f"{name}:grad_norms_{flag}"]
+        err = np.abs(gn - ref) / np.maximum(ref, 1e-6)
+        report(test="selfcond_grads", case=name, flag=flag, loss=loss.item(), worst_grad_norm_rel=float(err.max()))
+        assert err.max() <= 5e-3, (flag, float(err.max()), spec[int(err.argmax())][0])
+
+
+def test_selfcond_training_step_bf16_runs_and_matches_oracle():
+    """bf16 mode: loss of the self-conditioned step against the fp32 oracle; the coin flip is the reference's."""
+    ch, s, b = 3, 32, 2
+    unet, gd = build(ch, s, "bf16")
+    x, t, noise, _ = seeded_inputs(b, ch, s)
+    orc = O.DiffusionOracle({k: v.to(DEV) for k, v in O.synth_state_dict(64, ch, seed=10, self_condition=True).items()},
+                            img_size=s, channels=ch).to(DEV)
+    for sc in (True, False):
+        unet.zero_grad()
+        loss = gd.p_losses(x, t, noise=noise, _normalize=True, _self_cond=sc)
+        loss.backward()
+        with torch.no_grad():
+            want = orc.p_losses(x * 2 - 1, t, noise, self_cond=sc).item()
+        assert math.isfinite(loss.item()) and abs(loss.item() - want) <= 2e-2 * abs(want), (sc, loss.item(), want)
+    torch.manual_seed(0)
+    unet.zero_grad()
+    gd(x).backward()                      # the public forward(): random t, random coin
+    assert all(torch.isfinite(p.grad).all() for p in unet.parameters())
+
+
+@pytest.mark.parametrize("name,ch,s,b", CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_selfcond_ddim_and_p_sample(name, ch, s, b, precision):
+    skip_small_bf16(s, precision)
+    unet, gd = build(ch, s, precision, sampling_timesteps=4)
+    _, _, noise, init = seeded_inputs(b, ch, s)
+    img = gd.sample(batch_size=b, init_noise=init)
+    ref = torch.from_numpy(GOLD[f"{name}:ddim4"])
+    p, li = psnr(img, ref), linf(img, ref)
+    report(test="selfcond_ddim4", case=name, precision=precision, psnr=p, linf=li)
+    assert p >= (80 if precision == "fp32" else 38), (p, li)
+    cond = torch.from_numpy(GOLD[f"{name}:cond"]).to(DEV)
+    out, x0 = gd.p_sample(init, 500, cond, noise=noise)
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    assert rel(out, torch.from_numpy(GOLD[f"{name}:p_sample_500"])) <= tol
+    assert rel(x0, torch.from_numpy(GOLD[f"{name}:p_sample_500_x0"])) <= tol
+
+
+def test_selfcond_ancestral_chain_fp32():
+    unet, gd = build(1, 32, "fp32", timesteps=6)
+    noises = [torch.from_numpy(a).to(DEV) for a in GOLD["ddpm6:noises"]]
+    step = {t: noises[1 + (5 - t)] for t in range(5, 0, -1)}
+    img = gd.sample(batch_size=2, init_noise=noises[0], step_noise=lambda t: step[t])
+    p = psnr(img, torch.from_numpy(GOLD["ddpm6:img"]))
+    report(test="selfcond_ddpm6", psnr=p)
+    assert p >= 80, p
