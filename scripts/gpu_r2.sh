@@ -29,10 +29,14 @@ if [ "$WHAT" = "evidence" ] || [ "$WHAT" = "all" ]; then
   for cfg in "128 32" "256 64"; do set -- $cfg; echo "== batch $1 size $2"; timeout 300 python scripts/conv_microbench.py --what both --batch $1 --size $2; done > $O/${TAG}_conv_micro.log 2>&1
   timeout 120 python scripts/phase_timing.py --batch 256 --size 64 > $O/${TAG}_phase_halo.log 2>&1
   timeout 120 python scripts/phase_timing_gn.py --batch 256 --size 64 > $O/${TAG}_phase_gn.log 2>&1
+  timeout 120 python scripts/phase_timing_linattn.py > $O/${TAG}_phase_linattn.log 2>&1
+  timeout 200 python scripts/side_cost.py > $O/${TAG}_side_cost.log 2>&1
+  timeout 200 python scripts/side_cost.py --size 64 --batch 64 >> $O/${TAG}_side_cost.log 2>&1
+  B200DM_FUSE_LINATTN=0 timeout 600 python bench.py --workload ddim --steps 2 --no-cpu-baseline --no-gpu-baseline > $O/${TAG}_bench_ddim_nofuse_linattn.log 2> /dev/null
   M="gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread"
   python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_plain_ddim.log 2>&1 &&
   NEV=$(grep "eval 1" $O/${TAG}_plain_ddim.log | sed 's/.*, \([0-9]*\) launches/\1/') &&
-  ncu --metrics $M --clock-control none -k 'regex:attn_fwd|conv3x3|conv_tc|final_conv|gn_fwd|im2col7|linattn|la_ctx|la_out|rmsnorm|sgemm|sinusoidal' -s $NEV -c $NEV --csv --log-file $O/${TAG}_eval_ddim_metrics.csv python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_ncu3.log 2>&1
+  ncu --metrics $M --clock-control none -k 'regex:attn_fwd|conv3x3|conv_tc|final_conv|gn_fwd|im2col7|linattn|la_kmax|la_ctx|la_mid|la_out|rmsnorm|sgemm|sinusoidal|linear_fwd' -s $NEV -c $NEV --csv --log-file $O/${TAG}_eval_ddim_metrics.csv python scripts/profile_step.py --workload eval --batch 256 --size 64 --steps 2 > $O/${TAG}_ncu3.log 2>&1
   grep -c b200dm $O/${TAG}_eval_ddim_metrics.csv; cat $O/${TAG}_plain_ddim.log
   ls $O | grep ${TAG}_ | tr '\n' ' '
 fi

@@ -117,7 +117,8 @@ lines = [f"# Round-2 profiles (ncu runs `{ptag}`, evidence run `{etag}`; scripts
 traffic = {}
 for name, title in (("conv_gn_ddim", "fused conv3x3 + GroupNorm + FiLM + SiLU at the DDIM shape (B=256, 64x64, level 0)"),
                     ("halo_train", "3x3 data-gradient / weight-gradient halo kernels of a training step (B=128, 32x32)"),
-                    ("hbmk", "HBM-bound kernels of a training step")):
+                    ("hbmk", "HBM-bound kernels of a training step"),
+                    ("lablock", "fused LinearAttention block (inference) at the DDIM shape (B=256, 64x64, level 0, C=64)")):
     recs, labels = raw_table(os.path.join(SRC, f"{ptag}_{name}_raw.csv"))
     if not recs:
         continue
@@ -166,6 +167,9 @@ for f, note in ((f"{etag}_bench.log", "bench.py as the driver runs it (train + D
                 (f"{etag}_conv_micro.log", "scripts/conv_microbench.py (forward / weight gradient per layer)"),
                 (f"{etag}_phase_halo.log", "scripts/phase_timing.py (SM-clock timeline of one conv3x3_halo CTA)"),
                 (f"{etag}_phase_gn.log", "scripts/phase_timing_gn.py (timeline of one fused conv+GroupNorm CTA)"),
+                (f"{etag}_phase_linattn.log", "scripts/phase_timing_linattn.py (timelines of the fused LinearAttention passes)"),
+                (f"{etag}_side_cost.log", "scripts/side_cost.py (what the second-stream kernels cost the training step)"),
+                (f"{etag}_bench_ddim_nofuse_linattn.log", "bench.py --workload ddim with B200DM_FUSE_LINATTN=0 (unfused attention chain)"),
                 (f"{etag}_parity_report.jsonl", "measured distances of every GPU parity test"),
                 (f"{etag}_pytest.log", "pytest -m gpu")):
     if os.path.isfile(os.path.join(SRC, f)):
