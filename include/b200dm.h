@@ -232,6 +232,13 @@ int b200dm_colsum_batched(int32_t dtype, const b200dm_colsum_item* items, int32_
  * s_co = C*49) its weight gradient. */
 int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, void* stream);
 int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream);
+
+/* The 7x7 stem as ONE tensor-core launch (csrc/stem_tc.cu): the im2col patches are built in shared memory instead of
+ * HBM.  x NCHW fp32 [B][C][H][W], wp = b200dm_pack_stem_weight's bf16 rows [64][KP], y NHWC bf16 (row pitch y_ld).
+ * init_conv, ddpm.py:304,437.  Needs W in {8,16,32,64,128}, H*W a multiple of 128, KP <= 256 (up to 5 input channels). */
+int b200dm_stem7_supported(int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, int32_t y_ld);
+int b200dm_stem7_fwd(const float* x, const void* wp, const float* bias, void* y, int32_t y_ld, int32_t B, int32_t C,
+                     int32_t H, int32_t W, int32_t KP, void* stream);
 /* Weights of conv_fwd mode 3 (nearest-2x upsample + 3x3 conv in one launch, Upsample ddpm.py:93-97) from the fp32
  * master weight in [ky*3+kx][Cout][Cin] order: out = bf16 [4 taps][4 phases][Cout][Cin] (see b200dm_conv_desc). */
 int b200dm_pack_upconv_weight(const float* w, void* out, int32_t Cout, int32_t Cin, void* stream);

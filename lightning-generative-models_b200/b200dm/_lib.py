@@ -109,6 +109,7 @@ PROTOTYPES = {
     "b200dm_colsum": [_I, _P, _I, _L, _I, _P, _I, _P],
     "b200dm_colsum_batched": [_I, _P, _I, _P],
     "b200dm_concat2_nchw": [_P, _P, _P, _I, _L, _L, _P],
+    "b200dm_stem7_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200dm_pack_linattn_qkv": [_P, _P, _P, _I, _P],
     "b200dm_linattn_block_fwd": [_P, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -158,6 +159,7 @@ _SPECIAL = {
     "b200dm_conv_gn_supported": ([C.POINTER(ConvDesc), C.POINTER(GnDesc)], C.c_int),
     "b200dm_linattn_block_ws_floats": ([_I, _I, _I], C.c_int64),
     "b200dm_linattn_block_supported": ([_P], C.c_int),
+    "b200dm_stem7_supported": ([_I, _I, _I, _I, _I, _I], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
 

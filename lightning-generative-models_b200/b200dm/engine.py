@@ -190,6 +190,7 @@ class Plan:
         self.fuse_gn = os.environ.get("B200DM_FUSE_GN", "1") != "0"       # conv + GroupNorm + FiLM + SiLU in one launch
         self.batch_colsum = os.environ.get("B200DM_BATCH_COLSUM", "1") != "0"   # one bias-gradient launch per bucket
         self.fuse_linattn = os.environ.get("B200DM_FUSE_LINATTN", "1") != "0"   # inference: LinearAttention block fused
+        self.fuse_stem = os.environ.get("B200DM_FUSE_STEM", "1") != "0"         # 7x7 stem: patches built in shared memory
         self._la_ws = None
         self._la_descs = []
         self.side_stream = torch.cuda.Stream(device=self.dev) if self.side_enabled else None
@@ -606,13 +607,22 @@ class Plan:
         if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None:
             # stem on the tensor cores: im2col patches (kept for the weight gradient) + 1x1 GEMM conv
             KP, K = self.pack.stem_kp, self.pack.stem_k
-            P = self.buf(S, KP)
-            self.F("b200dm_im2col7", self.stem_in.data_ptr(), P.ptr, B, chi, S, S, KP)
-            d = L.ConvDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim, x=P.ptr,
-                           x_ld=P.ld, w=self.pack.stem.data_ptr(), bias=a.ptr("init_conv.bias"), y=r.ptr,
-                           y_ld=r.ld, res=None, res_ld=0, accumulate=0)
-            self.F("b200dm_conv_fwd", C.byref(d), kname="conv_tc_fwd", flops=2.0 * B * S * S * dim * K)
-            self._keep.append(d)
+            # inference: ONE launch, patches built in shared memory (csrc/stem_tc.cu; DDIM-50 862 -> 868 img/s: 166 us
+            # against 103 + 87, the gather is bound by 4-byte shared-memory reads).  Training needs the patch matrix for
+            # the weight gradient anyway and measured 0.03 ms slower with it rebuilt in backward: it keeps the GEMM path.
+            fused_stem = (self.fuse_stem and not tr and dim == 64
+                          and self.lib.b200dm_stem7_supported(B, chi, S, S, KP, r.ld) == 1)
+            P = None if fused_stem else self.buf(S, KP)
+            if fused_stem:
+                self.F("b200dm_stem7_fwd", self.stem_in.data_ptr(), self.pack.stem.data_ptr(), a.ptr("init_conv.bias"),
+                       r.ptr, r.ld, B, chi, S, S, KP, kname="stem7_fwd", flops=2.0 * B * S * S * dim * K, writes=(r,))
+            else:
+                self.F("b200dm_im2col7", self.stem_in.data_ptr(), P.ptr, B, chi, S, S, KP)
+                d = L.ConvDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim, x=P.ptr,
+                               x_ld=P.ld, w=self.pack.stem.data_ptr(), bias=a.ptr("init_conv.bias"), y=r.ptr,
+                               y_ld=r.ld, res=None, res_ld=0, accumulate=0)
+                self.F("b200dm_conv_fwd", C.byref(d), kname="conv_tc_fwd", flops=2.0 * B * S * S * dim * K)
+                self._keep.append(d)
             if tr:
                 wd = L.WgradDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim,
                                  x=P.ptr, x_ld=P.ld, dy=gr.ptr, dy_ld=gr.ld, dw=a.gptr("init_conv.weight"),

@@ -494,8 +494,12 @@ gn_fwd_cluster_kernel(const T* __restrict__ x, int x_ld, float* __restrict__ sta
 }
 
 // UB pixels per thread and iteration; PIPE: the next UB are requested before the current UB are processed
-// (software pipeline, twice the raw registers); MINB: resident CTAs per SM the register budget is set for
-template <typename T, int UB, bool PIPE, int MINB>
+// (software pipeline, twice the raw registers); MINB: resident CTAs per SM the register budget is set for.
+// DZ (bf16 only): phase 1 parks dz = dy * silu'(z), rounded to bf16, in dynamic shared memory — every thread its own
+// vectors, [iteration][thread] x 16 B, no synchronisation — and phase 2 only reads x again: dx = P*dz + Q + R*x.
+// ncu at the training shape showed the kernel instruction-bound (61 % issue slots, DRAM 17 % of peak): the second
+// evaluation of the sigmoid and its derivative was a third of the instructions.
+template <typename T, int UB, bool PIPE, int MINB, bool DZ>
 __global__ void __launch_bounds__(GNC_THREADS, MINB)
 gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__ x, int x_ld,
                       const float* __restrict__ stats, const float* __restrict__ gamma,
@@ -517,6 +521,7 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   __shared__ float ctot[GNC_MAXC * 3];                 // cluster totals
   __shared__ float gm[64][2];                          // (M1, M2) per group
   __shared__ float coef_s[GNC_MAXC * 3];               // per channel: gamma, beta, FiLM scale + 1
+  extern __shared__ uint4 dz_park[];                   // DZ: [iteration * UB + u][thread]
   const T* xp = x + (int64_t)b * HW * x_ld + c0;
   const T* gp = dy + (int64_t)b * HW * dy_ld + c0;
   // the first pixels of the chunk are requested before anything else: their latency overlaps the coefficient setup
@@ -573,7 +578,8 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
   // ---- phase 1: S1 = sum dz, S2 = sum dz*xn, S0 = sum x   (per channel, over the chunk); the loads of the
   //      next two pixels are in flight while the current two are processed
   float s1[8] = {}, s2[8] = {}, s0[8] = {};
-  for (int p = p0 + lane; p < p1; p += UB * lanes) {
+  int slot = 0;
+  for (int p = p0 + lane; p < p1; p += UB * lanes, slot += UB) {
     Raw8<T> cx[UB], cg2[UB];
     if (!PIPE && p != p0 + lane) fetch(p);
 #pragma unroll
@@ -597,12 +603,25 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
           s1[j] += dz;
           s2[j] = fmaf(dz, xn, s2[j]);
           s0[j] += xv[j];
+          gv[j] = dz;
+        }
+        if (DZ) {
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(gv[2 * j], gv[2 * j + 1]);
+          dz_park[(slot + u) * GNC_THREADS + threadIdx.x] = *reinterpret_cast<const uint4*>(h);
         }
       }
     }
   }
   // phase 2 starts from the first pixels again: request them now, the reductions below hide the latency
-  fetch(p0 + lane);
+  auto fetchx = [&](int p) {
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (p + u * lanes < p1) rx[u].load(xp + (int64_t)(p + u * lanes) * x_ld);
+  };
+  if (DZ) fetchx(p0 + lane);
+  else fetch(p0 + lane);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float* r = red + ((lane * C + c0 + j) * 3);
@@ -667,27 +686,46 @@ gn_bwd_cluster_kernel(const T* __restrict__ dy, int dy_ld, const T* __restrict__
 #pragma unroll
   for (int j = 0; j < 8; ++j) P[j] = rstd * sc[j] * gamma[c0 + j];
   T* dp = dx + (int64_t)b * HW * dx_ld + c0;
-  for (int p = p0 + lane; p < p1; p += UB * lanes) {
+  slot = 0;
+  for (int p = p0 + lane; p < p1; p += UB * lanes, slot += UB) {
     Raw8<T> cx[UB], cg2[UB];
-    if (!PIPE && p != p0 + lane) fetch(p);
+    if (DZ) {
+      if (!PIPE && p != p0 + lane) fetchx(p);
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      cx[u] = rx[u];
-      cg2[u] = rg[u];
+      for (int u = 0; u < UB; ++u) cx[u] = rx[u];
+      if (PIPE && p + UB * lanes < p1) fetchx(p + UB * lanes);
+    } else {
+      if (!PIPE && p != p0 + lane) fetch(p);
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        cx[u] = rx[u];
+        cg2[u] = rg[u];
+      }
+      if (PIPE && p + UB * lanes < p1) fetch(p + UB * lanes);
     }
-    if (PIPE && p + UB * lanes < p1) fetch(p + UB * lanes);
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
       if (p + u * lanes < p1) {
         float xv[8], gv[8];
         cx[u].unpack(xv);
-        cg2[u].unpack(gv);
+        if (DZ) {
+          const uint4 d4 = dz_park[(slot + u) * GNC_THREADS + threadIdx.x];
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&d4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = fmaf(A[j], xv[j], Bc[j]);
-          const float sg = sigmoid_t<T>(z);
-          const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
-          xv[j] = fmaf(P[j], dz, fmaf(R, xv[j], Q));
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            xv[2 * j] = fmaf(P[2 * j], f.x, fmaf(R, xv[2 * j], Q));
+            xv[2 * j + 1] = fmaf(P[2 * j + 1], f.y, fmaf(R, xv[2 * j + 1], Q));
+          }
+        } else {
+          cg2[u].unpack(gv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(A[j], xv[j], Bc[j]);
+            const float sg = sigmoid_t<T>(z);
+            const float dz = gv[j] * sg * (1.f + z * (1.f - sg));
+            xv[j] = fmaf(P[j], dz, fmaf(R, xv[j], Q));
+          }
         }
         st8(dp + (int64_t)(p + u * lanes) * dx_ld, xv);
       }
@@ -1088,12 +1126,30 @@ extern "C" int b200dm_gn_apply_bwd(int32_t dtype, const void* dy, int32_t dy_ld,
     const int cl = gn_cluster_size(B, HW, C, minb);
     dim3 grid(cl, B);
     cudaError_t e;
-#define GN_BWD_LAUNCH(TT, UB, PIPE, MINB)                                                                          \
-  e = launch_cluster(gn_bwd_cluster_kernel<TT, UB, PIPE, MINB>, grid, cl, 0, st, (const TT*)dy, (int)dy_ld,        \
+#define GN_BWD_LAUNCH(TT, UB, PIPE, MINB, DZ, SMEM)                                                                 \
+  e = launch_cluster(gn_bwd_cluster_kernel<TT, UB, PIPE, MINB, DZ>, grid, cl, SMEM, st, (const TT*)dy, (int)dy_ld,  \
                      (const TT*)x, (int)x_ld, stats, gamma, beta, film, (int)film_ld, (TT*)dx, (int)dx_ld, dgamma, \
                      dbeta, dfilm, dbias, (int)HW, (int)C, (int)G)
-    if (dtype == B200DM_F32) GN_BWD_LAUNCH(float, 2, true, 3);
-    else GN_BWD_LAUNCH(bf16, 3, true, 2);
+    if (dtype == B200DM_F32) {
+      GN_BWD_LAUNCH(float, 2, true, 3, false, 0);
+    } else {
+      // dz parked in shared memory when the chunk's vectors fit next to a second resident CTA: one 16-byte slot per
+      // (pixel of the thread, thread); 2 x (43.5 KiB static + 68 KiB) stays under the SM's 227 KiB
+      const int lanes = GNC_THREADS / (C / 8), ppb = (HW + cl - 1) / cl;
+      const size_t park = (size_t)((ppb + lanes - 1) / lanes) * GNC_THREADS * 16;
+      static const bool dz_on = []() { const char* v = getenv("B200DM_GNB_DZ"); return !(v && v[0] == '0'); }();
+      if (dz_on && park <= 68 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+          cudaFuncSetAttribute(gn_bwd_cluster_kernel<bf16, 3, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               68 * 1024);
+          configured = true;
+        }
+        GN_BWD_LAUNCH(bf16, 3, true, 2, true, park);
+      } else {
+        GN_BWD_LAUNCH(bf16, 3, true, 2, false, 0);
+      }
+    }
 #undef GN_BWD_LAUNCH
     B200DM_REQUIRE(e == cudaSuccess, B200DM_ERR_CUDA, "gn_apply_bwd: launch failed: %s", cudaGetErrorString(e));
     count_launch();
