@@ -328,7 +328,7 @@ int b200dm_linattn_bwd(int32_t dtype, const void* dout, int32_t dout_ld, const v
                        float* dctx, void* dqkv, int32_t dqkv_ld, float* dmem_kv, int32_t B,
                        int32_t n, void* stream);
 
-/* LinearAttention block for inference in three launches that never store q, k, v (csrc/linattn_tc.cu):
+/* LinearAttention block for inference in four launches that never store q, k, v (csrc/linattn_tc.cu):
  *   y = RMSNorm(to_out(LinearAttention(to_qkv(RMSNorm(x))))) + x
  * reference ddpm.py:205-238 (LinearAttention.forward), :184-191 (RMSNorm), :449,:464 (`attn(x) + x`).  bf16 only.
  * wqkv is to_qkv.weight with the first RMSNorm's gain folded in (b200dm_pack_linattn_qkv); wout is to_out.0.weight as

@@ -1,15 +1,16 @@
-// LinearAttention block of the UNet for INFERENCE as three tcgen05 launches that never write q, k, v:
+// LinearAttention block of the UNet for INFERENCE as four launches that never write q, k, v:
 //
 //     y = RMSNorm_out( to_out( LinearAttention( to_qkv( RMSNorm(x) ) ) ) ) + x
-//         (reference ddpm.py:205-238 LinearAttention.forward, :184-191 RMSNorm, :449/:464 the `attn(x) + x` skip)
+//         (reference ddpm.py:205-238 LinearAttention.forward, :107-113 RMSNorm, :449/:464 the `attn(x) + x` skip)
 //
 // The unfused path (rmsnorm_fwd -> 1x1 conv -> linattn_fwd -> 1x1 conv -> rmsnorm_fwd) moves the [pixels][384] qkv
 // tensor through HBM twice (write-bound conv, then the attention core); at the DDIM benchmark's first level that is
 // 1.6 GB per block for 134 MB of input.  Here every pixel tile is projected on the tensor cores where it is needed:
 //
-//   pass 0  la_ctx_kernel<0>   kmax[b][h,d]  = max_n k[h,d,n]                       (k = Wk' x / |x|, not stored)
-//   pass 1  la_ctx_kernel<1>   ctx[b][h][d][e] = sum_n exp(k - kmax) v[e,n],  s[b][h,d] = sum_n exp(k - kmax)
-//   pass 2  la_out_kernel      q = softmax_d(Wq' x / |x|);  o = ctx^T q / s;  y = RMSNorm(Wout o + b) + x
+//   pass 0  la_kmax_kernel  rn[pixel] = 1 / |x|;  kmax[b][h,d] = max_n k[h,d,n]        (k = Wk' x / |x|, not stored)
+//   pass 1  la_ctx_kernel   ctx[b][h][d][e] = sum_n exp(k - kmax) v[e,n],  s[b][h,d] = sum_n exp(k - kmax)
+//   mid     la_mid_kernel   Mb[b] = Wout * blockdiag_h(scale * (ctx + memory kv)^T / s)              ([C][128] bf16)
+//   pass 2  la_out_kernel   q = softmax_d(Wq' x / |x|);  y = RMSNorm(Mb q + bias) + x
 //
 // RMSNorm(x) = x / max(|x|, 1e-12) * g * sqrt(C): the gain g * sqrt(C) is folded into the projection weights
 // (b200dm_pack_linattn_qkv) and the per-pixel 1/|x| is applied to the accumulators, so the kernels read the raw x.
@@ -17,8 +18,9 @@
 // row and the softmax over pixels and the bf16 operand rows of the second product (P V^T, K = pixels) are thread-local;
 // pass 2 computes rows = pixels, so the softmax over d, the RMSNorm over channels and the residual are thread-local.
 // All products are tcgen05.mma (M = 128) with TMEM accumulators; the four heads' 32x32 contexts are the diagonal
-// blocks of one 128x128 product (the off-diagonal blocks are computed and ignored / multiplied by zeros: < 2 % of
-// the UNet's FLOPs).  Softmax over n uses the exact maximum (pass 0), as the reference does.
+// blocks of one 128x128 product (the off-diagonal blocks are computed and ignored: < 2 % of the UNet's FLOPs), and
+// to_out is applied to the per-sample context once (mid) instead of to every pixel.  Softmax over n uses the exact
+// maximum (pass 0), as the reference does.  18 warps per CTA: TMA producer, MMA issuer, 16 transform warps.
 #include "tc_common.cuh"
 
 namespace b200dm {
