@@ -234,8 +234,10 @@ int b200dm_im2col7(const float* x, void* P, int32_t B, int32_t C, int32_t H, int
 int b200dm_pack_stem_weight(const float* w, void* wp, int32_t Cout, int32_t K, int32_t KP, void* stream);
 
 /* The 7x7 stem as ONE tensor-core launch (csrc/stem_tc.cu): the im2col patches are built in shared memory instead of
- * HBM.  x NCHW fp32 [B][C][H][W], wp = b200dm_pack_stem_weight's bf16 rows [64][KP], y NHWC bf16 (row pitch y_ld).
- * init_conv, ddpm.py:304,437.  Needs W in {8,16,32,64,128}, H*W a multiple of 128, KP <= 256 (up to 5 input channels). */
+ * HBM.  x NCHW fp32 [B][C][H][W], y NHWC bf16 (row pitch y_ld).
+ * wp = b200dm_pack_stem_rows' bf16 rows [64][KP]: K order (channel, ky) filter rows of 7 taps + one zero, KP >= C*56.
+ * init_conv, ddpm.py:304,437.  Needs W in {8,16,32,64,128}, H*W a multiple of 128, its buffers within 227 KiB. */
+int b200dm_pack_stem_rows(const float* w, void* wp, int32_t Cout, int32_t C, int32_t KP, void* stream);
 int b200dm_stem7_supported(int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, int32_t y_ld);
 int b200dm_stem7_fwd(const float* x, const void* wp, const float* bias, void* y, int32_t y_ld, int32_t B, int32_t C,
                      int32_t H, int32_t W, int32_t KP, void* stream);

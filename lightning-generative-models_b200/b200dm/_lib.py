@@ -110,6 +110,7 @@ PROTOTYPES = {
     "b200dm_colsum_batched": [_I, _P, _I, _P],
     "b200dm_concat2_nchw": [_P, _P, _P, _I, _L, _L, _P],
     "b200dm_stem7_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200dm_pack_stem_rows": [_P, _P, _I, _I, _I, _P],
     "b200dm_pack_linattn_qkv": [_P, _P, _P, _I, _P],
     "b200dm_linattn_block_fwd": [_P, _P],
     "b200dm_im2col7": [_P, _P, _I, _I, _I, _I, _I, _P],

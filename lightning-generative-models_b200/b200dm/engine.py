@@ -52,6 +52,10 @@ class WeightPack:
         self.stem_k = arena.in_channels * 49
         self.stem_kp = (self.stem_k + 63) // 64 * 64
         self.stem = torch.zeros(arena.dim * self.stem_kp, dtype=tdt, device=dev) if dt == L.BF16 else None
+        # the same weights in filter-row order (7 taps + a zero per 16-byte chunk) for the one-launch stem of inference
+        self.stem_rows_kp = (arena.in_channels * 56 + 63) // 64 * 64
+        self.stem_rows = (torch.zeros(arena.dim * self.stem_rows_kp, dtype=tdt, device=dev)
+                          if dt == L.BF16 else None)
         # Upsample convs (ddpm.py:93-97) for inference: weights of the fused upsample + 3x3 launch (conv mode 3),
         # [4 taps][4 phases][Cout][Cin]; packed on demand (inference plans only)
         self.up = {}
@@ -112,6 +116,8 @@ class WeightPack:
         if self.stem is not None:
             L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
                    self.arena.dim, self.stem_k, self.stem_kp)
+            L.call("b200dm_pack_stem_rows", self.arena.ptr("init_conv.weight"), self.stem_rows.data_ptr(),
+                   self.arena.dim, self.arena.in_channels, self.stem_rows_kp)
         self.version = v
 
 
@@ -153,6 +159,8 @@ class WeightPack:
         if has_stem:
             L.call("b200dm_pack_stem_weight", self.arena.ptr("init_conv.weight"), self.stem.data_ptr(),
                    self.arena.dim, self.stem_k, self.stem_kp)
+            L.call("b200dm_pack_stem_rows", self.arena.ptr("init_conv.weight"), self.stem_rows.data_ptr(),
+                   self.arena.dim, self.arena.in_channels, self.stem_rows_kp)
         for nm, buf in self.up.items():
             if begin <= self.arena.offset[nm + ".weight"] < end:
                 ci = self.arena.convs[nm]
@@ -607,15 +615,16 @@ class Plan:
         if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None:
             # stem on the tensor cores: im2col patches (kept for the weight gradient) + 1x1 GEMM conv
             KP, K = self.pack.stem_kp, self.pack.stem_k
-            # inference: ONE launch, patches built in shared memory (csrc/stem_tc.cu; DDIM-50 862 -> 868 img/s: 166 us
-            # against 103 + 87, the gather is bound by 4-byte shared-memory reads).  Training needs the patch matrix for
-            # the weight gradient anyway and measured 0.03 ms slower with it rebuilt in backward: it keeps the GEMM path.
+            # inference: ONE launch, patches built in shared memory (csrc/stem_tc.cu).  Training needs the patch matrix
+            # for the weight gradient anyway and measured 0.03 ms slower with it rebuilt in backward: it keeps the GEMM path.
+            KR = self.pack.stem_rows_kp
             fused_stem = (self.fuse_stem and not tr and dim == 64
-                          and self.lib.b200dm_stem7_supported(B, chi, S, S, KP, r.ld) == 1)
+                          and self.lib.b200dm_stem7_supported(B, chi, S, S, KR, r.ld) == 1)
             P = None if fused_stem else self.buf(S, KP)
             if fused_stem:
-                self.F("b200dm_stem7_fwd", self.stem_in.data_ptr(), self.pack.stem.data_ptr(), a.ptr("init_conv.bias"),
-                       r.ptr, r.ld, B, chi, S, S, KP, kname="stem7_fwd", flops=2.0 * B * S * S * dim * K, writes=(r,))
+                self.F("b200dm_stem7_fwd", self.stem_in.data_ptr(), self.pack.stem_rows.data_ptr(),
+                       a.ptr("init_conv.bias"), r.ptr, r.ld, B, chi, S, S, KR, kname="stem7_fwd",
+                       flops=2.0 * B * S * S * dim * K, writes=(r,))
             else:
                 self.F("b200dm_im2col7", self.stem_in.data_ptr(), P.ptr, B, chi, S, S, KP)
                 d = L.ConvDesc(dtype=self.dt, mode=0, ksize=1, impl=1, B=B, H=S, W=S, Cin=KP, Cout=dim, x=P.ptr,

@@ -8,10 +8,12 @@
 //                          A operand [128 px][K] as 128-byte-swizzled bf16 blocks by hand (fence.proxy.async)
 //   warp 0      MMA      : D[128 px][64] = A W^T, K / 16 tcgen05.mma, two A buffers and two TMEM accumulators
 //   warps 9..12 epilogue : tcgen05.ld -> + bias -> bf16 -> staged rows -> coalesced 16-byte stores
-// The weights [64][K] (b200dm_pack_stem_weight) are TMA-loaded once per CTA.  Used by inference plans; training needs the
-// patch matrix for the weight gradient and keeps the GEMM path.  Measured at the DDIM shape: 166 us (im2col 103 + GEMM
-// 87 before) - the builders' 4-byte shared-memory gathers (98 KB per tile) are what bounds it; a K order of
-// (channel, ky) rows padded to 8 taps would make them conflict-free.
+// K order: one 16-byte chunk of the A operand = one filter ROW (channel, ky) = 7 taps + a zero: k = (c*7 + ky)*8 + kx
+// (b200dm_pack_stem_rows packs the weights the same way, K = C*56 padded to a multiple of 64).  A builder thread owns a
+// pixel, so the 32 lanes of a warp read 32 consecutive window elements per tap: conflict-free (the OIHW order of the
+// im2col GEMM made every chunk straddle filter rows: per-tap offset tables and 2-3-way bank conflicts, 166 us).
+// The weights are TMA-loaded once per CTA.  Used by inference plans; training needs the patch matrix for the weight
+// gradient and keeps the GEMM path (im2col 103 + GEMM 87 us at the DDIM shape).
 #include "tc_common.cuh"
 
 namespace b200dm {
@@ -34,7 +36,7 @@ struct StemParams {
   const float* x;
   const float* bias;
   __nv_bfloat16* y;
-  int y_ld, B, C, H, W, K, KB, rows;       // rows = 128 / W image rows per tile
+  int y_ld, B, C, H, W, KB, rows;          // rows = 128 / W image rows per tile
 };
 
 __device__ __forceinline__ uint32_t st_pack(float a, float b) {
@@ -58,8 +60,7 @@ stem7_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
   auto d_empty = [&](int s) { return w_full + 56u + 8u * s; };
   const uint32_t tmem_slot = w_full + 72u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + OFF_BAR + 72);
-  int* koff = reinterpret_cast<int*>(base_ptr + OFF_BAR + 128);             // [KB * 64] window offset of tap k, -1 = pad
-  float* bias_s = reinterpret_cast<float*>(base_ptr + OFF_BAR + 128 + ST_MAXKB * 64 * 4);   // [64]
+  float* bias_s = reinterpret_cast<float*>(base_ptr + OFF_BAR + 128);       // [64]
   float* win = bias_s + 64;                                                  // [2 buffers][C][rows + 6][W + 6]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,10 +82,6 @@ stem7_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
-  for (int k = threadIdx.x; k < KB * 64; k += ST_THREADS) {
-    const int ch = k / 49, r = k - ch * 49, ky = r / 7, kx = r - ky * 7;
-    koff[k] = k < p.K ? (ch * PH + ky) * PW + kx : -1;
-  }
   if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -126,17 +123,12 @@ stem7_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
     }
   } else if (warp <= ST_BUILD / 32) {
     // ===================== builders =====================
-    // thread = (16-byte chunk c of the K axis, pixel lane): the window offsets of its eight taps live in registers for
-    // the whole kernel; it walks the tile's pixels lane, lane + lanes, ...
+    // thread = (pixel of the tile, chunk parity): chunk c = filter row (channel c / 7, ky = c % 7), chunks >= 7 C are padding
     const int tb = threadIdx.x - 32;
-    const int nchunk = KB * 8, lanes = ST_BUILD / nchunk;
-    const int c = tb % nchunk, plane = tb / nchunk;
-    const bool active = plane < lanes;
-    int off[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) off[i] = koff[c * 8 + i];
-    const int blk = c >> 3, cc = c & 7;
+    const int px = tb & 127, chalf = tb >> 7;
+    const int nchunk = KB * 8, nrows = p.C * 7;
     const int wsh = 31 - __clz(p.W);                     // W is a power of two
+    const int pbase = (px >> wsh) * PW + (px & (p.W - 1));
     const int bw = tb >> 5, bl = tb & 31;
     // input window of tile j into window buffer j & 1: one warp per (channel, window row), 4-byte cp.async (the rows
     // start 3 pixels left of the image: no wider alignment), zero padding by plain stores
@@ -169,16 +161,15 @@ stem7_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
       named_bar_sync(1, ST_BUILD);                       // window j complete; the gathers of tile j-1 are done
       if (j + 1 < nt) load_window(j + 1);                // in flight while this tile is gathered
       mbar_wait(a_empty(s), (uint32_t)((j >> 1) & 1) ^ 1u);      // the MMAs of tile j-2 have read this buffer
-      uint8_t* arow = base_ptr + OFF_A + (s * KB + blk) * ST_BLK;
-      if (active) {
-        for (int px = plane; px < 128; px += lanes) {
-          const int pbase = (px >> wsh) * PW + (px & (p.W - 1));
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = off[i] >= 0 ? wcur[off[i] + pbase] : 0.f;
-          *reinterpret_cast<uint4*>(arow + px * 128 + ((cc ^ (px & 7)) << 4)) =
-              make_uint4(st_pack(v[0], v[1]), st_pack(v[2], v[3]), st_pack(v[4], v[5]), st_pack(v[6], v[7]));
+      uint8_t* abuf = base_ptr + OFF_A + s * KB * ST_BLK;
+      for (int c = chalf; c < nchunk; c += 2) {
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (c < nrows) {
+          const int ch = c / 7, ky = c - ch * 7;
+          const float* wr = wcur + (ch * PH + ky) * PW + pbase;
+          out = make_uint4(st_pack(wr[0], wr[1]), st_pack(wr[2], wr[3]), st_pack(wr[4], wr[5]), st_pack(wr[6], 0.f));
         }
+        *reinterpret_cast<uint4*>(abuf + (c >> 3) * ST_BLK + px * 128 + (((c & 7) ^ (px & 7)) << 4)) = out;
       }
       fence_proxy_async();
       __syncwarp();
@@ -233,6 +224,17 @@ stem7_tc_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
   }
 }
 
+// wp[co][(c*7 + ky)*8 + kx] = bf16(w[co][c][ky][kx]) for kx < 7, zero elsewhere (row padding and K padding)
+__global__ void stem_pack_rows_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int C, int KP) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Cout * KP) {
+    const int co = i / KP, k = i - co * KP;
+    const int row = k >> 3, kx = k & 7;
+    wp[i] = __float2bfloat16_rn((kx < 7 && row < C * 7) ? w[(co * C * 7 + row) * 7 + kx] : 0.f);
+  }
+}
+
 }  // namespace
 }  // namespace b200dm
 
@@ -240,12 +242,12 @@ using namespace b200dm;
 
 static int stem7_smem_bytes(int C, int W, int KP) {
   const int KB = KP / 64, win = C * (128 / W + 6) * (W + 6);
-  return KB * ST_WBLK + 2 * KB * ST_BLK + ST_BLK + 128 + ST_MAXKB * 64 * 4 + 64 * 4 + 2 * win * 4 + 1024;
+  return KB * ST_WBLK + 2 * KB * ST_BLK + ST_BLK + 128 + 64 * 4 + 2 * win * 4 + 1024;
 }
 
 extern "C" int b200dm_stem7_supported(int32_t B, int32_t C, int32_t H, int32_t W, int32_t KP, int32_t y_ld) {
   if (!tc_supported()) return 0;
-  if (B <= 0 || C < 1 || C * 49 > KP || KP % 64 || KP / 64 > ST_MAXKB) return 0;
+  if (B <= 0 || C < 1 || C * 56 > KP || KP % 64 || KP / 64 > ST_MAXKB) return 0;
   if (W < 8 || W > 128 || 128 % W || (H * W) % 128 || H % (128 / W)) return 0;
   if (y_ld % 8 || y_ld < 64) return 0;
   if ((long long)B * H * W >= (1ll << 31)) return 0;
@@ -253,10 +255,18 @@ extern "C" int b200dm_stem7_supported(int32_t B, int32_t C, int32_t H, int32_t W
   return 1;
 }
 
+extern "C" int b200dm_pack_stem_rows(const float* w, void* wp, int32_t Cout, int32_t C, int32_t KP, void* stream) {
+  B200DM_REQUIRE(w && wp && Cout > 0 && C > 0 && C * 56 <= KP, B200DM_ERR_SHAPE, "pack_stem_rows: C=%d KP=%d", C, KP);
+  launch_k(stem_pack_rows_kernel, (Cout * KP + 255) / 256, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)wp, (int)Cout,
+           (int)C, (int)KP);
+  count_launch();
+  return check_launch("pack_stem_rows");
+}
+
 extern "C" int b200dm_stem7_fwd(const float* x, const void* wp, const float* bias, void* y, int32_t y_ld, int32_t B,
                                 int32_t C, int32_t H, int32_t W, int32_t KP, void* stream) {
   B200DM_REQUIRE(b200dm_stem7_supported(B, C, H, W, KP, y_ld) == 1, B200DM_ERR_UNSUPPORTED,
-                 "stem7_fwd: needs sm_100, C*49 <= KP <= 256, KP %% 64 == 0, W in {8..128} dividing 128, H*W %% 128 == 0 "
+                 "stem7_fwd: needs sm_100, C*56 <= KP, KP %% 64 == 0, W in {8..128} dividing 128, H*W %% 128 == 0, buffers in 227 KiB "
                  "(C=%d KP=%d H=%d W=%d)", C, KP, H, W);
   B200DM_REQUIRE(x && wp && y && ((uintptr_t)y & 15) == 0 && ((uintptr_t)wp & 15) == 0, B200DM_ERR_SHAPE,
                  "stem7_fwd: null or misaligned pointer");
@@ -271,7 +281,7 @@ extern "C" int b200dm_stem7_fwd(const float* x, const void* wp, const float* bia
   }
   StemParams p{};
   p.x = x; p.bias = bias; p.y = (__nv_bfloat16*)y; p.y_ld = y_ld; p.B = B; p.C = C; p.H = H; p.W = W;
-  p.K = C * 49; p.KB = KB; p.rows = 128 / W;
+  p.KB = KB; p.rows = 128 / W;
   const int smem = stem7_smem_bytes(C, W, KP);
   static int configured = 0;
   if (configured < smem) {

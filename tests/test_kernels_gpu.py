@@ -461,17 +461,20 @@ def test_stem_on_tensor_cores_im2col_gemm_and_wgrad(C, S, B):
     del guard
 
 
-@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 64, 2), (5, 32, 2), (3, 16, 5), (2, 128, 1), (3, 64, 37), (4, 16, 2)])
+@pytest.mark.parametrize("C,S,B", [(3, 32, 4), (1, 32, 3), (3, 64, 2), (3, 16, 5), (2, 128, 1), (3, 64, 37), (4, 16, 2), (4, 32, 1)])
 def test_stem_one_launch_patches_in_shared_memory(C, S, B):
     """b200dm_stem7_fwd (csrc/stem_tc.cu) against F.conv2d on the bf16-rounded operands, output as a channel slice."""
     if not L.load().b200dm_tc_available():
         pytest.skip("needs the tcgen05 path")
-    K, KP = C * 49, (C * 49 + 63) // 64 * 64
+    KP = (C * 56 + 63) // 64 * 64
     x = rnd(B, C, S, S, seed=81)
     w = rnd(64, C, 7, 7, seed=82, scale=0.1)
     bias = rnd(64, seed=83, scale=0.1)
-    wp = torch.empty(64, KP, dtype=torch.bfloat16, device=DEV)
-    L.call("b200dm_pack_stem_weight", w.data_ptr(), wp.data_ptr(), 64, K, KP)
+    wp = torch.full((64, KP), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.call("b200dm_pack_stem_rows", w.data_ptr(), wp.data_ptr(), 64, C, KP)
+    rows = wp[:, :C * 56].float().view(64, C, 7, 8)
+    assert torch.equal(rows[..., :7], q(w, L.BF16)) and rows[..., 7].abs().max().item() == 0
+    assert wp[:, C * 56:].abs().max().item() == 0
     yv = View.zeros(B, S, S, 64, torch.bfloat16, DEV, ld=128, off=64)
     yv.buf.fill_(7.0)
     assert L.load().b200dm_stem7_supported(B, C, S, S, KP, yv.ld) == 1
@@ -481,7 +484,7 @@ def test_stem_one_launch_patches_in_shared_memory(C, S, B):
     assert (yv.buf[..., :64] == 7.0).all()                 # the other half of the concat buffer is untouched
     assert L.load().b200dm_stem7_supported(B, C, 8, 8, KP, yv.ld) == 0       # fewer than 128 pixels per image
     assert L.load().b200dm_stem7_supported(B, C, 48, 48, KP, yv.ld) == 0     # W does not divide 128
-    assert L.load().b200dm_stem7_supported(B, 6, 64, 64, 320, yv.ld) == 0    # six channels at 64x64: buffers + window do not fit
+    assert L.load().b200dm_stem7_supported(B, 6, 64, 64, 384, yv.ld) == 0    # six channels: K = 384 is more than five blocks
 
 
 @pytest.mark.parametrize("dtype", [L.F32, L.BF16], ids=["f32", "bf16"])
