@@ -778,24 +778,30 @@ la_out_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         uint32_t qr[32];
         tmem_ld32(tmem_base + tlane + (uint32_t)(slot * 256 + half * 64 + hh * 32), qr);
         tmem_ld_wait();
+        if (warp == 2 && lane == 0 && j < 8 && hh == 0) LA_TS(300 + j * 4);
         float mxv = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) mxv = fmaxf(mxv, __uint_as_float(qr[i]) * sc);
+        if (warp == 2 && lane == 0 && j < 8 && hh == 0) LA_TS(300 + j * 4 + 1);
         float e[32], sum = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           e[i] = ex2f(fmaf(__uint_as_float(qr[i]), sc, -mxv));
           sum += e[i];
         }
+        if (warp == 2 && lane == 0 && j < 8 && hh == 0) LA_TS(300 + j * 4 + 2);
         const float inv = 1.f / sum;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           sw128_store(qs, r, hh * 4 + g,
                       make_uint4(pack_bf16(e[8 * g] * inv, e[8 * g + 1] * inv), pack_bf16(e[8 * g + 2] * inv, e[8 * g + 3] * inv),
                                  pack_bf16(e[8 * g + 4] * inv, e[8 * g + 5] * inv), pack_bf16(e[8 * g + 6] * inv, e[8 * g + 7] * inv)));
+        if (warp == 2 && lane == 0 && j < 8 && hh == 0) LA_TS(300 + j * 4 + 3);
       }
       tc_fence_before();
+      if (warp == 2 && lane == 0 && j < 8) LA_TS(340 + j * 2);
       fence_proxy_async();
+      if (warp == 2 && lane == 0 && j < 8) LA_TS(340 + j * 2 + 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full(slot));
       if (warp == 2 && lane == 0 && j < 8) LA_TS(16 + j * 8 + 2);

@@ -23,6 +23,9 @@ c = lambda i: (t[i] - t0) if t[i] else -1
 print("pass 2 (cycles since the transform warps start): per tile j: T1[wait-start, dq ready, done]  E[wait-start, dy ready, pre-bar, post-bar, done]")
 for j in range(8):
     print(j, [c(16 + j * 8 + k) for k in range(8)], " mma[wait q, Y issued, Q(j+2) issued]", [c(100 + j * 4 + k) for k in range(3)])
+print("pass 2, softmax warp, first head of tile j: [dq ready, TMEM loaded, max done, exp done, stored]  then [before, after] fence.proxy.async")
+for j in range(8):
+    print(j, [c(16 + j * 8 + 1)] + [c(300 + j * 4 + k) for k in range(4)], [c(340 + j * 2 + k) for k in range(2)])
 t1 = t[200]
 c1 = lambda i: (t[i] - t1) if t[i] else -1
 print("pass 1: per 64-px tile: [wait-start, d1 ready, slot free, done]")
