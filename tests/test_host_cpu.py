@@ -35,6 +35,10 @@ def test_struct_layouts_match_c():
     assert ctypes.sizeof(L.WgradDesc) == 112 and L.WgradDesc.dw.offset == 72 and L.WgradDesc.s_tap.offset == 88
     assert ctypes.sizeof(L.NoiseDesc) == 104 and L.NoiseDesc.offset_strength.offset == 48
     assert L.NoiseDesc.chw.offset == 64 and L.NoiseDesc.seed.offset == 80
+    # b200dm_colsum_item {ptr, ptr, int64, int32, int32}; b200dm_linattn_block_desc {6 int32, 8 pointers}
+    assert ctypes.sizeof(L.ColsumItem) == 32 and L.ColsumItem.rows.offset == 16 and L.ColsumItem.C.offset == 28
+    assert ctypes.sizeof(L.LinAttnBlockDesc) == 88 and L.LinAttnBlockDesc.x.offset == 24
+    assert L.LinAttnBlockDesc.ws.offset == 80
 
 
 def test_schedules_bit_equal_to_oracle():
@@ -188,6 +192,54 @@ def test_linear_attention_partial_merge_and_backward_closed_form():
         assert (dq - q.grad).abs().max().item() < 1e-12
         assert (dkk[:, nm:] - k.grad).abs().max().item() < 1e-12 and (dkk[:, :nm] - mk.grad).abs().max().item() < 1e-12
         assert (dvv[:, nm:] - v.grad).abs().max().item() < 1e-12 and (dvv[:, :nm] - mv.grad).abs().max().item() < 1e-12
+
+
+def test_fused_linear_attention_block_algebra():
+    """fp64 restatement of what csrc/linattn_tc.cu computes (per-pixel 1/|x| applied to the accumulators with the
+    RMSNorm gain folded into the projection, softmax over pixels against the exact row maximum with partial sums over
+    pixel ranges, memory key/values added once, to_out folded into a per-sample operand Mb) against the oracle's
+    LinearAttention + skip (ddpm.py:205-238, :449)."""
+    g = torch.Generator().manual_seed(3)
+    b, c, h = 2, 64, 16
+    n = h * h
+    dd = torch.float64
+    x = torch.randn(b, c, h, h, generator=g, dtype=dd)
+    sd = {"a.norm.g": 1 + 0.2 * torch.randn(1, c, 1, 1, generator=g, dtype=dd),
+          "a.to_qkv.weight": torch.randn(384, c, 1, 1, generator=g, dtype=dd) / c ** 0.5,
+          "a.mem_kv": torch.randn(2, 4, 32, 4, generator=g, dtype=dd),
+          "a.to_out.0.weight": torch.randn(c, 128, 1, 1, generator=g, dtype=dd) / 128 ** 0.5,
+          "a.to_out.0.bias": 0.1 * torch.randn(c, generator=g, dtype=dd),
+          "a.to_out.1.g": 1 + 0.2 * torch.randn(1, c, 1, 1, generator=g, dtype=dd)}
+    want = O.linear_attention(sd, "a", x, O.Emu(None)) + x
+    # ---- the kernels' formulation
+    X = x.permute(0, 2, 3, 1).reshape(b, n, c)                                  # NHWC rows
+    Wf = sd["a.to_qkv.weight"].view(384, c) * sd["a.norm.g"].view(1, c) * c ** 0.5   # b200dm_pack_linattn_qkv
+    rn = 1.0 / X.norm(dim=2).clamp_min(1e-12)                                   # pass 0
+    q = (X @ Wf[:128].T) * rn[..., None]
+    k = (X @ Wf[128:256].T) * rn[..., None]
+    v = (X @ Wf[256:].T) * rn[..., None]
+    mk, mv = sd["a.mem_kv"][0].reshape(128, 4), sd["a.mem_kv"][1].reshape(128, 4)
+    split = 4
+    kmax = torch.stack([k[:, i * n // split:(i + 1) * n // split].max(dim=1).values for i in range(split)]).max(0).values
+    m = torch.maximum(kmax, mk.max(dim=1).values[None])                         # [b, 128]
+    ctx = torch.zeros(b, 4, 32, 32, dtype=dd)
+    ssum = torch.zeros(b, 128, dtype=dd)
+    for i in range(split):                                                      # pass 1, partial sums per pixel range
+        sl = slice(i * n // split, (i + 1) * n // split)
+        p = torch.exp(k[:, sl] - m[:, None])
+        ssum += p.sum(dim=1)
+        ctx += torch.einsum("bnhd,bnhe->bhde", p.view(b, -1, 4, 32), v[:, sl].reshape(b, -1, 4, 32))
+    pm = torch.exp(mk[None] - m[..., None])                                     # mid: memory key/values
+    ssum += pm.sum(dim=2)
+    ctx += torch.einsum("bhdj,hej->bhde", pm.view(b, 4, 32, 4), mv.view(4, 32, 4))
+    ctxn = ctx * (32 ** -0.5) / ssum.view(b, 4, 32, 1)
+    Wout = sd["a.to_out.0.weight"].view(c, 4, 32)
+    Mb = torch.einsum("che,bhde->bchd", Wout, ctxn).reshape(b, c, 128)          # [C][(h, d)]
+    qs = q.view(b, n, 4, 32).softmax(dim=3).reshape(b, n, 128)                  # pass 2
+    y = qs @ Mb.transpose(1, 2) + sd["a.to_out.0.bias"]
+    y = y / y.norm(dim=2, keepdim=True).clamp_min(1e-12) * sd["a.to_out.1.g"].view(1, 1, c) * c ** 0.5 + X
+    got = y.reshape(b, h, h, c).permute(0, 3, 1, 2)
+    assert (got - want).abs().max().item() < 1e-10
 
 
 def test_softmax_attention_backward_closed_form():
