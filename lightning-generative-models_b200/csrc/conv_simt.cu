@@ -446,7 +446,7 @@ init_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, in
 // for the reduction, but slower than one-thread-per-pixel for the forward / dx streams at the sampling batch.)
 constexpr int FC_U = 4;
 
-template <typename T>
+template <typename T, bool CIN64>
 __global__ void __launch_bounds__(256)
 final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w,
                   const float* __restrict__ bias, float* __restrict__ y, int64_t total, int HW,
@@ -459,15 +459,29 @@ final_conv_kernel(const T* __restrict__ x, int x_ld, const float* __restrict__ w
   if (p >= total) return;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const T* xr = x + p * x_ld;
-  for (int k = 0; k < Cin; k += 8) {
-    float v[8];
-    ld8(xr + k, v);
+  if (CIN64) {       // the UNet's head (dim = 64): the whole 64-channel row is requested before the first use
+    float v[8][8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-      if (c < C) {
+    for (int kk = 0; kk < 8; ++kk) ld8(xr + kk * 8, v[kk]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[c] = fmaf(v[j], wsm[c * Cin + k + j], acc[c]);
-      }
+    for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c] = fmaf(v[kk][j], wsm[c * 64 + kk * 8 + j], acc[c]);
+        }
+  } else {
+    for (int k = 0; k < Cin; k += 8) {
+      float v[8];
+      ld8(xr + k, v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[c] = fmaf(v[j], wsm[c * Cin + k + j], acc[c]);
+        }
+    }
   }
   int64_t b = p / HW;
   int pix = (int)(p - b * HW);
@@ -879,9 +893,11 @@ extern "C" int b200dm_final_conv_fwd(int32_t dtype, const void* x, int32_t x_ld,
   unsigned grid = (unsigned)((total + 255) / 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200DM_F32)
-    launch_k(final_conv_kernel<float>, grid, 256, smem, st, (const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<float, false>, grid, 256, smem, st, (const float*)x, x_ld, w, bias, y, total, HW, Cin, C);
+  else if (Cin == 64)
+    launch_k(final_conv_kernel<__nv_bfloat16, true>, grid, 256, smem, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
   else
-    launch_k(final_conv_kernel<__nv_bfloat16>, grid, 256, smem, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
+    launch_k(final_conv_kernel<__nv_bfloat16, false>, grid, 256, smem, st, (const __nv_bfloat16*)x, x_ld, w, bias, y, total, HW, Cin, C);
   count_launch();
   return check_launch("final_conv_fwd");
 }
