@@ -304,8 +304,16 @@ class Plan:
             segs.append(seg)
         return segs
 
-    def _impl(self, cin, cout):
-        return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0) else 0
+    @staticmethod
+    def _tc_size_ok(H):
+        """The tcgen05 kernels tile 128 pixels as whole image rows: H = W must be a power of two in [4, 128]."""
+        return 4 <= H <= 128 and (H & (H - 1)) == 0
+
+    def _impl(self, cin, cout, H):
+        """1 = tcgen05 kernels, 0 = SIMT kernels (fp32 mode; channel counts that are not multiples of 64; levels whose
+        size the tensor-core tiling does not cover, e.g. the 2x2 level of a 16x16 image or any non-power-of-two size)."""
+        return 1 if (self.use_tc and self.dt == L.BF16 and cin % 64 == 0 and cout % 64 == 0
+                     and self._tc_size_ok(H)) else 0
 
     def conv_fwd(self, lst_fn, nm, x: View, y: View, *, dgrad=False, res: Optional[View] = None,
                  accumulate=0, bias=True, side=False, gn_part: Optional[torch.Tensor] = None):
@@ -322,7 +330,7 @@ class Plan:
             b = None
         assert x.C == cin and y.C == cout, (nm, x.C, cin, y.C, cout)
         d = L.ConvDesc(dtype=self.dt, mode=mode, ksize=ci.ksize if ci.mode == 0 else 1,
-                       impl=self._impl(cin, cout), B=self.B, H=H, W=H, Cin=cin, Cout=cout,
+                       impl=self._impl(cin, cout, H), B=self.B, H=H, W=H, Cin=cin, Cout=cout,
                        x=x.ptr, x_ld=x.ld, w=w, bias=b, y=y.ptr, y_ld=y.ld,
                        res=None if res is None else res.ptr, res_ld=0 if res is None else res.ld,
                        accumulate=accumulate, gn_part=None if gn_part is None else gn_part.data_ptr(),
@@ -339,7 +347,7 @@ class Plan:
         """Block.forward as ONE launch (b200dm_conv_gn_fwd): y = SiLU(GN(conv(x)+b)*(scale+1)+shift) (+ res); the
         conv accumulators stay in TMEM across the norm.  emit=False only asks whether the layer is supported."""
         a, ci = self.arena, self.arena.convs[nm]
-        d = L.ConvDesc(dtype=self.dt, mode=0, ksize=3, impl=self._impl(ci.cin, ci.cout), B=self.B, H=y.H, W=y.H,
+        d = L.ConvDesc(dtype=self.dt, mode=0, ksize=3, impl=self._impl(ci.cin, ci.cout, y.H), B=self.B, H=y.H, W=y.H,
                        Cin=ci.cin, Cout=ci.cout, x=x.ptr, x_ld=x.ld, w=self.pack.fwd[nm].data_ptr(),
                        bias=a.ptr(nm + ".bias"), y=y.ptr, y_ld=y.ld, res=None if res is None else res.ptr,
                        res_ld=0 if res is None else res.ld, accumulate=0, gn_part=None, gn_groups=0)
@@ -366,7 +374,7 @@ class Plan:
         else:
             s_tap, s_co, s_ci = 1, 4 * ci.cin, 4
         d = L.WgradDesc(dtype=self.dt, mode=ci.mode, ksize=ci.ksize if ci.mode == 0 else 1,
-                        impl=self._impl(ci.cin, ci.cout), B=self.B, H=H, W=H, Cin=ci.cin, Cout=ci.cout,
+                        impl=self._impl(ci.cin, ci.cout, H), B=self.B, H=H, W=H, Cin=ci.cin, Cout=ci.cout,
                         x=x.ptr, x_ld=x.ld, dy=dy.ptr, dy_ld=dy.ld, dw=self.arena.gptr(nm + ".weight"),
                         accumulate=1, s_tap=s_tap, s_co=s_co, s_ci=s_ci)
         self.Bk("b200dm_conv_wgrad", C.byref(d), kname="wgrad_tc" if d.impl == 1 else "wgrad_simt",
@@ -401,7 +409,7 @@ class Plan:
             self.conv_fwd(self.F, nm + ".res_conv", x, rc, side=True)
         res = rc if has_res_conv else x
         gs = cout // GROUPS
-        fused = (self.fuse_gn_stats and self._impl(cin, cout) == 1 and self._impl(cout, cout) == 1
+        fused = (self.fuse_gn_stats and self._impl(cin, cout, H) == 1 and self._impl(cout, cout, H) == 1
                  and gs % 8 == 0)
         one_launch = (fused and self.fuse_gn
                       and self.conv_gn(b1 + ".proj", b1 + ".norm", x, h1, emit=False)
@@ -527,7 +535,7 @@ class Plan:
     def upsample_conv(self, nm, x: View, out: View, gx, gout):
         self.begin_unit()
         ci = self.arena.convs[nm]
-        if nm in self.pack.up and self._impl(ci.cin, ci.cout) == 1 and self.fuse_upsample:
+        if nm in self.pack.up and self._impl(ci.cin, ci.cout, x.H) == 1 and self.fuse_upsample:
             # nearest-2x upsample + 3x3 conv as ONE launch over the low-resolution tensor (conv mode 3: four 2x2
             # convs, one per output phase; 16 instead of 36 multiply-adds per output, no upsampled copy on the chain)
             d = L.ConvDesc(dtype=self.dt, mode=3, ksize=3, impl=1, B=self.B, H=x.H, W=x.H, Cin=ci.cin, Cout=ci.cout,
@@ -612,7 +620,7 @@ class Plan:
         if a.self_condition:     # torch.cat((x_self_cond, x), dim=1), ddpm.py:435
             self.F("b200dm_concat2_nchw", self.xc_in.data_ptr(), self.x_in.data_ptr(), self.stem_in.data_ptr(), B,
                    ch * S * S, ch * S * S)
-        if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None:
+        if self.use_tc and self.dt == L.BF16 and self.pack.stem is not None and self._tc_size_ok(S):
             # stem on the tensor cores: im2col patches (kept for the weight gradient) + 1x1 GEMM conv
             KP, K = self.pack.stem_kp, self.pack.stem_k
             # inference: ONE launch, patches built in shared memory (csrc/stem_tc.cu).  Training needs the patch matrix

@@ -132,6 +132,35 @@ def test_unet_forward_vs_golden_and_oracle(name, precision):
         assert r2 <= 1e-2 + r3, (r2, r3)
 
 
+@pytest.mark.parametrize("s", [16, 24, 40])
+def test_bf16_sizes_outside_the_tensor_core_tiling(s):
+    """Images whose levels the tcgen05 kernels do not tile (2x2 innermost level, non-power-of-two sizes) run those levels
+    on the SIMT kernels in bf16: loss, UNet output and gradients against the oracle, DDIM-4 against its samples."""
+    ch, b = 3, 2
+    x, t, noise, init = seeded_inputs(b, ch, s)
+    unet, gd = build(ch, s, "bf16")
+    orc = cuda_oracle(ch, s, grads=True, sampling_timesteps=4)
+    xd, td, nd = x.to(DEV), t.to(DEV), noise.to(DEV)
+    loss = gd.p_losses(xd, td, noise=nd, _normalize=True)
+    loss.backward()
+    with precision_ctx("fp32"):
+        want, _, out_ref, _ = orc.p_losses(xd * 2 - 1, td, nd, return_parts=True)
+    want.backward()
+    plan = unet._plan(b, s, training=True)
+    r_out = rel(plan.out, out_ref)
+    num = sum((p.grad.double().cpu() - orc.sd[n].grad.double().cpu()).pow(2).sum().item() for n, p in unet.named_parameters())
+    den = sum(orc.sd[n].grad.double().pow(2).sum().item() for n, _ in unet.named_parameters())
+    r_grad = (num / den) ** 0.5
+    with torch.no_grad(), precision_ctx("fp32"):
+        img_ref = orc.sample(init.to(DEV))
+    img = gd.sample(batch_size=b, init_noise=init.to(DEV))
+    p = psnr(img, img_ref)
+    report(test="bf16_odd_sizes", size=s, loss_rel=abs(loss.item() - want.item()) / abs(want.item()), out_rel=r_out,
+           grad_rel=r_grad, ddim4_psnr=p)
+    assert abs(loss.item() - want.item()) <= 1e-2 * abs(want.item())
+    assert r_out <= 1.25e-2 and r_grad <= 5e-2 and p >= 38, (r_out, r_grad, p)
+
+
 @pytest.mark.parametrize("name", ["c3s32", "c1s32", "c3s64", "c3s32_x0"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_loss_and_all_gradients(name, precision):
