@@ -56,7 +56,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // collective (b200dm_set_reserved_sms).  A conv CTA needs a whole SM (>= 200 KiB of shared memory), so while NCCL's
 // CTAs hold SMs a 148-CTA grid runs as two waves; sizing it to the free SMs keeps it at one.
 int reserved_sms();
-inline int num_sms() {
+inline int device_sms() {      // the device's SM count, whatever is reserved (sizes that must not change between calls)
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -64,7 +64,10 @@ inline int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  const int r = reserved_sms();
+  return n;
+}
+inline int num_sms() {
+  const int n = device_sms(), r = reserved_sms();
   return n - r > 16 ? n - r : n;
 }
 

@@ -921,7 +921,8 @@ __global__ void la_pack_qkv_kernel(const float* __restrict__ w, const float* __r
 int la_split(int B, int n) {
   const int tps = n / LB_TILE;
   int split = 1;
-  while (split * 2 <= 8 && tps % (split * 2) == 0 && (long long)B * split < 4ll * num_sms()) split *= 2;
+  // device_sms(), not num_sms(): the workspace layout must not depend on SMs reserved for a collective at call time
+  while (split * 2 <= 8 && tps % (split * 2) == 0 && (long long)B * split < 4ll * device_sms()) split *= 2;
   return split;
 }
 
